@@ -1,0 +1,396 @@
+/* oracle/oracle.c — TEST INFRASTRUCTURE ONLY (see oracle.h for the rules).
+ *
+ * CPU restatement of the reference's scalar semantics for the hot path.  It is
+ * written from the behaviour described in SURVEY.md Appendix A and the cited
+ * reference lines, as one decode-one-character routine per encoding rather
+ * than a transcription of the reference's loops.
+ */
+#include "oracle.h"
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* UTF-8: decode exactly one character at in[pos].                           */
+/* Follows reference src/scalar/utf8.h:102-200 (validate_with_errors) and    */
+/* src/scalar/utf8_to_utf16/utf8_to_utf16.h:128-255 (same error rules, same  */
+/* order: length/continuation checks -> OVERLONG -> SURROGATE / TOO_LARGE).  */
+/* Returns the error code; on success *cp and *adv are set.                  */
+/* ------------------------------------------------------------------------- */
+static int is_cont(uint8_t b) { return (b & 0xC0) == 0x80; }
+
+static int utf8_decode_one(const uint8_t *in, size_t len, size_t pos, uint32_t *cp, unsigned *adv) {
+  uint8_t b0 = in[pos];
+  if (b0 < 0x80) { *cp = b0; *adv = 1; return ORACLE_SUCCESS; }
+  if ((b0 & 0xE0) == 0xC0) {
+    if (pos + 2 > len || !is_cont(in[pos + 1])) return ORACLE_TOO_SHORT;
+    uint32_t c = ((uint32_t)(b0 & 0x1F) << 6) | (in[pos + 1] & 0x3F);
+    if (c < 0x80) return ORACLE_OVERLONG;
+    *cp = c; *adv = 2; return ORACLE_SUCCESS;
+  }
+  if ((b0 & 0xF0) == 0xE0) {
+    if (pos + 3 > len || !is_cont(in[pos + 1]) || !is_cont(in[pos + 2])) return ORACLE_TOO_SHORT;
+    uint32_t c = ((uint32_t)(b0 & 0x0F) << 12) | ((uint32_t)(in[pos + 1] & 0x3F) << 6) | (in[pos + 2] & 0x3F);
+    if (c < 0x800) return ORACLE_OVERLONG;
+    if (c >= 0xD800 && c <= 0xDFFF) return ORACLE_SURROGATE;
+    *cp = c; *adv = 3; return ORACLE_SUCCESS;
+  }
+  if ((b0 & 0xF8) == 0xF0) {
+    if (pos + 4 > len || !is_cont(in[pos + 1]) || !is_cont(in[pos + 2]) || !is_cont(in[pos + 3]))
+      return ORACLE_TOO_SHORT;
+    uint32_t c = ((uint32_t)(b0 & 0x07) << 18) | ((uint32_t)(in[pos + 1] & 0x3F) << 12) |
+                 ((uint32_t)(in[pos + 2] & 0x3F) << 6) | (in[pos + 3] & 0x3F);
+    if (c <= 0xFFFF) return ORACLE_OVERLONG;
+    if (c > 0x10FFFF) return ORACLE_TOO_LARGE;
+    *cp = c; *adv = 4; return ORACLE_SUCCESS;
+  }
+  /* stray continuation byte, or a header with 5+ leading ones (0xF8..0xFF) */
+  return is_cont(b0) ? ORACLE_TOO_LONG : ORACLE_HEADER_BITS;
+}
+
+/* reference src/scalar/utf8.h:102-200; empty input -> {SUCCESS,0}
+ * (src/icelake/implementation.cpp:204-206). */
+oracle_result oracle_validate_utf8_with_errors(const uint8_t *in, size_t len) {
+  oracle_result r;
+  size_t pos = 0;
+  while (pos < len) {
+    uint32_t cp; unsigned adv;
+    int e = utf8_decode_one(in, len, pos, &cp, &adv);
+    if (e) { r.error = e; r.count = pos; return r; }
+    pos += adv;
+  }
+  r.error = ORACLE_SUCCESS; r.count = len;
+  return r;
+}
+
+/* reference include/simdutf/implementation.h:3378-3379 (validate_utf8) */
+int oracle_validate_utf8(const uint8_t *in, size_t len) {
+  return oracle_validate_utf8_with_errors(in, len).error == ORACLE_SUCCESS;
+}
+
+/* reference src/scalar/utf8.h:230-241 — never validates */
+uint64_t oracle_count_utf8(const uint8_t *in, size_t len) {
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++) n += !is_cont(in[i]);
+  return n;
+}
+
+/* reference src/scalar/utf8.h:243-255 — never validates */
+uint64_t oracle_utf16_length_from_utf8(const uint8_t *in, size_t len) {
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++) n += (uint64_t)!is_cont(in[i]) + (in[i] >= 0xF0);
+  return n;
+}
+
+/* reference src/icelake/implementation.cpp:1596-1599 (== count_utf8) */
+uint64_t oracle_utf32_length_from_utf8(const uint8_t *in, size_t len) { return oracle_count_utf8(in, len); }
+
+/* reference src/scalar/utf8_to_utf16/utf8_to_utf16.h:128-255 (LITTLE endian; host is LE) */
+oracle_result oracle_convert_utf8_to_utf16le_with_errors(const uint8_t *in, size_t len, uint16_t *out) {
+  oracle_result r;
+  size_t pos = 0; uint64_t w = 0;
+  while (pos < len) {
+    uint32_t cp; unsigned adv;
+    int e = utf8_decode_one(in, len, pos, &cp, &adv);
+    if (e) { r.error = e; r.count = pos; return r; }
+    if (cp < 0x10000) {
+      out[w++] = (uint16_t)cp;
+    } else {
+      cp -= 0x10000;
+      out[w++] = (uint16_t)(0xD800 + (cp >> 10));
+      out[w++] = (uint16_t)(0xDC00 + (cp & 0x3FF));
+    }
+    pos += adv;
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+
+/* reference src/scalar/utf8_to_utf16/utf8_to_utf16.h:9-126: units written, 0 on any error */
+uint64_t oracle_convert_utf8_to_utf16le(const uint8_t *in, size_t len, uint16_t *out) {
+  oracle_result r = oracle_convert_utf8_to_utf16le_with_errors(in, len, out);
+  return r.error ? 0 : r.count;
+}
+
+/* reference src/scalar/utf8_to_utf32/utf8_to_utf32.h:106-212 */
+oracle_result oracle_convert_utf8_to_utf32_with_errors(const uint8_t *in, size_t len, uint32_t *out) {
+  oracle_result r;
+  size_t pos = 0; uint64_t w = 0;
+  while (pos < len) {
+    uint32_t cp; unsigned adv;
+    int e = utf8_decode_one(in, len, pos, &cp, &adv);
+    if (e) { r.error = e; r.count = pos; return r; }
+    out[w++] = cp;
+    pos += adv;
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+
+uint64_t oracle_convert_utf8_to_utf32(const uint8_t *in, size_t len, uint32_t *out) {
+  oracle_result r = oracle_convert_utf8_to_utf32_with_errors(in, len, out);
+  return r.error ? 0 : r.count;
+}
+
+/* ------------------------------------------------------------------------- */
+/* UTF-16LE                                                                   */
+/* ------------------------------------------------------------------------- */
+static int is_high(uint16_t w) { return (w & 0xFC00) == 0xD800; }
+static int is_low(uint16_t w) { return (w & 0xFC00) == 0xDC00; }
+
+/* reference src/scalar/utf16.h:39-67 */
+oracle_result oracle_validate_utf16le_with_errors(const uint16_t *in, size_t len) {
+  oracle_result r;
+  size_t pos = 0;
+  while (pos < len) {
+    uint16_t w = in[pos];
+    if ((w & 0xF800) == 0xD800) {
+      if (!is_high(w) || pos + 1 >= len || !is_low(in[pos + 1])) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+      pos += 2;
+    } else {
+      pos += 1;
+    }
+  }
+  r.error = ORACLE_SUCCESS; r.count = len;
+  return r;
+}
+
+/* reference src/scalar/utf16.h:69-78 */
+uint64_t oracle_count_utf16le(const uint16_t *in, size_t len) {
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++) n += !is_low(in[i]);
+  return n;
+}
+
+/* reference src/scalar/utf16.h:80-94 — every surrogate unit counts 2 */
+uint64_t oracle_utf8_length_from_utf16le(const uint16_t *in, size_t len) {
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++) {
+    uint16_t w = in[i];
+    n += 1 + (w > 0x7F) + ((w > 0x7FF && w <= 0xD7FF) || w >= 0xE000);
+  }
+  return n;
+}
+
+/* reference src/scalar/utf16.h:96-105 */
+uint64_t oracle_utf32_length_from_utf16le(const uint16_t *in, size_t len) { return oracle_count_utf16le(in, len); }
+
+/* reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153 */
+oracle_result oracle_convert_utf16le_to_utf8_with_errors(const uint16_t *in, size_t len, uint8_t *out) {
+  oracle_result r;
+  size_t pos = 0; uint64_t w = 0;
+  while (pos < len) {
+    uint32_t u = in[pos];
+    if (u < 0x80) {
+      out[w++] = (uint8_t)u; pos++;
+    } else if (u < 0x800) {
+      out[w++] = (uint8_t)(0xC0 | (u >> 6));
+      out[w++] = (uint8_t)(0x80 | (u & 0x3F)); pos++;
+    } else if ((u & 0xF800) != 0xD800) {
+      out[w++] = (uint8_t)(0xE0 | (u >> 12));
+      out[w++] = (uint8_t)(0x80 | ((u >> 6) & 0x3F));
+      out[w++] = (uint8_t)(0x80 | (u & 0x3F)); pos++;
+    } else {
+      if (pos + 1 >= len || !is_high((uint16_t)u) || !is_low(in[pos + 1])) {
+        r.error = ORACLE_SURROGATE; r.count = pos; return r;
+      }
+      uint32_t cp = 0x10000 + ((u - 0xD800) << 10) + (in[pos + 1] - 0xDC00u);
+      out[w++] = (uint8_t)(0xF0 | (cp >> 18));
+      out[w++] = (uint8_t)(0x80 | ((cp >> 12) & 0x3F));
+      out[w++] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F));
+      out[w++] = (uint8_t)(0x80 | (cp & 0x3F)); pos += 2;
+    }
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+
+/* reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:9-80: bytes written, 0 on error */
+uint64_t oracle_convert_utf16le_to_utf8(const uint16_t *in, size_t len, uint8_t *out) {
+  oracle_result r = oracle_convert_utf16le_to_utf8_with_errors(in, len, out);
+  return r.error ? 0 : r.count;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Base64 (WHATWG forgiving decode)                                          */
+/* ------------------------------------------------------------------------- */
+/* Character class: 0..63 sextet, 64 = ASCII whitespace (' ' \t \n \r \f),   */
+/* 255 = anything else.  Mirrors the three lookup tables at reference        */
+/* src/tables/base64_tables.h:791-849 (default / url / default_or_url).     */
+static uint8_t b64_class(uint8_t c, uint64_t options) {
+  int url = (options & ORACLE_B64_URL) != 0;
+  int both = (options & ORACLE_B64_DEFAULT_OR_URL) != 0;
+  if (c >= 'A' && c <= 'Z') return (uint8_t)(c - 'A');
+  if (c >= 'a' && c <= 'z') return (uint8_t)(c - 'a' + 26);
+  if (c >= '0' && c <= '9') return (uint8_t)(c - '0' + 52);
+  if (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f') return 64;
+  if (c == '+' && (both || !url)) return 62;
+  if (c == '/' && (both || !url)) return 63;
+  if (c == '-' && (both || url)) return 62;
+  if (c == '_' && (both || url)) return 63;
+  return 255;
+}
+
+static int b64_ignore_garbage(uint64_t options) {
+  return options == ORACLE_B64_URL_ACCEPT_GARBAGE || options == ORACLE_B64_DEFAULT_ACCEPT_GARBAGE ||
+         options == ORACLE_B64_DEFAULT_OR_URL_ACCEPT_GARBAGE;
+}
+
+/* reference src/scalar/base64.h:493-513 */
+uint64_t oracle_maximal_binary_length_from_base64(const uint8_t *in, size_t len) {
+  size_t padding = 0;
+  if (len > 0 && in[len - 1] == '=') {
+    padding++;
+    if (len > 1 && in[len - 2] == '=') padding++;
+  }
+  size_t actual = len - padding;
+  if (actual % 4 <= 1) return actual / 4 * 3;
+  return actual / 4 * 3 + (actual % 4) - 1;
+}
+
+/* The decode proper: reference src/fallback/implementation.cpp:570-621
+ * (trailing whitespace / '=' stripping, empty-input rules, padding
+ * consistency check) around reference src/scalar/base64.h:33-216
+ * (base64_tail_decode: sextet gathering, last-chunk rules).  Only
+ * (error, input_count) are pinned on INVALID_BASE64_CHARACTER — output_count
+ * differs between the reference's own kernels there; this
+ * oracle reports the scalar/fallback value.
+ */
+oracle_full_result oracle_base64_to_binary_details(const uint8_t *in, size_t len, uint8_t *out,
+                                                   uint64_t options, uint64_t last_chunk) {
+  oracle_full_result r;
+  const int garbage = b64_ignore_garbage(options);
+  /* Strip trailing whitespace and up to two '=' (whitespace allowed between).
+   * The SIMD kernels (generic/base64.h:50-73, icelake_base64.inl.cpp) skip this
+   * step entirely in accept_garbage mode, whereas the fallback kernel strips
+   * regardless (fallback/implementation.cpp:577-596); the two differ only in
+   * full_result.input_count on success.  North star = icelake/haswell, so the
+   * SIMD behaviour is the one restated here. */
+  while (!garbage && len > 0 && b64_class(in[len - 1], options) == 64) len--;
+  size_t equallocation = len;
+  size_t equalsigns = 0;
+  if (!garbage && len > 0 && in[len - 1] == '=') {
+    equallocation = len - 1; len--; equalsigns = 1;
+    while (len > 0 && b64_class(in[len - 1], options) == 64) len--;
+    if (len > 0 && in[len - 1] == '=') { equallocation = len - 1; len--; equalsigns = 2; }
+  }
+  if (len == 0) { /* fallback/implementation.cpp:597-608 */
+    r.input_count = 0; r.output_count = 0; r.error = ORACLE_SUCCESS;
+    if (!garbage && equalsigns > 0) {
+      if (last_chunk == ORACLE_STRICT) { r.error = ORACLE_BASE64_INPUT_REMAINDER; }
+      else if (last_chunk == ORACLE_STOP_BEFORE_PARTIAL) { r.error = ORACLE_SUCCESS; }
+      else { r.error = ORACLE_INVALID_BASE64_CHARACTER; r.input_count = equallocation; }
+    }
+    return r;
+  }
+  /* scalar/base64.h:76-216: gather sextets four at a time */
+  size_t src = 0; uint64_t dst = 0;
+  for (;;) {
+    uint8_t q[4]; unsigned idx = 0;
+    size_t chunk_start = src;
+    while (idx < 4 && src < len) {
+      uint8_t v = b64_class(in[src], options);
+      if (v <= 63) { q[idx++] = v; }
+      else if (!garbage && v > 64) {
+        r.error = ORACLE_INVALID_BASE64_CHARACTER; r.input_count = src; r.output_count = dst; return r;
+      }
+      src++;
+    }
+    if (idx == 4) {
+      uint32_t t = ((uint32_t)q[0] << 18) | ((uint32_t)q[1] << 12) | ((uint32_t)q[2] << 6) | q[3];
+      out[dst++] = (uint8_t)(t >> 16); out[dst++] = (uint8_t)(t >> 8); out[dst++] = (uint8_t)t;
+      continue;
+    }
+    /* partial (or empty) final chunk: scalar/base64.h:138-200 */
+    if (!garbage && last_chunk == ORACLE_STRICT && idx != 1 && ((idx + equalsigns) & 3) != 0) {
+      r.error = ORACLE_BASE64_INPUT_REMAINDER; r.input_count = src; r.output_count = dst; return r;
+    }
+    if (!garbage && last_chunk == ORACLE_STOP_BEFORE_PARTIAL && ((idx + equalsigns) & 3) != 0) {
+      src = chunk_start;
+      while (src < len && b64_class(in[src], options) > 63) src++;
+      r.error = ORACLE_SUCCESS; r.input_count = src; r.output_count = dst; return r;
+    }
+    if (idx == 2) {
+      uint32_t t = ((uint32_t)q[0] << 18) | ((uint32_t)q[1] << 12);
+      if (!garbage && last_chunk == ORACLE_STRICT && (t & 0xFFFF)) {
+        r.error = ORACLE_BASE64_EXTRA_BITS; r.input_count = src; r.output_count = dst; return r;
+      }
+      out[dst++] = (uint8_t)(t >> 16);
+    } else if (idx == 3) {
+      uint32_t t = ((uint32_t)q[0] << 18) | ((uint32_t)q[1] << 12) | ((uint32_t)q[2] << 6);
+      if (!garbage && last_chunk == ORACLE_STRICT && (t & 0xFF)) {
+        r.error = ORACLE_BASE64_EXTRA_BITS; r.input_count = src; r.output_count = dst; return r;
+      }
+      out[dst++] = (uint8_t)(t >> 16); out[dst++] = (uint8_t)(t >> 8);
+    } else if (!garbage && idx == 1 && last_chunk != ORACLE_STOP_BEFORE_PARTIAL) {
+      r.error = ORACLE_BASE64_INPUT_REMAINDER; r.input_count = src; r.output_count = dst; return r;
+    }
+    r.error = ORACLE_SUCCESS; r.input_count = src; r.output_count = dst;
+    break;
+  }
+  /* fallback/implementation.cpp:611-619: padding must complete the last quantum */
+  if (last_chunk != ORACLE_STOP_BEFORE_PARTIAL && r.error == ORACLE_SUCCESS && equalsigns > 0 && !garbage) {
+    if ((r.output_count % 3 == 0) || ((r.output_count % 3) + 1 + equalsigns != 4)) {
+      r.error = ORACLE_INVALID_BASE64_CHARACTER; r.input_count = equallocation;
+    }
+  }
+  return r;
+}
+
+/* full_result -> result: reference include/simdutf/error.h:66-73 */
+oracle_result oracle_base64_to_binary(const uint8_t *in, size_t len, uint8_t *out, uint64_t options, uint64_t last_chunk) {
+  oracle_full_result f = oracle_base64_to_binary_details(in, len, out, options, last_chunk);
+  oracle_result r;
+  r.error = f.error;
+  r.count = (f.error == ORACLE_SUCCESS || f.error == ORACLE_BASE64_INPUT_REMAINDER) ? f.output_count : f.input_count;
+  return r;
+}
+
+static int b64_use_padding(uint64_t options) {
+  return ((options & ORACLE_B64_URL) == 0) ^ ((options & ORACLE_B64_REVERSE_PADDING) == ORACLE_B64_REVERSE_PADDING);
+}
+
+/* reference src/scalar/base64.h:515-533 */
+uint64_t oracle_base64_length_from_binary(size_t len, uint64_t options) {
+  if (!b64_use_padding(options)) return len / 3 * 4 + ((len % 3) ? (len % 3) + 1 : 0);
+  return (len + 2) / 3 * 4;
+}
+
+/* reference src/scalar/base64.h:435-491 (encoder; used by tests to build inputs) */
+uint64_t oracle_binary_to_base64(const uint8_t *in, size_t len, uint8_t *out, uint64_t options) {
+  static const char std_abc[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  static const char url_abc[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_";
+  const char *abc = (options & ORACLE_B64_URL) ? url_abc : std_abc;
+  const int pad = b64_use_padding(options);
+  uint64_t w = 0; size_t i = 0;
+  for (; i + 3 <= len; i += 3) {
+    uint32_t t = ((uint32_t)in[i] << 16) | ((uint32_t)in[i + 1] << 8) | in[i + 2];
+    out[w++] = (uint8_t)abc[t >> 18]; out[w++] = (uint8_t)abc[(t >> 12) & 63];
+    out[w++] = (uint8_t)abc[(t >> 6) & 63]; out[w++] = (uint8_t)abc[t & 63];
+  }
+  if (len - i == 1) {
+    uint32_t t = (uint32_t)in[i] << 16;
+    out[w++] = (uint8_t)abc[t >> 18]; out[w++] = (uint8_t)abc[(t >> 12) & 63];
+    if (pad) { out[w++] = '='; out[w++] = '='; }
+  } else if (len - i == 2) {
+    uint32_t t = ((uint32_t)in[i] << 16) | ((uint32_t)in[i + 1] << 8);
+    out[w++] = (uint8_t)abc[t >> 18]; out[w++] = (uint8_t)abc[(t >> 12) & 63]; out[w++] = (uint8_t)abc[(t >> 6) & 63];
+    if (pad) { out[w++] = '='; }
+  }
+  return w;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Shard-cut helpers                                                          */
+/* ------------------------------------------------------------------------- */
+/* reference src/scalar/utf8.h:257-288 (trim_partial_utf8) */
+uint64_t oracle_trim_partial_utf8(const uint8_t *in, size_t len) {
+  if (len >= 1 && in[len - 1] >= 0xC0) return len - 1;
+  if (len >= 2 && in[len - 2] >= 0xE0) return len - 2;
+  if (len >= 3 && in[len - 3] >= 0xF0) return len - 3;
+  return len;
+}
+
+/* reference src/scalar/utf16.h:114-124 (trim_partial_utf16<LITTLE>) */
+uint64_t oracle_trim_partial_utf16le(const uint16_t *in, size_t len) {
+  if (len <= 1) return len;
+  return len - (is_high(in[len - 1]) ? 1 : 0);
+}
