@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 backend (BASELINE.json metric: input GB/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the reference's own CPU kernels
+
+Workload (config.workload):
+  N = 1   BASELINE.json configs[1]: utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors on 1 GiB of
+          synthetic mixed 1-4-byte UTF-8 (25% ASCII / Latin / CJK / emoji by code point, seed 2).
+  N > 1   configs[4] run weak: every rank owns one 1 GiB shard of that distribution (cut on a code-point
+          boundary), runs the same two calls, then the two tiny collectives of the sharded path
+          (all_gather of lengths, all_reduce-min of the first-error key) — see simdutf_b200/sharded.py.
+A step = one pass of that path over the batch.  value = all ranks' input bytes / max-over-ranks device time
+(CUDA events on the launching stream), inputs resident in HBM.  e2e = the same two calls through the
+host-pointer C ABI (b200_host_*), pinned host buffers, H2D and D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GIB = 1 << 30
+METRIC = "input GB/s, utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors (UTF-8 -> UTF-16LE)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own kernels (oracle/_ref) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(sample_bytes: int, threads: int, steps: int, warmup: int, seed: int = 2):
+    """Times utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors of the UNMODIFIED reference library
+    (best kernel of this host: icelake or haswell) on a `sample_bytes` sample of the config-2 distribution,
+    split over `threads` host threads with the recipe of the reference's benchmarks/threaded.cpp:69-88.
+    Falls back to the oracle port (1 thread) only if oracle/_ref did not travel."""
+    import numpy as np
+    from simdutf_b200 import synth
+    from tests._oracle import Oracle, Reference
+    data = synth.mixed_utf8(sample_bytes, seed=seed).numpy()
+    n = int(data.size)
+    ref = Reference.load_or_none()
+    out = np.empty(n + 64, dtype=np.uint16)
+    times = []
+    if ref is not None:
+        kind, impl = "reference", ref.best
+        fn = ref.L.ref_mt_utf16_length_then_convert_utf8_to_utf16le
+        args = (impl.encode(), ctypes.c_void_p(data.ctypes.data), ctypes.c_size_t(n), ctypes.c_void_p(out.ctypes.data), threads)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            units = fn(*args)
+            dt = time.perf_counter() - t0
+            assert units > 0
+            if i >= warmup:
+                times.append(dt)
+    else:
+        kind, impl, threads = "port", "oracle.c", 1
+        o = Oracle()
+        small = data[: min(n, 32 << 20)]
+        cut = o.trim_partial_utf8(small)
+        small = small[:cut]
+        n = int(small.size)
+        for i in range(max(1, min(warmup, 1)) + max(1, min(steps, 3))):
+            t0 = time.perf_counter()
+            o.utf16_length_from_utf8(small)
+            o.convert_utf8_to_utf16le_with_errors(small)
+            dt = time.perf_counter() - t0
+            if i >= 1:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": n / sec / 1e9, "unit": "GB/s", "cores": threads, "kind": kind, "impl": impl,
+            "sample": f"{n} bytes of the config-2 mixed UTF-8 distribution (seed {seed}), {len(times)} timed passes, "
+                      f"mean; utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors per pass",
+            "ms_per_step": sec * 1e3, "bytes": n}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    r = cpu_reference_run(args.cpu_sample_bytes, threads, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1] (bounded sample): utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors, "
+                               "mixed 1-4-byte UTF-8", "bytes_per_step": r["bytes"], "threads": threads,
+                   "kernel": r["impl"], "l2_policy": "n/a (CPU)"},
+        "cpu_baseline": {"value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shard-bytes", type=int, default=GIB, help="input bytes per GPU")
+    ap.add_argument("--cpu-sample-bytes", type=int, default=256 << 20)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-1/3/4 side measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import simdutf_b200 as b
+    from simdutf_b200 import sharded, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = b.load()
+    b.set_device(local_rank)
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    # ---- inputs resident in HBM ------------------------------------------------------------------------------
+    d_in = synth.mixed_utf8(args.shard_bytes, seed=2 + rank, device=device)  # whole characters: an independent shard
+    n = int(d_in.numel())
+    units = b.utf16_length_from_utf8(d_in)
+    d_out = torch.empty(units, dtype=torch.int16, device=device)
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=device)
+    d_res = torch.zeros(2, dtype=torch.int64, device=device)  # b200_result {int32 error; pad; uint64 count}
+    stream = torch.cuda.current_stream(device)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    in_p, out_p = ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr())
+    cnt_p, res_p = ctypes.c_void_p(d_cnt.data_ptr()), ctypes.c_void_p(d_res.data_ptr())
+    gather_in = torch.zeros(2, dtype=torch.int64, device=device)
+    gather_out = torch.zeros(2 * world, dtype=torch.int64, device=device)
+    key = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        st = lib.b200_utf16_length_from_utf8_async(in_p, n, cnt_p, sp)
+        if ev:
+            ev[1].record(stream)
+        st |= lib.b200_convert_utf8_to_utf16le_async(in_p, n, out_p, res_p, sp)
+        if ev:
+            ev[2].record(stream)
+        if st:
+            raise RuntimeError("b200 launch failed: " + lib.b200_last_error().decode())
+        if world > 1:  # the sharded path's two collectives, fed from the device-side results (no host sync)
+            gather_in[0] = n
+            gather_in[1] = d_res[1]
+            dist.all_gather_into_tensor(gather_out, gather_in)
+            key.copy_(torch.where(d_res[0:1] & 0xFFFFFFFF != 0, (d_res[1:2] << 8) | (d_res[0:1] & 0xFF),
+                                  torch.full_like(key, sharded.NO_ERROR_KEY)))
+            dist.all_reduce(key, op=dist.ReduceOp.MIN)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize(device)
+    assert int(d_cnt.item()) == units and int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == units
+
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    launches0 = b.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    if rank == 0:
+        sampler.start()
+    t_beg.record(stream)
+    for i in range(K):
+        step(evs[i])
+    t_end.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = b.launch_count() - launches0
+    ms_total = t_beg.elapsed_time(t_end)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    nbytes = torch.tensor([n], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    total_bytes = int(nbytes.item())
+    ms_per_step = ms_total / K
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+    conv_ms = [e[1].elapsed_time(e[2]) for e in evs]
+    len_ms = [e[0].elapsed_time(e[1]) for e in evs]
+    conv_avg = sum(conv_ms) / len(conv_ms)
+    peak, peak_src = measured_peak()
+    algo_bytes = n + 2 * units  # input read once + output written once
+    achieved = algo_bytes / (conv_avg * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("k_convert_utf8<uint16_t>", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == units
+
+    # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region ---------------------------
+    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(d_in)
+    h_out = torch.empty(units, dtype=torch.int16, pin_memory=True)
+    hres, hcnt = b.Result(), ctypes.c_uint64()
+    hin_p, hout_p = ctypes.c_void_p(h_in.data_ptr()), ctypes.c_void_p(h_out.data_ptr())
+
+    def e2e_step():
+        st = lib.b200_host_utf16_length_from_utf8(hin_p, n, ctypes.byref(hcnt))
+        st |= lib.b200_host_convert_utf8_to_utf16le(hin_p, n, hout_p, ctypes.byref(hres))
+        if st:
+            raise RuntimeError("b200 host call failed: " + lib.b200_last_error().decode())
+
+    e2e_step()
+    assert hcnt.value == units and hres.astuple() == (0, units)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_bytes / float(te.item()) / 1e9
+    same = bool(torch.equal(h_out[: 1 << 20], d_out[: 1 << 20].cpu()))
+    assert same, "host path and device path disagree"
+    del h_in, h_out
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = side_measurements(b, lib, synth, torch, device, stream, sp, peak, K)
+
+    cpu = None
+    if rank == 0:
+        cpu = cpu_reference_run(args.cpu_sample_bytes, os.cpu_count() or 1, 3, 1)
+        cpu1 = cpu_reference_run(min(args.cpu_sample_bytes, 128 << 20), 1, 2, 1)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": ("configs[1]: utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors, 1 GiB mixed 1-4-byte UTF-8"
+                             if world == 1 else
+                             "configs[4] weak: one mixed-UTF-8 shard per GPU (code-point-boundary cuts), length + convert per shard, "
+                             "all_gather(lengths) + all_reduce-min(first error) per step"),
+                "bytes_per_gpu": n, "utf16_units_per_gpu": units, "seed": "2+rank", "char_mix": "25% each 1/2/3/4-byte, i.i.d.",
+                "l2_policy": "inputs (1 GiB) and outputs (1 GiB) far exceed the 126 MB L2; no flush needed",
+                "parallelism": f"shards x{world}",
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_convert_utf8<uint16_t> (UTF-8 -> UTF-16LE, one pass)",
+                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg, "peak_source": peak_src,
+                         "length_kernel_ms": sum(len_ms) / len(len_ms),
+                         "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9},
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline_1thread": {k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 2 * units + 24,
+                    "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers)",
+                    "ms_per_step": float(te.item()) * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "extra": extras,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def side_measurements(b, lib, synth, torch, device, stream, sp, peak, K):
+    """Other BASELINE.json configs, timed the same way (device-resident, CUDA events), reported under "extra"."""
+    out = {}
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / reps
+
+    d_res = torch.zeros(4, dtype=torch.int64, device=device)
+    res_p = ctypes.c_void_p(d_res.data_ptr())
+    # config 1: validate_utf8_with_errors, 1 GiB ASCII
+    a = synth.ascii_text(GIB, seed=1, device=device)
+    n = int(a.numel())
+    ap_ = ctypes.c_void_p(a.data_ptr())
+    ms = timeit(lambda: lib.b200_validate_utf8_with_errors_async(ap_, n, res_p, sp), K)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == n
+    out["config1_validate_utf8_ascii_1GiB"] = {"input_gbs": n / ms / 1e6, "ms": ms, "frac_of_peak": n / ms / 1e6 / peak}
+    ms = timeit(lambda: lib.b200_count_utf8_async(ap_, n, res_p, sp), K)
+    out["count_utf8_ascii_1GiB"] = {"input_gbs": n / ms / 1e6, "ms": ms, "frac_of_peak": n / ms / 1e6 / peak}
+    del a
+    # validate on the mixed buffer (no fast path applies)
+    m = synth.mixed_utf8(GIB, seed=2, device=device)
+    n = int(m.numel())
+    mp = ctypes.c_void_p(m.data_ptr())
+    ms = timeit(lambda: lib.b200_validate_utf8_with_errors_async(mp, n, res_p, sp), K)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == n
+    out["validate_utf8_mixed_1GiB"] = {"input_gbs": n / ms / 1e6, "ms": ms, "frac_of_peak": n / ms / 1e6 / peak}
+    chars = b.count_utf8(m)
+    o32 = torch.empty(chars, dtype=torch.int32, device=device)
+    ms = timeit(lambda: lib.b200_convert_utf8_to_utf32_async(mp, n, ctypes.c_void_p(o32.data_ptr()), res_p, sp), max(3, K // 2))
+    out["convert_utf8_to_utf32_mixed_1GiB"] = {"input_gbs": n / ms / 1e6, "ms": ms, "frac_of_peak": (n + 4 * chars) / ms / 1e6 / peak}
+    del m, o32
+    # config 3: UTF-16LE -> UTF-8, 2 GiB
+    u = synth.mixed_utf16le(GIB, seed=3, device=device)
+    nu = int(u.numel())
+    up = ctypes.c_void_p(u.data_ptr())
+    nb = b.utf8_length_from_utf16le(u)
+    o8 = torch.empty(nb, dtype=torch.uint8, device=device)
+    ms = timeit(lambda: lib.b200_convert_utf16le_to_utf8_async(up, nu, ctypes.c_void_p(o8.data_ptr()), res_p, sp), max(3, K // 2))
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == nb
+    out["config3_convert_utf16le_to_utf8_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": (2 * nu + nb) / ms / 1e6 / peak}
+    ms = timeit(lambda: lib.b200_count_utf16le_async(up, nu, res_p, sp), K)
+    out["config3_count_utf16le_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": 2 * nu / ms / 1e6 / peak}
+    del u, o8
+    # config 4: base64 decode, 2 GiB of text with CRLF every 76 + sparse whitespace
+    text, payload = synth.base64_text(2 * GIB, seed=4, device=device)
+    nt = int(text.numel())
+    ob = torch.empty(nt // 4 * 3 + 3, dtype=torch.uint8, device=device)
+    ms = timeit(lambda: lib.b200_base64_to_binary_async(ctypes.c_void_p(text.data_ptr()), nt, ctypes.c_void_p(ob.data_ptr()), 0, 0, res_p, sp),
+                max(3, K // 2))
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[2].item()) == int(payload.numel())
+    out["config4_base64_to_binary_2GiB"] = {"input_gbs": nt / ms / 1e6, "ms": ms,
+                                            "frac_of_peak": (nt + int(payload.numel())) / ms / 1e6 / peak}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,219 @@
+/* simdutf_b200.h — C ABI of the B200 (sm_100a) backend for simdutf's hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every entry point names the virtual of `class simdutf::implementation`
+ * (reference include/simdutf/implementation.h) it stands behind; the C++
+ * subclass `simdutf::b200::implementation` (simdutf_b200/csrc/b200_implementation.cpp)
+ * forwards each of those virtuals to the matching `b200_host_*` function and
+ * nothing else.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Three flavours per operation:
+ *   b200_<op>_async(d_in, ..., d_result, stream)
+ *       DEVICE pointers in and out, result written to a DEVICE slot when the
+ *       stream reaches it; no host synchronisation, graph-capturable.
+ *   b200_<op>(d_in, ..., h_result, stream)
+ *       DEVICE data pointers, result returned to the HOST (synchronises stream).
+ *   b200_host_<op>(h_in, ..., h_result)
+ *       HOST pointers (pinned or pageable): staged through the context's device
+ *       buffers in pipelined chunks.  This is what the C++ virtuals call.
+ *
+ * Return value of every function: 0 on success, otherwise a CUDA error code
+ * (cudaError_t, > 0) or a negative B200_E_* code.  simdutf-level outcomes
+ * (error_code + position/count) travel in the result structs exactly as in the
+ * reference (include/simdutf/error.h:5-74).  The library never prints, aborts
+ * or throws (reference CMakeLists.txt:173-214), and it has NO CPU fallback: with
+ * no sm_100 device present every compute entry point returns B200_E_NO_DEVICE.
+ *
+ * Lengths are in CODE UNITS of the input encoding (bytes for UTF-8 / base64,
+ * 16-bit units for UTF-16), as in the reference.
+ */
+#ifndef SIMDUTF_B200_H
+#define SIMDUTF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SIMDUTF_B200_API __attribute__((visibility("default")))
+#else
+#define SIMDUTF_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_E_NO_DEVICE (-1) /* no usable sm_100 device / CUDA not initialisable */
+#define B200_E_BAD_ARGUMENT (-2)
+#define B200_E_NO_MEMORY (-3)
+
+/* simdutf::error_code, reference include/simdutf/error.h:5-32 (same values). */
+enum b200_error_code {
+  B200_SUCCESS = 0,
+  B200_HEADER_BITS = 1,
+  B200_TOO_SHORT = 2,
+  B200_TOO_LONG = 3,
+  B200_OVERLONG = 4,
+  B200_TOO_LARGE = 5,
+  B200_SURROGATE = 6,
+  B200_INVALID_BASE64_CHARACTER = 7,
+  B200_BASE64_INPUT_REMAINDER = 8,
+  B200_BASE64_EXTRA_BITS = 9,
+  B200_OUTPUT_BUFFER_TOO_SMALL = 10,
+  B200_OTHER = 11
+};
+
+/* simdutf::result, reference include/simdutf/error.h:34-37 ({enum; size_t} = 16 B on LP64). */
+typedef struct b200_result {
+  int32_t error;
+  uint32_t reserved_;
+  uint64_t count;
+} b200_result;
+
+/* simdutf::full_result, reference include/simdutf/error.h:54-57 (24 B on LP64). */
+typedef struct b200_full_result {
+  int32_t error;
+  uint32_t reserved_;
+  uint64_t input_count;
+  uint64_t output_count;
+} b200_full_result;
+
+/* simdutf::base64_options / last_chunk_handling_options,
+ * reference include/simdutf/implementation.h:2782-2811 (same values). */
+enum {
+  B200_BASE64_DEFAULT = 0,
+  B200_BASE64_URL = 1,
+  B200_BASE64_REVERSE_PADDING = 2,
+  B200_BASE64_DEFAULT_ACCEPT_GARBAGE = 4,
+  B200_BASE64_URL_ACCEPT_GARBAGE = 5,
+  B200_BASE64_DEFAULT_OR_URL = 8,
+  B200_BASE64_DEFAULT_OR_URL_ACCEPT_GARBAGE = 12
+};
+enum { B200_LOOSE = 0, B200_STRICT = 1, B200_STOP_BEFORE_PARTIAL = 2 };
+
+/* ------------------------------------------------------------------------- */
+/* Runtime                                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* Number of usable compute-capability-10.x devices (0 if none / no driver).
+ * Backs implementation::required_instruction_sets() / supported_by_runtime_system()
+ * (reference include/simdutf/implementation.h:3344-3366, src/implementation.cpp:35-41). */
+SIMDUTF_B200_API int b200_device_count(void);
+/* Select the device used by the calling thread's subsequent b200_* calls (default 0). */
+SIMDUTF_B200_API int b200_set_device(int device);
+SIMDUTF_B200_API int b200_get_device(void);
+/* "b200" / description string, for implementation::name()/description(). */
+SIMDUTF_B200_API const char *b200_name(void);
+SIMDUTF_B200_API const char *b200_description(void);
+/* Number of kernel launches issued by this library since load (all threads); bench.py's gpu_launches. */
+SIMDUTF_B200_API uint64_t b200_launch_count(void);
+/* Text of the last failure on this thread ("" if none). Never printed by the library. */
+SIMDUTF_B200_API const char *b200_last_error(void);
+/* Pinned host memory helpers for callers that want the fast host path. */
+SIMDUTF_B200_API int b200_host_alloc(void **ptr, size_t bytes);
+SIMDUTF_B200_API int b200_host_free(void *ptr);
+
+/* ------------------------------------------------------------------------- */
+/* UTF-8 validation — implementation::validate_utf8_with_errors               */
+/* (reference include/simdutf/implementation.h:3395-3396; semantics            */
+/*  src/scalar/utf8.h:102-200) and ::validate_utf8 (:3378-3379).               */
+/* result = {SUCCESS, len} or {first error, byte index}.                       */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_validate_utf8_with_errors_async(const char *d_in, size_t len, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_validate_utf8_with_errors(const char *d_in, size_t len, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_validate_utf8_with_errors(const char *h_in, size_t len, b200_result *h_res);
+
+/* ------------------------------------------------------------------------- */
+/* UTF-8 counting — implementation::count_utf8 (:4802) == utf32_length_from_utf8 */
+/* (:3882); implementation::utf16_length_from_utf8 (:3863).                    */
+/* Semantics src/scalar/utf8.h:230-255; never validate.                        */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_count_utf8_async(const char *d_in, size_t len, uint64_t *d_count, void *stream);
+SIMDUTF_B200_API int b200_count_utf8(const char *d_in, size_t len, uint64_t *h_count, void *stream);
+SIMDUTF_B200_API int b200_host_count_utf8(const char *h_in, size_t len, uint64_t *h_count);
+SIMDUTF_B200_API int b200_utf16_length_from_utf8_async(const char *d_in, size_t len, uint64_t *d_count, void *stream);
+SIMDUTF_B200_API int b200_utf16_length_from_utf8(const char *d_in, size_t len, uint64_t *h_count, void *stream);
+SIMDUTF_B200_API int b200_host_utf16_length_from_utf8(const char *h_in, size_t len, uint64_t *h_count);
+
+/* ------------------------------------------------------------------------- */
+/* UTF-8 -> UTF-16LE — implementation::convert_utf8_to_utf16le_with_errors     */
+/* (:3743-3745), ::convert_utf8_to_utf16le (:3709, = count or 0 on error),     */
+/* ::convert_valid_utf8_to_utf16le (:3815).                                    */
+/* Semantics src/scalar/utf8_to_utf16/utf8_to_utf16.h:128-255.                 */
+/* result = {SUCCESS, units written} or {error, input byte index}.  d_out must */
+/* hold utf16_length_from_utf8(in) units (it is never overrun, even for        */
+/* invalid input: reference tests/convert_utf8_to_utf16le_tests.cpp:23-52).    */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_convert_utf8_to_utf16le_async(const char *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf8_to_utf16le(const char *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf8_to_utf16le(const char *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+
+/* UTF-8 -> UTF-32 — implementation::convert_utf8_to_utf32_with_errors (:3799-3800),
+ * ::convert_utf8_to_utf32 (:3781).  Semantics src/scalar/utf8_to_utf32/utf8_to_utf32.h:106-212.
+ * d_out must hold count_utf8(in) words. */
+SIMDUTF_B200_API int b200_convert_utf8_to_utf32_async(const char *d_in, size_t len, uint32_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf8_to_utf32(const char *d_in, size_t len, uint32_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf8_to_utf32(const char *h_in, size_t len, uint32_t *h_out, b200_result *h_res);
+
+/* ------------------------------------------------------------------------- */
+/* UTF-16LE counting — implementation::count_utf16le (:4767) ==                */
+/* utf32_length_from_utf16le; ::utf8_length_from_utf16le (:4277-4278).         */
+/* Semantics src/scalar/utf16.h:69-94.  `len` in 16-bit units.                 */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_count_utf16le_async(const uint16_t *d_in, size_t len, uint64_t *d_count, void *stream);
+SIMDUTF_B200_API int b200_count_utf16le(const uint16_t *d_in, size_t len, uint64_t *h_count, void *stream);
+SIMDUTF_B200_API int b200_host_count_utf16le(const uint16_t *h_in, size_t len, uint64_t *h_count);
+SIMDUTF_B200_API int b200_utf8_length_from_utf16le_async(const uint16_t *d_in, size_t len, uint64_t *d_count, void *stream);
+SIMDUTF_B200_API int b200_utf8_length_from_utf16le(const uint16_t *d_in, size_t len, uint64_t *h_count, void *stream);
+SIMDUTF_B200_API int b200_host_utf8_length_from_utf16le(const uint16_t *h_in, size_t len, uint64_t *h_count);
+
+/* UTF-16LE validation — implementation::validate_utf16le_with_errors
+ * (reference include/simdutf/implementation.h:3481-3483; src/scalar/utf16.h:39-67). */
+SIMDUTF_B200_API int b200_validate_utf16le_with_errors_async(const uint16_t *d_in, size_t len, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_validate_utf16le_with_errors(const uint16_t *d_in, size_t len, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_validate_utf16le_with_errors(const uint16_t *h_in, size_t len, b200_result *h_res);
+
+/* ------------------------------------------------------------------------- */
+/* UTF-16LE -> UTF-8 — implementation::convert_utf16le_to_utf8_with_errors     */
+/* (:4079-4080), ::convert_utf16le_to_utf8 (:4038).                            */
+/* Semantics src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153.                  */
+/* result = {SUCCESS, bytes written} or {SURROGATE, unit index}.  d_out must   */
+/* hold utf8_length_from_utf16le(in) bytes.                                    */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_convert_utf16le_to_utf8_async(const uint16_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf16le_to_utf8(const uint16_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf16le_to_utf8(const uint16_t *h_in, size_t len, char *h_out, b200_result *h_res);
+
+/* ------------------------------------------------------------------------- */
+/* WHATWG forgiving base64 decode — implementation::base64_to_binary_details   */
+/* (:4902-4906) and ::base64_to_binary (:4866-4870; result derived from the    */
+/* full_result as in include/simdutf/error.h:66-73).  Semantics                */
+/* src/generic/base64.h:40-246 + src/scalar/base64.h:33-216.                   */
+/* d_out must hold maximal_binary_length_from_base64(in) bytes.                */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_base64_to_binary_async(const char *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
+                                b200_full_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_base64_to_binary(const char *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
+                          b200_full_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_base64_to_binary(const char *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
+                               b200_full_result *h_res);
+/* implementation::maximal_binary_length_from_base64 (reference src/implementation.cpp:87-90 ->
+ * src/scalar/base64.h:493-513): O(1), looks at the last two characters only; host pointer. */
+SIMDUTF_B200_API size_t b200_host_maximal_binary_length_from_base64(const char *h_in, size_t len);
+
+/* ------------------------------------------------------------------------- */
+/* Shard-cut helpers (multi-GPU / chunked streaming): the largest prefix that   */
+/* does not end inside a character — simdutf::trim_partial_utf8 / _utf16le      */
+/* (reference src/implementation.cpp:2502-2525, src/scalar/utf8.h:257-288,      */
+/*  src/scalar/utf16.h:114-124; split idiom benchmarks/threaded.cpp:69-74).     */
+/* Host pointers; they read at most the last 3 bytes / 1 unit.                  */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API size_t b200_host_trim_partial_utf8(const char *h_in, size_t len);
+SIMDUTF_B200_API size_t b200_host_trim_partial_utf16le(const uint16_t *h_in, size_t len);
+/* Same, on device data (synchronous, copies <= 4 bytes back). */
+SIMDUTF_B200_API int b200_trim_partial_utf8(const char *d_in, size_t len, size_t *h_trimmed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMDUTF_B200_H */

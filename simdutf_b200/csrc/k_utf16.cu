@@ -1,0 +1,275 @@
+// k_utf16.cu — sm_100a kernels whose input is UTF-16LE:
+//   K5  count_utf16le / utf8_length_from_utf16le   (reference src/scalar/utf16.h:69-94)
+//       validate_utf16le_with_errors                (reference src/scalar/utf16.h:39-67)
+//   K6  convert_utf16le_to_utf8[_with_errors]       (reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153)
+//
+// Same data path as k_utf8.cu: 16-byte granules (8 units) loaded with coalesced 128-bit streaming loads,
+// neighbour unit by warp shuffle, one-pass look-back scan for the output offsets, shared-memory staging,
+// 16-byte coalesced stores.  Surrogate verdicts are exact per unit, so the first error is
+// a plain atomicMin of (unit index << 8 | SURROGATE).
+#include "device_common.cuh"
+#include "launch.h"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ InView make_view16(const uint16_t *p, size_t len_units) {
+  InView v;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
+  v.vbeg = a & 15u;
+  v.vend = v.vbeg + 2ull * len_units;
+  return v;
+}
+
+// 8-bit mask of the units of granule g that lie inside the buffer.
+__device__ __forceinline__ uint32_t inrange_units(const InView &in, unsigned long long g) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const unsigned long long pos = g * 16ull + 2u * i;
+    if (pos >= in.vbeg && pos < in.vend) m |= 1u << i;
+  }
+  return m;
+}
+
+// Reports the first bad surrogate of one granule, if any.  Zero filler outside the buffer is neither a
+// high nor a low surrogate, so buffer edges need no special case.
+__device__ __forceinline__ void check_surrogates(const InView &in, Scratch *scr, unsigned long long g,
+                                                 const uint32_t w[4], uint32_t pw, uint32_t nw, uint32_t valid) {
+  // any unit in D800..DFFF?  (u & 0xF800) == 0xD800, on both halves of each word at once
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t x = (w[k] & 0xF800F800u) ^ 0xD800D800u;           // halves equal to zero are surrogates
+    any |= ~((x | ((x & 0x7FFF7FFFu) + 0x7FFF7FFFu)) | 0x7FFF7FFFu);  // 0x8000 per zero half
+  }
+  if (!any) return;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (!((valid >> i) & 1u)) continue;
+    const uint32_t u = u16_unit(w, i);
+    const uint32_t pu = i == 0 ? (pw >> 16) : u16_unit(w, i - 1);
+    const uint32_t nu = i == 7 ? (nw & 0xFFFFu) : u16_unit(w, i + 1);
+    if (u16_bad(u, pu, true, nu, true)) {
+      const unsigned long long idx = (g * 16ull + 2u * i - in.vbeg) >> 1;
+      const unsigned long long cur = ld_relaxed_u64(&scr->err_key);
+      const unsigned long long key = err_key(idx, kSurrogate);
+      if (key < cur) report_error(scr, key);
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ void write_result_from_key16(ResultPOD *res, unsigned long long key,
+                                                        unsigned long long success_count) {
+  if (key == kNoError) {
+    res->error = kSuccess;
+    res->reserved_ = 0;
+    res->count = success_count;
+  } else {
+    res->error = (int32_t)(key & 0xFFu);
+    res->reserved_ = 0;
+    res->count = key >> 8;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: MODE 0 count_utf16le, MODE 1 utf8_length_from_utf16le, MODE 2 validate_utf16le_with_errors.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int ITEMS>
+__global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size_t len, Scratch *scr, void *out) {
+  __shared__ unsigned long long s_part[kWarps];
+  const InView in = make_view16(ptr, len);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long ngran = (in.vend + 15ull) >> 4;
+  const unsigned long long chunk_gran = 32ull * ITEMS;
+  const unsigned long long nchunks = (ngran + chunk_gran - 1) / chunk_gran;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarps;
+  unsigned long long total = 0;
+  for (unsigned long long chunk = (unsigned long long)blockIdx.x * kWarps + warp; chunk < nchunks; chunk += nwarps) {
+    const unsigned long long g0 = chunk * chunk_gran;
+    uint32_t w[ITEMS][4];
+    bool inside[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    if (MODE == 2) {
+      uint32_t pw[ITEMS], nw[ITEMS];
+      neighbour_words<ITEMS>(in, g0, w, pw, nw);
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+        const uint32_t valid = inside[j] ? 0xFFu : inrange_units(in, g);
+        check_surrogates(in, scr, g, w[j], pw[j], nw[j], valid);
+      }
+    } else {
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+        const uint32_t valid = inside[j] ? 0xFFu : inrange_units(in, g);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const uint32_t u = u16_unit(w[j], i);
+          const uint32_t c = MODE == 0 ? (uint32_t)((u & 0xFC00u) != 0xDC00u) : u16_utf8_bytes(u);
+          cnt += ((valid >> i) & 1u) ? c : 0u;
+        }
+      }
+      total += cnt;
+    }
+  }
+  if (MODE != 2) {
+    total = warp_sum_u64(total);
+    if (lane == 0) s_part[warp] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+#pragma unroll
+      for (int i = 0; i < kWarps; i++) t += s_part[i];
+      if (t) atomicAdd(&scr->acc0, t);
+    }
+  }
+  if (grid_last_thread(scr)) {
+    if (MODE == 2) write_result_from_key16(static_cast<ResultPOD *>(out), ld_relaxed_u64(&scr->err_key), len);
+    else *static_cast<unsigned long long *>(out) = ld_relaxed_u64(&scr->acc0);
+    scratch_reset(scr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: UTF-16LE -> UTF-8, validating.
+// ---------------------------------------------------------------------------------------------
+template <int ITEMS>
+struct Convert16Smem {
+  static constexpr uint32_t kTileUnits = kBlock * ITEMS * 8;
+  alignas(16) uint8_t out[kTileUnits * 3 + 16];  // at most 3 bytes per unit
+  uint32_t warp_tot[kWarps];
+  uint32_t tile;
+  unsigned long long excl;
+};
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kBlock) k_convert_utf16_to_utf8(const uint16_t *ptr, size_t len, uint8_t *out,
+                                                                  Scratch *scr, unsigned long long *desc,
+                                                                  uint32_t epoch, uint32_t num_tiles, ResultPOD *res) {
+  __shared__ Convert16Smem<ITEMS> sm;
+  const InView in = make_view16(ptr, len);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+  while (true) {
+    if (threadIdx.x == 0) sm.tile = atomicAdd(&scr->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile >= num_tiles) break;
+    const unsigned long long g0 = ((unsigned long long)tile * kWarps + warp) * (32ull * ITEMS);
+
+    uint32_t w[ITEMS][4];
+    bool inside[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    uint32_t pw[ITEMS], nw[ITEMS];
+    neighbour_words<ITEMS>(in, g0, w, pw, nw);
+
+    uint32_t valid[ITEMS], cnt[ITEMS], off[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+      valid[j] = inside[j] ? 0xFFu : inrange_units(in, g);
+      uint32_t c = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) c += ((valid[j] >> i) & 1u) ? u16_utf8_bytes(u16_unit(w[j], i)) : 0u;
+      cnt[j] = c;
+      check_surrogates(in, scr, g, w[j], pw[j], nw[j], valid[j]);
+    }
+    const uint32_t tile_total = block_exclusive_offsets<ITEMS>(cnt, off, sm.warp_tot);
+
+    if (warp == 0) {
+      unsigned long long excl;
+      uint32_t aux;
+      tile_lookback(desc, epoch, tile, tile_total, 0u, excl, aux);
+      if (lane == 0) {
+        sm.excl = excl;
+        if (tile == num_tiles - 1) st_relaxed_u64(&scr->acc0, excl + tile_total);
+      }
+    }
+    __syncthreads();
+    const unsigned long long excl = sm.excl;
+    uint8_t *gdst = out + excl;
+    const uint32_t shift = staging_shift(gdst);
+
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      uint32_t o = shift + off[j];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (!((valid[j] >> i) & 1u)) continue;
+        const uint32_t u = u16_unit(w[j], i);
+        const uint32_t pu = i == 0 ? (pw[j] >> 16) : u16_unit(w[j], i - 1);
+        u16_emit8_unit(u, pu, [&](uint8_t b) { sm.out[o++] = b; });
+      }
+    }
+    __syncthreads();
+    copy_out_aligned<uint8_t>(sm.out, gdst, shift, tile_total);
+    __syncthreads();
+  }
+
+  if (grid_last_thread(scr)) {
+    write_result_from_key16(res, ld_relaxed_u64(&scr->err_key), ld_relaxed_u64(&scr->acc0));
+    scratch_reset(scr);
+  }
+}
+
+constexpr int kStreamItems = 4;
+constexpr int kConvItems = 4;  // 8192 units per tile, 24 KiB staging
+
+inline unsigned reduction_grid(const LaunchCtx &c, size_t len_bytes, int items) {
+  const unsigned long long chunks = (len_bytes + 16 + 511ull * items) / (512ull * items);
+  const unsigned long long ctas = (chunks + kWarps - 1) / kWarps;
+  const unsigned long long cap = (unsigned long long)c.sm_count * 8;
+  return (unsigned)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
+}
+
+inline size_t tiles_for(const void *in, size_t len_bytes, int items) {
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
+  const size_t gran = (span + 15) / 16;
+  const size_t per_tile = (size_t)kBlock * items;
+  return (gran + per_tile - 1) / per_tile;
+}
+
+}  // namespace
+
+size_t utf16_convert_tiles(const void *in, size_t len) { return tiles_for(in, 2 * len, kConvItems); }
+
+cudaError_t launch_count_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode) {
+  const unsigned grid = reduction_grid(c, 2 * len, kStreamItems);
+  if (mode == 0) k_scan_utf16<0, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  else k_scan_utf16<1, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_validate_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, void *res) {
+  const unsigned grid = reduction_grid(c, 2 * len, kStreamItems);
+  k_scan_utf16<2, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, res);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_utf16le_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res) {
+  const size_t tiles = tiles_for(in, 2 * len, kConvItems);
+  if (tiles > c.desc_capacity || tiles > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_convert_utf16_to_utf8<kConvItems>, kBlock, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const size_t cap = (size_t)c.sm_count * per_sm;
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+  k_convert_utf16_to_utf8<kConvItems><<<grid, kBlock, 0, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), c.scratch,
+                                                                    c.desc, c.epoch, (uint32_t)tiles,
+                                                                    static_cast<ResultPOD *>(res));
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

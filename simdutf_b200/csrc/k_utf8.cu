@@ -1,0 +1,357 @@
+// k_utf8.cu — sm_100a kernels whose input is UTF-8:
+//   K1  validate_utf8_with_errors          (reference src/scalar/utf8.h:102-200)
+//   K2  count_utf8 / utf16_length_from_utf8 (reference src/scalar/utf8.h:230-255)
+//   K3  convert_utf8_to_utf16le[_with_errors] (reference src/scalar/utf8_to_utf16/utf8_to_utf16.h:128-255)
+//   K4  convert_utf8_to_utf32[_with_errors]   (reference src/scalar/utf8_to_utf32/utf8_to_utf32.h:106-212)
+//
+// Data layout: the input is read once, as 16-byte granules with fully coalesced 128-bit streaming loads
+// (lane l of a warp owns granule g0 + j*32 + l, j = 0..ITEMS-1, so one load instruction covers 512
+// contiguous bytes).  The 3-byte look-behind / look-ahead a byte's verdict and value depend on come from
+// the neighbouring lane by warp shuffle; only the two words flanking a warp's 2 KiB chunk are re-read from
+// L2.  Validation and counting are reductions (first error = atomicMin of position<<8|code).  Transcoding
+// is one pass: per-granule output counts -> block scan -> decoupled look-back across tiles (device_common.cuh)
+// -> units staged in shared memory at their final offsets -> 16-byte coalesced streaming stores.
+#include "device_common.cuh"
+#include "launch.h"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ InView make_view(const void *p, size_t len_bytes) {
+  InView v;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
+  v.vbeg = a & 15u;
+  v.vend = v.vbeg + len_bytes;
+  return v;
+}
+
+// Validation of the ITEMS granules a thread holds.  Flags a granule with the SWAR detector, then pins the
+// exact (code, position) with u8_locate_error on [lo-3, hi).  The granule that contains the last byte of
+// the buffer also checks for a sequence cut short by the end of the buffer.
+template <int ITEMS>
+__device__ __forceinline__ void validate_items(const InView &in, Scratch *scr, unsigned long long g0,
+                                               const uint32_t (&w)[ITEMS][4], const uint32_t (&pw)[ITEMS]) {
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int j = 0; j < ITEMS; j++) {
+    const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+    const unsigned long long lo = g * 16ull;
+    const uint32_t any_hi = (w[j][0] | w[j][1] | w[j][2] | w[j][3] | pw[j]) & kH;
+    bool flagged = false;
+    if (any_hi) flagged = u8_check_granule(w[j], pw[j]) != 0;
+    if (lo < in.vend && in.vend <= lo + 16ull) {  // this granule holds the final byte
+      const long long e = (long long)in.vend;
+      const uint8_t *p = reinterpret_cast<const uint8_t *>(in.base);
+      const uint32_t b1 = p[e - 1];
+      const uint32_t b2 = (e - 2 >= (long long)in.vbeg) ? p[e - 2] : 0u;
+      const uint32_t b3 = (e - 3 >= (long long)in.vbeg) ? p[e - 3] : 0u;
+      flagged = flagged || u8_incomplete_tail(b1, b2, b3);
+    }
+    if (flagged) u8_locate_error(in, scr, (long long)lo - 3, (long long)lo + 16);
+  }
+}
+
+__device__ __forceinline__ void write_result_from_key(ResultPOD *res, unsigned long long key,
+                                                      unsigned long long success_count) {
+  if (key == kNoError) {
+    res->error = kSuccess;
+    res->reserved_ = 0;
+    res->count = success_count;
+  } else {
+    res->error = (int32_t)(key & 0xFFu);
+    res->reserved_ = 0;
+    res->count = key >> 8;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: validate_utf8_with_errors
+// ---------------------------------------------------------------------------------------------
+template <int ITEMS>
+__global__ void __launch_bounds__(kBlock) k_validate_utf8(const char *ptr, size_t len, Scratch *scr, ResultPOD *res) {
+  const InView in = make_view(ptr, len);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long ngran = (in.vend + 15ull) >> 4;
+  const unsigned long long chunk_gran = 32ull * ITEMS;
+  const unsigned long long nchunks = (ngran + chunk_gran - 1) / chunk_gran;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarps;
+  for (unsigned long long chunk = (unsigned long long)blockIdx.x * kWarps + (threadIdx.x >> 5); chunk < nchunks;
+       chunk += nwarps) {
+    const unsigned long long g0 = chunk * chunk_gran;
+    uint32_t w[ITEMS][4];
+    bool inside[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    uint32_t hi = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) hi |= w[j][0] | w[j][1] | w[j][2] | w[j][3];
+    // Word that precedes the chunk: a lead there may still be waiting for continuation bytes.
+    uint32_t before = 0;
+    if (lane == 0) before = load_word_guarded(in, (long long)(g0 * 4ull) - 1);
+    const bool last_chunk = chunk == nchunks - 1;
+    // All-ASCII fast path (config 1): nothing to verify unless the buffer ends here.
+    if (!last_chunk && !__any_sync(kFull, ((hi | before) & kH) != 0u)) continue;
+    uint32_t pw[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const uint32_t give = (lane == 31 && j > 0) ? w[j - 1][3] : w[j][3];
+      uint32_t p = __shfl_sync(kFull, give, (lane + 31u) & 31u);
+      if (j == 0 && lane == 0) p = before;
+      pw[j] = p;
+    }
+    validate_items<ITEMS>(in, scr, g0, w, pw);
+  }
+  if (grid_last_thread(scr)) {
+    write_result_from_key(res, ld_relaxed_u64(&scr->err_key), len);
+    scratch_reset(scr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: count_utf8 (MODE 0) / utf16_length_from_utf8 (MODE 1).  Never validates.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int ITEMS>
+__global__ void __launch_bounds__(kBlock) k_count_utf8(const char *ptr, size_t len, Scratch *scr,
+                                                       unsigned long long *out) {
+  __shared__ unsigned long long s_part[kWarps];
+  const InView in = make_view(ptr, len);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long ngran = (in.vend + 15ull) >> 4;
+  const unsigned long long chunk_gran = 32ull * ITEMS;
+  const unsigned long long nchunks = (ngran + chunk_gran - 1) / chunk_gran;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * kWarps;
+  unsigned long long total = 0;
+  for (unsigned long long chunk = (unsigned long long)blockIdx.x * kWarps + warp; chunk < nchunks; chunk += nwarps) {
+    const unsigned long long g0 = chunk * chunk_gran;
+    uint32_t w[ITEMS][4];
+    bool inside[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t m = u8_noncont(w[j][k]);
+        if (MODE == 1) m |= u8_ge_f0(w[j][k]) >> 1;  // bit 6 of the same byte: one popc counts both
+        if (!inside[j]) {
+          const uint32_t r = inrange_mask_word(in, g, k);
+          m &= r | (r >> 1);
+        }
+        cnt += (uint32_t)__popc(m);
+      }
+    }
+    total += cnt;
+  }
+  total = warp_sum_u64(total);
+  if (lane == 0) s_part[warp] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < kWarps; i++) t += s_part[i];
+    if (t) atomicAdd(&scr->acc0, t);
+  }
+  if (grid_last_thread(scr)) {
+    *out = ld_relaxed_u64(&scr->acc0);
+    scratch_reset(scr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 / K4: UTF-8 -> UTF-16LE (OutT = uint16_t) / UTF-32 (OutT = uint32_t), validating.
+// Persistent CTAs take tiles of kBlock*ITEMS granules from an atomic ticket (in order: required by the
+// look-back scan).
+// ---------------------------------------------------------------------------------------------
+template <typename OutT, int ITEMS>
+struct ConvertSmem {
+  static constexpr uint32_t kTileBytes = kBlock * ITEMS * 16;
+  static constexpr uint32_t kPad = 16 / sizeof(OutT);
+  alignas(16) OutT out[kTileBytes + kPad];  // at most one element per input byte
+  uint32_t warp_tot[kWarps];
+  uint32_t tile;
+  unsigned long long excl;
+};
+
+template <typename OutT, int ITEMS, bool VALIDATE>
+__global__ void __launch_bounds__(kBlock) k_convert_utf8(const char *ptr, size_t len, OutT *out, Scratch *scr,
+                                                         unsigned long long *desc, uint32_t epoch, uint32_t num_tiles,
+                                                         ResultPOD *res) {
+  __shared__ ConvertSmem<OutT, ITEMS> sm;
+  constexpr bool k16 = sizeof(OutT) == 2;
+  const InView in = make_view(ptr, len);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+  while (true) {
+    if (threadIdx.x == 0) sm.tile = atomicAdd(&scr->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile >= num_tiles) break;
+    const unsigned long long g0 = ((unsigned long long)tile * kWarps + warp) * (32ull * ITEMS);
+
+    // ---- load + neighbours -------------------------------------------------------------------
+    uint32_t w[ITEMS][4];
+    bool inside[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    uint32_t pw[ITEMS], nw[ITEMS];
+    neighbour_words<ITEMS>(in, g0, w, pw, nw);
+
+    // ---- emit masks + counts -----------------------------------------------------------------
+    uint32_t em[ITEMS][4];
+    uint32_t cnt[ITEMS], off[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      if (k16) u8_emit16_masks(w[j], pw[j], em[j]);
+      else u8_emit32_masks(w[j], em[j]);
+      if (!inside[j]) {
+        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) em[j][k] &= inrange_mask_word(in, g, k);
+      }
+      cnt[j] = (uint32_t)(__popc(em[j][0]) + __popc(em[j][1]) + __popc(em[j][2]) + __popc(em[j][3]));
+    }
+    const uint32_t tile_total = block_exclusive_offsets<ITEMS>(cnt, off, sm.warp_tot);
+
+    // ---- validation (independent of the scan) -------------------------------------------------
+    if (VALIDATE) validate_items<ITEMS>(in, scr, g0, w, pw);
+
+    // ---- publish aggregate, look back for this tile's output offset ---------------------------
+    if (warp == 0) {
+      unsigned long long excl;
+      uint32_t aux;
+      tile_lookback(desc, epoch, tile, tile_total, 0u, excl, aux);
+      if (lane == 0) {
+        sm.excl = excl;
+        if (tile == num_tiles - 1) st_relaxed_u64(&scr->acc0, excl + tile_total);
+      }
+    }
+    __syncthreads();
+    const unsigned long long excl = sm.excl;
+    OutT *gdst = out + excl;
+    const uint32_t shift = staging_shift(gdst);
+
+    // ---- decode into the staging buffer at final (tile-relative) offsets ----------------------
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      uint32_t o = shift + off[j];
+      if (k16) {
+        u8_emit16_granule(w[j], pw[j], nw[j], em[j], [&](uint16_t u) { sm.out[o++] = (OutT)u; });
+      } else {
+        u8_emit32_granule(w[j], nw[j], em[j], [&](uint32_t u) { sm.out[o++] = (OutT)u; });
+      }
+    }
+    __syncthreads();
+    copy_out_aligned<OutT>(sm.out, gdst, shift, tile_total);
+    __syncthreads();  // staging buffer and sm.tile are reused by the next tile
+  }
+
+  if (grid_last_thread(scr)) {
+    write_result_from_key(res, ld_relaxed_u64(&scr->err_key), ld_relaxed_u64(&scr->acc0));
+    scratch_reset(scr);
+  }
+}
+
+__global__ void k_write_result(ResultPOD *res, int32_t error, unsigned long long count) {
+  res->error = error;
+  res->reserved_ = 0;
+  res->count = count;
+}
+__global__ void k_write_full_result(FullResultPOD *res, int32_t error, unsigned long long in_count,
+                                    unsigned long long out_count) {
+  res->error = error;
+  res->reserved_ = 0;
+  res->input_count = in_count;
+  res->output_count = out_count;
+}
+__global__ void k_write_u64(unsigned long long *dst, unsigned long long v) { *dst = v; }
+__global__ void k_scratch_init(Scratch *scr) { scratch_reset(scr); }
+
+constexpr int kStreamItems = 4;   // granules per thread per iteration in the reduction kernels
+constexpr int kConv16Items = 4;   // 16 KiB tiles, 32 KiB staging
+constexpr int kConv32Items = 2;   //  8 KiB tiles, 32 KiB staging
+
+inline unsigned reduction_grid(const LaunchCtx &c, size_t len_bytes, int items) {
+  const unsigned long long chunks = (len_bytes + 16 + 511ull * items) / (512ull * items);
+  const unsigned long long ctas = (chunks + kWarps - 1) / kWarps;
+  const unsigned long long cap = (unsigned long long)c.sm_count * 8;  // 8 CTAs x 256 threads = full SM
+  return (unsigned)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
+}
+
+inline size_t tiles_for(const void *in, size_t len_bytes, int items) {
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
+  const size_t gran = (span + 15) / 16;
+  const size_t per_tile = (size_t)kBlock * items;
+  return (gran + per_tile - 1) / per_tile;
+}
+
+template <typename OutT, int ITEMS>
+cudaError_t launch_convert(const LaunchCtx &c, const char *in, size_t len, OutT *out, void *res) {
+  const size_t tiles = tiles_for(in, len, ITEMS);
+  if (tiles > c.desc_capacity || tiles > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_convert_utf8<OutT, ITEMS, true>, kBlock, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  const size_t cap = (size_t)c.sm_count * per_sm;
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+  k_convert_utf8<OutT, ITEMS, true><<<grid, kBlock, 0, c.stream>>>(in, len, out, c.scratch, c.desc, c.epoch,
+                                                                  (uint32_t)tiles, static_cast<ResultPOD *>(res));
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t utf8_convert_tiles(const void *in, size_t len, int out_elem_bytes) {
+  return tiles_for(in, len, out_elem_bytes == 2 ? kConv16Items : kConv32Items);
+}
+
+cudaError_t launch_write_result(void *res, int32_t error, unsigned long long count, cudaStream_t stream) {
+  k_write_result<<<1, 1, 0, stream>>>(static_cast<ResultPOD *>(res), error, count);
+  count_launch(1);
+  return cudaGetLastError();
+}
+cudaError_t launch_write_full_result(void *res, int32_t error, unsigned long long in_count,
+                                     unsigned long long out_count, cudaStream_t stream) {
+  k_write_full_result<<<1, 1, 0, stream>>>(static_cast<FullResultPOD *>(res), error, in_count, out_count);
+  count_launch(1);
+  return cudaGetLastError();
+}
+cudaError_t launch_write_u64(unsigned long long *dst, unsigned long long v, cudaStream_t stream) {
+  k_write_u64<<<1, 1, 0, stream>>>(dst, v);
+  count_launch(1);
+  return cudaGetLastError();
+}
+cudaError_t launch_scratch_init(Scratch *scr, cudaStream_t stream) {
+  k_scratch_init<<<1, 1, 0, stream>>>(scr);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_validate_utf8(const LaunchCtx &c, const char *in, size_t len, void *res) {
+  const unsigned grid = reduction_grid(c, len, kStreamItems);
+  k_validate_utf8<kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, static_cast<ResultPOD *>(res));
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_utf8(const LaunchCtx &c, const char *in, size_t len, unsigned long long *count, int mode) {
+  const unsigned grid = reduction_grid(c, len, kStreamItems);
+  if (mode == 0) k_count_utf8<0, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  else k_count_utf8<1, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res) {
+  return launch_convert<uint16_t, kConv16Items>(c, in, len, out, res);
+}
+cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res) {
+  return launch_convert<uint32_t, kConv32Items>(c, in, len, out, res);
+}
+
+}  // namespace b200

@@ -1,0 +1,50 @@
+// launch.h — host-side launch wrappers implemented next to their kernels (k_*.cu) and used by capi.cu.
+// All pointers are DEVICE pointers (or host-mapped pinned memory for result slots).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct Scratch;
+
+// Everything a launch needs besides its data pointers: the per-stream scratch line, the tile
+// descriptor array of the look-back scan (and how many descriptors it holds), the epoch that tags this
+// launch's descriptors, the device's SM count, and the stream.
+struct LaunchCtx {
+  Scratch *scratch;
+  unsigned long long *desc;
+  size_t desc_capacity;
+  uint32_t epoch;
+  int sm_count;
+  cudaStream_t stream;
+};
+
+// Tiles (descriptors) the look-back kernels need for an input of `len` elements.
+size_t utf8_convert_tiles(const void *in, size_t len, int out_elem_bytes);
+size_t utf16_convert_tiles(const void *in, size_t len);
+size_t base64_tiles(const void *in, size_t len);
+
+// result slots: b200_result* / b200_full_result* / uint64_t* (device or mapped-host)
+cudaError_t launch_write_result(void *res, int32_t error, unsigned long long count, cudaStream_t stream);
+cudaError_t launch_write_full_result(void *res, int32_t error, unsigned long long in_count,
+                                     unsigned long long out_count, cudaStream_t stream);
+cudaError_t launch_write_u64(unsigned long long *dst, unsigned long long v, cudaStream_t stream);
+cudaError_t launch_scratch_init(Scratch *scr, cudaStream_t stream);
+
+cudaError_t launch_validate_utf8(const LaunchCtx &c, const char *in, size_t len, void *res);
+cudaError_t launch_count_utf8(const LaunchCtx &c, const char *in, size_t len, unsigned long long *count, int mode);
+cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res);
+cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res);
+
+cudaError_t launch_count_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode);
+cudaError_t launch_validate_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, void *res);
+cudaError_t launch_convert_utf16le_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res);
+
+cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
+                                    uint64_t last_chunk, void *full_res);
+
+void count_launch(int n);  // bumps the library-wide launch counter (b200_launch_count)
+
+}  // namespace b200

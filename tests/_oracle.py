@@ -1,0 +1,211 @@
+"""ctypes windows onto the TEST-ONLY checkers: oracle/liboracle.so (plain-C restatement) and, when present,
+oracle/_ref/libsimdutf_ref.so (the unmodified reference compiled from /root/reference).  Imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs only."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsimdutf_ref.so")
+
+
+class Res(ctypes.Structure):
+    _fields_ = [("error", ctypes.c_int32), ("count", ctypes.c_uint64)]
+
+
+class Full(ctypes.Structure):
+    _fields_ = [("error", ctypes.c_int32), ("input_count", ctypes.c_uint64), ("output_count", ctypes.c_uint64)]
+
+
+def _u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def _u16(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data).view(np.uint16).reshape(-1)
+    return np.frombuffer(bytes(data), dtype=np.uint16)
+
+
+def _p(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data if a.size else 0)
+
+
+class Oracle:
+    """oracle/oracle.c"""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "oracle.c")):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
+        L = ctypes.CDLL(ORACLE_SO)
+        for f in ("oracle_validate_utf8_with_errors", "oracle_convert_utf8_to_utf16le_with_errors",
+                  "oracle_convert_utf8_to_utf32_with_errors", "oracle_convert_utf16le_to_utf8_with_errors",
+                  "oracle_validate_utf16le_with_errors", "oracle_base64_to_binary"):
+            getattr(L, f).restype = Res
+        L.oracle_base64_to_binary_details.restype = Full
+        for f in ("oracle_count_utf8", "oracle_utf16_length_from_utf8", "oracle_utf32_length_from_utf8",
+                  "oracle_count_utf16le", "oracle_utf8_length_from_utf16le", "oracle_utf32_length_from_utf16le",
+                  "oracle_maximal_binary_length_from_base64", "oracle_trim_partial_utf8", "oracle_trim_partial_utf16le",
+                  "oracle_base64_length_from_binary", "oracle_binary_to_base64"):
+            getattr(L, f).restype = ctypes.c_uint64
+        self.L = L
+
+    # --- UTF-8 ---
+    def validate_utf8_with_errors(self, data):
+        a = _u8(data)
+        r = self.L.oracle_validate_utf8_with_errors(_p(a), ctypes.c_size_t(a.size))
+        return (r.error, r.count)
+
+    def count_utf8(self, data):
+        a = _u8(data)
+        return int(self.L.oracle_count_utf8(_p(a), ctypes.c_size_t(a.size)))
+
+    def utf16_length_from_utf8(self, data):
+        a = _u8(data)
+        return int(self.L.oracle_utf16_length_from_utf8(_p(a), ctypes.c_size_t(a.size)))
+
+    def convert_utf8_to_utf16le_with_errors(self, data):
+        a = _u8(data)
+        out = np.zeros(a.size + 8, dtype=np.uint16)
+        r = self.L.oracle_convert_utf8_to_utf16le_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf8_to_utf32_with_errors(self, data):
+        a = _u8(data)
+        out = np.zeros(a.size + 8, dtype=np.uint32)
+        r = self.L.oracle_convert_utf8_to_utf32_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    # --- UTF-16 ---
+    def validate_utf16le_with_errors(self, data):
+        a = _u16(data)
+        r = self.L.oracle_validate_utf16le_with_errors(_p(a), ctypes.c_size_t(a.size))
+        return (r.error, r.count)
+
+    def count_utf16le(self, data):
+        a = _u16(data)
+        return int(self.L.oracle_count_utf16le(_p(a), ctypes.c_size_t(a.size)))
+
+    def utf8_length_from_utf16le(self, data):
+        a = _u16(data)
+        return int(self.L.oracle_utf8_length_from_utf16le(_p(a), ctypes.c_size_t(a.size)))
+
+    def convert_utf16le_to_utf8_with_errors(self, data):
+        a = _u16(data)
+        out = np.zeros(3 * a.size + 8, dtype=np.uint8)
+        r = self.L.oracle_convert_utf16le_to_utf8_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    # --- base64 ---
+    def maximal_binary_length_from_base64(self, data):
+        a = _u8(data)
+        return int(self.L.oracle_maximal_binary_length_from_base64(_p(a), ctypes.c_size_t(a.size)))
+
+    def base64_to_binary_details(self, data, options=0, last_chunk=0):
+        a = _u8(data)
+        out = np.zeros(a.size + 8, dtype=np.uint8)
+        r = self.L.oracle_base64_to_binary_details(_p(a), ctypes.c_size_t(a.size), _p(out), ctypes.c_uint64(options),
+                                                   ctypes.c_uint64(last_chunk))
+        return (r.error, r.input_count, r.output_count), out[: r.output_count]
+
+    def binary_to_base64(self, data, options=0):
+        a = _u8(data)
+        n = int(self.L.oracle_base64_length_from_binary(ctypes.c_size_t(a.size), ctypes.c_uint64(options)))
+        out = np.zeros(n + 8, dtype=np.uint8)
+        w = int(self.L.oracle_binary_to_base64(_p(a), ctypes.c_size_t(a.size), _p(out), ctypes.c_uint64(options)))
+        return out[:w].tobytes()
+
+    def trim_partial_utf8(self, data):
+        a = _u8(data)
+        return int(self.L.oracle_trim_partial_utf8(_p(a), ctypes.c_size_t(a.size)))
+
+
+class Reference:
+    """oracle/_ref/libsimdutf_ref.so — the unmodified reference (icelake / haswell / westmere / fallback)."""
+
+    @staticmethod
+    def load_or_none():
+        if not os.path.exists(REF_SO):
+            return None
+        try:
+            return Reference()
+        except OSError:
+            return None
+
+    def __init__(self):
+        L = ctypes.CDLL(REF_SO)
+        L.ref_best_name.restype = ctypes.c_char_p
+        for f in ("ref_count_utf8", "ref_utf16_length_from_utf8", "ref_utf32_length_from_utf8", "ref_count_utf16le",
+                  "ref_utf8_length_from_utf16le", "ref_maximal_binary_length_from_base64", "ref_convert_utf8_to_utf16le",
+                  "ref_convert_utf8_to_utf32", "ref_convert_utf16le_to_utf8", "ref_binary_to_base64",
+                  "ref_base64_length_from_binary", "ref_trim_partial_utf8",
+                  "ref_mt_utf16_length_then_convert_utf8_to_utf16le"):
+            getattr(L, f).restype = ctypes.c_int64
+        self.L = L
+        self.best = L.ref_best_name().decode()
+
+    def impls(self):
+        return [n for n in ("icelake", "haswell", "westmere", "fallback") if self.L.ref_has_impl(n.encode())]
+
+    def validate_utf8_with_errors(self, impl, data):
+        a = _u8(data); r = Res()
+        assert self.L.ref_validate_utf8_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), ctypes.byref(r)) == 0
+        return (r.error, r.count)
+
+    def count_utf8(self, impl, data):
+        a = _u8(data)
+        return int(self.L.ref_count_utf8(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def utf16_length_from_utf8(self, impl, data):
+        a = _u8(data)
+        return int(self.L.ref_utf16_length_from_utf8(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def convert_utf8_to_utf16le_with_errors(self, impl, data):
+        a = _u8(data); r = Res()
+        out = np.zeros(a.size + 64, dtype=np.uint16)
+        assert self.L.ref_convert_utf8_to_utf16le_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf8_to_utf32_with_errors(self, impl, data):
+        a = _u8(data); r = Res()
+        out = np.zeros(a.size + 64, dtype=np.uint32)
+        assert self.L.ref_convert_utf8_to_utf32_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def count_utf16le(self, impl, data):
+        a = _u16(data)
+        return int(self.L.ref_count_utf16le(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def utf8_length_from_utf16le(self, impl, data):
+        a = _u16(data)
+        return int(self.L.ref_utf8_length_from_utf16le(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def validate_utf16le_with_errors(self, impl, data):
+        a = _u16(data); r = Res()
+        assert self.L.ref_validate_utf16le_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), ctypes.byref(r)) == 0
+        return (r.error, r.count)
+
+    def convert_utf16le_to_utf8_with_errors(self, impl, data):
+        a = _u16(data); r = Res()
+        out = np.zeros(3 * a.size + 64, dtype=np.uint8)
+        assert self.L.ref_convert_utf16le_to_utf8_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def base64_to_binary_details(self, impl, data, options=0, last_chunk=0):
+        a = _u8(data); r = Full()
+        out = np.zeros(a.size + 64, dtype=np.uint8)
+        assert self.L.ref_base64_to_binary_details(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.c_uint64(options),
+                                                   ctypes.c_uint64(last_chunk), ctypes.byref(r)) == 0
+        return (r.error, r.input_count, r.output_count), out[: r.output_count]
+
+    def maximal_binary_length_from_base64(self, data):
+        a = _u8(data)
+        return int(self.L.ref_maximal_binary_length_from_base64(_p(a), ctypes.c_size_t(a.size)))

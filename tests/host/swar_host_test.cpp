@@ -1,0 +1,308 @@
+// tests/host/swar_host_test.cpp — CPU emulation of the kernels' per-granule pipeline.
+//
+// There is no GPU in the build container, so the exact `__host__ __device__` code the kernels run
+// (simdutf_b200/csrc/swar.h) is driven here by a sequential stand-in for the CUDA plumbing (granule loads
+// with zero filler, neighbour words, per-tile carry) and compared with the oracle (oracle/oracle.c) on
+// seeded random and adversarial inputs, at every buffer misalignment.  This is a TEST: the product never
+// runs this path.
+//
+// usage: swar_host_test [iterations] [seed]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../oracle/oracle.h"
+#include "../../simdutf_b200/csrc/swar.h"
+
+using namespace b200;
+
+static std::mt19937_64 rng;
+static uint32_t rnd(uint32_t n) { return (uint32_t)(rng() % n); }
+
+// A buffer placed at `misalign` bytes past a 16-byte boundary, viewed as granules with zero filler.
+struct View {
+  std::vector<uint8_t> mem;  // aligned storage
+  uint64_t vbeg, vend;
+  View(const uint8_t *data, size_t len, unsigned misalign) {
+    vbeg = misalign;
+    vend = misalign + len;
+    mem.assign(((vend + 15) / 16 + 2) * 16, 0);
+    if (len) memcpy(mem.data() + vbeg, data, len);
+  }
+  uint64_t ngran() const { return (vend + 15) / 16; }
+  uint32_t word(long long wi) const {  // zero outside [vbeg, vend)
+    uint32_t r = 0;
+    for (int b = 0; b < 4; b++) {
+      long long pos = wi * 4 + b;
+      if (pos >= (long long)vbeg && pos < (long long)vend) r |= (uint32_t)mem[pos] << (8 * b);
+    }
+    return r;
+  }
+  void granule(uint64_t g, uint32_t w[4]) const { for (int k = 0; k < 4; k++) w[k] = word((long long)g * 4 + k); }
+  uint32_t inrange_word(uint64_t g, int k) const {
+    uint32_t m = 0;
+    for (int b = 0; b < 4; b++) { uint64_t pos = g * 16 + 4 * k + b; if (pos >= vbeg && pos < vend) m |= 0x80u << (8 * b); }
+    return m;
+  }
+};
+
+static int failures = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { failures++; if (failures < 20) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } } } while (0)
+
+static std::string hex(const std::vector<uint8_t> &d) { std::string s; char b[4]; for (uint8_t c : d) { snprintf(b, 4, "%02x", c); s += b; } return s; }
+
+// ---- UTF-8 ---------------------------------------------------------------------------------------------
+static void test_utf8(const std::vector<uint8_t> &d, unsigned misalign) {
+  const size_t len = d.size();
+  View v(d.data(), len, misalign);
+  const oracle_result want = oracle_validate_utf8_with_errors(d.data(), len);
+  // validation: detector + exact locate, exactly as k_utf8.cu:validate_items
+  uint64_t best_pos = ~0ull; int best_code = 0;
+  bool any_flag = false;
+  auto at = [&](uint64_t j) -> uint32_t { return d[j]; };
+  for (uint64_t g = 0; g < v.ngran(); g++) {
+    uint32_t w[4]; v.granule(g, w);
+    uint32_t pw = v.word((long long)g * 4 - 1);
+    bool flagged = u8_check_granule(w, pw) != 0;
+    uint64_t lo = g * 16;
+    if (lo < v.vend && v.vend <= lo + 16 && len > 0) {
+      uint32_t b1 = d[len - 1], b2 = len >= 2 ? d[len - 2] : 0, b3 = len >= 3 ? d[len - 3] : 0;
+      flagged = flagged || u8_incomplete_tail(b1, b2, b3);
+    }
+    if (flagged) {
+      any_flag = true;
+      long long a = (long long)lo - 3, b = (long long)lo + 16;
+      if (a < (long long)v.vbeg) a = (long long)v.vbeg;
+      if (b > (long long)v.vend) b = (long long)v.vend;
+      for (long long p = a; p < b; p++) {
+        uint64_t i = (uint64_t)p - v.vbeg;
+        int code = u8_verdict(at, i, len);
+        if (code) { if (i < best_pos) { best_pos = i; best_code = code; } break; }
+      }
+    }
+  }
+  if (want.error == 0) {
+    CHECK(best_code == 0, "utf8 false error code=%d pos=%llu mis=%u %s", best_code, (unsigned long long)best_pos, misalign, hex(d).c_str());
+    CHECK(!any_flag, "utf8 detector flagged valid input mis=%u %s", misalign, hex(d).c_str());
+  } else {
+    CHECK(best_code == want.error && best_pos == want.count, "utf8 error mismatch got (%d,%llu) want (%d,%llu) mis=%u %s", best_code,
+          (unsigned long long)best_pos, want.error, (unsigned long long)want.count, misalign, hex(d).c_str());
+  }
+  // min over ALL local verdicts == oracle (the claim the kernels rely on)
+  {
+    int code = 0; uint64_t pos = len;
+    for (uint64_t i = 0; i < len; i++) { int c = u8_verdict(at, i, len); if (c) { code = c; pos = i; break; } }
+    CHECK(code == want.error && (code == 0 || pos == want.count), "verdict-min mismatch %s", hex(d).c_str());
+  }
+  // counts + emission
+  uint64_t c8 = 0, c16 = 0;
+  std::vector<uint16_t> out16; std::vector<uint32_t> out32;
+  uint64_t n16 = 0, n32 = 0;
+  for (uint64_t g = 0; g < v.ngran(); g++) {
+    uint32_t w[4]; v.granule(g, w);
+    uint32_t pw = v.word((long long)g * 4 - 1), nw = v.word((long long)g * 4 + 4);
+    uint32_t e16[4], e32[4];
+    u8_emit16_masks(w, pw, e16);
+    u8_emit32_masks(w, e32);
+    for (int k = 0; k < 4; k++) {
+      uint32_t r = v.inrange_word(g, k);
+      uint32_t m = u8_noncont(w[k]) & r;
+      c8 += popc(m);
+      c16 += popc((u8_noncont(w[k]) | (u8_ge_f0(w[k]) >> 1)) & (r | (r >> 1)));
+      e16[k] &= r; e32[k] &= r;
+      n16 += popc(e16[k]); n32 += popc(e32[k]);
+      CHECK(mask4(e16[k]) == ((e16[k] >> 7 & 1) | (e16[k] >> 14 & 2) | (e16[k] >> 21 & 4) | (e16[k] >> 28 & 8)), "mask4");
+    }
+    u8_emit16_granule(w, pw, nw, e16, [&](uint16_t u) { out16.push_back(u); });
+    u8_emit32_granule(w, nw, e32, [&](uint32_t u) { out32.push_back(u); });
+  }
+  CHECK(c8 == oracle_count_utf8(d.data(), len), "count_utf8 %s", hex(d).c_str());
+  CHECK(c16 == oracle_utf16_length_from_utf8(d.data(), len), "utf16_length %s", hex(d).c_str());
+  CHECK(n16 == out16.size() && n32 == out32.size(), "emit count vs mask");
+  CHECK(out16.size() <= oracle_utf16_length_from_utf8(d.data(), len), "utf16 overrun %s", hex(d).c_str());
+  CHECK(out32.size() <= oracle_count_utf8(d.data(), len), "utf32 overrun %s", hex(d).c_str());
+  std::vector<uint16_t> w16(2 * len + 8); std::vector<uint32_t> w32(len + 8);
+  oracle_result r16 = oracle_convert_utf8_to_utf16le_with_errors(d.data(), len, w16.data());
+  oracle_result r32 = oracle_convert_utf8_to_utf32_with_errors(d.data(), len, w32.data());
+  if (r16.error == 0) {
+    CHECK(out16.size() == r16.count && memcmp(out16.data(), w16.data(), 2 * r16.count) == 0, "utf16 output %s", hex(d).c_str());
+    CHECK(out32.size() == r32.count && memcmp(out32.data(), w32.data(), 4 * r32.count) == 0, "utf32 output %s", hex(d).c_str());
+  }
+}
+
+// ---- UTF-16 --------------------------------------------------------------------------------------------
+static void test_utf16(const std::vector<uint16_t> &u, unsigned misalign_units) {
+  const size_t len = u.size();
+  View v(reinterpret_cast<const uint8_t *>(u.data()), 2 * len, 2 * misalign_units);
+  uint64_t cnt = 0, bytes = 0; uint64_t bad_pos = ~0ull;
+  std::vector<uint8_t> out;
+  for (uint64_t g = 0; g < v.ngran(); g++) {
+    uint32_t w[4]; v.granule(g, w);
+    uint32_t pw = v.word((long long)g * 4 - 1), nw = v.word((long long)g * 4 + 4);
+    for (int i = 0; i < 8; i++) {
+      uint64_t pos = g * 16 + 2 * i;
+      if (pos < v.vbeg || pos >= v.vend) continue;
+      uint32_t x = u16_unit(w, i);
+      uint32_t pu = i == 0 ? (pw >> 16) : u16_unit(w, i - 1);
+      uint32_t nu = i == 7 ? (nw & 0xFFFF) : u16_unit(w, i + 1);
+      cnt += (x & 0xFC00) != 0xDC00;
+      bytes += u16_utf8_bytes(x);
+      if (u16_bad(x, pu, true, nu, true)) { uint64_t idx = (pos - v.vbeg) / 2; if (idx < bad_pos) bad_pos = idx; }
+      u16_emit8_unit(x, pu, [&](uint8_t b) { out.push_back(b); });
+    }
+  }
+  CHECK(cnt == oracle_count_utf16le(u.data(), len), "count_utf16le");
+  CHECK(bytes == oracle_utf8_length_from_utf16le(u.data(), len), "utf8_length_from_utf16le");
+  CHECK(out.size() == bytes, "utf16 emit size");
+  std::vector<uint8_t> want(3 * len + 8);
+  oracle_result r = oracle_convert_utf16le_to_utf8_with_errors(u.data(), len, want.data());
+  oracle_result rv = oracle_validate_utf16le_with_errors(u.data(), len);
+  if (r.error == 0) {
+    CHECK(bad_pos == ~0ull, "utf16 false error");
+    CHECK(out.size() == r.count && memcmp(out.data(), want.data(), r.count) == 0, "utf16->utf8 output");
+  } else {
+    CHECK(bad_pos == r.count, "utf16 error pos got %llu want %llu", (unsigned long long)bad_pos, (unsigned long long)r.count);
+    CHECK(rv.error == r.error && rv.count == r.count, "oracle validate16 vs convert");
+  }
+}
+
+// ---- base64 --------------------------------------------------------------------------------------------
+static void test_b64(const std::vector<uint8_t> &d, uint64_t options, uint64_t last_chunk) {
+  const size_t len = d.size();
+  const bool url = options & 1, both = options & 8, garbage = (options == 4 || options == 5 || options == 12);
+  // main pass over [0, len): sextets (compacted), first invalid index
+  std::vector<uint8_t> sx; uint64_t first_bad = ~0ull;
+  for (size_t i = 0; i < len; i++) {
+    uint32_t c = b64_class(d[i], url, both);
+    if (c <= 63) sx.push_back((uint8_t)c);
+    else if (c != 64 && !garbage && first_bad == ~0ull) first_bad = i;
+  }
+  const uint64_t V = sx.size();
+  std::vector<uint8_t> out(b64_bytes_from_sextets(V) + 4);
+  for (uint64_t b = 0; b < b64_bytes_from_sextets(V); b++) {
+    uint64_t q = b / 3, m = b % 3, r = 4 * q + m;
+    out[b] = (uint8_t)((sx[r] << (2 + 2 * m)) | (sx[r + 1] >> (4 - 2 * m)));
+  }
+  // epilogue exactly as k_base64.cu
+  uint64_t srclen = len, equallocation = len; uint32_t equalsigns = 0;
+  auto find_last = [&](long long end, bool sextet_only) -> long long {
+    for (long long j = end - 1; j >= 0; j--) { uint32_t c = b64_class(d[j], url, both); if (sextet_only ? c <= 63 : c != 64) return j; }
+    return -1;
+  };
+  if (!garbage) {
+    srclen = (uint64_t)(find_last((long long)srclen, false) + 1);
+    equallocation = srclen;
+    if (srclen > 0 && d[srclen - 1] == '=') {
+      equallocation = srclen - 1; srclen--; equalsigns = 1;
+      srclen = (uint64_t)(find_last((long long)srclen, false) + 1);
+      if (srclen > 0 && d[srclen - 1] == '=') { equallocation = srclen - 1; srclen--; equalsigns = 2; }
+    }
+  }
+  int error; uint64_t in_count, out_count;
+  const bool invalid = first_bad != ~0ull && first_bad < srclen;
+  if (invalid) { error = kInvalidBase64Character; in_count = first_bad; out_count = 0; }
+  else {
+    uint32_t tail_val[3] = {0, 0, 0}; uint64_t tail_pos[3] = {0, 0, 0};
+    long long end = (long long)srclen;
+    for (uint32_t k = 0; k < (V & 3) && srclen > 0; k++) { long long f = find_last(end, true); if (f < 0) break; tail_pos[k] = f; tail_val[k] = b64_class(d[f], url, both); end = f; }
+    b64_finish(srclen, equalsigns, equallocation, V, garbage, last_chunk, tail_val, tail_pos, &error, &in_count, &out_count);
+  }
+  std::vector<uint8_t> want(len + 8);
+  oracle_full_result r = oracle_base64_to_binary_details(d.data(), len, want.data(), options, last_chunk);
+  bool same = r.error == error && r.input_count == in_count;
+  if (r.error != kInvalidBase64Character && r.error != kBase64ExtraBits) {
+    same = same && r.output_count == out_count && out_count <= b64_bytes_from_sextets(V) && memcmp(out.data(), want.data(), out_count) == 0;
+  }
+  CHECK(same, "b64 opt=%llu lc=%llu got (%d,%llu,%llu) want (%d,%llu,%llu) in=%s", (unsigned long long)options, (unsigned long long)last_chunk, error,
+        (unsigned long long)in_count, (unsigned long long)out_count, r.error, (unsigned long long)r.input_count, (unsigned long long)r.output_count, hex(d).c_str());
+}
+
+// ---- generators ----------------------------------------------------------------------------------------
+static const uint8_t kSpecial[] = {0x20, 0x41, 0x7F, 0x80, 0x8F, 0x90, 0x9F, 0xA0, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1, 0xF3, 0xF4, 0xF5, 0xF7, 0xF8, 0xFF};
+static void push_cp(std::vector<uint8_t> &o, uint32_t cp) {
+  if (cp < 0x80) o.push_back(cp);
+  else if (cp < 0x800) { o.push_back(0xC0 | cp >> 6); o.push_back(0x80 | (cp & 63)); }
+  else if (cp < 0x10000) { o.push_back(0xE0 | cp >> 12); o.push_back(0x80 | (cp >> 6 & 63)); o.push_back(0x80 | (cp & 63)); }
+  else { o.push_back(0xF0 | cp >> 18); o.push_back(0x80 | (cp >> 12 & 63)); o.push_back(0x80 | (cp >> 6 & 63)); o.push_back(0x80 | (cp & 63)); }
+}
+static uint32_t rand_cp() {
+  switch (rnd(6)) {
+    case 0: return rnd(0x80);
+    case 1: return 0x80 + rnd(0x780);
+    case 2: { uint32_t c = 0x800 + rnd(0xF800); return (c >= 0xD800 && c < 0xE000) ? 0x4E00 : c; }
+    case 3: return 0x10000 + rnd(0x100000);
+    case 4: { static const uint32_t edge[] = {0x7F, 0x80, 0x7FF, 0x800, 0xD7FF, 0xE000, 0xFFFF, 0x10000, 0x10FFFF, 0xFFF, 0x1000, 0x3FFFF, 0x40000}; return edge[rnd(13)]; }
+    default: return 0x20 + rnd(0x5F);
+  }
+}
+static std::vector<uint8_t> gen_utf8(size_t n) {
+  std::vector<uint8_t> o;
+  const uint32_t mode = rnd(5);
+  if (mode == 0) { for (size_t i = 0; i < n; i++) o.push_back(kSpecial[rnd(sizeof(kSpecial))]); return o; }
+  if (mode == 1) { for (size_t i = 0; i < n; i++) o.push_back((uint8_t)rnd(256)); return o; }
+  while (o.size() < n) push_cp(o, rand_cp());
+  if (mode == 3 && !o.empty()) { for (uint32_t k = 0, e = 1 + rnd(2); k < e; k++) o[rnd((uint32_t)o.size())] = kSpecial[rnd(sizeof(kSpecial))]; }
+  if (mode == 4 && !o.empty()) o.resize(o.size() - rnd((uint32_t)std::min<size_t>(o.size(), 4)));  // truncate mid-character
+  return o;
+}
+static std::vector<uint16_t> gen_utf16(size_t n) {
+  std::vector<uint16_t> o;
+  const uint32_t mode = rnd(3);
+  static const uint16_t edge[] = {0x41, 0x7F, 0x80, 0x7FF, 0x800, 0xD7FF, 0xD800, 0xDBFF, 0xDC00, 0xDFFF, 0xE000, 0xFFFF};
+  while (o.size() < n) {
+    if (mode == 0) { o.push_back(edge[rnd(12)]); continue; }
+    uint32_t cp = rand_cp();
+    if (cp < 0x10000) o.push_back((uint16_t)cp);
+    else { cp -= 0x10000; o.push_back(0xD800 + (cp >> 10)); o.push_back(0xDC00 + (cp & 0x3FF)); }
+    if (mode == 2 && rnd(40) == 0) o.push_back(0xD800 + rnd(0x800));
+  }
+  if (rnd(4) == 0 && !o.empty()) o.pop_back();
+  return o;
+}
+static std::vector<uint8_t> gen_b64(size_t n) {
+  static const char abc[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/-_";
+  static const char ws[] = " \t\n\r\f";
+  static const char junk[] = "=*\x80\xff\x00.\x0b";
+  std::vector<uint8_t> o;
+  const uint32_t mode = rnd(4);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t x = rnd(100);
+    if (x < 80) o.push_back(mode == 1 ? abc[rnd(62) < 60 ? rnd(62) : 64 + rnd(2)] : abc[rnd(64)]);
+    else if (x < 93) o.push_back(ws[rnd(5)]);
+    else if (x < 97 && mode >= 2) o.push_back(rnd(2) ? junk[rnd(7)] : abc[62 + rnd(4)]);
+    else o.push_back(abc[rnd(62)]);
+  }
+  static const char *tails[] = {"", "=", "==", " = = ", "= ", "=\n=", "===", " ", "  \n", "= =="};
+  const char *t = tails[rnd(10)];
+  for (; *t; t++) o.push_back(*t);
+  return o;
+}
+
+int main(int argc, char **argv) {
+  const long iters = argc > 1 ? atol(argv[1]) : 20000;
+  rng.seed(argc > 2 ? atoll(argv[2]) : 12345);
+  for (long it = 0; it < iters; it++) {
+    const size_t n8 = rnd(4) ? rnd(120) : rnd(700);
+    std::vector<uint8_t> d = gen_utf8(n8);
+    test_utf8(d, rnd(16));
+    std::vector<uint16_t> u = gen_utf16(rnd(4) ? rnd(60) : rnd(300));
+    test_utf16(u, rnd(8));
+    std::vector<uint8_t> b = gen_b64(rnd(4) ? rnd(100) : rnd(400));
+    static const uint64_t opts[] = {0, 1, 2, 3, 4, 5, 8, 12};
+    test_b64(b, opts[rnd(8)], rnd(3));
+    if (failures > 50) break;
+  }
+  // known-answer edge cases
+  test_utf8({}, 0);
+  test_utf8({0x80}, 3);
+  for (unsigned mis = 0; mis < 16; mis++) {
+    std::vector<uint8_t> d(64, 0x20); d.push_back(0xFF); test_utf8(d, mis);
+    std::vector<uint8_t> e(64, 0x20); e.push_back(0xA9); test_utf8(e, mis);
+    for (int cut = 1; cut <= 3; cut++) { std::vector<uint8_t> f(29 + mis, 'a'); push_cp(f, 0x1F600); f.resize(f.size() - cut); test_utf8(f, mis); }
+  }
+  printf("swar_host_test: %ld iterations, %d failures\n", iters, failures);
+  return failures ? 1 : 0;
+}

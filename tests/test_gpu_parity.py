@@ -1,0 +1,491 @@
+"""GPU parity tests (-m gpu): the sm_100a kernels, called through the C ABI (include/simdutf_b200.h), against
+the oracle (oracle/oracle.c — pinned by tests/test_oracle.py) and the committed golden vectors.
+
+Bit-exact everywhere: validity flag, error code, error position, counts and output bytes.
+Nothing here reads /root/reference; oracle/_ref (prebuilt reference library) is used only if it travelled.
+"""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden.json")
+GUARD = 64  # canary elements after every output buffer
+
+
+@pytest.fixture(scope="module")
+def b():
+    import simdutf_b200
+    simdutf_b200.load()
+    assert simdutf_b200.device_count() >= 1, "no sm_100 device visible: the CUDA path cannot run"
+    simdutf_b200.set_device(0)
+    return simdutf_b200
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def dev(data, dtype=torch.uint8, misalign=0):
+    """Device copy of `data` (bytes / numpy) placed `misalign` elements past an aligned allocation."""
+    a = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data)
+    t = torch.from_numpy(a.copy()).view(dtype) if a.size else torch.empty(0, dtype=dtype)
+    buf = torch.zeros(t.numel() + misalign + 16, dtype=dtype, device="cuda")
+    buf[misalign:misalign + t.numel()] = t.cuda()
+    return buf[misalign:misalign + t.numel()]
+
+
+FILL = {torch.uint8: 0x5A, torch.int16: 0x5A5A, torch.int32: 0x5A5A5A5A}
+
+
+def out_buf(n, dtype, misalign=0):
+    buf = torch.full((n + misalign + GUARD,), FILL[dtype], dtype=dtype, device="cuda")
+    return buf, buf[misalign:misalign + n + GUARD]
+
+
+def check_guard(view, n, fill=None):
+    tail = view[n:n + GUARD].cpu()
+    assert bool((tail == FILL[view.dtype]).all()), "output buffer overrun"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# helpers that run one input through both call flavours and compare with the oracle
+# ------------------------------------------------------------------------------------------------------------
+def run_utf8(b, oracle, data: bytes, misalign=0, host_too=True):
+    want_v = oracle.validate_utf8_with_errors(data)
+    want16, o16 = oracle.convert_utf8_to_utf16le_with_errors(data)
+    want32, o32 = oracle.convert_utf8_to_utf32_with_errors(data)
+    n16 = oracle.utf16_length_from_utf8(data)
+    n8 = oracle.count_utf8(data)
+    d = dev(data, misalign=misalign)
+    assert b.validate_utf8_with_errors(d) == want_v, (data[:64].hex(), len(data), misalign)
+    assert b.count_utf8(d) == n8
+    assert b.utf16_length_from_utf8(d) == n16
+    # output buffers sized EXACTLY by the length query, as the reference's callers do
+    _, v16 = out_buf(n16, torch.int16, misalign=misalign % 8)
+    assert b.convert_utf8_to_utf16le_with_errors(d, v16) == want16, (data[:64].hex(), len(data), misalign)
+    check_guard(v16, n16, 0x5A5A)
+    if want16[0] == 0:
+        assert v16[:n16].cpu().numpy().view(np.uint16).tobytes() == o16.tobytes()
+    _, v32 = out_buf(n8, torch.int32, misalign=misalign % 4)
+    assert b.convert_utf8_to_utf32_with_errors(d, v32) == want32
+    check_guard(v32, n8, 0x5A5A5A5A)
+    if want32[0] == 0:
+        assert v32[:n8].cpu().numpy().view(np.uint32).tobytes() == o32.tobytes()
+    if host_too:
+        assert b.validate_utf8_with_errors(data) == want_v
+        assert b.count_utf8(data) == n8 and b.utf16_length_from_utf8(data) == n16
+        h16 = np.full(n16 + GUARD, 0x5A5A, dtype=np.uint16)
+        assert b.convert_utf8_to_utf16le_with_errors(data, h16) == want16
+        assert (h16[n16:] == 0x5A5A).all()
+        if want16[0] == 0:
+            assert h16[:n16].tobytes() == o16.tobytes()
+        h32 = np.full(n8 + GUARD, 0x5A5A5A5A, dtype=np.uint32)
+        assert b.convert_utf8_to_utf32_with_errors(data, h32) == want32
+        if want32[0] == 0:
+            assert h32[:n8].tobytes() == o32.tobytes()
+
+
+def run_utf16(b, oracle, units: np.ndarray, misalign=0, host_too=True):
+    units = np.ascontiguousarray(units, dtype=np.uint16)
+    want, o8 = oracle.convert_utf16le_to_utf8_with_errors(units)
+    n8 = oracle.utf8_length_from_utf16le(units)
+    d = dev(units.view(np.uint8), dtype=torch.uint8, misalign=2 * misalign).view(torch.int16)
+    assert b.count_utf16le(d) == oracle.count_utf16le(units)
+    assert b.utf8_length_from_utf16le(d) == n8
+    assert b.validate_utf16le_with_errors(d) == oracle.validate_utf16le_with_errors(units)
+    _, v8 = out_buf(n8, torch.uint8, misalign=misalign)
+    assert b.convert_utf16le_to_utf8_with_errors(d, v8) == want, (units[:32], len(units), misalign)
+    check_guard(v8, n8)
+    if want[0] == 0:
+        assert v8[:n8].cpu().numpy().tobytes() == o8.tobytes()
+    if host_too:
+        h8 = np.full(n8 + GUARD, 0x5A, dtype=np.uint8)
+        assert b.convert_utf16le_to_utf8_with_errors(units, h8) == want
+        assert (h8[n8:] == 0x5A).all()
+        if want[0] == 0:
+            assert h8[:n8].tobytes() == o8.tobytes()
+        assert b.count_utf16le(units) == oracle.count_utf16le(units)
+
+
+def run_b64(b, oracle, data: bytes, options=0, last_chunk=0, misalign=0, host_too=True):
+    want, wout = oracle.base64_to_binary_details(data, options, last_chunk)
+    cap = oracle.maximal_binary_length_from_base64(data)
+    d = dev(data, misalign=misalign)
+    _, v = out_buf(cap, torch.uint8, misalign=(misalign * 7) % 16)
+    got = b.base64_to_binary_details(d, v, options, last_chunk)
+    assert got[:2] == want[:2], (data[:80], len(data), options, last_chunk, got, want)
+    check_guard(v, cap)
+    if want[0] not in (7, 9):  # output_count is not pinned on INVALID_BASE64_CHARACTER / EXTRA_BITS
+        assert got == want, (data[:80], options, last_chunk, got, want)
+        assert v[:want[2]].cpu().numpy().tobytes() == wout.tobytes()
+    if host_too:
+        h = np.full(cap + GUARD, 0x5A, dtype=np.uint8)
+        got = b.base64_to_binary_details(data, h, options, last_chunk)
+        assert got[:2] == want[:2]
+        assert (h[cap:] == 0x5A).all()
+        if want[0] not in (7, 9):
+            assert got == want and h[:want[2]].tobytes() == wout.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# golden vectors
+# ------------------------------------------------------------------------------------------------------------
+def test_golden_kat(b, oracle, golden):
+    for v in golden["kat"]:
+        data = bytes.fromhex(v["input"])
+        f = v["func"]
+        d = dev(data)
+        if f == "validate_utf8":
+            assert b.validate_utf8(d) == v["expect"], v
+            assert b.validate_utf8(data) == v["expect"], v
+        elif f == "validate_utf8_with_errors":
+            assert list(b.validate_utf8_with_errors(d)) == v["expect"], v
+            assert list(b.validate_utf8_with_errors(data)) == v["expect"], v
+        elif f == "convert_utf8_to_utf16le_with_errors":
+            n = oracle.utf16_length_from_utf8(data)
+            _, o = out_buf(n, torch.int16)
+            assert list(b.convert_utf8_to_utf16le_with_errors(d, o)) == v["expect"], v
+            check_guard(o, n, 0x5A5A)
+        elif f == "base64_to_binary":
+            cap = oracle.maximal_binary_length_from_base64(data)
+            _, o = out_buf(cap, torch.uint8)
+            assert list(b.base64_to_binary(d, o, v["options"], v["last_chunk"])) == v["expect"], v
+            if "output" in v:
+                assert o[:v["expect"][1]].cpu().numpy().tobytes().hex() == v["output"], v
+
+
+def test_golden_recorded(b, oracle, golden):
+    for v in golden["recorded"]:
+        data = bytes.fromhex(v["input"])
+        if v["kind"] == "utf8":
+            d = dev(data)
+            assert list(b.validate_utf8_with_errors(d)) == v["validate"]
+            assert b.count_utf8(d) == v["count_utf8"] and b.utf16_length_from_utf8(d) == v["utf16_length"]
+            _, o = out_buf(v["utf16_length"], torch.int16)
+            assert list(b.convert_utf8_to_utf16le_with_errors(d, o)) == v["to_utf16"]
+            if v["to_utf16"][0] == 0:
+                assert o[:v["utf16_length"]].cpu().numpy().tobytes().hex() == v["utf16_out"]
+            _, o = out_buf(v["count_utf8"], torch.int32)
+            assert list(b.convert_utf8_to_utf32_with_errors(d, o)) == v["to_utf32"]
+            if v["to_utf32"][0] == 0:
+                assert o[:v["count_utf8"]].cpu().numpy().tobytes().hex() == v["utf32_out"]
+        elif v["kind"] == "utf16":
+            d = dev(data).view(torch.int16)
+            assert b.count_utf16le(d) == v["count_utf16le"] and b.utf8_length_from_utf16le(d) == v["utf8_length"]
+            assert list(b.validate_utf16le_with_errors(d)) == v["validate"]
+            _, o = out_buf(v["utf8_length"], torch.uint8)
+            assert list(b.convert_utf16le_to_utf8_with_errors(d, o)) == v["to_utf8"]
+            if v["to_utf8"][0] == 0:
+                assert o[:v["utf8_length"]].cpu().numpy().tobytes().hex() == v["utf8_out"]
+        else:
+            d = dev(data)
+            assert b.maximal_binary_length_from_base64(data) == v["maxlen"]
+            for c in v["cases"]:
+                _, o = out_buf(v["maxlen"], torch.uint8)
+                got = b.base64_to_binary_details(d, o, c["options"], c["last_chunk"])
+                assert list(got)[:2] == c["result"][:2], (data, c, got)
+                if c["output"] is not None:
+                    assert list(got) == c["result"], (data, c, got)
+                    assert o[:got[2]].cpu().numpy().tobytes().hex() == c["output"]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# seeded random / adversarial inputs, all sizes and misalignments
+# ------------------------------------------------------------------------------------------------------------
+SPECIAL = [0x20, 0x41, 0x7F, 0x80, 0x8F, 0x90, 0x9F, 0xA0, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xEC, 0xED, 0xEE, 0xEF, 0xF0,
+           0xF1, 0xF3, 0xF4, 0xF5, 0xF7, 0xF8, 0xFF]
+
+
+def rand_text(rng, nchars):
+    return "".join(chr(rng.choice([rng.randrange(0x20, 0x7f), rng.randrange(0xa0, 0x250), rng.randrange(0x4e00, 0xa000),
+                                   rng.randrange(0x1f300, 0x1f650)])) for _ in range(nchars)).encode()
+
+
+def test_utf8_small_random(b, oracle):
+    rng = random.Random(101)
+    for it in range(400):
+        n = rng.choice([0, 1, 2, 3, 4, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 511, 512, 513, 2047, 2049, 5000])
+        mode = it % 5
+        if mode == 0:
+            d = bytes(rng.choice(SPECIAL) for _ in range(n))
+        elif mode == 1:
+            d = bytes(rng.randrange(256) for _ in range(n))
+        else:
+            bb = bytearray(rand_text(rng, n // 2 + 1)[:n + 3])
+            if mode == 3 and bb:
+                bb[rng.randrange(len(bb))] = rng.choice(SPECIAL)
+            if mode == 4 and bb:
+                del bb[len(bb) - rng.randrange(min(4, len(bb))):]
+            d = bytes(bb)
+        run_utf8(b, oracle, d, misalign=rng.randrange(16), host_too=(it % 4 == 0))
+
+
+def test_utf8_error_classes_at_tile_edges(b, oracle):
+    """Each of the six error classes planted at granule / warp-chunk / tile boundaries of a
+    multi-tile buffer of valid text; also the last byte (truncation)."""
+    rng = random.Random(5)
+    base = bytearray(rand_text(rng, 40000))  # ~100 KB: several 16 KiB tiles
+    n = len(base)
+    bad = {
+        "HEADER_BITS": b"\xf8", "TOO_SHORT": b"\xe4\x20", "TOO_LONG": b"\x80", "OVERLONG": b"\xc0\x80",
+        "TOO_LARGE": b"\xf4\x90\x80\x80", "SURROGATE": b"\xed\xa0\x80", "OVERLONG3": b"\xe0\x80\x80", "OVERLONG4": b"\xf0\x80\x80\x80",
+        "TOO_LARGE2": b"\xf5\x80\x80\x80",
+    }
+    spots = [0, 13, 15, 16, 17, 511, 512, 513, 2047, 2048, 2049, 16383, 16384, 16385, 32767, 32768, 49151, 49152, n - 5, n - 1]
+    for name, seq in bad.items():
+        for pos in spots:
+            d = bytearray(base)
+            # move to a character start so the planted sequence is what the parser meets first
+            p = min(pos, n - 1)
+            while p > 0 and (d[p] & 0xC0) == 0x80:
+                p -= 1
+            d[p:p + len(seq)] = seq
+            run_utf8(b, oracle, bytes(d), misalign=pos % 16, host_too=False)
+    for cut in range(1, 4):  # buffer ends inside a 4-byte character
+        d = bytes(base[:30000])
+        while (d[-1] & 0xC0) == 0x80:
+            d = d[:-1]
+        d = d[:-1] + "\U0001F600".encode()[:4 - cut]
+        run_utf8(b, oracle, d, host_too=True)
+
+
+def test_utf8_medium_exact(b, oracle):
+    from simdutf_b200 import synth
+    for n, seed in ((1 << 20, 21), (3 * (1 << 20) + 12345, 22), (1 << 23, 23)):
+        d = synth.mixed_utf8(n, seed=seed).numpy().tobytes()
+        run_utf8(b, oracle, d, misalign=seed % 16, host_too=(n <= 1 << 21))
+    a = synth.ascii_text((1 << 22) + 7, seed=1).numpy().tobytes()
+    run_utf8(b, oracle, a, misalign=3, host_too=False)
+
+
+def rand_units(rng, n, mode):
+    u = []
+    edge = [0x41, 0x7f, 0x80, 0x7ff, 0x800, 0xd7ff, 0xd800, 0xdbff, 0xdc00, 0xdfff, 0xe000, 0xffff]
+    while len(u) < n:
+        c = rng.randrange(6)
+        if mode == 0: u.append(rng.choice(edge))
+        elif c == 0: u.append(rng.randrange(0x80))
+        elif c == 1: u.append(rng.randrange(0x80, 0x800))
+        elif c == 2: u.append(rng.choice([rng.randrange(0x800, 0xd800), rng.randrange(0xe000, 0x10000)]))
+        elif c == 3: u += [rng.randrange(0xd800, 0xdc00), rng.randrange(0xdc00, 0xe000)]
+        elif mode == 2 and rng.random() < 0.05: u.append(rng.randrange(0xd800, 0xe000))
+        else: u.append(0x20)
+    return np.array(u, dtype=np.uint16)
+
+
+def test_utf16_random_and_surrogate_errors(b, oracle):
+    rng = random.Random(202)
+    for it in range(200):
+        n = rng.choice([0, 1, 2, 7, 8, 9, 15, 16, 17, 255, 256, 257, 1000, 4095, 4097, 9000])
+        run_utf16(b, oracle, rand_units(rng, n, it % 3), misalign=rng.randrange(8), host_too=(it % 4 == 0))
+    from simdutf_b200 import synth
+    base = synth.mixed_utf16le(100000, seed=31).numpy().view(np.uint16)
+    run_utf16(b, oracle, base, host_too=True)
+    # lone low / lone high / low-low / pair-then-high at tile edges (reference tests/convert_utf16le_to_utf8_with_errors_tests.cpp:110-212)
+    for pos in (0, 7, 8, 255, 256, 8191, 8192, 8193, 16383, 16384, len(base) - 1):
+        for planted in ([0xDC00], [0xD800], [0xDC00, 0xDC00], [0xD800, 0xD800], [0xD800, 0x41]):
+            u = base.copy()
+            p = pos
+            while p > 0 and (u[p] & 0xFC00) == 0xDC00:
+                p -= 1
+            u[p:p + len(planted)] = planted[:len(u) - p]
+            run_utf16(b, oracle, u, misalign=pos % 8, host_too=False)
+
+
+ABC = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/-_"
+
+
+def test_base64_random_all_options(b, oracle):
+    rng = random.Random(303)
+    fixed = [b"", b" ", b"=", b"==", b"A", b"AA", b"AAA", b"AAAA", b"AA=", b"AA==", b"AAA=", b"AAA==", b"AAAA=", b"A=", b"QQ===",
+             b"AA=A", b"AAAA*AAA", b"AAAA AAAA\r\n", b"AAAAA", b" A A = = ", b"AAA\x80", b"AA-A", b"AA+A"]
+    for it in range(260):
+        if it < len(fixed):
+            d = fixed[it]
+        else:
+            n = rng.choice([3, 4, 5, 15, 16, 17, 63, 64, 65, 66, 100, 1000, 4095, 4096, 4097, 20000, 40000])
+            out = bytearray()
+            for _ in range(n):
+                x = rng.random()
+                if x < 0.85: out.append(rng.choice(ABC[:64] if it % 2 else ABC[:62] + ABC[64:]))
+                elif x < 0.97: out.append(rng.choice(b" \t\n\r\x0c"))
+                elif it % 5 == 0: out.append(rng.choice(b"=*\x80\xff.\x0b"))
+                else: out.append(rng.choice(ABC[:62]))
+            d = bytes(out) + rng.choice([b"", b"=", b"==", b" = = ", b"= ", b"=\n=", b" ", b"   \r\n" * 50])
+        for opt in ((0, 1, 2, 3, 4, 5, 8, 12) if it % 3 == 0 or it < len(fixed) else (it % 2,)):
+            for lc in (0, 1, 2):
+                run_b64(b, oracle, d, opt, lc, misalign=rng.randrange(16), host_too=(it % 8 == 0))
+
+
+def test_base64_large_with_whitespace(b, oracle):
+    from simdutf_b200 import synth
+    for url in (False, True):
+        text, payload = synth.base64_text(3 << 20, seed=41 + url, url=url)
+        data = text.numpy().tobytes()
+        run_b64(b, oracle, data, options=1 if url else 0, misalign=5, host_too=True)
+        cap = oracle.maximal_binary_length_from_base64(data)
+        _, o = out_buf(cap, torch.uint8)
+        e, i, n = b.base64_to_binary_details(dev(data), o, 1 if url else 0, 0)
+        assert e == 0 and n == payload.numel() and o[:n].cpu().numpy().tobytes() == payload.numpy().tobytes()
+        # one bad character deep inside; a dangling single sextet at the end
+        for q in (0, 77, 16384, 16385, 1 << 20, len(data) - 9):
+            bad = bytearray(data); bad[q] = ord("*")
+            run_b64(b, oracle, bytes(bad), options=1 if url else 0, host_too=False)
+        stripped = data.rstrip(b"=\r\n \t")
+        for k in range(1, 5):  # a dangling single sextet at the very end -> BASE64_INPUT_REMAINDER
+            cand = stripped + b"A" * k
+            if oracle.base64_to_binary_details(cand, 1 if url else 0, 0)[0][0] == 8:
+                break
+        assert oracle.base64_to_binary_details(cand, 1 if url else 0, 0)[0][0] == 8
+        run_b64(b, oracle, cand, options=1 if url else 0, host_too=False)
+
+
+def test_repeated_calls_and_epoch_wrap(b, oracle):
+    """More than 4096 scan launches on one stream: the 12-bit descriptor epoch wraps and must be handled."""
+    from simdutf_b200 import synth
+    d = synth.mixed_utf8(70000, seed=51).numpy().tobytes()
+    want, o16 = oracle.convert_utf8_to_utf16le_with_errors(d)
+    dd = dev(d)
+    n16 = want[1]
+    _, v = out_buf(n16, torch.int16)
+    for it in range(4300):
+        assert b.convert_utf8_to_utf16le_with_errors(dd, v) == want
+        if it % 500 == 0 or it > 4090:
+            assert v[:n16].cpu().numpy().view(np.uint16).tobytes() == o16.tobytes()
+            v[:n16].fill_(0)
+    check_guard(v, n16, 0x5A5A)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs 1-4) — sizes the oracle cannot walk in seconds
+# ------------------------------------------------------------------------------------------------------------
+def test_config1_ascii_1gib(b, oracle):
+    from simdutf_b200 import synth
+    n = 1 << 30
+    d = synth.ascii_text(n, seed=1, device="cuda")
+    assert b.validate_utf8_with_errors(d) == (0, n)
+    assert b.count_utf8(d) == n and b.utf16_length_from_utf8(d) == n
+    rng = random.Random(9)
+    for pos in (0, 63, 64, 16383, 16384, (1 << 29) + 5, n - 2, n - 1):
+        for byte, code in ((0xFF, 1), (0x80, 3), (0xC0, None), (0xE4, 2)):
+            old = int(d[pos].item())
+            d[pos] = byte
+            err, cnt = b.validate_utf8_with_errors(d)
+            lo = max(0, pos - 64)
+            want = oracle.validate_utf8_with_errors(d[lo:min(n, pos + 64)].cpu().numpy().tobytes())
+            assert (err, cnt) == (want[0], want[1] + lo), (pos, byte)
+            if code is not None:
+                assert err == code and cnt == pos
+            d[pos] = old
+    assert b.validate_utf8_with_errors(d) == (0, n)
+
+
+def test_config2_mixed_1gib_roundtrip(b, oracle):
+    from simdutf_b200 import synth
+    d = synth.mixed_utf8(1 << 30, seed=2, device="cuda")
+    n = d.numel()
+    assert b.validate_utf8_with_errors(d) == (0, n)
+    units = b.utf16_length_from_utf8(d)
+    chars = b.count_utf8(d)
+    _, out = out_buf(units, torch.int16)
+    assert b.convert_utf8_to_utf16le_with_errors(d, out) == (0, units)
+    check_guard(out, units, 0x5A5A)
+    u16 = out[:units]
+    # size-independent properties: counts agree across encodings, and UTF-16 -> UTF-8 gives the input back
+    assert b.count_utf16le(u16) == chars
+    assert b.utf8_length_from_utf16le(u16) == n
+    _, back = out_buf(n, torch.uint8)
+    assert b.convert_utf16le_to_utf8_with_errors(u16, back) == (0, n)
+    assert torch.equal(back[:n], d)
+    # and a slice checked bit-for-bit against the oracle
+    head = d[:1 << 22].cpu().numpy().tobytes()
+    cut = oracle.trim_partial_utf8(head)
+    (e, c), o = oracle.convert_utf8_to_utf16le_with_errors(head[:cut])
+    assert e == 0 and u16[:c].cpu().numpy().view(np.uint16).tobytes() == o.tobytes()
+    # UTF-32 at a quarter of the size
+    qlen = 1 << 28
+    while (int(d[qlen].item()) & 0xC0) == 0x80:
+        qlen -= 1
+    q = d[:qlen]
+    nq = b.count_utf8(q)
+    _, o32 = out_buf(nq, torch.int32)
+    assert b.convert_utf8_to_utf32_with_errors(q, o32) == (0, nq)
+    check_guard(o32, nq, 0x5A5A5A5A)
+    (e, c), o = oracle.convert_utf8_to_utf32_with_errors(head[:cut])
+    assert o32[:c].cpu().numpy().view(np.uint32).tobytes() == o.tobytes()
+    # an error deep inside: position must be exact
+    p = (1 << 29) + 12345
+    while (int(d[p].item()) & 0xC0) == 0x80:
+        p -= 1
+    d[p] = 0xFF
+    assert b.validate_utf8_with_errors(d) == (1, p)
+    assert b.convert_utf8_to_utf16le_with_errors(d, out) == (1, p)
+    check_guard(out, units, 0x5A5A)
+
+
+def test_config3_utf16_2gib(b, oracle):
+    from simdutf_b200 import synth
+    u = synth.mixed_utf16le(1 << 30, seed=3, device="cuda")
+    n = u.numel()
+    nbytes = b.utf8_length_from_utf16le(u)
+    chars = b.count_utf16le(u)
+    assert b.validate_utf16le_with_errors(u) == (0, n)
+    _, out = out_buf(nbytes, torch.uint8)
+    assert b.convert_utf16le_to_utf8_with_errors(u, out) == (0, nbytes)
+    check_guard(out, nbytes)
+    o8 = out[:nbytes]
+    assert b.validate_utf8_with_errors(o8) == (0, nbytes)
+    assert b.count_utf8(o8) == chars and b.utf16_length_from_utf8(o8) == n
+    head = u[:1 << 21].cpu().numpy().view(np.uint16)
+    if (head[-1] & 0xFC00) == 0xD800:
+        head = head[:-1]
+    (e, c), o = oracle.convert_utf16le_to_utf8_with_errors(head)
+    assert e == 0 and o8[:c].cpu().numpy().tobytes() == o.tobytes()
+    # back to UTF-16: identical units
+    _, back = out_buf(n, torch.int16)
+    assert b.convert_utf8_to_utf16le_with_errors(o8, back) == (0, n)
+    assert torch.equal(back[:n], u)
+    # one injected unpaired surrogate at 0.9*len (BASELINE.json config 3)
+    p = int(0.9 * n)
+    while (int(u[p].item()) & 0xF800) == 0xD800:
+        p += 1
+    if (int(u[p - 1].item()) & 0xFC00) == 0xD800:  # previous is a high surrogate: it becomes the error instead
+        p += 1
+    old = int(u[p].item())
+    u[p] = -9216  # 0xDC00
+    assert b.convert_utf16le_to_utf8_with_errors(u, out) == (6, p)
+    assert b.validate_utf16le_with_errors(u) == (6, p)
+    u[p] = -10240  # 0xD800 followed by a non-surrogate
+    assert b.convert_utf16le_to_utf8_with_errors(u, out) == (6, p)
+    u[p] = old
+
+
+def test_config4_base64_2gib(b, oracle):
+    from simdutf_b200 import synth
+    for url in (False, True):
+        text, payload = synth.base64_text(1 << 31, seed=4, device="cuda", url=url)
+        opt = 1 if url else 0
+        cap = text.numel() // 4 * 3 + 3
+        _, out = out_buf(cap, torch.uint8)
+        e, i, n = b.base64_to_binary_details(text, out, opt, 0)
+        assert (e, n) == (0, payload.numel()), (e, i, n, payload.numel())
+        assert torch.equal(out[:n], payload)
+        check_guard(out, cap)
+        q = (1 << 30) + 77
+        old = int(text[q].item())
+        text[q] = ord("=")
+        assert b.base64_to_binary(text, out, opt, 0) == (7, q)
+        text[q] = 0xC3
+        assert b.base64_to_binary(text, out, opt, 0) == (7, q)
+        text[q] = old
+        del text, payload, out
+        torch.cuda.empty_cache()

@@ -1,0 +1,148 @@
+"""CPU tests (-m "not gpu") of everything around the kernels that does not need a GPU:
+  * the shared library loads and exports every symbol include/simdutf_b200.h declares;
+  * without a device the compute entry points FAIL LOUDLY (no CPU fallback);
+  * the kernels' per-granule logic (csrc/swar.h), driven on the CPU by tests/host/swar_host_test.cpp,
+    agrees with the oracle;
+  * the multi-GPU composition (simdutf_b200/sharded.py) over gloo, world_size 2, with the oracle standing in
+    for the per-shard kernel call.
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from simdutf_b200 import build
+    build.build_library()
+    import simdutf_b200
+    return simdutf_b200.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    import simdutf_b200
+    hdr = open(os.path.join(ROOT, "include", "simdutf_b200.h")).read()
+    declared = set(re.findall(r"SIMDUTF_B200_API\s+[\w \*]+?\b(b200_\w+)\s*\(", hdr))
+    assert len(declared) >= 40
+    assert declared == set(simdutf_b200.SYMBOLS), declared ^ set(simdutf_b200.SYMBOLS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", simdutf_b200.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (b200_\w+)", nm))
+    assert declared <= exported, declared - exported
+    # and nothing from the oracle / reference is linked in
+    assert "oracle_" not in nm and "simdutf" not in nm.replace("libsimdutf_b200", "")
+
+
+def test_library_is_silent(lib):
+    """reference CMakeLists.txt:173-214: the library must not reference printf/abort/cout/cerr/stdout/stderr."""
+    import simdutf_b200
+    nm = subprocess.run(["nm", "-D", "--undefined-only", simdutf_b200.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for sym in ("abort", "printf", "puts", "_ZSt4cout", "_ZSt4cerr", "stdout", "stderr"):
+        assert not re.search(r"\bU %s\b" % re.escape(sym), nm), sym
+
+
+def test_trivial_and_o1_entry_points(lib, oracle):
+    import simdutf_b200 as b
+    assert lib.b200_name() == b"b200"
+    # len == 0 never touches CUDA (reference tests/null_safety_tests.cpp:7-95)
+    r = b.Result()
+    assert lib.b200_host_validate_utf8_with_errors(None, 0, ctypes.byref(r)) == 0 and r.astuple() == (0, 0)
+    c = ctypes.c_uint64(7)
+    assert lib.b200_host_count_utf8(None, 0, ctypes.byref(c)) == 0 and c.value == 0
+    f = b.FullResult()
+    assert lib.b200_host_base64_to_binary(None, 0, None, 0, 0, ctypes.byref(f)) == 0 and f.astuple() == (0, 0, 0)
+    for s in (b"", b"A", b"AA=", b"AAAA==", b"QUJD", b"QUJDRA==", b"abc=="):
+        assert b.maximal_binary_length_from_base64(s) == oracle.maximal_binary_length_from_base64(s)
+    for s in (b"", b"a", b"\xc3", b"a\xe2\x82", b"ab\xf0\x9f\x98", b"abc\xc3\xa9", b"\xf0\x9f", "héllo€".encode()):
+        assert b.trim_partial_utf8(s) == oracle.trim_partial_utf8(s)
+
+
+def test_no_device_means_loud_failure(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import simdutf_b200 as b
+    assert b.device_count() == 0
+    r = b.Result()
+    data = b"hello"
+    assert lib.b200_host_validate_utf8_with_errors(data, len(data), ctypes.byref(r)) == -1  # B200_E_NO_DEVICE
+    assert b"device" in lib.b200_last_error()
+    with pytest.raises(b.B200Error):
+        b.validate_utf8_with_errors(data)
+    with pytest.raises(b.B200Error):
+        b.count_utf8(data)
+
+
+def test_swar_logic_against_oracle_on_cpu():
+    from simdutf_b200 import build
+    exe = build.build_host_tests()
+    p = subprocess.run([exe, "6000", "99"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-4000:]
+    assert "0 failures" in p.stdout
+
+
+def test_shard_bounds(oracle):
+    from simdutf_b200 import sharded, synth
+    data = synth.mixed_utf8(20000, seed=5).numpy()
+    for world in (1, 2, 3, 4, 8):
+        cuts = sharded.utf8_shard_bounds(lambda i: int(data[i]), data.size, world)
+        assert cuts[0] == 0 and cuts[-1] == data.size and len(cuts) == world + 1
+        total = 0
+        for a, b_ in zip(cuts, cuts[1:]):
+            assert a <= b_ and b_ - a <= data.size // world + 4
+            assert oracle.validate_utf8_with_errors(data[a:b_]) == (0, b_ - a)  # every shard is whole characters
+            total += oracle.utf16_length_from_utf8(data[a:b_])
+        assert total == oracle.utf16_length_from_utf8(data)
+    u = synth.mixed_utf16le(5000, seed=6).numpy().view(np.uint16)
+    for world in (2, 3, 8):
+        cuts = sharded.utf16_shard_bounds(lambda i: int(u[i]), u.size, world)
+        for a, b_ in zip(cuts, cuts[1:]):
+            assert oracle.validate_utf16le_with_errors(u[a:b_]) == (0, b_ - a)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from simdutf_b200 import sharded, synth
+from tests._oracle import Oracle
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank(); o = Oracle()
+data = synth.mixed_utf8(30000, seed=11).numpy().copy()
+for case in ("valid", "err_rank1", "err_rank0", "err_both"):
+    d = data.copy()
+    if case in ("err_rank1", "err_both"): d[22001] = 0xFF
+    if case in ("err_rank0", "err_both"): d[100] = 0xC0
+    cuts = sharded.utf8_shard_bounds(lambda i: int(data[i]), d.size, 2)
+    mine = d[cuts[rank]:cuts[rank + 1]]
+    (err, cnt), out = o.convert_utf8_to_utf16le_with_errors(mine)           # stands in for the per-shard kernel call
+    g = sharded.combine(err, cnt, mine.size, torch.device("cpu"))
+    (werr, wcnt), wout = o.convert_utf8_to_utf16le_with_errors(d)           # whole buffer, one call
+    assert (g.error, g.count) == (werr, wcnt), (case, rank, g, werr, wcnt)
+    assert g.in_offset == cuts[rank]
+    if werr == 0:
+        assert np.array_equal(wout[g.out_offset:g.out_offset + cnt], out), case
+    verr, vcnt = o.validate_utf8_with_errors(mine)
+    gv = sharded.combine(verr, vcnt, mine.size, torch.device("cpu"), count_is_length=True)
+    assert (gv.error, gv.count) == o.validate_utf8_with_errors(d), (case, rank, gv)
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_sharded_combine_gloo_world2(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in o, o[-3000:]
