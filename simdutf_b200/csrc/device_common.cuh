@@ -89,15 +89,18 @@ __device__ __forceinline__ void load_granule(const InView &in, unsigned long lon
   }
 }
 
+// 16-bit mask (bit b = byte b) of the bytes of granule g that lie inside [vbeg, vend).
+__device__ __forceinline__ uint32_t inrange_mask16(const InView &in, unsigned long long g) {
+  const long long lo = (long long)(g * 16ull);
+  long long a = (long long)in.vbeg - lo, b = (long long)in.vend - lo;
+  a = a < 0 ? 0 : (a > 16 ? 16 : a);
+  b = b < 0 ? 0 : (b > 16 ? 16 : b);
+  if (b <= a) return 0u;
+  return ((1u << (unsigned)b) - 1u) & ~((1u << (unsigned)a) - 1u);
+}
 // Bit-7 mask of the bytes of word `k` of granule g that lie inside [vbeg, vend).
 __device__ __forceinline__ uint32_t inrange_mask_word(const InView &in, unsigned long long g, int k) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    const unsigned long long pos = g * 16ull + 4u * k + b;
-    if (pos >= in.vbeg && pos < in.vend) m |= 0x80u << (8 * b);
-  }
-  return m;
+  return unmask4((inrange_mask16(in, g) >> (4 * k)) & 0xFu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -281,7 +284,13 @@ __device__ __forceinline__ void report_error(Scratch *scr, unsigned long long ke
 // Exact UTF-8 first-error search over byte positions [lo, hi) (virtual positions, clipped to the buffer),
 // reading the bytes straight from global memory.  Called only by threads whose granule tripped
 // u8_check_granule / the truncated-tail check.  Skips the work if an earlier error is already recorded.
-static __device__ __noinline__ void u8_locate_error(const InView &in, Scratch *scr, long long lo, long long hi) {
+static __device__ __noinline__ void u8_locate_error_impl(const uint4 *base, unsigned long long vbeg,
+                                                         unsigned long long vend, Scratch *scr, long long lo,
+                                                         long long hi) {
+  InView in;
+  in.base = base;
+  in.vbeg = vbeg;
+  in.vend = vend;
   if (lo < (long long)in.vbeg) lo = (long long)in.vbeg;
   if (hi > (long long)in.vend) hi = (long long)in.vend;
   if (lo >= hi) return;
@@ -298,6 +307,10 @@ static __device__ __noinline__ void u8_locate_error(const InView &in, Scratch *s
       return;
     }
   }
+}
+
+__device__ __forceinline__ void u8_locate_error(const InView &in, Scratch *scr, long long lo, long long hi) {
+  u8_locate_error_impl(in.base, in.vbeg, in.vend, scr, lo, hi);
 }
 
 // ---------------------------------------------------------------------------------------------

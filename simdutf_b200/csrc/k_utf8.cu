@@ -11,6 +11,8 @@
 // L2.  Validation and counting are reductions (first error = atomicMin of position<<8|code).  Transcoding
 // is one pass: per-granule output counts -> block scan -> decoupled look-back across tiles (device_common.cuh)
 // -> units staged in shared memory at their final offsets -> 16-byte coalesced streaming stores.
+#include <cstdlib>
+
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -27,6 +29,16 @@ __device__ __forceinline__ InView make_view(const void *p, size_t len_bytes) {
   return v;
 }
 
+// True iff the last three bytes of the buffer start a sequence that the end of the buffer cuts short.
+__device__ __forceinline__ bool tail_truncated(const InView &in) {
+  const long long e = (long long)in.vend;
+  const uint8_t *p = reinterpret_cast<const uint8_t *>(in.base);
+  const uint32_t b1 = p[e - 1];
+  const uint32_t b2 = (e - 2 >= (long long)in.vbeg) ? p[e - 2] : 0u;
+  const uint32_t b3 = (e - 3 >= (long long)in.vbeg) ? p[e - 3] : 0u;
+  return u8_incomplete_tail(b1, b2, b3);
+}
+
 // Validation of the ITEMS granules a thread holds.  Flags a granule with the SWAR detector, then pins the
 // exact (code, position) with u8_locate_error on [lo-3, hi).  The granule that contains the last byte of
 // the buffer also checks for a sequence cut short by the end of the buffer.
@@ -41,14 +53,7 @@ __device__ __forceinline__ void validate_items(const InView &in, Scratch *scr, u
     const uint32_t any_hi = (w[j][0] | w[j][1] | w[j][2] | w[j][3] | pw[j]) & kH;
     bool flagged = false;
     if (any_hi) flagged = u8_check_granule(w[j], pw[j]) != 0;
-    if (lo < in.vend && in.vend <= lo + 16ull) {  // this granule holds the final byte
-      const long long e = (long long)in.vend;
-      const uint8_t *p = reinterpret_cast<const uint8_t *>(in.base);
-      const uint32_t b1 = p[e - 1];
-      const uint32_t b2 = (e - 2 >= (long long)in.vbeg) ? p[e - 2] : 0u;
-      const uint32_t b3 = (e - 3 >= (long long)in.vbeg) ? p[e - 3] : 0u;
-      flagged = flagged || u8_incomplete_tail(b1, b2, b3);
-    }
+    if (lo < in.vend && in.vend <= lo + 16ull) flagged = flagged || tail_truncated(in);  // holds the final byte
     if (flagged) u8_locate_error(in, scr, (long long)lo - 3, (long long)lo + 16);
   }
 }
@@ -176,8 +181,8 @@ struct ConvertSmem {
   unsigned long long excl;
 };
 
-template <typename OutT, int ITEMS, bool VALIDATE>
-__global__ void __launch_bounds__(kBlock) k_convert_utf8(const char *ptr, size_t len, OutT *out, Scratch *scr,
+template <typename OutT, int ITEMS, bool VALIDATE, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_convert_utf8(const char *ptr, size_t len, OutT *out, Scratch *scr,
                                                          unsigned long long *desc, uint32_t epoch, uint32_t num_tiles,
                                                          ResultPOD *res) {
   __shared__ ConvertSmem<OutT, ITEMS> sm;
@@ -200,24 +205,21 @@ __global__ void __launch_bounds__(kBlock) k_convert_utf8(const char *ptr, size_t
     uint32_t pw[ITEMS], nw[ITEMS];
     neighbour_words<ITEMS>(in, g0, w, pw, nw);
 
-    // ---- emit masks + counts -----------------------------------------------------------------
-    uint32_t em[ITEMS][4];
+    // ---- per-granule output counts (phase 1: cheap SWAR popcounts, nothing is kept but the counts) ------
     uint32_t cnt[ITEMS], off[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-      if (k16) u8_emit16_masks(w[j], pw[j], em[j]);
-      else u8_emit32_masks(w[j], em[j]);
+      uint32_t em[4];
+      if (k16) u8_emit16_masks(w[j], pw[j], em);
+      else u8_emit32_masks(w[j], em);
       if (!inside[j]) {
         const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
 #pragma unroll
-        for (int k = 0; k < 4; k++) em[j][k] &= inrange_mask_word(in, g, k);
+        for (int k = 0; k < 4; k++) em[k] &= inrange_mask_word(in, g, k);
       }
-      cnt[j] = (uint32_t)(__popc(em[j][0]) + __popc(em[j][1]) + __popc(em[j][2]) + __popc(em[j][3]));
+      cnt[j] = (uint32_t)(__popc(em[0]) + __popc(em[1]) + __popc(em[2]) + __popc(em[3]));
     }
     const uint32_t tile_total = block_exclusive_offsets<ITEMS>(cnt, off, sm.warp_tot);
-
-    // ---- validation (independent of the scan) -------------------------------------------------
-    if (VALIDATE) validate_items<ITEMS>(in, scr, g0, w, pw);
 
     // ---- publish aggregate, look back for this tile's output offset ---------------------------
     if (warp == 0) {
@@ -234,14 +236,46 @@ __global__ void __launch_bounds__(kBlock) k_convert_utf8(const char *ptr, size_t
     OutT *gdst = out + excl;
     const uint32_t shift = staging_shift(gdst);
 
-    // ---- decode into the staging buffer at final (tile-relative) offsets ----------------------
+    // ---- phase 2: decode (+ validate) into the staging buffer at final (tile-relative) offsets ----------
+    if (k16) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-      uint32_t o = shift + off[j];
-      if (k16) {
-        u8_emit16_granule(w[j], pw[j], nw[j], em[j], [&](uint16_t u) { sm.out[o++] = (OutT)u; });
-      } else {
-        u8_emit32_granule(w[j], nw[j], em[j], [&](uint32_t u) { sm.out[o++] = (OutT)u; });
+      for (int j = 0; j < ITEMS; j++) {
+        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+        OutT *sp = sm.out + shift + off[j];
+        U8Carry carry = u8_carry_of(pw[j]);
+        uint32_t flagged = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t xn = (k < 3 ? w[j][(k + 1) & 3] : nw[j]) & 0x3F3F3F3Fu;
+          const U8Word16 r = u8_to_utf16_word<VALIDATE>(w[j][k], xn, carry);
+          uint32_t em = r.emit;
+          if (!inside[j]) em &= inrange_mask_word(in, g, k);
+          flagged |= r.err;
+          if (em & 0x00000080u) *sp++ = (OutT)(r.u01 & 0xFFFFu);
+          if (em & 0x00008000u) *sp++ = (OutT)(r.u01 >> 16);
+          if (em & 0x00800000u) *sp++ = (OutT)(r.u23 & 0xFFFFu);
+          if (em & 0x80000000u) *sp++ = (OutT)(r.u23 >> 16);
+        }
+        if (VALIDATE) {
+          const unsigned long long lo = g * 16ull;
+          bool bad = flagged != 0;
+          if (lo < in.vend && in.vend <= lo + 16ull) bad = bad || tail_truncated(in);
+          if (bad) u8_locate_error(in, scr, (long long)lo - 3, (long long)lo + 16);
+        }
+      }
+    } else {
+      if (VALIDATE) validate_items<ITEMS>(in, scr, g0, w, pw);
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        uint32_t em[4];
+        u8_emit32_masks(w[j], em);
+        if (!inside[j]) {
+          const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+#pragma unroll
+          for (int k = 0; k < 4; k++) em[k] &= inrange_mask_word(in, g, k);
+        }
+        uint32_t o = shift + off[j];
+        u8_emit32_granule(w[j], nw[j], em, [&](uint32_t u) { sm.out[o++] = (OutT)u; });
       }
     }
     __syncthreads();
@@ -288,20 +322,43 @@ inline size_t tiles_for(const void *in, size_t len_bytes, int items) {
   return (gran + per_tile - 1) / per_tile;
 }
 
+template <typename OutT, int ITEMS, int MINB>
+cudaError_t launch_convert_v(const LaunchCtx &c, const char *in, size_t len, OutT *out, void *res, size_t tiles) {
+  static int per_sm = 0;  // resident CTAs per SM for this instantiation (queried once)
+  if (per_sm == 0) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_convert_utf8<OutT, ITEMS, true, MINB>, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    per_sm = n < 1 ? 1 : n;
+  }
+  const size_t cap = (size_t)c.sm_count * per_sm;
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+  k_convert_utf8<OutT, ITEMS, true, MINB><<<grid, kBlock, 0, c.stream>>>(in, len, out, c.scratch, c.desc, c.epoch,
+                                                                        (uint32_t)tiles, static_cast<ResultPOD *>(res));
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+// Resident CTAs per SM the kernels are compiled for (register budget = 65536 / (256 * MINB)).
+// B200_TUNE_MINB=2|3|4 overrides the default for experiments (tools/, profiles/).
+inline int tuned_minb(int dflt) {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("B200_TUNE_MINB");
+    v = (e && e[0] >= '2' && e[0] <= '4' && e[1] == 0) ? e[0] - '0' : 0;
+  }
+  return v ? v : dflt;
+}
+
 template <typename OutT, int ITEMS>
 cudaError_t launch_convert(const LaunchCtx &c, const char *in, size_t len, OutT *out, void *res) {
   const size_t tiles = tiles_for(in, len, ITEMS);
   if (tiles > c.desc_capacity || tiles > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_convert_utf8<OutT, ITEMS, true>, kBlock, 0);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  const size_t cap = (size_t)c.sm_count * per_sm;
-  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-  k_convert_utf8<OutT, ITEMS, true><<<grid, kBlock, 0, c.stream>>>(in, len, out, c.scratch, c.desc, c.epoch,
-                                                                  (uint32_t)tiles, static_cast<ResultPOD *>(res));
-  count_launch(1);
-  return cudaGetLastError();
+  switch (tuned_minb(4)) {
+    case 2: return launch_convert_v<OutT, ITEMS, 2>(c, in, len, out, res, tiles);
+    case 3: return launch_convert_v<OutT, ITEMS, 3>(c, in, len, out, res, tiles);
+    default: return launch_convert_v<OutT, ITEMS, 4>(c, in, len, out, res, tiles);
+  }
 }
 
 }  // namespace

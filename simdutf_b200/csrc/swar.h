@@ -283,6 +283,94 @@ B200_HD void u8_emit32_granule(const uint32_t w[4], uint32_t next, const uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Branch-free SWAR transcoder UTF-8 -> UTF-16LE, four byte positions per 32-bit word, fused with the
+// validation detector.  Every position computes the unit it WOULD emit from its own byte and the payloads
+// of the next two bytes (x1, x2):
+//     ASCII         b                                   2-byte lead   (b&1F)<<6 | x1
+//     3-byte lead   (b&0F)<<12 | x1<<6 | x2             4-byte lead   0xD800 | ((cp>>16)-1)<<6 | (x1&0F)<<2 | x2>>4
+//     byte after a 4-byte lead (its own x1,x2 are bytes 3,4 of the sequence)   0xDC00 | (x1&0F)<<6 | x2
+// as a low-byte plane and a high-byte plane, then interleaves the planes into units.  Which positions
+// really emit is the caller's mask (non-continuation bytes + the byte after a byte >= 0xF0), so the number
+// of units per byte equals utf16_length_from_utf8's count (reference src/scalar/utf8.h:243-255).
+// Values: reference src/scalar/utf8_to_utf16/utf8_to_utf16.h:154-242.
+// The detector flags exactly the invalid inputs (structure: "must be continuation" vs "is continuation";
+// ranges: on the decoded bits — overlong 2/3/4-byte, surrogates, > U+10FFFF, 0xF8..0xFF), see
+// u8_check_granule for how a flag is turned into the exact (error, position).
+// ---------------------------------------------------------------------------------------------
+struct U8Carry {       // class masks of the previous word (what the current word looks back at)
+  uint32_t l2, l3, l4;
+};
+struct U8Word16 {
+  uint32_t u01, u23;   // candidate units of positions 0,1 and 2,3 (low half = lower position)
+  uint32_t emit;       // bit-7 mask: positions that emit a unit
+  uint32_t err;        // bit-7 mask: validation detector (non-zero => run the exact locator)
+};
+
+B200_HD U8Carry u8_carry_of(uint32_t w) {
+  const U8Class c = u8_classify(w);
+  U8Carry k;
+  k.l2 = c.l2; k.l3 = c.l3; k.l4 = c.l4;
+  return k;
+}
+
+// Full-byte (0xFF / 0x00) mask from a bit-7 mask: PRMT with the sign-replicate selector.
+B200_HD uint32_t fullmask(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;  // prmt's selector msb = "replicate the sign of the selected byte" (__byte_perm ignores that bit)
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(m), "r"(0u), "r"(0xBA98u));
+  return r;
+#else
+  return ((m >> 7) & 0x01010101u) * 0xFFu;
+#endif
+}
+// bit 7 of each byte set iff (t & 0xFE) != 0, for t with bit 0 clear in every byte... generalised below:
+// nz7(t): t must have bit 0 of every byte clear; returns bit-7 mask of the non-zero bytes.
+B200_HD uint32_t nz7(uint32_t t) { return ((t >> 1) + 0x7F7F7F7Fu) & kH; }
+
+template <bool VALIDATE>
+B200_HD U8Word16 u8_to_utf16_word(uint32_t w, uint32_t xnext, U8Carry &carry) {
+  const uint32_t s1 = w << 1, s2 = w << 2, s3 = w << 3;
+  const uint32_t l2 = w & s1 & kH, l3 = l2 & s2, l4 = l3 & s3;
+  const uint32_t cont = w & ~s1 & kH;
+  const uint32_t x = w & 0x3F3F3F3Fu;
+  const uint32_t x1 = prmt(x, xnext, 0x4321), x2 = prmt(x, xnext, 0x5432);
+  const uint32_t afterf0 = back1(carry.l4, l4);  // the byte after a byte >= 0xF0 carries the low surrogate
+  // ---- low / high byte planes per class ----
+  const uint32_t lo2 = ((w << 6) & 0xC0C0C0C0u) | x1;
+  const uint32_t hi2 = (w >> 2) & 0x07070707u;
+  const uint32_t x1r2 = x1 >> 2;
+  const uint32_t lo3 = ((x1 << 6) & 0xC0C0C0C0u) | x2;                   // also the low surrogate's low byte
+  const uint32_t hi3 = (s2 << 2 & 0xF0F0F0F0u) | (x1r2 & 0x0F0F0F0Fu);   // (w<<4 & F0) | (x1>>2 & 0F)
+  const uint32_t v = (s2 & 0x1C1C1C1Cu) | ((x1 >> 4) & 0x03030303u);     // cp >> 16 (5 bits) at 4-byte leads
+  const uint32_t v1 = v + 0x7F7F7F7Fu;                                   // low 7 bits: v - 1 ; bit 7: v >= 1
+  const uint32_t lo4 = ((x1 << 2) & 0x3C3C3C3Cu) | ((((v1 << 6) & 0xC0C0C0C0u) | ((x2 >> 4) & 0x3F3F3F3Fu)) & 0xC3C3C3C3u);
+  const uint32_t l4F = fullmask(l4), contF = fullmask(cont), hiF = fullmask(w), is2F = fullmask(l2 & ~l3);
+  // surrogate high bytes: 0xD8 | ((cp>>16)-1)>>2 at the lead, 0xDC | (x1>>2 & 3) at the byte after it
+  const uint32_t sp = (((v1 >> 2) & l4F) | (x1r2 & ~l4F)) & 0x03030303u;
+  const uint32_t hs = (sp | 0xD8D8D8D8u) | (contF & 0x04040404u);
+  const uint32_t surrF = l4F | contF;
+  const uint32_t lo = (w & ~hiF) | (hiF & ((is2F & lo2) | (~is2F & ((l4F & lo4) | (~l4F & lo3)))));
+  const uint32_t hi = hiF & ((surrF & hs) | (~surrF & ((is2F & hi2) | (~is2F & hi3))));
+  U8Word16 r;
+  r.u01 = prmt(lo, hi, 0x5140);
+  r.u23 = prmt(lo, hi, 0x7362);
+  r.emit = (~cont & kH) | afterf0;
+  r.err = 0;
+  if (VALIDATE) {
+    const uint32_t must = back1(carry.l2, l2) | back2(carry.l3, l3) | back3(carry.l4, l4);
+    const uint32_t is2 = l2 & ~l3, is3 = l3 & ~l4;
+    const uint32_t over2 = is2 & ~(((w & 0x1E1E1E1Eu) + 0x7F7F7F7Fu));           // C0 / C1
+    const uint32_t h8 = hi3 & 0xF8F8F8F8u;
+    const uint32_t over3 = is3 & ~nz7(h8);                                         // E0 80..9F
+    const uint32_t surr3 = is3 & ~nz7(h8 ^ 0xD8D8D8D8u);                           // ED A0..BF
+    const uint32_t bad4 = l4 & (nz7((v1 ^ kH) & 0xF0F0F0F0u) | (s3 << 1));         // cp>>16 not in 1..16, or F8..FF
+    r.err = (must ^ cont) | over2 | over3 | surr3 | bad4;
+  }
+  carry.l2 = l2; carry.l3 = l3; carry.l4 = l4;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // UTF-16LE.  A granule is 8 units u[0..7]; `pu` / `nu` are the units before / after it.
 // ---------------------------------------------------------------------------------------------
 B200_HD uint32_t u16_unit(const uint32_t w[4], int i) { return (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; }

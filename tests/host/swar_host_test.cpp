@@ -133,6 +133,43 @@ static void test_utf8(const std::vector<uint8_t> &d, unsigned misalign) {
   }
 }
 
+
+// ---- UTF-8 -> UTF-16 through the branch-free word transcoder (k_utf8.cu v2 path) -------------------------
+static void test_utf8_word16(const std::vector<uint8_t> &d, unsigned misalign) {
+  const size_t len = d.size();
+  View v(d.data(), len, misalign);
+  const oracle_result want = oracle_validate_utf8_with_errors(d.data(), len);
+  std::vector<uint16_t> out;
+  bool flagged_any = false;
+  uint64_t n_emit = 0;
+  for (uint64_t g = 0; g < v.ngran() + 1; g++) {  // one extra granule: truncation shows up on the filler
+    uint32_t w[4]; v.granule(g, w);
+    uint32_t pw = v.word((long long)g * 4 - 1), nw = v.word((long long)g * 4 + 4);
+    U8Carry carry = u8_carry_of(pw);
+    for (int k = 0; k < 4; k++) {
+      const uint32_t xn = (k < 3 ? w[k + 1] : nw) & 0x3F3F3F3Fu;
+      U8Word16 r = u8_to_utf16_word<true>(w[k], xn, carry);
+      U8Carry c2 = u8_carry_of(k ? w[k - 1] : pw);
+      U8Word16 r0 = u8_to_utf16_word<false>(w[k], xn, c2);
+      CHECK(r0.u01 == r.u01 && r0.u23 == r.u23 && r0.emit == r.emit && r0.err == 0, "VALIDATE=false differs");
+      if (r.err) flagged_any = true;
+      const uint32_t em = r.emit & v.inrange_word(g, k);
+      n_emit += popc(em);
+      const uint32_t units[4] = {r.u01 & 0xFFFF, r.u01 >> 16, r.u23 & 0xFFFF, r.u23 >> 16};
+      for (int b = 0; b < 4; b++) if (em >> (8 * b + 7) & 1) out.push_back((uint16_t)units[b]);
+    }
+  }
+  // reference emit masks (the counting kernel's definition) must agree with the transcoder's
+  CHECK(n_emit <= oracle_utf16_length_from_utf8(d.data(), len), "word16 overrun %s", hex(d).c_str());
+  CHECK(flagged_any == (want.error != 0), "word16 detector: flagged=%d want.error=%d mis=%u %s", (int)flagged_any, want.error, misalign, hex(d).c_str());
+  if (want.error == 0) {
+    std::vector<uint16_t> w16(2 * len + 8);
+    oracle_result r16 = oracle_convert_utf8_to_utf16le_with_errors(d.data(), len, w16.data());
+    CHECK(out.size() == r16.count && memcmp(out.data(), w16.data(), 2 * r16.count) == 0, "word16 output mis=%u %s", misalign, hex(d).c_str());
+    CHECK(n_emit == oracle_utf16_length_from_utf8(d.data(), len), "word16 count");
+  }
+}
+
 // ---- UTF-16 --------------------------------------------------------------------------------------------
 static void test_utf16(const std::vector<uint16_t> &u, unsigned misalign_units) {
   const size_t len = u.size();
@@ -288,6 +325,7 @@ int main(int argc, char **argv) {
     const size_t n8 = rnd(4) ? rnd(120) : rnd(700);
     std::vector<uint8_t> d = gen_utf8(n8);
     test_utf8(d, rnd(16));
+    test_utf8_word16(d, rnd(16));
     std::vector<uint16_t> u = gen_utf16(rnd(4) ? rnd(60) : rnd(300));
     test_utf16(u, rnd(8));
     std::vector<uint8_t> b = gen_b64(rnd(4) ? rnd(100) : rnd(400));
@@ -299,9 +337,9 @@ int main(int argc, char **argv) {
   test_utf8({}, 0);
   test_utf8({0x80}, 3);
   for (unsigned mis = 0; mis < 16; mis++) {
-    std::vector<uint8_t> d(64, 0x20); d.push_back(0xFF); test_utf8(d, mis);
+    std::vector<uint8_t> d(64, 0x20); d.push_back(0xFF); test_utf8(d, mis); test_utf8_word16(d, mis);
     std::vector<uint8_t> e(64, 0x20); e.push_back(0xA9); test_utf8(e, mis);
-    for (int cut = 1; cut <= 3; cut++) { std::vector<uint8_t> f(29 + mis, 'a'); push_cp(f, 0x1F600); f.resize(f.size() - cut); test_utf8(f, mis); }
+    for (int cut = 1; cut <= 3; cut++) { std::vector<uint8_t> f(29 + mis, 'a'); push_cp(f, 0x1F600); f.resize(f.size() - cut); test_utf8(f, mis); test_utf8_word16(f, mis); }
   }
   printf("swar_host_test: %ld iterations, %d failures\n", iters, failures);
   return failures ? 1 : 0;

@@ -428,8 +428,11 @@ def test_config2_mixed_1gib_roundtrip(b, oracle):
         p -= 1
     d[p] = 0xFF
     assert b.validate_utf8_with_errors(d) == (1, p)
+    units_bad = b.utf16_length_from_utf8(d)  # the caller sizes the buffer from the SAME (invalid) input
+    del out, back, u16
+    _, out = out_buf(units_bad, torch.int16)
     assert b.convert_utf8_to_utf16le_with_errors(d, out) == (1, p)
-    check_guard(out, units, 0x5A5A)
+    check_guard(out, units_bad)
 
 
 def test_config3_utf16_2gib(b, oracle):

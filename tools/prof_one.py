@@ -1,0 +1,72 @@
+"""Tiny driver for ncu: runs ONE hot-path operation a few times on a device-resident synthetic buffer.
+usage: python tools/prof_one.py <op> [bytes] [reps]
+   op: convert16 | convert32 | validate_ascii | validate_mixed | length | utf16to8 | base64
+"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import simdutf_b200 as b
+from simdutf_b200 import synth
+
+op = sys.argv[1]
+nbytes = int(sys.argv[2]) if len(sys.argv) > 2 else 256 << 20
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+lib = b.load()
+b.set_device(0)
+dev = torch.device("cuda", 0)
+sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+res = torch.zeros(4, dtype=torch.int64, device=dev)
+rp = ctypes.c_void_p(res.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def run(fn, nin, nout):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{op}: {ms:.4f} ms/launch, input {nin / ms / 1e6:.1f} GB/s, in+out {(nin + nout) / ms / 1e6:.1f} GB/s, result {res.tolist()}")
+
+
+if op in ("convert16", "convert32", "validate_mixed", "length"):
+    d = synth.mixed_utf8(nbytes, seed=2, device=dev)
+    n = d.numel()
+    p = ctypes.c_void_p(d.data_ptr())
+    if op == "convert16":
+        units = b.utf16_length_from_utf8(d)
+        o = torch.empty(units, dtype=torch.int16, device=dev)
+        run(lambda: lib.b200_convert_utf8_to_utf16le_async(p, n, ctypes.c_void_p(o.data_ptr()), rp, sp), n, 2 * units)
+    elif op == "convert32":
+        c = b.count_utf8(d)
+        o = torch.empty(c, dtype=torch.int32, device=dev)
+        run(lambda: lib.b200_convert_utf8_to_utf32_async(p, n, ctypes.c_void_p(o.data_ptr()), rp, sp), n, 4 * c)
+    elif op == "validate_mixed":
+        run(lambda: lib.b200_validate_utf8_with_errors_async(p, n, rp, sp), n, 0)
+    else:
+        run(lambda: lib.b200_utf16_length_from_utf8_async(p, n, rp, sp), n, 0)
+elif op == "validate_ascii":
+    d = synth.ascii_text(nbytes, seed=1, device=dev)
+    n = d.numel()
+    run(lambda: lib.b200_validate_utf8_with_errors_async(ctypes.c_void_p(d.data_ptr()), n, rp, sp), n, 0)
+elif op == "utf16to8":
+    u = synth.mixed_utf16le(nbytes // 2, seed=3, device=dev)
+    n = u.numel()
+    nb = b.utf8_length_from_utf16le(u)
+    o = torch.empty(nb, dtype=torch.uint8, device=dev)
+    run(lambda: lib.b200_convert_utf16le_to_utf8_async(ctypes.c_void_p(u.data_ptr()), n, ctypes.c_void_p(o.data_ptr()), rp, sp), 2 * n, nb)
+elif op == "base64":
+    t, pay = synth.base64_text(nbytes, seed=4, device=dev)
+    n = t.numel()
+    o = torch.empty(n // 4 * 3 + 3, dtype=torch.uint8, device=dev)
+    run(lambda: lib.b200_base64_to_binary_async(ctypes.c_void_p(t.data_ptr()), n, ctypes.c_void_p(o.data_ptr()), 0, 0, rp, sp), n, pay.numel())
+else:
+    raise SystemExit("unknown op " + op)
