@@ -181,106 +181,130 @@ struct ConvertSmem {
   unsigned long long excl;
 };
 
+// One tile.  EDGE = the tile touches the first or last byte of the buffer (granules may be partial: guarded
+// loads, in-range masks, truncated-tail check); interior tiles compile all of that away.
+template <typename OutT, int ITEMS, bool VALIDATE, bool EDGE>
+__device__ __forceinline__ void convert_tile(const InView &in, OutT *out, Scratch *scr, unsigned long long *desc,
+                                             uint32_t epoch, uint32_t num_tiles, uint32_t tile,
+                                             ConvertSmem<OutT, ITEMS> &sm) {
+  constexpr bool k16 = sizeof(OutT) == 2;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long g0 = ((unsigned long long)tile * kWarps + warp) * (32ull * ITEMS);
+
+  // ---- load + neighbours -------------------------------------------------------------------
+  uint32_t w[ITEMS][4];
+  bool inside[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; j++) {
+    const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+    if (EDGE) {
+      load_granule(in, g, w[j], inside[j]);
+    } else {
+      const uint4 v = ldg_stream_v4(in.base + g);
+      w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
+      inside[j] = true;
+    }
+  }
+  uint32_t pw[ITEMS], nw[ITEMS];
+  neighbour_words<ITEMS>(in, g0, w, pw, nw);
+
+  // ---- per-granule output counts (phase 1: cheap SWAR popcounts, nothing is kept but the counts) ------
+  uint32_t cnt[ITEMS], off[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; j++) {
+    uint32_t em[4];
+    if (k16) u8_emit16_masks(w[j], pw[j], em);
+    else u8_emit32_masks(w[j], em);
+    if (EDGE && !inside[j]) {
+      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+#pragma unroll
+      for (int k = 0; k < 4; k++) em[k] &= inrange_mask_word(in, g, k);
+    }
+    cnt[j] = (uint32_t)(__popc(em[0]) + __popc(em[1]) + __popc(em[2]) + __popc(em[3]));
+  }
+  const uint32_t tile_total = block_exclusive_offsets<ITEMS>(cnt, off, sm.warp_tot);
+
+  // ---- publish aggregate, look back for this tile's output offset ---------------------------
+  if (warp == 0) {
+    unsigned long long excl;
+    uint32_t aux;
+    tile_lookback(desc, epoch, tile, tile_total, 0u, excl, aux);
+    if (lane == 0) {
+      sm.excl = excl;
+      if (tile == num_tiles - 1) st_relaxed_u64(&scr->acc0, excl + tile_total);
+    }
+  }
+  __syncthreads();
+  const unsigned long long excl = sm.excl;
+  OutT *gdst = out + excl;
+  const uint32_t shift = staging_shift(gdst);
+
+  // ---- phase 2: decode (+ validate) into the staging buffer at final (tile-relative) offsets ----------
+  if (k16) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+      OutT *sp = sm.out + shift + off[j];
+      U8Carry carry = u8_carry_of(pw[j]);
+      uint32_t flagged = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t xn = (k < 3 ? w[j][(k + 1) & 3] : nw[j]) & 0x3F3F3F3Fu;
+        const U8Word16 r = u8_to_utf16_word<VALIDATE>(w[j][k], xn, carry);
+        uint32_t em = r.emit;
+        if (EDGE && !inside[j]) em &= inrange_mask_word(in, g, k);
+        flagged |= r.err;
+        if (em & 0x00000080u) *sp++ = (OutT)(r.u01 & 0xFFFFu);
+        if (em & 0x00008000u) *sp++ = (OutT)(r.u01 >> 16);
+        if (em & 0x00800000u) *sp++ = (OutT)(r.u23 & 0xFFFFu);
+        if (em & 0x80000000u) *sp++ = (OutT)(r.u23 >> 16);
+      }
+      if (VALIDATE) {
+        const unsigned long long lo = g * 16ull;
+        bool bad = flagged != 0;
+        if (EDGE && lo < in.vend && in.vend <= lo + 16ull) bad = bad || tail_truncated(in);
+        if (bad) u8_locate_error(in, scr, (long long)lo - 3, (long long)lo + 16);
+      }
+    }
+  } else {
+    if (VALIDATE) validate_items<ITEMS>(in, scr, g0, w, pw);
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      uint32_t em[4];
+      u8_emit32_masks(w[j], em);
+      if (EDGE && !inside[j]) {
+        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) em[k] &= inrange_mask_word(in, g, k);
+      }
+      uint32_t o = shift + off[j];
+      u8_emit32_granule(w[j], nw[j], em, [&](uint32_t u) { sm.out[o++] = (OutT)u; });
+    }
+  }
+  __syncthreads();
+  copy_out_aligned<OutT>(sm.out, gdst, shift, tile_total);
+  __syncthreads();  // staging buffer and sm.tile are reused by the next tile
+}
+
 template <typename OutT, int ITEMS, bool VALIDATE, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_convert_utf8(const char *ptr, size_t len, OutT *out, Scratch *scr,
-                                                         unsigned long long *desc, uint32_t epoch, uint32_t num_tiles,
-                                                         ResultPOD *res) {
+                                                               unsigned long long *desc, uint32_t epoch,
+                                                               uint32_t num_tiles, ResultPOD *res) {
   __shared__ ConvertSmem<OutT, ITEMS> sm;
-  constexpr bool k16 = sizeof(OutT) == 2;
   const InView in = make_view(ptr, len);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  constexpr unsigned long long kTileBytes = (unsigned long long)kBlock * ITEMS * 16ull;
 
   while (true) {
     if (threadIdx.x == 0) sm.tile = atomicAdd(&scr->ticket, 1u);
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile >= num_tiles) break;
-    const unsigned long long g0 = ((unsigned long long)tile * kWarps + warp) * (32ull * ITEMS);
-
-    // ---- load + neighbours -------------------------------------------------------------------
-    uint32_t w[ITEMS][4];
-    bool inside[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
-    uint32_t pw[ITEMS], nw[ITEMS];
-    neighbour_words<ITEMS>(in, g0, w, pw, nw);
-
-    // ---- per-granule output counts (phase 1: cheap SWAR popcounts, nothing is kept but the counts) ------
-    uint32_t cnt[ITEMS], off[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-      uint32_t em[4];
-      if (k16) u8_emit16_masks(w[j], pw[j], em);
-      else u8_emit32_masks(w[j], em);
-      if (!inside[j]) {
-        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-#pragma unroll
-        for (int k = 0; k < 4; k++) em[k] &= inrange_mask_word(in, g, k);
-      }
-      cnt[j] = (uint32_t)(__popc(em[0]) + __popc(em[1]) + __popc(em[2]) + __popc(em[3]));
-    }
-    const uint32_t tile_total = block_exclusive_offsets<ITEMS>(cnt, off, sm.warp_tot);
-
-    // ---- publish aggregate, look back for this tile's output offset ---------------------------
-    if (warp == 0) {
-      unsigned long long excl;
-      uint32_t aux;
-      tile_lookback(desc, epoch, tile, tile_total, 0u, excl, aux);
-      if (lane == 0) {
-        sm.excl = excl;
-        if (tile == num_tiles - 1) st_relaxed_u64(&scr->acc0, excl + tile_total);
-      }
-    }
-    __syncthreads();
-    const unsigned long long excl = sm.excl;
-    OutT *gdst = out + excl;
-    const uint32_t shift = staging_shift(gdst);
-
-    // ---- phase 2: decode (+ validate) into the staging buffer at final (tile-relative) offsets ----------
-    if (k16) {
-#pragma unroll
-      for (int j = 0; j < ITEMS; j++) {
-        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-        OutT *sp = sm.out + shift + off[j];
-        U8Carry carry = u8_carry_of(pw[j]);
-        uint32_t flagged = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t xn = (k < 3 ? w[j][(k + 1) & 3] : nw[j]) & 0x3F3F3F3Fu;
-          const U8Word16 r = u8_to_utf16_word<VALIDATE>(w[j][k], xn, carry);
-          uint32_t em = r.emit;
-          if (!inside[j]) em &= inrange_mask_word(in, g, k);
-          flagged |= r.err;
-          if (em & 0x00000080u) *sp++ = (OutT)(r.u01 & 0xFFFFu);
-          if (em & 0x00008000u) *sp++ = (OutT)(r.u01 >> 16);
-          if (em & 0x00800000u) *sp++ = (OutT)(r.u23 & 0xFFFFu);
-          if (em & 0x80000000u) *sp++ = (OutT)(r.u23 >> 16);
-        }
-        if (VALIDATE) {
-          const unsigned long long lo = g * 16ull;
-          bool bad = flagged != 0;
-          if (lo < in.vend && in.vend <= lo + 16ull) bad = bad || tail_truncated(in);
-          if (bad) u8_locate_error(in, scr, (long long)lo - 3, (long long)lo + 16);
-        }
-      }
+    const unsigned long long lo = (unsigned long long)tile * kTileBytes;
+    if (lo >= in.vbeg && lo + kTileBytes <= in.vend) {
+      convert_tile<OutT, ITEMS, VALIDATE, false>(in, out, scr, desc, epoch, num_tiles, tile, sm);
     } else {
-      if (VALIDATE) validate_items<ITEMS>(in, scr, g0, w, pw);
-#pragma unroll
-      for (int j = 0; j < ITEMS; j++) {
-        uint32_t em[4];
-        u8_emit32_masks(w[j], em);
-        if (!inside[j]) {
-          const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-#pragma unroll
-          for (int k = 0; k < 4; k++) em[k] &= inrange_mask_word(in, g, k);
-        }
-        uint32_t o = shift + off[j];
-        u8_emit32_granule(w[j], nw[j], em, [&](uint32_t u) { sm.out[o++] = (OutT)u; });
-      }
+      convert_tile<OutT, ITEMS, VALIDATE, true>(in, out, scr, desc, epoch, num_tiles, tile, sm);
     }
-    __syncthreads();
-    copy_out_aligned<OutT>(sm.out, gdst, shift, tile_total);
-    __syncthreads();  // staging buffer and sm.tile are reused by the next tile
   }
 
   if (grid_last_thread(scr)) {
