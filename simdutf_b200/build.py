@@ -85,9 +85,78 @@ def build_host_tests() -> str:
     return out
 
 
+REF_TESTS = [
+    "validate_utf8_basic_tests", "validate_utf8_puzzler_tests", "validate_utf8_brute_force_tests",
+    "validate_utf8_with_errors_tests", "convert_utf8_to_utf16le_tests", "convert_utf8_to_utf16le_with_errors_tests",
+    "convert_valid_utf8_to_utf16le_tests", "convert_utf8_to_utf32_tests", "convert_utf8_to_utf32_with_errors_tests",
+    "convert_valid_utf8_to_utf32_tests", "convert_utf16le_to_utf8_tests", "convert_utf16le_to_utf8_with_errors_tests",
+    "convert_valid_utf16le_to_utf8_tests", "count_utf8", "count_utf16le", "utf8_length_from_utf16_tests",
+    "validate_utf16le_basic_tests", "validate_utf16le_with_errors_tests", "base64_tests", "select_implementation",
+    "null_safety_tests", "random_fuzzer",
+]
+WITH_B200 = os.path.join(OBJ, "with_b200")
+
+
+def build_reference_integration(ref: str = "/root/reference", tests: bool = True) -> str | None:
+    """The drop-in boundary, exercised for real: the UNMODIFIED reference tree compiled (where it lies) together
+    with simdutf::b200::implementation into simdutf_b200/build/with_b200/libsimdutf_with_b200.so, plus the
+    reference's OWN test binaries for the hot path linked against it, so that on the GPU box
+    `<test> -a b200` runs the reference's tests on the CUDA kernels.  Only possible where the
+    reference tree exists (this container); the binaries travel to the GPU box with the snapshot."""
+    if not os.path.isdir(os.path.join(ref, "src")):
+        return None
+    os.makedirs(WITH_B200, exist_ok=True)
+    lib = os.path.join(WITH_B200, "libsimdutf_with_b200.so")
+    gen = os.path.join(ROOT, "tools", "gen_b200_cxx.py")
+    srcs = [gen, os.path.join(CSRC, "b200_implementation.cpp"), os.path.join(CSRC, "b200_implementation.h"),
+            os.path.join(ROOT, "include", "simdutf_b200.h")]
+    inc = ["-I" + os.path.join(ref, "include"), "-I" + os.path.join(ref, "src"), "-I" + WITH_B200, "-I" + CSRC,
+           "-I" + os.path.join(ROOT, "include")]
+    if not _newer(lib, srcs + [LIB]):
+        _run([sys.executable, gen, ref, WITH_B200])
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", lib] + inc +
+             [os.path.join(WITH_B200, "simdutf_b200_unity.cpp"), os.path.join(CSRC, "b200_implementation.cpp"),
+              "-L" + PKG, "-lsimdutf_b200", "-Wl,-rpath,$ORIGIN/../.."])
+    if tests:
+        tinc = ["-I" + os.path.join(ref, "include"), "-I" + ref, "-I" + os.path.join(ref, "tests")]
+        helpers = sorted(os.path.join(ref, "tests", d, f) for d in ("helpers", "reference")
+                         for f in os.listdir(os.path.join(ref, "tests", d)) if f.endswith(".cpp"))
+        hobjs = [os.path.join(WITH_B200, "h_" + os.path.basename(h).replace(".cpp", ".o")) for h in helpers]
+
+        def cc(job):
+            src, obj = job
+            if not _newer(obj, [src]):
+                _run(["g++", "-O2", "-std=c++17", "-c", src, "-o", obj] + tinc)
+
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            list(ex.map(cc, zip(helpers, hobjs)))
+        # two static archives, as tests/helpers/CMakeLists.txt and tests/reference/CMakeLists.txt do
+        arch = []
+        for d in ("helpers", "reference"):
+            a = os.path.join(WITH_B200, f"libtests_{d}.a")
+            members = [o for h, o in zip(helpers, hobjs) if os.sep + d + os.sep in h]
+            if not _newer(a, members):
+                if os.path.exists(a):
+                    os.remove(a)
+                _run(["ar", "rcs", a] + members)
+            arch.append(a)
+
+        def link(name):
+            exe = os.path.join(WITH_B200, name)
+            src = os.path.join(ref, "tests", name + ".cpp")
+            if not _newer(exe, [src, lib]):
+                _run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, src] + arch + tinc +
+                     ["-L" + WITH_B200, "-lsimdutf_with_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../.."])
+
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            list(ex.map(link, REF_TESTS))
+    return lib
+
+
 if __name__ == "__main__":
     build_library(force="--force" in sys.argv)
     if "--all" in sys.argv:
         build_oracle()
         build_host_tests()
+        build_reference_integration()
     print(LIB)

@@ -1,0 +1,136 @@
+// b200_implementation.cpp — bodies of simdutf::b200::implementation (see b200_implementation.h).
+//
+// Each hot-path virtual is one call into the C ABI of libsimdutf_b200.so with the caller's HOST pointers;
+// staging to the device, the kernels and the copy back all happen behind b200_host_*.  Error conventions are
+// the reference's: `_with_errors` return result{error, position | count}; the plain converters return the count
+// or 0 on any error (reference include/simdutf/implementation.h:3705-3706); an infrastructure failure (no
+// device, CUDA error) becomes error_code::OTHER / 0 / false, never an exception, a message or an abort
+// (reference include/simdutf/error.h:31, src/implementation.cpp:819-822, CMakeLists.txt:173-214).
+#include "b200_implementation.h"
+
+#include "simdutf_b200.h"
+
+namespace simdutf {
+namespace b200 {
+
+namespace {
+simdutf_really_inline result to_result(int status, const b200_result &r) {
+  if (status != 0) return result(error_code::OTHER, 0);
+  return result(error_code(r.error), size_t(r.count));
+}
+simdutf_really_inline const uint16_t *u16(const char16_t *p) { return reinterpret_cast<const uint16_t *>(p); }
+} // namespace
+
+uint32_t implementation::required_instruction_sets() const {
+  return b200_device_count() > 0 ? 0u : 0x80000000u;
+}
+
+// ---- UTF-8 validation (reference include/simdutf/implementation.h:3378-3396) ----
+bool implementation::validate_utf8(const char *buf, size_t len) const noexcept {
+  b200_result r;
+  return b200_host_validate_utf8_with_errors(buf, len, &r) == 0 && r.error == B200_SUCCESS;
+}
+result implementation::validate_utf8_with_errors(const char *buf, size_t len) const noexcept {
+  b200_result r;
+  return to_result(b200_host_validate_utf8_with_errors(buf, len, &r), r);
+}
+
+// ---- UTF-8 counting (:3863, :3882, :4802) ----
+size_t implementation::count_utf8(const char *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_count_utf8(input, length, &n) == 0 ? size_t(n) : 0;
+}
+size_t implementation::utf32_length_from_utf8(const char *input, size_t length) const noexcept {
+  return count_utf8(input, length);
+}
+size_t implementation::utf16_length_from_utf8(const char *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_utf16_length_from_utf8(input, length, &n) == 0 ? size_t(n) : 0;
+}
+
+// ---- UTF-8 -> UTF-16LE (:3709, :3743-3745, :3815) ----
+result implementation::convert_utf8_to_utf16le_with_errors(const char *input, size_t length,
+                                                           char16_t *utf16_output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf8_to_utf16le(input, length, reinterpret_cast<uint16_t *>(utf16_output), &r), r);
+}
+size_t implementation::convert_utf8_to_utf16le(const char *input, size_t length, char16_t *utf16_output) const noexcept {
+  const result r = convert_utf8_to_utf16le_with_errors(input, length, utf16_output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf8_to_utf16le(const char *input, size_t length,
+                                                     char16_t *utf16_output) const noexcept {
+  return convert_utf8_to_utf16le(input, length, utf16_output);
+}
+
+// ---- UTF-8 -> UTF-32 (:3781, :3799-3800) ----
+result implementation::convert_utf8_to_utf32_with_errors(const char *input, size_t length,
+                                                         char32_t *utf32_output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf8_to_utf32(input, length, reinterpret_cast<uint32_t *>(utf32_output), &r), r);
+}
+size_t implementation::convert_utf8_to_utf32(const char *input, size_t length, char32_t *utf32_output) const noexcept {
+  const result r = convert_utf8_to_utf32_with_errors(input, length, utf32_output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf8_to_utf32(const char *input, size_t length,
+                                                   char32_t *utf32_output) const noexcept {
+  return convert_utf8_to_utf32(input, length, utf32_output);
+}
+
+// ---- UTF-16LE counting / validation (:3465-3483, :4277-4278, :4767) ----
+size_t implementation::count_utf16le(const char16_t *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_count_utf16le(u16(input), length, &n) == 0 ? size_t(n) : 0;
+}
+size_t implementation::utf32_length_from_utf16le(const char16_t *input, size_t length) const noexcept {
+  return count_utf16le(input, length);
+}
+size_t implementation::utf8_length_from_utf16le(const char16_t *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_utf8_length_from_utf16le(u16(input), length, &n) == 0 ? size_t(n) : 0;
+}
+bool implementation::validate_utf16le(const char16_t *buf, size_t len) const noexcept {
+  b200_result r;
+  return b200_host_validate_utf16le_with_errors(u16(buf), len, &r) == 0 && r.error == B200_SUCCESS;
+}
+result implementation::validate_utf16le_with_errors(const char16_t *buf, size_t len) const noexcept {
+  b200_result r;
+  return to_result(b200_host_validate_utf16le_with_errors(u16(buf), len, &r), r);
+}
+
+// ---- UTF-16LE -> UTF-8 (:4038, :4079-4080) ----
+result implementation::convert_utf16le_to_utf8_with_errors(const char16_t *input, size_t length,
+                                                           char *utf8_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf16le_to_utf8(u16(input), length, utf8_buffer, &r), r);
+}
+size_t implementation::convert_utf16le_to_utf8(const char16_t *input, size_t length, char *utf8_buffer) const noexcept {
+  const result r = convert_utf16le_to_utf8_with_errors(input, length, utf8_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf16le_to_utf8(const char16_t *input, size_t length,
+                                                     char *utf8_buffer) const noexcept {
+  return convert_utf16le_to_utf8(input, length, utf8_buffer);
+}
+
+// ---- base64 decode, char input (:4866-4870, :4902-4906); result derived as in include/simdutf/error.h:66-73 ----
+full_result implementation::base64_to_binary_details(const char *input, size_t length, char *output,
+                                                     base64_options options,
+                                                     last_chunk_handling_options last_chunk_options) const noexcept {
+  b200_full_result r;
+  if (b200_host_base64_to_binary(input, length, output, uint64_t(options), uint64_t(last_chunk_options), &r) != 0) {
+    return full_result(error_code::OTHER, 0, 0);
+  }
+  return full_result(error_code(r.error), size_t(r.input_count), size_t(r.output_count));
+}
+result implementation::base64_to_binary(const char *input, size_t length, char *output, base64_options options,
+                                        last_chunk_handling_options last_chunk_options) const noexcept {
+  return base64_to_binary_details(input, length, output, options, last_chunk_options);
+}
+
+// ---- everything outside the hot path: the reference's "unsupported" answers (generated) ----
+#include "b200_stubs.inc"
+
+} // namespace b200
+} // namespace simdutf

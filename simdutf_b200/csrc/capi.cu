@@ -341,8 +341,7 @@ int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint
     if (op == kOpBase64) {
       const b200_full_result *r = static_cast<const b200_full_result *>(h_res);
       produced = (size_t)r->output_count;
-      // on INVALID_BASE64_CHARACTER everything decoded before the bad character is still delivered
-      if (r->error == B200_INVALID_BASE64_CHARACTER) produced = 0;
+      // output_count is 0 on INVALID_BASE64_CHARACTER (unpinned by the reference), so nothing is copied back then
     } else {
       const b200_result *r = static_cast<const b200_result *>(h_res);
       produced = r->error == B200_SUCCESS ? (size_t)r->count : 0;
@@ -408,15 +407,12 @@ B200_DEFINE_RESULT_OP(validate_utf16le_with_errors, kOpValidateUtf16, uint16_t, 
 
 #define B200_DEFINE_CONVERT_OP(NAME, OP, INTYPE, OUTTYPE)                                                          \
   int b200_##NAME##_async(const INTYPE *d_in, size_t len, OUTTYPE *d_out, b200_result *d_res, void *stream) {      \
-    if (!d_out && len) return fail(B200_E_BAD_ARGUMENT, "null output");                                            \
     return run_async(OP, d_in, len, d_out, d_res, stream);                                                         \
   }                                                                                                                \
   int b200_##NAME(const INTYPE *d_in, size_t len, OUTTYPE *d_out, b200_result *h_res, void *stream) {              \
-    if (!d_out && len) return fail(B200_E_BAD_ARGUMENT, "null output");                                            \
     return run_sync(OP, d_in, len, d_out, h_res, stream);                                                          \
   }                                                                                                                \
   int b200_host_##NAME(const INTYPE *h_in, size_t len, OUTTYPE *h_out, b200_result *h_res) {                       \
-    if (!h_out && len) return fail(B200_E_BAD_ARGUMENT, "null output");                                            \
     return run_host(OP, h_in, len, h_out, h_res);                                                                  \
   }
 
@@ -429,17 +425,17 @@ static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
 }
 int b200_base64_to_binary_async(const char *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
                                 b200_full_result *d_res, void *stream) {
-  if (!b64_options_ok(options, last_chunk) || (!d_out && len)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
   return run_async(kOpBase64, d_in, len, d_out, d_res, stream, options, last_chunk);
 }
 int b200_base64_to_binary(const char *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
                           b200_full_result *h_res, void *stream) {
-  if (!b64_options_ok(options, last_chunk) || (!d_out && len)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
   return run_sync(kOpBase64, d_in, len, d_out, h_res, stream, options, last_chunk);
 }
 int b200_host_base64_to_binary(const char *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
                                b200_full_result *h_res) {
-  if (!b64_options_ok(options, last_chunk) || (!h_out && len)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
   return run_host(kOpBase64, h_in, len, h_out, h_res, options, last_chunk);
 }
 

@@ -1,0 +1,37 @@
+"""GPU test (-m gpu): the reference's OWN test binaries, linked against the unmodified reference tree plus
+simdutf::b200::implementation (simdutf_b200/build/with_b200, built by build.build_reference_integration() in the
+build container — they travel to the GPU box as prebuilt files), run with `-a b200`: every TEST in them then
+exercises the CUDA kernels through the C++ virtuals (reference tests/helpers/test.cpp:143-207).
+
+Only binaries whose tests stay inside the hot path are required to pass; the others call
+virtuals that are still "unsupported" stubs (§8f) and are reported, not asserted."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D = os.path.join(ROOT, "simdutf_b200", "build", "with_b200")
+
+HOT = [
+    "validate_utf8_basic_tests", "validate_utf8_puzzler_tests", "validate_utf8_brute_force_tests",
+    "validate_utf8_with_errors_tests", "convert_utf8_to_utf16le_tests", "convert_utf8_to_utf16le_with_errors_tests",
+    "convert_valid_utf8_to_utf16le_tests", "convert_utf8_to_utf32_tests", "convert_utf8_to_utf32_with_errors_tests",
+    "convert_valid_utf8_to_utf32_tests", "convert_utf16le_to_utf8_tests", "convert_utf16le_to_utf8_with_errors_tests",
+    "convert_valid_utf16le_to_utf8_tests", "count_utf8", "count_utf16le", "validate_utf16le_basic_tests",
+    "validate_utf16le_with_errors_tests", "select_implementation",
+]
+
+
+@pytest.mark.parametrize("name", HOT)
+def test_reference_binary_with_b200(name):
+    exe = os.path.join(D, name)
+    if not os.path.exists(exe):
+        pytest.skip("reference test binaries were not built (no /root/reference at build time)")
+    p = subprocess.run([exe, "-a", "b200"], capture_output=True, text=True, timeout=900)
+    out = p.stdout + p.stderr
+    assert "unsupported by the current processor" not in out, "b200 reported itself unsupported on a GPU box"
+    assert p.returncode == 0, out[-3000:]
+    if name != "select_implementation":
+        assert "OK" in out
