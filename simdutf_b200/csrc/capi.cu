@@ -212,8 +212,8 @@ enum Op {
 
 size_t tiles_needed(Op op, const void *in, size_t len) {
   switch (op) {
-    case kOpUtf8ToUtf16: return utf8_convert_tiles(in, len, 2);
-    case kOpUtf8ToUtf32: return utf8_convert_tiles(in, len, 4);
+    case kOpUtf8ToUtf16: return utf8_to_utf16_tiles(in, len);
+    case kOpUtf8ToUtf32: return utf8_to_utf32_tiles(in, len);
     case kOpUtf16ToUtf8: return utf16_convert_tiles(in, len);
     case kOpBase64: return base64_tiles(in, len);
     default: return 0;

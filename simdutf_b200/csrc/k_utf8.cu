@@ -387,9 +387,7 @@ cudaError_t launch_convert(const LaunchCtx &c, const char *in, size_t len, OutT 
 
 }  // namespace
 
-size_t utf8_convert_tiles(const void *in, size_t len, int out_elem_bytes) {
-  return tiles_for(in, len, out_elem_bytes == 2 ? kConv16Items : kConv32Items);
-}
+size_t utf8_to_utf32_tiles(const void *in, size_t len) { return tiles_for(in, len, kConv32Items); }
 
 cudaError_t launch_write_result(void *res, int32_t error, unsigned long long count, cudaStream_t stream) {
   k_write_result<<<1, 1, 0, stream>>>(static_cast<ResultPOD *>(res), error, count);
@@ -428,9 +426,6 @@ cudaError_t launch_count_utf8(const LaunchCtx &c, const char *in, size_t len, un
   return cudaGetLastError();
 }
 
-cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res) {
-  return launch_convert<uint16_t, kConv16Items>(c, in, len, out, res);
-}
 cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res) {
   return launch_convert<uint32_t, kConv32Items>(c, in, len, out, res);
 }

@@ -22,7 +22,8 @@ struct LaunchCtx {
 };
 
 // Tiles (descriptors) the look-back kernels need for an input of `len` elements.
-size_t utf8_convert_tiles(const void *in, size_t len, int out_elem_bytes);
+size_t utf8_to_utf16_tiles(const void *in, size_t len);
+size_t utf8_to_utf32_tiles(const void *in, size_t len);
 size_t utf16_convert_tiles(const void *in, size_t len);
 size_t base64_tiles(const void *in, size_t len);
 
