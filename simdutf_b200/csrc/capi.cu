@@ -64,12 +64,24 @@ struct DeviceCtx {
   std::mutex mu;
   std::unordered_map<cudaStream_t, StreamWs> ws;
   // host-pointer path
-  cudaStream_t s_main = nullptr, s_copy = nullptr;
+  cudaStream_t s_main = nullptr, s_copy = nullptr, s_back = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   void *d_in = nullptr;
   size_t d_in_cap = 0;
   void *d_out = nullptr;
   size_t d_out_cap = 0;
+  // streaming host path: a ring of segment slots (device staging in/out, events, a pinned result slot each)
+  static constexpr int kRing = 3;
+  struct Slot {
+    void *d_in = nullptr;
+    size_t d_in_cap = 0;
+    void *d_out = nullptr;
+    size_t d_out_cap = 0;
+    cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
+    void *h_res = nullptr;  // 64 B pinned + mapped
+    bool d2h_pending = false;
+  } ring[kRing];
+  bool ring_ok = false;
 };
 
 constexpr int kMaxDevices = 16;
@@ -125,6 +137,7 @@ DeviceCtx *current_ctx(int *err) {
   if (!c->ok) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -313,6 +326,161 @@ size_t out_elem_bytes(Op op) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming host path.  Large host buffers are cut into segments (on a character boundary where the operation
+// validates: the rule of simdutf::trim_partial_utf8 / _utf16le, reference src/scalar/utf8.h:257-288,
+// src/scalar/utf16.h:114-124, as benchmarks/threaded.cpp:69-74 uses it) and pipelined through a ring of device
+// staging slots: H2D of segment c+1 (copy stream) overlaps the kernels of segment c (main stream) and the D2H of
+// segment c-1 (back stream), so a call costs about max(H2D, D2H) instead of H2D + kernel + D2H, and device
+// memory stays bounded by the ring whatever the input size.  Segments are independent calls of the very same
+// kernels; their results are combined exactly like the shards of the multi-GPU path (first error in buffer
+// order wins, counts add up).
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kSegmentBytes = size_t(32) << 20;
+
+bool op_streams(Op op) { return op != kOpBase64; }  // base64 quanta straddle any cut: single shot
+
+// End (exclusive, in elements) of the segment that starts at `beg`.
+size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
+  const size_t per = kSegmentBytes / in_elem_bytes(op);
+  size_t cut = beg + per;
+  if (cut >= len) return len;
+  switch (op) {
+    case kOpValidateUtf8: case kOpUtf8ToUtf16: case kOpUtf8ToUtf32: {
+      const unsigned char *p = static_cast<const unsigned char *>(h_in);
+      for (int k = 0; k < 3 && cut > beg + 1 && (p[cut] & 0xC0) == 0x80; k++) cut--;
+      return cut;
+    }
+    case kOpValidateUtf16: case kOpUtf16ToUtf8: {
+      const uint16_t *p = static_cast<const uint16_t *>(h_in);
+      if ((p[cut] & 0xFC00u) == 0xDC00u && (p[cut - 1] & 0xFC00u) == 0xD800u) cut--;
+      return cut;
+    }
+    default: return cut;  // the counts are sums over any partition
+  }
+}
+
+int ring_init(DeviceCtx *c) {
+  if (c->ring_ok) return 0;
+  for (auto &sl : c->ring) {
+    B200_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+    B200_CUDA(cudaHostAlloc(&sl.h_res, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  }
+  c->ring_ok = true;
+  return 0;
+}
+
+int slot_ensure(void **buf, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*buf) {
+    B200_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *cap = 0;
+  }
+  B200_CUDA(cudaMalloc(buf, need));
+  *cap = need;
+  return 0;
+}
+
+int run_host_streamed(DeviceCtx *c, Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint64_t opt,
+                      uint64_t lastc) {
+  int err;
+  if ((err = ring_init(c))) return err;
+  const size_t ieb = in_elem_bytes(op), oeb = out_elem_bytes(op);
+  const bool converts = max_out_bytes(op, 1) != 0;
+  const bool is_count = result_bytes(op) == 8;
+  const unsigned char *in_bytes = static_cast<const unsigned char *>(h_in);
+  unsigned char *out_bytes = static_cast<unsigned char *>(h_out);
+
+  struct Seg { size_t beg, end; };
+  Seg segs[DeviceCtx::kRing];
+  size_t issued = 0, retired = 0;      // segment counters
+  size_t next_beg = 0, out_elems = 0;  // input cursor (elements), output cursor (elements)
+  unsigned long long count_sum = 0;
+  b200_result final_res = {B200_SUCCESS, 0, 0};
+  bool failed = false;
+
+  auto retire = [&](size_t s) -> int {  // wait for segment s, fold its result, start its copy back
+    DeviceCtx::Slot &sl = c->ring[s % DeviceCtx::kRing];
+    B200_CUDA(cudaEventSynchronize(sl.kernel_done));
+    if (is_count) {
+      count_sum += *static_cast<const uint64_t *>(sl.h_res);
+      return 0;
+    }
+    const b200_result r = *static_cast<const b200_result *>(sl.h_res);
+    if (r.error != B200_SUCCESS) {
+      if (!failed) {
+        failed = true;
+        final_res.error = r.error;
+        final_res.count = segs[s % DeviceCtx::kRing].beg + r.count;  // position in the whole buffer
+      }
+      return 0;
+    }
+    if (failed) return 0;
+    if (converts) {
+      if (r.count && out_bytes) {
+        B200_CUDA(cudaMemcpyAsync(out_bytes + out_elems * oeb, sl.d_out, (size_t)r.count * oeb, cudaMemcpyDeviceToHost, c->s_back));
+        B200_CUDA(cudaEventRecord(sl.d2h_done, c->s_back));
+        sl.d2h_pending = true;
+      }
+      out_elems += (size_t)r.count;
+    }
+    return 0;
+  };
+
+  while (next_beg < len && !failed) {
+    DeviceCtx::Slot &sl = c->ring[issued % DeviceCtx::kRing];
+    if (issued >= (size_t)DeviceCtx::kRing) {  // the slot's previous tenant must be completely done
+      if (retired + DeviceCtx::kRing <= issued) {
+        if ((err = retire(retired))) return err;
+        retired++;
+        if (failed) break;
+      }
+      if (sl.d2h_pending) {
+        B200_CUDA(cudaEventSynchronize(sl.d2h_done));
+        sl.d2h_pending = false;
+      }
+    }
+    const size_t beg = next_beg, end = segment_end(op, h_in, len, beg), n = end - beg;
+    segs[issued % DeviceCtx::kRing] = {beg, end};
+    if ((err = slot_ensure(&sl.d_in, &sl.d_in_cap, kSegmentBytes + 64))) return err;
+    if (converts && (err = slot_ensure(&sl.d_out, &sl.d_out_cap, max_out_bytes(op, kSegmentBytes / ieb) + 64))) return err;
+    B200_CUDA(cudaMemcpyAsync(sl.d_in, in_bytes + beg * ieb, n * ieb, cudaMemcpyHostToDevice, c->s_copy));
+    B200_CUDA(cudaEventRecord(sl.h2d_done, c->s_copy));
+    B200_CUDA(cudaStreamWaitEvent(c->s_main, sl.h2d_done, 0));
+    LaunchCtx lc;
+    if ((err = get_ws(c, c->s_main, tiles_needed(op, sl.d_in, n), &lc, nullptr))) return err;
+    if ((err = enqueue(op, lc, sl.d_in, n, sl.d_out, sl.h_res, opt, lastc))) return err;
+    B200_CUDA(cudaEventRecord(sl.kernel_done, c->s_main));
+    issued++;
+    next_beg = end;
+    // keep one segment in flight behind the one just issued: retire everything older
+    while (retired + 1 < issued && !failed) {
+      if ((err = retire(retired))) return err;
+      retired++;
+    }
+  }
+  while (retired < issued) {
+    if ((err = retire(retired))) return err;
+    retired++;
+  }
+  for (auto &sl : c->ring) {
+    if (sl.d2h_pending) {
+      B200_CUDA(cudaEventSynchronize(sl.d2h_done));
+      sl.d2h_pending = false;
+    }
+  }
+  if (is_count) {
+    *static_cast<uint64_t *>(h_res) = count_sum;
+    return 0;
+  }
+  if (!failed) final_res.count = converts ? out_elems : len;
+  *static_cast<b200_result *>(h_res) = final_res;
+  return 0;
+}
+
 // host flavour: host pointers in and out.  H2D on the context's stream, the kernel, then a D2H of exactly
 // the elements the result says were produced.
 int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint64_t opt = 0, uint64_t lastc = 0) {
@@ -325,6 +493,8 @@ int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint
   DeviceCtx *c = current_ctx(&err);
   if (!c) return err;
   std::lock_guard<std::mutex> lock(c->mu);
+  if (op_streams(op) && len * in_elem_bytes(op) > kSegmentBytes + kSegmentBytes / 2)
+    return run_host_streamed(c, op, h_in, len, h_out, h_res, opt, lastc);
   const size_t in_bytes = len * in_elem_bytes(op);
   const size_t out_cap = max_out_bytes(op, len);
   if ((err = ensure(&c->d_in, &c->d_in_cap, in_bytes + 16, c->s_main, c->s_copy))) return err;

@@ -492,3 +492,44 @@ def test_config4_base64_2gib(b, oracle):
         text[q] = old
         del text, payload, out
         torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# streaming host path (capi.cu run_host_streamed): buffers of several 32 MiB segments, host pointers
+# ------------------------------------------------------------------------------------------------------------
+def test_host_streaming_segments(b, oracle):
+    from simdutf_b200 import synth
+    data = synth.mixed_utf8(150 << 20, seed=11).numpy()
+    host = data.tobytes()
+    n16, n8 = oracle.utf16_length_from_utf8(host), oracle.count_utf8(host)
+    assert b.validate_utf8_with_errors(data) == (0, len(host))
+    assert b.count_utf8(data) == n8 and b.utf16_length_from_utf8(data) == n16
+    want16, o16 = oracle.convert_utf8_to_utf16le_with_errors(host)
+    h16 = np.full(n16 + GUARD, 0x5A5A, dtype=np.uint16)
+    assert b.convert_utf8_to_utf16le_with_errors(data, h16) == want16 == (0, n16)
+    assert (h16[n16:] == 0x5A5A).all() and h16[:n16].tobytes() == o16.tobytes()
+    want32, o32 = oracle.convert_utf8_to_utf32_with_errors(host)
+    h32 = np.full(n8 + GUARD, 0x5A5A5A5A, dtype=np.uint32)
+    assert b.convert_utf8_to_utf32_with_errors(data, h32) == want32
+    assert h32[:n8].tobytes() == o32.tobytes()
+    # UTF-16LE -> UTF-8 brings the input back (2 x 150 MiB-ish of units: ten segments)
+    back = np.full(len(host) + GUARD, 0x5A, dtype=np.uint8)
+    assert b.validate_utf16le_with_errors(h16[:n16]) == (0, n16)
+    assert b.count_utf16le(h16[:n16]) == n8 and b.utf8_length_from_utf16le(h16[:n16]) == len(host)
+    assert b.convert_utf16le_to_utf8_with_errors(h16[:n16], back) == (0, len(host))
+    assert back[:len(host)].tobytes() == host and (back[len(host):] == 0x5A).all()
+    # one bad byte in a late segment, one right at a segment seam, one in the first segment
+    for pos in (len(host) - 12345, (64 << 20) + 1, 7):
+        bad = data.copy()
+        bad[pos] = 0xFF
+        want = oracle.validate_utf8_with_errors(bad.tobytes())
+        assert b.validate_utf8_with_errors(bad) == want
+        assert b.convert_utf8_to_utf16le_with_errors(bad, h16) == want
+    # a lone surrogate in a late segment of the UTF-16 input
+    u = h16[:n16].copy()
+    p = n16 - 4321
+    while (u[p] & 0xF800) == 0xD800 or (u[p - 1] & 0xFC00) == 0xD800:
+        p -= 1
+    u[p] = 0xDC00
+    assert b.validate_utf16le_with_errors(u) == (6, p)
+    assert b.convert_utf16le_to_utf8_with_errors(u, back) == (6, p)
