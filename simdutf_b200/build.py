@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libsimdutf_b200.so")
 SOURCES = ["k_utf8.cu", "k_utf8_to_utf16.cu", "k_utf16.cu", "k_base64.cu", "capi.cu"]
-HEADERS = ["swar.h", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
+HEADERS = ["swar.h", "bitplane.h", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -76,7 +76,7 @@ def build_oracle() -> None:
 def build_host_tests() -> str:
     out = os.path.join(ROOT, "tests", "host", "swar_host_test")
     src = os.path.join(ROOT, "tests", "host", "swar_host_test.cpp")
-    deps = [src, os.path.join(CSRC, "swar.h"), os.path.join(ROOT, "oracle", "oracle.c")]
+    deps = [src, os.path.join(CSRC, "swar.h"), os.path.join(CSRC, "bitplane.h"), os.path.join(ROOT, "oracle", "oracle.c")]
     if not _newer(out, deps):
         obj = os.path.join(OBJ, "oracle_c.o")
         os.makedirs(OBJ, exist_ok=True)

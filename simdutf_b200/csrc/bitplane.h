@@ -1,0 +1,288 @@
+// bitplane.h — bit-plane ("transposed") formulation of the UTF-8 hot path for sm_100a.
+//
+// A *block* is 32 consecutive input bytes held by ONE thread as eight little-endian 32-bit words.  The block is
+// transposed into eight bit planes B[0..7]: bit p of plane k is bit k of byte p.  In that form every bitwise
+// instruction classifies / validates / assembles 32 byte positions at once, where the byte-SWAR form of
+// swar.h handles 4.  "The byte before" is a 1-bit funnel shift of a plane (the bits shifted in come from
+// the previous block's plane).  The 16 planes of the candidate UTF-16 unit of every position are transposed
+// back into sixteen words of two units each.
+//
+// Like swar.h everything is `__host__ __device__` so tests/host/ runs exactly this code on the CPU against
+// the oracle; nothing in the product path calls it on the host.
+//
+// Semantics (reference file:line):
+//   validation rules         src/scalar/utf8.h:102-200 (detected here, located exactly by swar.h:u8_verdict)
+//   UTF-16 unit values       src/scalar/utf8_to_utf16/utf8_to_utf16.h:154-242
+//   UTF-32 values            src/scalar/utf8_to_utf32/utf8_to_utf32.h:128-200
+//
+// Emission rule ("end of character"): position p emits the unit of the character that ENDS at p, i.e. when
+// byte p+1 is not a continuation byte (the zero filler past the end of the buffer counts as one); a 4-byte
+// character additionally emits its high surrogate at its THIRD byte (the position two after a byte >= 0xF0),
+// where lead, second and third byte are all behind or at the position.  All data dependencies therefore
+// look backwards (<= 3 bytes) except the one "is the next byte a continuation" bit.
+// For a buffer whose first byte is not a continuation byte the number of emitting positions is
+//   #non-continuation bytes in (0, len]  +  #bytes >= 0xF0 in [0, len-2)  <=  utf16_length_from_utf8(buf),
+// with equality for valid input (reference src/scalar/utf8.h:243-255), so an output buffer sized by that query
+// is never overrun.  A buffer that starts with a continuation byte is invalid at position 0 (TOO_LONG); the
+// kernels emit nothing for it.
+#pragma once
+#include "swar.h"
+
+namespace b200 {
+namespace bp {
+
+// (hi:lo) << n, upper word: the plane `hi` moved n positions later, filled from the top of `lo`.
+B200_HD uint32_t fsl(uint32_t lo, uint32_t hi, int n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, n);
+#else
+  return (hi << n) | (lo >> (32 - n));
+#endif
+}
+// (hi:lo) >> n, lower word.
+B200_HD uint32_t fsr(uint32_t lo, uint32_t hi, int n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, n);
+#else
+  return (lo >> n) | (hi << (32 - n));
+#endif
+}
+
+// Exchange one word-index bit with one bit-index bit: a holds the elements whose word-index bit is 0.
+//   a' = a's low-group bits in place, b's low-group bits moved up by s
+//   b' = a's high-group bits moved down by s, b's high-group bits in place
+template <int S, uint32_t M0>
+B200_HD void dswap(uint32_t &a, uint32_t &b) {
+  const uint32_t a2 = (a & M0) | ((b << S) & ~M0);
+  const uint32_t b2 = ((a >> S) & M0) | (b & ~M0);
+  a = a2;
+  b = b2;
+}
+B200_HD void dswap_bytes(uint32_t &a, uint32_t &b) {  // S = 8, M0 = 0x00FF00FF as two byte permutes
+  const uint32_t a2 = prmt(a, b, 0x6240);
+  const uint32_t b2 = prmt(a, b, 0x7351);
+  a = a2;
+  b = b2;
+}
+// 4x4 byte transpose: afterwards a = byte 0 of (a,b,c,d), b = byte 1 of each, ...
+B200_HD void tr4x4(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+  const uint32_t ab_lo = prmt(a, b, 0x5140), ab_hi = prmt(a, b, 0x7362);
+  const uint32_t cd_lo = prmt(c, d, 0x5140), cd_hi = prmt(c, d, 0x7362);
+  a = prmt(ab_lo, cd_lo, 0x5410);
+  b = prmt(ab_lo, cd_lo, 0x7632);
+  c = prmt(ab_hi, cd_hi, 0x5410);
+  d = prmt(ab_hi, cd_hi, 0x7632);
+}
+
+// 32 bytes (w[i] = bytes 4i..4i+3) -> 8 planes, in place: afterwards w[k] = plane k.
+//   byte transposes put positions {c, c+8, c+16, c+24} (c = 0..3) and {c+4, ...} into one word each; three
+//   delta-swap stages then trade the three "bit within byte" index bits for the three remaining position bits.
+B200_HD void transpose_in(uint32_t (&w)[8]) {
+  uint32_t e0 = w[0], e1 = w[2], e2 = w[4], e3 = w[6];
+  uint32_t o0 = w[1], o1 = w[3], o2 = w[5], o3 = w[7];
+  tr4x4(e0, e1, e2, e3);  // e_c: positions c + 8j      (p2 = 0)
+  tr4x4(o0, o1, o2, o3);  // o_c: positions c + 4 + 8j  (p2 = 1)
+  dswap<4, 0x0F0F0F0Fu>(e0, o0);
+  dswap<4, 0x0F0F0F0Fu>(e1, o1);
+  dswap<4, 0x0F0F0F0Fu>(e2, o2);
+  dswap<4, 0x0F0F0F0Fu>(e3, o3);
+  dswap<2, 0x33333333u>(e0, e2);
+  dswap<2, 0x33333333u>(e1, e3);
+  dswap<2, 0x33333333u>(o0, o2);
+  dswap<2, 0x33333333u>(o1, o3);
+  dswap<1, 0x55555555u>(e0, e1);
+  dswap<1, 0x55555555u>(e2, e3);
+  dswap<1, 0x55555555u>(o0, o1);
+  dswap<1, 0x55555555u>(o2, o3);
+  w[0] = e0; w[1] = e1; w[2] = e2; w[3] = e3;
+  w[4] = o0; w[5] = o1; w[6] = o2; w[7] = o3;
+}
+
+// 16 planes (u[k] = plane k of a 16-bit value per position) -> 16 words, in place: afterwards
+// u[q] = value of position q in the low half, value of position q + 16 in the high half.
+B200_HD void transpose_out16(uint32_t (&u)[16]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i += 2) dswap<1, 0x55555555u>(u[i], u[i + 1]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i++)
+    if (!(i & 2)) dswap<2, 0x33333333u>(u[i], u[i + 2]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i++)
+    if (!(i & 4)) dswap<4, 0x0F0F0F0Fu>(u[i], u[i + 4]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; i++) dswap_bytes(u[i], u[i + 8]);
+}
+
+// The top four positions (28..31) of the planes of a virtual block whose last word is `pw`; the other bits
+// are unspecified (only the top <= 3 bits are ever shifted into the block that follows).
+B200_HD void planes_of_tail_word(uint32_t pw, uint32_t (&v)[8]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 8; k++) v[k] = ((pw >> k) & 0x01010101u) * 0x10204080u;
+}
+
+// Class planes a block hands to the block after it.
+struct Carry {
+  uint32_t b[6];            // planes 0..5 (payload bits)
+  uint32_t l2, l3, l4;      // bytes >= 0xC0 / >= 0xE0 / >= 0xF0
+  uint32_t e0, ed, f0, f4;  // the four leads whose second byte has a restricted range
+};
+
+struct Classes {
+  uint32_t cont, l2, l3, l4;
+};
+B200_HD Classes classify(const uint32_t (&B)[8]) {
+  Classes c;
+  c.cont = B[7] & ~B[6];
+  c.l2 = B[7] & B[6];
+  c.l3 = c.l2 & B[5];
+  c.l4 = c.l3 & B[4];
+  return c;
+}
+
+// Emitting positions of a block (before clipping to the buffer): ends of characters + third bytes of
+// 4-byte sequences.  `next_noncont` = 1 iff the byte after the block is not a continuation byte;
+// `prev_l4` = the >= 0xF0 plane of the previous block.
+B200_HD uint32_t emit16_mask(const uint32_t (&B)[8], uint32_t prev_l4, uint32_t next_noncont) {
+  const uint32_t nc = ~B[7] | B[6];
+  const uint32_t l4 = B[7] & B[6] & B[5] & B[4];
+  return fsr(nc, next_noncont, 1) | fsl(prev_l4, l4, 2);
+}
+// UTF-32 / count_utf8 flavour: one element per character, at its last byte.
+B200_HD uint32_t emit32_mask(const uint32_t (&B)[8], uint32_t next_noncont) {
+  const uint32_t nc = ~B[7] | B[6];
+  return fsr(nc, next_noncont, 1);
+}
+
+// Seeds the carry of the first block of a run from the 4 bytes in front of it.
+B200_HD Carry carry_from_word(uint32_t pw) {
+  uint32_t v[8];
+  planes_of_tail_word(pw, v);
+  Carry c;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) c.b[k] = v[k];
+  c.l2 = v[7] & v[6];
+  c.l3 = c.l2 & v[5];
+  c.l4 = c.l3 & v[4];
+  const uint32_t n321 = ~(v[3] | v[2] | v[1]);
+  const uint32_t is3 = c.l3 & ~v[4];
+  c.e0 = is3 & n321 & ~v[0];
+  c.ed = is3 & v[3] & v[2] & ~v[1] & v[0];
+  c.f0 = c.l4 & n321 & ~v[0];
+  c.f4 = c.l4 & ~v[3] & v[2] & ~v[1] & ~v[0];
+  return c;
+}
+
+// One block: validation detector + the 16 planes of the candidate UTF-16 unit of every position.
+//   B      planes of the block (transpose_in)
+//   c      in: class planes / payload planes of the previous block; out: those of this block
+//   U      out: unit planes (meaningful at emitting positions only)
+//   returns the detector plane: a set bit means "some rule is violated at or up to 3 bytes before this
+//   position" (never set on valid input; every invalid input sets at least one bit within 3 positions after
+//   its first offending byte, possibly on the zero filler behind the buffer — see swar.h:u8_incomplete_tail for
+//   the one case without filler).
+template <bool VALIDATE>
+B200_HD uint32_t utf8_to_utf16_block(const uint32_t (&B)[8], Carry &c, uint32_t (&U)[16]) {
+  const uint32_t b7 = B[7];
+  const uint32_t cont = b7 & ~B[6];
+  const uint32_t l2 = b7 & B[6], l3 = l2 & B[5], l4 = l3 & B[4];
+  const uint32_t must2 = fsl(c.l3, l3, 2);  // second continuation of a 3-/4-byte sequence is due here
+  const uint32_t m4e = fsl(c.l4, l4, 3);    // fourth byte of a 4-byte sequence (low surrogate)
+  const uint32_t m4t = fsl(c.l4, l4, 2);    // third byte (high surrogate)
+  uint32_t P[6], Q[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) P[k] = fsl(c.b[k], B[k], 1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; k++) Q[k] = fsl(c.b[k], B[k], 2);
+  // high surrogate: 0xD800 | ((cp >> 10) - 0x40), cp >> 10 = Q[2:0]:P[5:0]:B[5:4]
+  const uint32_t bw = ~(P[5] | P[4]);  // borrow out of the two bits above P[3:0]
+  const uint32_t t8 = Q[0] ^ bw;
+  const uint32_t t9 = Q[1] ^ (bw & ~Q[0]);
+  const uint32_t m4 = m4t | m4e;
+  U[0] = (m4t & B[4]) | (~m4t & B[0]);
+  U[1] = (m4t & B[5]) | (~m4t & B[1]);
+  U[2] = (m4t & P[0]) | (~m4t & B[2]);
+  U[3] = (m4t & P[1]) | (~m4t & B[3]);
+  U[4] = (m4t & P[2]) | (~m4t & B[4]);
+  U[5] = (m4t & P[3]) | (~m4t & B[5]);
+  U[6] = (m4t & ~P[4]) | (~m4t & (B[6] | (b7 & P[0])));
+  U[7] = (m4t & ~(P[5] ^ P[4])) | (~m4t & b7 & P[1]);
+  U[8] = (m4t & t8) | (~m4t & b7 & P[2]);
+  U[9] = (m4t & t9) | (~m4t & b7 & P[3]);
+  U[10] = ~m4t & ((b7 & P[4]) | m4e);
+  U[11] = m4 | (b7 & P[5]);
+  U[12] = (must2 & Q[0]) | m4;
+  U[13] = must2 & Q[1] & ~m4t;
+  U[14] = (must2 & Q[2]) | m4;
+  U[15] = (must2 & Q[3]) | m4;
+  uint32_t err = 0;
+  uint32_t e0 = 0, ed = 0, f0 = 0, f4 = 0;
+  if (VALIDATE) {
+    const uint32_t must = fsl(c.l2, l2, 1) | must2 | m4e;
+    const uint32_t n321 = ~(B[3] | B[2] | B[1]);
+    const uint32_t is3 = l3 & ~B[4];
+    e0 = is3 & n321 & ~B[0];
+    ed = is3 & B[3] & B[2] & ~B[1] & B[0];
+    f0 = l4 & n321 & ~B[0];
+    f4 = l4 & ~B[3] & B[2] & ~B[1] & ~B[0];
+    const uint32_t over2 = l2 & ~B[5] & ~B[4] & n321;            // C0, C1
+    const uint32_t big = l4 & (B[3] | (B[2] & (B[1] | B[0])));   // F5..FF
+    const uint32_t pe0 = fsl(c.e0, e0, 1), ped = fsl(c.ed, ed, 1), pf0 = fsl(c.f0, f0, 1), pf4 = fsl(c.f4, f4, 1);
+    const uint32_t rng = (pe0 & ~B[5]) | (ped & B[5]) | (pf0 & ~B[5] & ~B[4]) | (pf4 & (B[5] | B[4]));
+    err = (must ^ cont) | over2 | big | rng;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) c.b[k] = B[k];
+  c.l2 = l2; c.l3 = l3; c.l4 = l4;
+  c.e0 = e0; c.ed = ed; c.f0 = f0; c.f4 = f4;
+  return err;
+}
+
+// Validation detector alone (validate_utf8[_with_errors]): needs no payload planes.
+struct VCarry {
+  uint32_t l2, l3, l4, e0, ed, f0, f4;
+};
+B200_HD VCarry vcarry_from_word(uint32_t pw) {
+  const Carry c = carry_from_word(pw);
+  VCarry v;
+  v.l2 = c.l2; v.l3 = c.l3; v.l4 = c.l4; v.e0 = c.e0; v.ed = c.ed; v.f0 = c.f0; v.f4 = c.f4;
+  return v;
+}
+B200_HD uint32_t utf8_check_block(const uint32_t (&B)[8], VCarry &c) {
+  const uint32_t b7 = B[7];
+  const uint32_t cont = b7 & ~B[6];
+  const uint32_t l2 = b7 & B[6], l3 = l2 & B[5], l4 = l3 & B[4];
+  const uint32_t must = fsl(c.l2, l2, 1) | fsl(c.l3, l3, 2) | fsl(c.l4, l4, 3);
+  const uint32_t n321 = ~(B[3] | B[2] | B[1]);
+  const uint32_t is3 = l3 & ~B[4];
+  const uint32_t e0 = is3 & n321 & ~B[0];
+  const uint32_t ed = is3 & B[3] & B[2] & ~B[1] & B[0];
+  const uint32_t f0 = l4 & n321 & ~B[0];
+  const uint32_t f4 = l4 & ~B[3] & B[2] & ~B[1] & ~B[0];
+  const uint32_t over2 = l2 & ~B[5] & ~B[4] & n321;
+  const uint32_t big = l4 & (B[3] | (B[2] & (B[1] | B[0])));
+  const uint32_t pe0 = fsl(c.e0, e0, 1), ped = fsl(c.ed, ed, 1), pf0 = fsl(c.f0, f0, 1), pf4 = fsl(c.f4, f4, 1);
+  const uint32_t rng = (pe0 & ~B[5]) | (ped & B[5]) | (pf0 & ~B[5] & ~B[4]) | (pf4 & (B[5] | B[4]));
+  c.l2 = l2; c.l3 = l3; c.l4 = l4; c.e0 = e0; c.ed = ed; c.f0 = f0; c.f4 = f4;
+  return (must ^ cont) | over2 | big | rng;
+}
+
+}  // namespace bp
+}  // namespace b200

@@ -1,28 +1,27 @@
 // k_utf8_to_utf16.cu — sm_100a kernels K3a/K3b: convert_utf8_to_utf16le[_with_errors]
 // (reference include/simdutf/implementation.h:3709-3745; semantics src/scalar/utf8_to_utf16/utf8_to_utf16.h:128-255).
 //
-// Two phases, both pure streaming kernels made of independent warps (no CTA barrier in the hot loop, no
-// inter-CTA wait):
+// Two streaming kernels made of independent warps (no CTA barrier in the hot loop, no inter-CTA wait):
 //
-//   K3a  k_utf16_tile_counts   per warp-tile (32*G granules = 512*G contiguous input bytes) the number of UTF-16
-//        units it will produce — the popcount reduction of utf16_length_from_utf8 (reference
-//        src/scalar/utf8.h:243-255) kept per tile — plus one total per chunk of 64 warp-tiles; the CTA that
-//        finishes last turns the chunk totals into exclusive chunk offsets (and the grand total).
-//        HBM-bound: reads the input once, writes 2 bytes per KiB.
-//   K3b  k_utf8_to_utf16_emit  every warp: output offset of its tile = chunk offset + the counts of the tiles
-//        before it in the chunk (one masked warp reduction); coalesced 128-bit loads; branch-free SWAR
-//        transcoder + validation detector (swar.h: u8_to_utf16_word) with the results kept in registers;
-//        popcount + warp scan; compaction into the warp's own shared-memory staging region, laid out so that
-//        its 16-byte vectors line up with 16-byte-aligned output addresses; 128-bit streaming stores.
-//        The next tile's granules are fetched while the current one is compacted and stored.
-//        ALU-pipe-bound (the per-byte SWAR work); the input comes from HBM a second time.  DESIGN.md explains
-//        why a one-pass chained scan lost to this on B200: with ~600 resident tiles every look-back waits
-//        for the slowest of its predecessors, and that convoy costs more than one extra streaming read.
+//   K3a  k_utf16_tile_counts   per warp-tile (32 lanes x K blocks x 32 bytes of contiguous input) the number of
+//        UTF-16 units the tile emits, plus one total per chunk of 64 tiles; the CTA that finishes last turns the
+//        chunk totals into exclusive chunk offsets (and the grand total).  Byte-SWAR popcounts, HBM-bound.
+//   K3b  k_utf8_to_utf16_bp    the transcoder, in BIT-PLANE form (bitplane.h): every lane owns 32*K contiguous
+//        bytes, transposes each 32-byte block into 8 bit planes, and then classifies, validates and assembles
+//        the 16 planes of the candidate unit of all 32 positions with ~75 bitwise instructions per block (the
+//        byte-SWAR transcoder this replaces needed ~70 per FOUR bytes).  The unit planes are transposed back
+//        to 16-bit units and compacted (predicated 16-bit shared stores) into the lane's PRIVATE staging region,
+//        whose odd word stride keeps the 32 lanes of a store instruction on 32 different banks whatever the
+//        text looks like.  The lane's region starts at the unit offset that makes its 16-byte vectors line up
+//        with 16-byte-aligned output addresses; a lane fetches the few units in front of its first vector from
+//        its left neighbour's region and then streams its own vectors to global memory.
 //
-// Emit rule and values: swar.h (one unit per non-continuation byte + one for the byte after a byte >= 0xF0, so
-// an output buffer of utf16_length_from_utf8() units is never overrun, even for invalid input).
+// Emission rule (bitplane.h): a unit is emitted at the LAST byte of its character (high surrogates at the third
+// byte of a 4-byte sequence), so everything except one "is the next byte a continuation" bit looks backwards.
+// K3a counts with exactly the same rule, which is what makes the per-tile offsets exact.
 #include <cstdlib>
 
+#include "bitplane.h"
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -33,6 +32,15 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr uint32_t kChunkTiles = 64;  // warp-tiles per chunk (one chunk total / chunk offset)
+
+template <int K>
+struct Geom {
+  static constexpr uint32_t kRegionBytes = 32u * K;              // contiguous input bytes per lane
+  static constexpr uint32_t kTileBytes = 32u * kRegionBytes;     // per warp
+  static constexpr uint32_t kTileGranules = kTileBytes / 16u;
+  static constexpr uint32_t kStrideWords = (16u * K + 4u) | 1u;  // (32K units + 8 units of alignment pad) / 2, odd
+  static constexpr uint32_t kSmemBytes = kWarpsPerCta * 32u * kStrideWords * 4u;
+};
 
 __device__ __forceinline__ InView make_view16(const void *p, size_t len_bytes) {
   InView v;
@@ -52,6 +60,14 @@ __device__ __forceinline__ bool tail_truncated16(const InView &in) {
   return u8_incomplete_tail(b1, b2, b3);
 }
 
+// A buffer that starts with a continuation byte is invalid at position 0; both kernels then emit nothing
+// (bitplane.h explains why the end-of-character rule needs this).
+__device__ __forceinline__ bool starts_with_continuation(const InView &in) {
+  if (in.vend <= in.vbeg) return false;
+  const uint32_t b = __ldg(reinterpret_cast<const uint8_t *>(in.base) + in.vbeg);
+  return (b & 0xC0u) == 0x80u;
+}
+
 // Packed emit mask of a granule: position p = 4k + b (word k, byte b) lives at bit 8b + 4 + k.
 __device__ __forceinline__ uint32_t pack_emit(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3) {
   return (e0 >> 3) | (e1 >> 2) | (e2 >> 1) | e3;
@@ -64,18 +80,20 @@ __device__ __forceinline__ uint32_t packed_inrange(const InView &in, unsigned lo
   return r;
 }
 
-// A tile is "interior" when all its granules lie inside the buffer (the words on either side are always
-// fetched with guarded loads).
+// ---------------------------------------------------------------------------------------------
+// K3a: per-tile unit counts (granule layout: lane l, item j owns granule g0 + 32 j + l)
+// ---------------------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ bool tile_is_interior(const InView &in, unsigned long long g0) {
+__device__ __forceinline__ bool granules_interior(const InView &in, unsigned long long g0) {
   const unsigned long long lo = g0 * 16ull, hi = (g0 + 32ull * G) * 16ull;
   return lo >= in.vbeg && hi <= in.vend;
 }
 
-// Loads the G granules of this lane (granule g0 + j*32 + lane).
 template <int G, bool EDGE>
-__device__ __forceinline__ void load_tile(const InView &in, unsigned long long g0, uint32_t (&w)[G][4], bool (&inside)[G]) {
+__device__ __forceinline__ uint32_t count_tile(const InView &in, unsigned long long g0) {
   const unsigned lane = threadIdx.x & 31u;
+  uint32_t w[G][4];
+  bool inside[G];
 #pragma unroll
   for (int j = 0; j < G; j++) {
     const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
@@ -87,26 +105,22 @@ __device__ __forceinline__ void load_tile(const InView &in, unsigned long long g
       inside[j] = true;
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3a: per-tile unit counts
-// ---------------------------------------------------------------------------------------------
-template <int G, bool EDGE>
-__device__ __forceinline__ uint32_t count_tile(const InView &in, unsigned long long g0) {
-  const unsigned lane = threadIdx.x & 31u;
-  uint32_t w[G][4];
-  bool inside[G];
-  load_tile<G, EDGE>(in, g0, w, inside);
+  uint32_t pw[G], nw[G];
+  neighbour_words<G>(in, g0, w, pw, nw);
   uint32_t cnt = 0;
 #pragma unroll
   for (int j = 0; j < G; j++) {
-    // the word before the granule: only its last byte matters (>= 0xF0 makes byte 0 emit a low surrogate)
-    const uint32_t give = (lane == 31 && j > 0) ? w[j - 1][3] : w[j][3];
-    uint32_t pw = __shfl_sync(kFull, give, (lane + 31u) & 31u);
-    if (j == 0 && lane == 0) pw = load_word_guarded(in, (long long)(g0 * 4ull) - 1);
+    uint32_t nc[5], f[5];
+    f[0] = u8_ge_f0(pw[j]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      nc[k] = u8_noncont(w[j][k]);
+      f[k + 1] = u8_ge_f0(w[j][k]);
+    }
+    nc[4] = u8_noncont(nw[j]);
     uint32_t em[4];
-    u8_emit16_masks(w[j], pw, em);
+#pragma unroll
+    for (int k = 0; k < 4; k++) em[k] = fwd1(nc[k], nc[k + 1]) | back2(f[k], f[k + 1]);
     uint32_t m = pack_emit(em[0], em[1], em[2], em[3]);
     if (EDGE && !inside[j]) m &= packed_inrange(in, g0 + (unsigned long long)j * 32u + lane);
     cnt += (uint32_t)__popc(m);
@@ -126,13 +140,15 @@ __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr,
   __shared__ bool s_last;
   const InView in = make_view16(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool poison = starts_with_continuation(in);
   for (uint32_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
     uint32_t mine = 0;
     for (uint32_t i = warp; i < kChunkTiles; i += kWarpsPerCta) {
       const uint32_t t = chunk * kChunkTiles + i;
       if (t >= num_tiles) break;
       const unsigned long long g0 = (unsigned long long)t * (32ull * G);
-      const uint32_t c = tile_is_interior<G>(in, g0) ? count_tile<G, false>(in, g0) : count_tile<G, true>(in, g0);
+      uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false>(in, g0) : count_tile<G, true>(in, g0);
+      if (poison) c = 0;
       if (lane == 0) tile_cnt[t] = (uint16_t)c;
       mine += c;
     }
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr,
     }
     __syncthreads();
   }
-  // the CTA that finishes last scans the chunk totals (num_chunks is small: 16 Ki per GiB of input at G = 2)
+  // the CTA that finishes last scans the chunk totals (num_chunks is small: 8 Ki per GiB of input at 2 KiB tiles)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -185,100 +201,38 @@ __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3b: transcode + emit
+// K3b: bit-plane transcoder
 // ---------------------------------------------------------------------------------------------
-template <int G>
-struct EmitSmem {
-  static constexpr uint32_t kWarpUnits = 32u * G * 16u;  // a warp emits at most one unit per input byte
-  static constexpr uint32_t kRegion = kWarpUnits + 16u;  // up to 7 units of alignment padding in front + vector tail
-  alignas(16) uint16_t stage[kWarpsPerCta][kRegion];
-};
-
-// Warp-relative exclusive offsets of per-lane per-item counts c[j] <= 16, in element order (item, lane).
-template <int G>
-__device__ __forceinline__ uint32_t warp_exclusive_offsets(const uint32_t (&c)[G], uint32_t (&off)[G]) {
-  const unsigned lane = threadIdx.x & 31u;
-  uint32_t run = 0;
-#pragma unroll
-  for (int j = 0; j < G; j += 2) {
-    const uint32_t c1 = (j + 1 < G) ? c[j + 1] : 0u;
-    uint32_t incl = c[j] | (c1 << 16);  // two 16-bit lanes; 32 * 16 < 65536
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= (unsigned)o) incl += t;
-    }
-    const uint32_t tot = __shfl_sync(kFull, incl, 31);
-    off[j] = run + (incl & 0xFFFFu) - c[j];
-    run += tot & 0xFFFFu;
-    if (j + 1 < G) {
-      off[j + 1] = run + (incl >> 16) - c1;
-      run += tot >> 16;
-    }
-  }
-  return run;
+// Bit p set iff byte b0 + p lies inside the buffer.
+__device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long long b0) {
+  long long lo = (long long)in.vbeg - (long long)b0, hi = (long long)in.vend - (long long)b0;
+  lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+  hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+  const uint32_t mhi = hi >= 32 ? 0xFFFFFFFFu : ((1u << (unsigned)hi) - 1u);
+  const uint32_t mlo = lo >= 32 ? 0xFFFFFFFFu : ((1u << (unsigned)lo) - 1u);
+  return mhi & ~mlo;
 }
 
-// The part of a tile that needs the input words: leaves candidate units and emit masks in registers.
-template <int G, bool EDGE>
-__device__ __forceinline__ void transcode_words(const InView &in, unsigned long long g0, const uint32_t (&w)[G][4],
-                                                const bool (&inside)[G], uint32_t (&U)[G][8], uint32_t (&M)[G],
-                                                uint32_t &flagged) {
-  const unsigned lane = threadIdx.x & 31u;
-  uint32_t pw[G], nw[G];
-  neighbour_words<G>(in, g0, w, pw, nw);
-#pragma unroll
-  for (int j = 0; j < G; j++) {
-    const uint32_t hi = (w[j][0] | w[j][1] | w[j][2] | w[j][3] | pw[j]) & kH;
-    if (!__any_sync(kFull, hi != 0u)) {
-      // 512 ASCII bytes: units are the bytes, every position emits
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        U[j][2 * k] = __byte_perm(w[j][k], 0u, 0x4140);
-        U[j][2 * k + 1] = __byte_perm(w[j][k], 0u, 0x4342);
-      }
-      M[j] = 0xF0F0F0F0u;
-    } else {
-      U8Carry carry = u8_carry_of(pw[j]);
-      uint32_t em[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t xn = (k < 3 ? w[j][(k + 1) & 3] : nw[j]) & 0x3F3F3F3Fu;
-        const U8Word16 r = u8_to_utf16_word<true>(w[j][k], xn, carry);
-        U[j][2 * k] = r.u01;
-        U[j][2 * k + 1] = r.u23;
-        em[k] = r.emit;
-        flagged |= r.err;
-      }
-      M[j] = pack_emit(em[0], em[1], em[2], em[3]);
-    }
-    if (EDGE && !inside[j]) M[j] &= packed_inrange(in, g0 + (unsigned long long)j * 32u + lane);
-  }
-}
-
-template <int G, int MINB>
+template <int K, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
-k_utf8_to_utf16_emit(const char *ptr, size_t len, uint16_t *out, const uint16_t *tile_cnt,
-                     const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
-                     ResultPOD *res) {
-  __shared__ EmitSmem<G> sm;
+k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *tile_cnt,
+                   const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
+                   ResultPOD *res) {
+  using Gm = Geom<K>;
+  extern __shared__ __align__(16) uint32_t smem[];
   const InView in = make_view16(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t nwarps = gridDim.x * kWarpsPerCta;
-  uint16_t *stage = sm.stage[warp];
+  uint32_t *region_w = smem + (warp * 32u + lane) * Gm::kStrideWords;  // this lane's private staging region
+  uint16_t *region = reinterpret_cast<uint16_t *>(region_w);
+  const bool poison = starts_with_continuation(in);
+  const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) >> 1);
 
-  uint32_t tile = blockIdx.x * kWarpsPerCta + warp;
-  uint32_t w[G][4];
-  bool inside[G];
-  bool interior = false;
-  if (tile < num_tiles) {
-    const unsigned long long g0 = (unsigned long long)tile * (32ull * G);
-    interior = tile_is_interior<G>(in, g0);
-    if (interior) load_tile<G, false>(in, g0, w, inside);
-    else load_tile<G, true>(in, g0, w, inside);
-  }
-  while (tile < num_tiles) {
-    const unsigned long long g0 = (unsigned long long)tile * (32ull * G);
+  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
+    const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;  // virtual byte offsets from in.base
+    const unsigned long long r0 = t0 + (unsigned long long)lane * Gm::kRegionBytes;
+    const bool interior = t0 >= in.vbeg + 16ull && t0 + Gm::kTileBytes + 16ull <= in.vend;
+
     // ---- where the tile's units go: chunk offset + counts of the chunk's earlier tiles ----
     const uint32_t chunk = tile / kChunkTiles, in_chunk = tile % kChunkTiles;
     uint32_t before = 0;
@@ -286,91 +240,189 @@ k_utf8_to_utf16_emit(const char *ptr, size_t len, uint16_t *out, const uint16_t 
       const uint16_t *c = tile_cnt + (size_t)chunk * kChunkTiles;
       if (lane < in_chunk) before += c[lane];
       if (lane + 32u < in_chunk) before += c[lane + 32u];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFull, before, o);
     }
-    const unsigned long long goff = chunk_off[chunk] + before;
+    const unsigned long long coff = chunk_off[chunk];
 
-    // ---- transcode into registers ----
-    uint32_t U[G][8], M[G], cnt[G], off[G];
-    uint32_t flagged = 0;
-    if (interior) transcode_words<G, false>(in, g0, w, inside, U, M, flagged);
-    else transcode_words<G, true>(in, g0, w, inside, U, M, flagged);
-    const bool was_interior = interior;
-
-    // ---- fetch the next tile while this one is compacted and stored ----
-    const uint32_t next = tile + nwarps;
-    if (next < num_tiles) {
-      const unsigned long long n0 = (unsigned long long)next * (32ull * G);
-      interior = tile_is_interior<G>(in, n0);
-      if (interior) load_tile<G, false>(in, n0, w, inside);
-      else load_tile<G, true>(in, n0, w, inside);
+    // ---- this lane's 32K contiguous bytes, the word before them and the byte after them ----
+    uint32_t B[K][8];
+    uint32_t pw, nbyte;
+    if (interior) {
+      const uint4 *gp = in.base + (r0 >> 4);
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const uint4 v0 = __ldg(gp + 2 * j), v1 = __ldg(gp + 2 * j + 1);
+        B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
+        B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
+      }
+      pw = __ldg(reinterpret_cast<const uint32_t *>(in.base) + (r0 >> 2) - 1);
+      nbyte = __ldg(reinterpret_cast<const uint8_t *>(in.base) + r0 + Gm::kRegionBytes);
+    } else {
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        bool ins;
+        load_granule(in, (r0 >> 4) + 2ull * j, &B[j][0], ins);
+        load_granule(in, (r0 >> 4) + 2ull * j + 1ull, &B[j][4], ins);
+      }
+      pw = load_word_guarded(in, (long long)(r0 >> 2) - 1);
+      const unsigned long long np = r0 + Gm::kRegionBytes;
+      nbyte = (np >= in.vbeg && np < in.vend) ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(in.base) + np) : 0u;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFull, before, o);
+    const unsigned long long goff = coff + before;
 
+    uint32_t next_nc[K];
 #pragma unroll
-    for (int j = 0; j < G; j++) cnt[j] = (uint32_t)__popc(M[j]);
-    const uint32_t total = warp_exclusive_offsets<G>(cnt, off);
+    for (int j = 0; j < K; j++) {
+      const uint32_t nb = (j + 1 < K) ? B[(j + 1 < K) ? j + 1 : j][0] : nbyte;
+      next_nc[j] = ((nb & 0xC0u) != 0x80u) ? 1u : 0u;
+    }
+    uint32_t hi = pw;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) hi |= B[j][i];
+    }
+    const bool ascii_tile = !__any_sync(kFull, (hi & kH) != 0u);
 
-    // ---- compact into the staging region; unit i sits at stage[a + i], a = misalignment of the destination ----
-    uint16_t *dst = out + goff;
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) >> 1) & 7u;
+    uint32_t em[K];
+    uint32_t cnt = 0;
+    uint32_t badblocks = 0;
+    bp::Carry carry;
+    if (!ascii_tile) {
+      // ---- pass 1: planes, emit masks, counts ----
+      carry = bp::carry_from_word(pw);
+      uint32_t prev_l4 = carry.l4;
 #pragma unroll
-    for (int j = 0; j < G; j++) {
-      uint16_t *sp = stage + a + off[j];
-      const uint32_t m = M[j];
+      for (int j = 0; j < K; j++) {
+        bp::transpose_in(B[j]);
+        uint32_t m = bp::emit16_mask(B[j], prev_l4, next_nc[j]);
+        prev_l4 = B[j][7] & B[j][6] & B[j][5] & B[j][4];
+        if (!interior) m &= range_mask32(in, r0 + 32ull * j);
+        if (poison) m = 0;
+        em[j] = m;
+        cnt += (uint32_t)__popc(m);
+      }
+    } else {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int j = 0; j < K; j++) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (!interior) m &= range_mask32(in, r0 + 32ull * j);
+        if (poison) m = 0;
+        em[j] = m;
+        cnt += (uint32_t)__popc(m);
+      }
+    }
+    // ---- lane offsets inside the tile ----
+    uint32_t incl = cnt;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const uint32_t reg = U[j][2 * k + (b >> 1)];
-          const uint16_t unit = (uint16_t)((b & 1) ? (reg >> 16) : reg);
-          if (m & (1u << (8 * b + 4 + k))) {
-            *sp = unit;
-            sp++;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= (unsigned)o) incl += t;
+    }
+    const unsigned long long G = goff + (incl - cnt);               // global index of this lane's first unit
+    const uint32_t a = (uint32_t)((out_units + G) & 7ull);          // its offset inside a 16-byte output vector
+
+    // ---- pass 2: units, compaction into the private region ----
+    {
+      uint16_t *sp = region + a;
+      if (!ascii_tile) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          uint32_t U[16];
+          const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
+          if (err) badblocks |= 1u << j;
+          bp::transpose_out16(U);
+          const uint32_t m = em[j];
+#pragma unroll
+          for (int p = 0; p < 16; p++) {
+            if (m & (1u << p)) {
+              *sp = (uint16_t)U[p];
+              sp++;
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < 16; p++) {
+            if (m & (1u << (16 + p))) {
+              *sp = (uint16_t)(U[p] >> 16);
+              sp++;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          const uint32_t m = em[j];
+#pragma unroll
+          for (int p = 0; p < 32; p++) {
+            if (m & (1u << p)) {
+              *sp = (uint16_t)((B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu);
+              sp++;
+            }
           }
         }
       }
     }
-    // exact error location (rare): the detector only says "somewhere in this granule or the 3 bytes before it"
-    {
-      bool bad = flagged != 0;
-      if (!was_interior) {
+    // ---- exact error location (rare): the detector only says "in this block or the 3 bytes before it" ----
+    if (!interior) {
 #pragma unroll
-        for (int j = 0; j < G; j++) {
-          const unsigned long long lo = (g0 + (unsigned long long)j * 32u + lane) * 16ull;
-          if (lo < in.vend && in.vend <= lo + 16ull) bad = bad || tail_truncated16(in);
-        }
+      for (int j = 0; j < K; j++) {
+        const unsigned long long b0 = r0 + 32ull * j;
+        if (b0 < in.vend && in.vend <= b0 + 32ull && tail_truncated16(in)) badblocks |= 1u << j;
       }
-      if (bad) {
+    }
+    if (badblocks) {
 #pragma unroll
-        for (int j = 0; j < G; j++) {
-          const unsigned long long lo = (g0 + (unsigned long long)j * 32u + lane) * 16ull;
-          u8_locate_error(in, scr, (long long)lo - 3, (long long)lo + 16);
-        }
+      for (int j = 0; j < K; j++) {
+        const long long b0 = (long long)(r0 + 32ull * j);
+        if (badblocks & (1u << j)) u8_locate_error(in, scr, b0 - 3, b0 + 32);
       }
     }
     __syncwarp();
 
-    // ---- staging -> global: vector v of the region is vector v of the 16-byte-aligned destination ----
+    // ---- staging -> global ----
     {
-      const uint32_t nvec = (a + total + 7u) >> 3;
-      uint16_t *dbase = dst - a;
-      const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
-      for (uint32_t v = lane; v < nvec; v += 32u) {
-        const bool full = (v > 0 || a == 0) && (8u * v + 8u <= a + total);
-        if (full) {
-          stg_stream_v4(reinterpret_cast<uint4 *>(dbase + 8u * v), sv[v]);
-        } else {
+      uint16_t *gbase = out + G - a;  // 16-byte aligned
+      const uint32_t end = a + cnt;
+      if (__all_sync(kFull, cnt >= 8u)) {
+        // every lane owns the 16-byte vectors that hold its units, except its last partial one (owned by the
+        // lane to its right, which copies the units in front of its own first unit from this lane's tail)
+        const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
+        if (lane > 0 && a > 0) {
+          const uint16_t *pr = region - 2u * Gm::kStrideWords + prev_end - a;
 #pragma unroll
-          for (uint32_t t = 0; t < 8; t++) {
-            const uint32_t e = 8u * v + t;
-            if (e >= a && e < a + total) dbase[e] = stage[e];
+          for (uint32_t u = 0; u < 7; u++)
+            if (u < a) region[u] = pr[u];
+        }
+        uint32_t v = 0;
+        if (lane == 0 && a > 0) {  // the tile's first partial vector: shared with the previous tile
+#pragma unroll
+          for (uint32_t u = 1; u < 8; u++)
+            if (u >= a) gbase[u] = region[u];
+          v = 1;
+        }
+        const uint32_t vfull = end >> 3;
+        if (lane == 31) {  // the tile's last partial vector: shared with the next tile
+#pragma unroll
+          for (uint32_t u = 0; u < 7; u++) {
+            const uint32_t idx = vfull * 8u + u;
+            if (idx < end) gbase[idx] = region[idx];
           }
         }
+        for (; v < vfull; v++) {
+          uint4 x;
+          x.x = region_w[4u * v];
+          x.y = region_w[4u * v + 1u];
+          x.z = region_w[4u * v + 2u];
+          x.w = region_w[4u * v + 3u];
+          stg_stream_v4(reinterpret_cast<uint4 *>(gbase + 8u * v), x);
+        }
+      } else {
+        // edge tiles and invalid input: unit by unit
+        for (uint32_t i = a; i < end; i++) gbase[i] = region[i];
       }
     }
-    __syncwarp();  // the region is rewritten by the next tile
-    tile = next;
+    __syncwarp();  // the regions are rewritten by the next tile
   }
 
   if (grid_last_thread(scr)) {
@@ -388,7 +440,7 @@ k_utf8_to_utf16_emit(const char *ptr, size_t len, uint16_t *out, const uint16_t 
   }
 }
 
-// Tuning knobs for experiments (tools/, profiles/): B200_TUNE_G = granules per lane (2..4),
+// Tuning knobs for experiments (tools/, profiles/): B200_TUNE_K = 32-byte blocks per lane (1, 2 or 4),
 // B200_TUNE_MINB = resident CTAs per SM the kernel is compiled for.
 inline int env_int(const char *name, int lo, int hi, int dflt) {
   const char *e = getenv(name);
@@ -396,28 +448,31 @@ inline int env_int(const char *name, int lo, int hi, int dflt) {
   const int v = atoi(e);
   return (v >= lo && v <= hi) ? v : dflt;
 }
-inline int tuned_g() {
-  static int v = env_int("B200_TUNE_G", 2, 4, 4);
-  return v;
+inline int tuned_k() {
+  static int v = env_int("B200_TUNE_K", 1, 4, 2);
+  return v == 3 ? 2 : v;
 }
 inline int tuned_minb16() {
-  static int v = env_int("B200_TUNE_MINB", 2, 4, 3);
+  static int v = env_int("B200_TUNE_MINB", 1, 4, 2);
   return v;
 }
 
-inline size_t tiles16_for(const void *in, size_t len_bytes, int g) {
+inline size_t tiles16_for(const void *in, size_t len_bytes, int k) {
   const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
-  const size_t gran = (span + 15) / 16;
-  const size_t per_tile = (size_t)32 * g;
-  return (gran + per_tile - 1) / per_tile;
+  const size_t per_tile = (size_t)1024 * k;
+  return (span + per_tile - 1) / per_tile;
 }
 
-template <int G, int MINB>
+template <int K, int MINB>
 cudaError_t launch_t16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res, size_t tiles) {
+  using Gm = Geom<K>;
   static int per_sm_emit = 0;
   if (per_sm_emit == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k_utf8_to_utf16_bp<K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Gm::kSmemBytes);
+    if (e != cudaSuccess) return e;
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf8_to_utf16_emit<G, MINB>, kThreads, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf8_to_utf16_bp<K, MINB>, kThreads, Gm::kSmemBytes);
     if (e != cudaSuccess) return e;
     per_sm_emit = n < 1 ? 1 : n;
   }
@@ -428,15 +483,15 @@ cudaError_t launch_t16(const LaunchCtx &c, const char *in, size_t len, uint16_t 
   {
     const size_t cap = (size_t)c.sm_count * 8;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_utf16_tile_counts<G><<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks,
-                                                           c.scratch);
+    k_utf16_tile_counts<2 * K><<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles,
+                                                               (uint32_t)chunks, c.scratch);
   }
   {
     const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t cap = (size_t)c.sm_count * per_sm_emit;
     const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_utf8_to_utf16_emit<G, MINB><<<grid, kThreads, 0, c.stream>>>(in, len, out, tile_cnt, chunk_off, (uint32_t)tiles,
-                                                                  (uint32_t)chunks, c.scratch, static_cast<ResultPOD *>(res));
+    k_utf8_to_utf16_bp<K, MINB><<<grid, kThreads, Gm::kSmemBytes, c.stream>>>(
+        in, len, out, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch, static_cast<ResultPOD *>(res));
   }
   count_launch(2);
   return cudaGetLastError();
@@ -446,27 +501,27 @@ cudaError_t launch_t16(const LaunchCtx &c, const char *in, size_t len, uint16_t 
 
 // Workspace, in 8-byte descriptor slots, the two kernels need for an input of `len` bytes.
 size_t utf8_to_utf16_tiles(const void *in, size_t len) {
-  const size_t tiles = tiles16_for(in, len, tuned_g());
+  const size_t tiles = tiles16_for(in, len, tuned_k());
   const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
   return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
 }
 
 cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res) {
-  const int g = tuned_g();
-  const size_t tiles = tiles16_for(in, len, g);
+  const int k = tuned_k();
+  const size_t tiles = tiles16_for(in, len, k);
   if (utf8_to_utf16_tiles(in, len) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
   const int mb = tuned_minb16();
-  switch (g) {
-    case 2:
-      if (mb == 2) return launch_t16<2, 2>(c, in, len, out, res, tiles);
-      if (mb == 4) return launch_t16<2, 4>(c, in, len, out, res, tiles);
-      return launch_t16<2, 3>(c, in, len, out, res, tiles);
-    case 3:
-      if (mb == 2) return launch_t16<3, 2>(c, in, len, out, res, tiles);
-      return launch_t16<3, 3>(c, in, len, out, res, tiles);
+  switch (k) {
+    case 1:
+      if (mb >= 3) return launch_t16<1, 3>(c, in, len, out, res, tiles);
+      return launch_t16<1, 2>(c, in, len, out, res, tiles);
+    case 4:
+      if (mb == 1) return launch_t16<4, 1>(c, in, len, out, res, tiles);
+      return launch_t16<4, 2>(c, in, len, out, res, tiles);
     default:
-      if (mb == 2) return launch_t16<4, 2>(c, in, len, out, res, tiles);
-      return launch_t16<4, 3>(c, in, len, out, res, tiles);
+      if (mb == 1) return launch_t16<2, 1>(c, in, len, out, res, tiles);
+      if (mb >= 3) return launch_t16<2, 3>(c, in, len, out, res, tiles);
+      return launch_t16<2, 2>(c, in, len, out, res, tiles);
   }
 }
 

@@ -16,6 +16,7 @@
 
 #include "../../oracle/oracle.h"
 #include "../../simdutf_b200/csrc/swar.h"
+#include "../../simdutf_b200/csrc/bitplane.h"
 
 using namespace b200;
 
@@ -168,6 +169,80 @@ static void test_utf8_word16(const std::vector<uint8_t> &d, unsigned misalign) {
     CHECK(out.size() == r16.count && memcmp(out.data(), w16.data(), 2 * r16.count) == 0, "word16 output mis=%u %s", misalign, hex(d).c_str());
     CHECK(n_emit == oracle_utf16_length_from_utf8(d.data(), len), "word16 count");
   }
+}
+
+
+// ---- UTF-8 -> UTF-16 through the bit-plane transcoder (bitplane.h; k_utf8_to_utf16.cu) --------------------
+// Emulates the kernel's plumbing: warp tiles of 32 lane regions of K blocks of 32 bytes, every region processed
+// front to back with the carry seeded from the 4 bytes before it.
+static uint32_t range_mask32(const View &v, uint64_t b0) {
+  uint32_t m = 0;
+  for (int p = 0; p < 32; p++) if (b0 + p >= v.vbeg && b0 + p < v.vend) m |= 1u << p;
+  return m;
+}
+static void test_utf8_bitplane(const std::vector<uint8_t> &d, unsigned misalign, int K) {
+  const size_t len = d.size();
+  View v(d.data(), len, misalign);
+  const oracle_result want = oracle_validate_utf8_with_errors(d.data(), len);
+  const bool poison = len > 0 && (d[0] & 0xC0) == 0x80;
+  std::vector<uint16_t> out;
+  uint64_t best_pos = ~0ull; int best_code = 0; bool any_flag = false;
+  auto at = [&](uint64_t j) -> uint32_t { return d[j]; };
+  auto vbyte = [&](uint64_t pos) -> uint32_t { return (pos >= v.vbeg && pos < v.vend) ? v.mem[pos] : 0u; };
+  const uint64_t region = 32ull * K, nregions = (v.vend + region - 1) / region + 1;  // one extra: truncation shows on the filler
+  for (uint64_t r = 0; r < nregions; r++) {
+    const uint64_t r0 = r * region;
+    bp::Carry carry = bp::carry_from_word(v.word((long long)(r0 / 4) - 1));
+    bp::VCarry vc = bp::vcarry_from_word(v.word((long long)(r0 / 4) - 1));
+    uint32_t prev_l4 = carry.l4;
+    for (int j = 0; j < K; j++) {
+      const uint64_t b0 = r0 + 32ull * j;
+      uint32_t B[8];
+      for (int i = 0; i < 8; i++) B[i] = v.word((long long)(b0 / 4) + i);
+      uint32_t raw[8]; memcpy(raw, B, sizeof raw);
+      bp::transpose_in(B);
+      for (int k = 0; k < 8; k++) for (int p = 0; p < 32; p++)
+        CHECK(((B[k] >> p) & 1) == ((vbyte(b0 + p) >> k) & 1), "transpose_in plane %d pos %d", k, p);
+      const uint32_t nb = vbyte(b0 + 32);
+      const uint32_t next_nc = (nb & 0xC0) != 0x80;
+      uint32_t em = bp::emit16_mask(B, prev_l4, next_nc) & range_mask32(v, b0);
+      if (poison) em = 0;
+      uint32_t U[16];
+      const uint32_t err = bp::utf8_to_utf16_block<true>(B, carry, U);
+      const uint32_t err2 = bp::utf8_check_block(B, vc);
+      CHECK(err == err2, "check_block differs from transcoder detector");
+      prev_l4 = carry.l4;
+      bp::transpose_out16(U);
+      for (int p = 0; p < 32; p++) if ((em >> p) & 1) out.push_back((uint16_t)(p < 16 ? U[p] : U[p - 16] >> 16));
+      bool flagged = err != 0;
+      if (b0 < v.vend && v.vend <= b0 + 32 && len > 0) {
+        uint32_t b1 = d[len - 1], b2 = len >= 2 ? d[len - 2] : 0, b3 = len >= 3 ? d[len - 3] : 0;
+        flagged = flagged || u8_incomplete_tail(b1, b2, b3);
+      }
+      if (flagged) {
+        any_flag = true;
+        long long a = (long long)b0 - 3, b = (long long)b0 + 32;
+        if (a < (long long)v.vbeg) a = (long long)v.vbeg;
+        if (b > (long long)v.vend) b = (long long)v.vend;
+        for (long long p = a; p < b; p++) {
+          uint64_t i = (uint64_t)p - v.vbeg;
+          int code = u8_verdict(at, i, len);
+          if (code) { if (i < best_pos) { best_pos = i; best_code = code; } break; }
+        }
+      }
+    }
+  }
+  if (want.error == 0) {
+    CHECK(!any_flag, "bitplane detector flagged valid input mis=%u K=%d %s", misalign, K, hex(d).c_str());
+    std::vector<uint16_t> w16(2 * len + 8);
+    oracle_result r16 = oracle_convert_utf8_to_utf16le_with_errors(d.data(), len, w16.data());
+    CHECK(out.size() == r16.count && memcmp(out.data(), w16.data(), 2 * r16.count) == 0, "bitplane utf16 output mis=%u K=%d %s", misalign, K, hex(d).c_str());
+  } else {
+    CHECK(best_code == want.error && best_pos == want.count, "bitplane error mismatch got (%d,%llu) want (%d,%llu) mis=%u K=%d %s", best_code,
+          (unsigned long long)best_pos, want.error, (unsigned long long)want.count, misalign, K, hex(d).c_str());
+  }
+  CHECK(out.size() <= oracle_utf16_length_from_utf8(d.data(), len), "bitplane overrun %zu > %llu mis=%u %s", out.size(),
+        (unsigned long long)oracle_utf16_length_from_utf8(d.data(), len), misalign, hex(d).c_str());
 }
 
 // ---- UTF-16 --------------------------------------------------------------------------------------------
@@ -326,6 +401,7 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> d = gen_utf8(n8);
     test_utf8(d, rnd(16));
     test_utf8_word16(d, rnd(16));
+    test_utf8_bitplane(d, rnd(16), 1 + rnd(4));
     std::vector<uint16_t> u = gen_utf16(rnd(4) ? rnd(60) : rnd(300));
     test_utf16(u, rnd(8));
     std::vector<uint8_t> b = gen_b64(rnd(4) ? rnd(100) : rnd(400));
@@ -337,9 +413,9 @@ int main(int argc, char **argv) {
   test_utf8({}, 0);
   test_utf8({0x80}, 3);
   for (unsigned mis = 0; mis < 16; mis++) {
-    std::vector<uint8_t> d(64, 0x20); d.push_back(0xFF); test_utf8(d, mis); test_utf8_word16(d, mis);
+    std::vector<uint8_t> d(64, 0x20); d.push_back(0xFF); test_utf8(d, mis); test_utf8_word16(d, mis); test_utf8_bitplane(d, mis, 2);
     std::vector<uint8_t> e(64, 0x20); e.push_back(0xA9); test_utf8(e, mis);
-    for (int cut = 1; cut <= 3; cut++) { std::vector<uint8_t> f(29 + mis, 'a'); push_cp(f, 0x1F600); f.resize(f.size() - cut); test_utf8(f, mis); test_utf8_word16(f, mis); }
+    for (int cut = 1; cut <= 3; cut++) { std::vector<uint8_t> f(29 + mis, 'a'); push_cp(f, 0x1F600); f.resize(f.size() - cut); test_utf8(f, mis); test_utf8_word16(f, mis); test_utf8_bitplane(f, mis, 1 + mis % 4); }
   }
   printf("swar_host_test: %ld iterations, %d failures\n", iters, failures);
   return failures ? 1 : 0;

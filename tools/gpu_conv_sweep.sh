@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "utf8 or golden or config2 or repeated" > gpurun_out/pytest_conv.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_conv.log
-tail -n 3 gpurun_out/pytest_conv.log
-for g in 2 3 4; do for mb in 2 3 4; do [ "$g$mb" = "34" -o "$g$mb" = "44" ] && continue
-  echo "G=$g MINB=$mb: $(B200_TUNE_G=$g B200_TUNE_MINB=$mb python tools/prof_one.py convert16 1073741824 5 2>&1 | tail -n 1)"
+tail -n 15 gpurun_out/pytest_conv.log
+for k in 1 2 4; do for mb in 1 2 3; do [ "$k$mb" = "43" -o "$k$mb" = "11" ] && continue
+  echo "K=$k MINB=$mb: $(B200_TUNE_K=$k B200_TUNE_MINB=$mb python tools/prof_one.py convert16 1073741824 5 2>&1 | tail -n 1)"
 done; done | tee gpurun_out/conv_sweep.log
