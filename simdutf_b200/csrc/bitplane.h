@@ -48,13 +48,37 @@ B200_HD uint32_t fsr(uint32_t lo, uint32_t hi, int n) {
 #endif
 }
 
+// (x & m) | (y & ~m) as ONE three-input logic op: written with two different immediates the compiler does not
+// see that the masks are complements and spends three.
+B200_HD uint32_t bitsel(uint32_t x, uint32_t y, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(x), "r"(y), "r"(m));
+  return r;
+#else
+  return (x & m) | (y & ~m);
+#endif
+}
+
+// x >> S through the multiplier: on sm_100 LOP3/SHF/PRMT share the half-rate ALU pipe, which bounds these kernels,
+// while IMAD / IMAD.HI issue on the FMA pipe (tools/ubench/pipes.cu: LOP3 + IMAD interleaved run at 3.7 warp
+// instructions per clock per SM, either alone at 2.0; IMAD.HI at 1.0).
+template <int S>
+B200_HD uint32_t shr_fma(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(x, 1u << (32 - S));
+#else
+  return x >> S;
+#endif
+}
+
 // Exchange one word-index bit with one bit-index bit: a holds the elements whose word-index bit is 0.
 //   a' = a's low-group bits in place, b's low-group bits moved up by s
 //   b' = a's high-group bits moved down by s, b's high-group bits in place
 template <int S, uint32_t M0>
 B200_HD void dswap(uint32_t &a, uint32_t &b) {
-  const uint32_t a2 = (a & M0) | ((b << S) & ~M0);
-  const uint32_t b2 = ((a >> S) & M0) | (b & ~M0);
+  const uint32_t a2 = bitsel(a, b << S, M0);
+  const uint32_t b2 = bitsel(shr_fma<S>(a), b, M0);
   a = a2;
   b = b2;
 }

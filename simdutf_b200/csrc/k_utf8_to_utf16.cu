@@ -213,6 +213,16 @@ __device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long
   return mhi & ~mlo;
 }
 
+// 16-bit shared store of the low half of `v` at a 32-bit shared-space address, and address + 2 on the FMA pipe.
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; st.shared.b16 [%0], l; }" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t bump2(uint32_t addr, uint32_t one) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(one), "r"(addr));
+  return r;
+}
+
 template <int K, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *tile_cnt,
@@ -227,6 +237,7 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
   uint16_t *region = reinterpret_cast<uint16_t *>(region_w);
   const bool poison = starts_with_continuation(in);
   const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) >> 1);
+  const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (see bump2)
 
   for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
     const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;  // virtual byte offsets from in.base
@@ -324,8 +335,11 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
     const uint32_t a = (uint32_t)((out_units + G) & 7ull);          // its offset inside a 16-byte output vector
 
     // ---- pass 2: units, compaction into the private region ----
+    // The running store address lives in a 32-bit shared-space register; it advances through the multiplier
+    // (`one` * 2 + address) and the upper unit of a word is extracted with IMAD.HI, so that the compaction costs
+    // the ALU pipe nothing but the predicate extraction.
     {
-      uint16_t *sp = region + a;
+      uint32_t spa = (uint32_t)__cvta_generic_to_shared(region + a);
       if (!ascii_tile) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
@@ -333,21 +347,33 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
           const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
           if (err) badblocks |= 1u << j;
           bp::transpose_out16(U);
+          // four independent store chains (positions 0-7, 8-15, 16-23, 24-31): a chain's address register can
+          // only advance once the store before it has read it, so one chain alone would serialise the block
           const uint32_t m = em[j];
+          uint32_t s0 = spa;
+          uint32_t s1 = spa + 2u * (uint32_t)__popc(m & 0xFFu);
+          uint32_t s2 = spa + 2u * (uint32_t)__popc(m & 0xFFFFu);
+          uint32_t s3 = spa + 2u * (uint32_t)__popc(m & 0xFFFFFFu);
 #pragma unroll
-          for (int p = 0; p < 16; p++) {
-            if (m & (1u << p)) {
-              *sp = (uint16_t)U[p];
-              sp++;
+          for (int i = 0; i < 8; i++) {
+            if (m & (1u << i)) {
+              sts_u16(s0, U[i]);
+              s0 = bump2(s0, one);
+            }
+            if (m & (1u << (8 + i))) {
+              sts_u16(s1, U[8 + i]);
+              s1 = bump2(s1, one);
+            }
+            if (m & (1u << (16 + i))) {
+              sts_u16(s2, __umulhi(U[i], 65536u));
+              s2 = bump2(s2, one);
+            }
+            if (m & (1u << (24 + i))) {
+              sts_u16(s3, __umulhi(U[8 + i], 65536u));
+              s3 = bump2(s3, one);
             }
           }
-#pragma unroll
-          for (int p = 0; p < 16; p++) {
-            if (m & (1u << (16 + p))) {
-              *sp = (uint16_t)(U[p] >> 16);
-              sp++;
-            }
-          }
+          spa = s3;
         }
       } else {
 #pragma unroll
@@ -356,8 +382,8 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
 #pragma unroll
           for (int p = 0; p < 32; p++) {
             if (m & (1u << p)) {
-              *sp = (uint16_t)((B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu);
-              sp++;
+              sts_u16(spa, (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu);
+              spa = bump2(spa, one);
             }
           }
         }
@@ -520,7 +546,8 @@ cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, s
       return launch_t16<4, 2>(c, in, len, out, res, tiles);
     default:
       if (mb == 1) return launch_t16<2, 1>(c, in, len, out, res, tiles);
-      if (mb >= 3) return launch_t16<2, 3>(c, in, len, out, res, tiles);
+      if (mb >= 4) return launch_t16<2, 4>(c, in, len, out, res, tiles);
+      if (mb == 3) return launch_t16<2, 3>(c, in, len, out, res, tiles);
       return launch_t16<2, 2>(c, in, len, out, res, tiles);
   }
 }
