@@ -145,6 +145,55 @@ B200_HD void transpose_out16(uint32_t (&u)[16]) {
   for (int i = 0; i < 8; i++) dswap_bytes(u[i], u[i + 8]);
 }
 
+// dswap whose second word is known to be zero.
+template <int S, uint32_t M0>
+B200_HD void dswap_z(uint32_t &a, uint32_t &b) {
+  const uint32_t a2 = a & M0;
+  b = shr_fma<S>(a) & M0;
+  a = a2;
+}
+// 21 planes (u[0..20]; u[21..31] are ignored and treated as zero) of a 21-bit value per position -> 32 words, in
+// place: afterwards u[q] = value of position q.  Five exchange stages; pairs of known-zero words are skipped.
+B200_HD void transpose_out21(uint32_t (&u)[32]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 20; i += 2) dswap<1, 0x55555555u>(u[i], u[i + 1]);
+  dswap_z<1, 0x55555555u>(u[20], u[21]);  // words 0..21 live
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 20; i++)
+    if (!(i & 2)) dswap<2, 0x33333333u>(u[i], u[i + 2]);
+  dswap_z<2, 0x33333333u>(u[20], u[22]);
+  dswap_z<2, 0x33333333u>(u[21], u[23]);  // words 0..23 live
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 24; i++)
+    if (!(i & 4)) dswap<4, 0x0F0F0F0Fu>(u[i], u[i + 4]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; i++) dswap_bytes(u[i], u[i + 8]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 16; i < 24; i++) {  // partner (24..31) is zero
+    const uint32_t a = u[i];
+    u[i] = a & 0x00FF00FFu;
+    u[i + 8] = prmt(a, 0u, 0x4341);
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i++) {  // halfword exchange
+    const uint32_t a = u[i], b = u[i + 16];
+    u[i] = prmt(a, b, 0x5410);
+    u[i + 16] = prmt(a, b, 0x7632);
+  }
+}
+
 // The top four positions (28..31) of the planes of a virtual block whose last word is `pw`; the other bits
 // are unspecified (only the top <= 3 bits are ever shifted into the block that follows).
 B200_HD void planes_of_tail_word(uint32_t pw, uint32_t (&v)[8]) {
@@ -266,6 +315,71 @@ B200_HD uint32_t utf8_to_utf16_block(const uint32_t (&B)[8], Carry &c, uint32_t 
     f4 = l4 & ~B[3] & B[2] & ~B[1] & ~B[0];
     const uint32_t over2 = l2 & ~B[5] & ~B[4] & n321;            // C0, C1
     const uint32_t big = l4 & (B[3] | (B[2] & (B[1] | B[0])));   // F5..FF
+    const uint32_t pe0 = fsl(c.e0, e0, 1), ped = fsl(c.ed, ed, 1), pf0 = fsl(c.f0, f0, 1), pf4 = fsl(c.f4, f4, 1);
+    const uint32_t rng = (pe0 & ~B[5]) | (ped & B[5]) | (pf0 & ~B[5] & ~B[4]) | (pf4 & (B[5] | B[4]));
+    err = (must ^ cont) | over2 | big | rng;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) c.b[k] = B[k];
+  c.l2 = l2; c.l3 = l3; c.l4 = l4;
+  c.e0 = e0; c.ed = ed; c.f0 = f0; c.f4 = f4;
+  return err;
+}
+
+// UTF-32 flavour: the 21 planes of the code point of the character that ENDS at each position.
+template <bool VALIDATE>
+B200_HD uint32_t utf8_to_utf32_block(const uint32_t (&B)[8], Carry &c, uint32_t (&C)[32]) {
+  const uint32_t b7 = B[7];
+  const uint32_t cont = b7 & ~B[6];
+  const uint32_t l2 = b7 & B[6], l3 = l2 & B[5], l4 = l3 & B[4];
+  const uint32_t must2 = fsl(c.l3, l3, 2);
+  const uint32_t m4e = fsl(c.l4, l4, 3);
+  const uint32_t m34 = must2 | m4e;
+  uint32_t P[6], Q[6], R[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) {
+    P[k] = fsl(c.b[k], B[k], 1);
+    Q[k] = fsl(c.b[k], B[k], 2);
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; k++) R[k] = fsl(c.b[k], B[k], 3);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) C[k] = B[k];
+  C[6] = B[6] | (b7 & P[0]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 1; k < 6; k++) C[6 + k] = b7 & P[k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; k++) C[12 + k] = m34 & Q[k];
+  C[16] = m4e & Q[4];
+  C[17] = m4e & Q[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; k++) C[18 + k] = m4e & R[k];
+  uint32_t err = 0;
+  uint32_t e0 = 0, ed = 0, f0 = 0, f4 = 0;
+  if (VALIDATE) {
+    const uint32_t must = fsl(c.l2, l2, 1) | must2 | m4e;
+    const uint32_t n321 = ~(B[3] | B[2] | B[1]);
+    const uint32_t is3 = l3 & ~B[4];
+    e0 = is3 & n321 & ~B[0];
+    ed = is3 & B[3] & B[2] & ~B[1] & B[0];
+    f0 = l4 & n321 & ~B[0];
+    f4 = l4 & ~B[3] & B[2] & ~B[1] & ~B[0];
+    const uint32_t over2 = l2 & ~B[5] & ~B[4] & n321;
+    const uint32_t big = l4 & (B[3] | (B[2] & (B[1] | B[0])));
     const uint32_t pe0 = fsl(c.e0, e0, 1), ped = fsl(c.ed, ed, 1), pf0 = fsl(c.f0, f0, 1), pf4 = fsl(c.f4, f4, 1);
     const uint32_t rng = (pe0 & ~B[5]) | (ped & B[5]) | (pf0 & ~B[5] & ~B[4]) | (pf4 & (B[5] | B[4]));
     err = (must ^ cont) | over2 | big | rng;

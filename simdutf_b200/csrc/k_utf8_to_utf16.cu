@@ -20,6 +20,7 @@
 // byte of a 4-byte sequence), so everything except one "is the next byte a continuation" bit looks backwards.
 // K3a counts with exactly the same rule, which is what makes the per-tile offsets exact.
 #include <cstdlib>
+#include <type_traits>
 
 #include "bitplane.h"
 #include "device_common.cuh"
@@ -33,13 +34,18 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr uint32_t kChunkTiles = 64;  // warp-tiles per chunk (one chunk total / chunk offset)
 
-template <int K>
+// W32 = false: UTF-16LE output (16-bit units, 8 per 16-byte vector); W32 = true: UTF-32 (4 per vector).
+template <int K, bool W32>
 struct Geom {
   static constexpr uint32_t kRegionBytes = 32u * K;              // contiguous input bytes per lane
   static constexpr uint32_t kTileBytes = 32u * kRegionBytes;     // per warp
   static constexpr uint32_t kTileGranules = kTileBytes / 16u;
-  static constexpr uint32_t kStrideWords = (16u * K + 4u) | 1u;  // (32K units + 8 units of alignment pad) / 2, odd
+  static constexpr uint32_t kVec = W32 ? 4u : 8u;                // output elements per 16-byte vector
+  static constexpr uint32_t kUnitBytes = W32 ? 4u : 2u;
+  // a lane emits at most one element per input byte, in front of which sit up to kVec-1 elements of alignment pad
+  static constexpr uint32_t kStrideWords = (((32u * K + kVec) * kUnitBytes) / 4u) | 1u;  // odd: conflict-free lanes
   static constexpr uint32_t kSmemBytes = kWarpsPerCta * 32u * kStrideWords * 4u;
+  static constexpr uint32_t kMaxVec = (32u * K + kVec - 1u) / kVec;
 };
 
 __device__ __forceinline__ InView make_view16(const void *p, size_t len_bytes) {
@@ -89,7 +95,7 @@ __device__ __forceinline__ bool granules_interior(const InView &in, unsigned lon
   return lo >= in.vbeg && hi <= in.vend;
 }
 
-template <int G, bool EDGE>
+template <int G, bool EDGE, bool W32>
 __device__ __forceinline__ uint32_t count_tile(const InView &in, unsigned long long g0) {
   const unsigned lane = threadIdx.x & 31u;
   uint32_t w[G][4];
@@ -120,7 +126,7 @@ __device__ __forceinline__ uint32_t count_tile(const InView &in, unsigned long l
     nc[4] = u8_noncont(nw[j]);
     uint32_t em[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) em[k] = fwd1(nc[k], nc[k + 1]) | back2(f[k], f[k + 1]);
+    for (int k = 0; k < 4; k++) em[k] = fwd1(nc[k], nc[k + 1]) | (W32 ? 0u : back2(f[k], f[k + 1]));
     uint32_t m = pack_emit(em[0], em[1], em[2], em[3]);
     if (EDGE && !inside[j]) m &= packed_inrange(in, g0 + (unsigned long long)j * 32u + lane);
     cnt += (uint32_t)__popc(m);
@@ -130,7 +136,7 @@ __device__ __forceinline__ uint32_t count_tile(const InView &in, unsigned long l
   return cnt;
 }
 
-template <int G>
+template <int G, bool W32>
 __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr, size_t len, uint16_t *tile_cnt,
                                                                  unsigned long long *chunk_off, uint32_t num_tiles,
                                                                  uint32_t num_chunks, Scratch *scr) {
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr,
       const uint32_t t = chunk * kChunkTiles + i;
       if (t >= num_tiles) break;
       const unsigned long long g0 = (unsigned long long)t * (32ull * G);
-      uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false>(in, g0) : count_tile<G, true>(in, g0);
+      uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
       if (poison) c = 0;
       if (lane == 0) tile_cnt[t] = (uint16_t)c;
       mine += c;
@@ -217,32 +223,45 @@ __device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; st.shared.b16 [%0], l; }" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t bump2(uint32_t addr, uint32_t one) {
   uint32_t r;
   asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(one), "r"(addr));
   return r;
 }
+__device__ __forceinline__ uint32_t bump4(uint32_t addr, uint32_t one) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(r) : "r"(one), "r"(addr));
+  return r;
+}
 
-template <int K, int MINB>
+template <int K, int MINB, bool W32>
 __global__ void __launch_bounds__(kThreads, MINB)
-k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *tile_cnt,
-                   const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
-                   ResultPOD *res) {
-  using Gm = Geom<K>;
+k_utf8_transcode_bp(const char *ptr, size_t len, typename std::conditional<W32, uint32_t, uint16_t>::type *out,
+                    const uint16_t *tile_cnt, const unsigned long long *chunk_off, uint32_t num_tiles,
+                    uint32_t num_chunks, Scratch *scr, ResultPOD *res) {
+  using Gm = Geom<K, W32>;
+  using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
   extern __shared__ __align__(16) uint32_t smem[];
   const InView in = make_view16(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t nwarps = gridDim.x * kWarpsPerCta;
   uint32_t *region_w = smem + (warp * 32u + lane) * Gm::kStrideWords;  // this lane's private staging region
-  uint16_t *region = reinterpret_cast<uint16_t *>(region_w);
+  OutT *region = reinterpret_cast<OutT *>(region_w);
   const bool poison = starts_with_continuation(in);
-  const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) >> 1);
+  const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) / sizeof(OutT));
   const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (see bump2)
 
   for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
     const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;  // virtual byte offsets from in.base
     const unsigned long long r0 = t0 + (unsigned long long)lane * Gm::kRegionBytes;
     const bool interior = t0 >= in.vbeg + 16ull && t0 + Gm::kTileBytes + 16ull <= in.vend;
+    if (tile + nwarps < num_tiles) {  // pull this warp's next tile into L2 while this one is transcoded
+      const char *nx = reinterpret_cast<const char *>(in.base) + r0 + (unsigned long long)nwarps * Gm::kTileBytes;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+    }
 
     // ---- where the tile's units go: chunk offset + counts of the chunk's earlier tiles ----
     const uint32_t chunk = tile / kChunkTiles, in_chunk = tile % kChunkTiles;
@@ -307,7 +326,7 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
 #pragma unroll
       for (int j = 0; j < K; j++) {
         bp::transpose_in(B[j]);
-        uint32_t m = bp::emit16_mask(B[j], prev_l4, next_nc[j]);
+        uint32_t m = W32 ? bp::emit32_mask(B[j], next_nc[j]) : bp::emit16_mask(B[j], prev_l4, next_nc[j]);
         prev_l4 = B[j][7] & B[j][6] & B[j][5] & B[j][4];
         if (!interior) m &= range_mask32(in, r0 + 32ull * j);
         if (poison) m = 0;
@@ -332,7 +351,7 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
       if (lane >= (unsigned)o) incl += t;
     }
     const unsigned long long G = goff + (incl - cnt);               // global index of this lane's first unit
-    const uint32_t a = (uint32_t)((out_units + G) & 7ull);          // its offset inside a 16-byte output vector
+    const uint32_t a = (uint32_t)((out_units + G) & (Gm::kVec - 1u));  // its offset inside a 16-byte output vector
 
     // ---- pass 2: units, compaction into the private region ----
     // The running store address lives in a 32-bit shared-space register; it advances through the multiplier
@@ -343,34 +362,61 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
       if (!ascii_tile) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
-          uint32_t U[16];
-          const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
-          if (err) badblocks |= 1u << j;
-          bp::transpose_out16(U);
           // four independent store chains (positions 0-7, 8-15, 16-23, 24-31): a chain's address register can
           // only advance once the store before it has read it, so one chain alone would serialise the block
           const uint32_t m = em[j];
+          constexpr uint32_t kUB = Gm::kUnitBytes;
           uint32_t s0 = spa;
-          uint32_t s1 = spa + 2u * (uint32_t)__popc(m & 0xFFu);
-          uint32_t s2 = spa + 2u * (uint32_t)__popc(m & 0xFFFFu);
-          uint32_t s3 = spa + 2u * (uint32_t)__popc(m & 0xFFFFFFu);
+          uint32_t s1 = spa + kUB * (uint32_t)__popc(m & 0xFFu);
+          uint32_t s2 = spa + kUB * (uint32_t)__popc(m & 0xFFFFu);
+          uint32_t s3 = spa + kUB * (uint32_t)__popc(m & 0xFFFFFFu);
+          if (W32) {
+            uint32_t C[32];
+            const uint32_t err = bp::utf8_to_utf32_block<true>(B[j], carry, C);
+            if (err) badblocks |= 1u << j;
+            bp::transpose_out21(C);
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            if (m & (1u << i)) {
-              sts_u16(s0, U[i]);
-              s0 = bump2(s0, one);
+            for (int i = 0; i < 8; i++) {
+              if (m & (1u << i)) {
+                sts_u32(s0, C[i]);
+                s0 = bump4(s0, one);
+              }
+              if (m & (1u << (8 + i))) {
+                sts_u32(s1, C[8 + i]);
+                s1 = bump4(s1, one);
+              }
+              if (m & (1u << (16 + i))) {
+                sts_u32(s2, C[16 + i]);
+                s2 = bump4(s2, one);
+              }
+              if (m & (1u << (24 + i))) {
+                sts_u32(s3, C[24 + i]);
+                s3 = bump4(s3, one);
+              }
             }
-            if (m & (1u << (8 + i))) {
-              sts_u16(s1, U[8 + i]);
-              s1 = bump2(s1, one);
-            }
-            if (m & (1u << (16 + i))) {
-              sts_u16(s2, __umulhi(U[i], 65536u));
-              s2 = bump2(s2, one);
-            }
-            if (m & (1u << (24 + i))) {
-              sts_u16(s3, __umulhi(U[8 + i], 65536u));
-              s3 = bump2(s3, one);
+          } else {
+            uint32_t U[16];
+            const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
+            if (err) badblocks |= 1u << j;
+            bp::transpose_out16(U);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (m & (1u << i)) {
+                sts_u16(s0, U[i]);
+                s0 = bump2(s0, one);
+              }
+              if (m & (1u << (8 + i))) {
+                sts_u16(s1, U[8 + i]);
+                s1 = bump2(s1, one);
+              }
+              if (m & (1u << (16 + i))) {
+                sts_u16(s2, __umulhi(U[i], 65536u));
+                s2 = bump2(s2, one);
+              }
+              if (m & (1u << (24 + i))) {
+                sts_u16(s3, __umulhi(U[8 + i], 65536u));
+                s3 = bump2(s3, one);
+              }
             }
           }
           spa = s3;
@@ -382,8 +428,14 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
 #pragma unroll
           for (int p = 0; p < 32; p++) {
             if (m & (1u << p)) {
-              sts_u16(spa, (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu);
-              spa = bump2(spa, one);
+              const uint32_t byte = (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu;
+              if (W32) {
+                sts_u32(spa, byte);
+                spa = bump4(spa, one);
+              } else {
+                sts_u16(spa, byte);
+                spa = bump2(spa, one);
+              }
             }
           }
         }
@@ -408,43 +460,72 @@ k_utf8_to_utf16_bp(const char *ptr, size_t len, uint16_t *out, const uint16_t *t
 
     // ---- staging -> global ----
     {
-      uint16_t *gbase = out + G - a;  // 16-byte aligned
+      OutT *gbase = out + G - a;  // 16-byte aligned
       const uint32_t end = a + cnt;
-      if (__all_sync(kFull, cnt >= 8u)) {
-        // every lane owns the 16-byte vectors that hold its units, except its last partial one (owned by the
-        // lane to its right, which copies the units in front of its own first unit from this lane's tail)
+      if (__all_sync(kFull, cnt >= Gm::kVec)) {
+        // every lane owns the 16-byte vectors that hold its elements, except its last partial one (owned by the
+        // lane to its right, which copies the elements in front of its own first one from this lane's tail;
+        // the source starts on a vector boundary of that region: prev_end = a mod kVec)
         const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
-        if (lane > 0 && a > 0) {
-          const uint16_t *pr = region - 2u * Gm::kStrideWords + prev_end - a;
+        const uint32_t vfull = end / Gm::kVec;
+        uint32_t v0 = 0;
+        if (W32) {
+          if (lane > 0) {
+            const uint32_t *src = region_w - Gm::kStrideWords + (prev_end - a);
 #pragma unroll
-          for (uint32_t u = 0; u < 7; u++)
-            if (u < a) region[u] = pr[u];
-        }
-        uint32_t v = 0;
-        if (lane == 0 && a > 0) {  // the tile's first partial vector: shared with the previous tile
+            for (uint32_t u = 0; u < 3; u++)
+              if (u < a) region_w[u] = src[u];
+          }
+          if (lane == 0 && a > 0) {  // the tile's first partial vector is shared with the previous tile
 #pragma unroll
-          for (uint32_t u = 1; u < 8; u++)
-            if (u >= a) gbase[u] = region[u];
-          v = 1;
-        }
-        const uint32_t vfull = end >> 3;
-        if (lane == 31) {  // the tile's last partial vector: shared with the next tile
+            for (uint32_t u = 1; u < 4; u++)
+              if (u >= a) gbase[u] = region[u];
+            v0 = 1;
+          }
+          if (lane == 31) {  // the tile's last partial vector is shared with the next tile
 #pragma unroll
-          for (uint32_t u = 0; u < 7; u++) {
-            const uint32_t idx = vfull * 8u + u;
-            if (idx < end) gbase[idx] = region[idx];
+            for (uint32_t u = 0; u < 3; u++) {
+              const uint32_t i = vfull * 4u + u;
+              if (i < end) gbase[i] = region[i];
+            }
+          }
+        } else {
+          if (lane > 0) {
+            const uint32_t *src = region_w - Gm::kStrideWords + ((prev_end - a) >> 1);
+#pragma unroll
+            for (uint32_t u = 0; u < 3; u++)
+              if (2u * u + 2u <= a) region_w[u] = src[u];
+            if (a & 1u) region[a - 1u] = reinterpret_cast<const OutT *>(src)[a - 1u];
+          }
+          if (lane == 0 && a > 0) {  // first partial vector of the tile: 2 + 4 + 8 bytes
+            uint32_t i = a;
+            if (i & 1u) { gbase[i] = region[i]; i++; }
+            if (i & 2u) { *reinterpret_cast<uint32_t *>(gbase + i) = region_w[i >> 1]; i += 2u; }
+            if (i == 4u) *reinterpret_cast<uint2 *>(gbase + 4) = make_uint2(region_w[2], region_w[3]);
+            v0 = 1;
+          }
+          if (lane == 31) {  // last partial vector of the tile: 8 + 4 + 2 bytes
+            const uint32_t r = end & 7u;
+            uint32_t i = vfull * 8u;
+            if (r & 4u) { *reinterpret_cast<uint2 *>(gbase + i) = make_uint2(region_w[i >> 1], region_w[(i >> 1) + 1u]); i += 4u; }
+            if (r & 2u) { *reinterpret_cast<uint32_t *>(gbase + i) = region_w[i >> 1]; i += 2u; }
+            if (r & 1u) gbase[i] = region[i];
           }
         }
-        for (; v < vfull; v++) {
-          uint4 x;
-          x.x = region_w[4u * v];
-          x.y = region_w[4u * v + 1u];
-          x.z = region_w[4u * v + 2u];
-          x.w = region_w[4u * v + 3u];
-          stg_stream_v4(reinterpret_cast<uint4 *>(gbase + 8u * v), x);
+        // a lane holds at most 32K + kVec - 1 elements: a fixed, fully predicated sequence with immediate offsets
+#pragma unroll
+        for (uint32_t v = 0; v < Gm::kMaxVec; v++) {
+          if (v >= v0 && v < vfull) {
+            uint4 x;
+            x.x = region_w[4u * v];
+            x.y = region_w[4u * v + 1u];
+            x.z = region_w[4u * v + 2u];
+            x.w = region_w[4u * v + 3u];
+            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, x);
+          }
         }
       } else {
-        // edge tiles and invalid input: unit by unit
+        // edge tiles and invalid input: element by element
         for (uint32_t i = a; i < end; i++) gbase[i] = region[i];
       }
     }
@@ -479,26 +560,31 @@ inline int tuned_k() {
   return v == 3 ? 2 : v;
 }
 inline int tuned_minb16() {
-  static int v = env_int("B200_TUNE_MINB", 1, 4, 2);
+  static int v = env_int("B200_TUNE_MINB", 1, 4, 3);
   return v;
 }
 
-inline size_t tiles16_for(const void *in, size_t len_bytes, int k) {
+inline size_t tiles_for(const void *in, size_t len_bytes, int k) {
   const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
   const size_t per_tile = (size_t)1024 * k;
   return (span + per_tile - 1) / per_tile;
 }
+inline size_t workspace_slots(size_t tiles) {
+  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
+  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
+}
 
-template <int K, int MINB>
-cudaError_t launch_t16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res, size_t tiles) {
-  using Gm = Geom<K>;
+template <int K, int MINB, bool W32>
+cudaError_t launch_bp(const LaunchCtx &c, const char *in, size_t len, void *out, void *res, size_t tiles) {
+  using Gm = Geom<K, W32>;
+  using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
   static int per_sm_emit = 0;
   if (per_sm_emit == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_utf8_to_utf16_bp<K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_utf8_transcode_bp<K, MINB, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Gm::kSmemBytes);
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf8_to_utf16_bp<K, MINB>, kThreads, Gm::kSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf8_transcode_bp<K, MINB, W32>, kThreads, Gm::kSmemBytes);
     if (e != cudaSuccess) return e;
     per_sm_emit = n < 1 ? 1 : n;
   }
@@ -509,15 +595,16 @@ cudaError_t launch_t16(const LaunchCtx &c, const char *in, size_t len, uint16_t 
   {
     const size_t cap = (size_t)c.sm_count * 8;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_utf16_tile_counts<2 * K><<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles,
-                                                               (uint32_t)chunks, c.scratch);
+    k_utf16_tile_counts<2 * K, W32><<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles,
+                                                                    (uint32_t)chunks, c.scratch);
   }
   {
     const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t cap = (size_t)c.sm_count * per_sm_emit;
     const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_utf8_to_utf16_bp<K, MINB><<<grid, kThreads, Gm::kSmemBytes, c.stream>>>(
-        in, len, out, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch, static_cast<ResultPOD *>(res));
+    k_utf8_transcode_bp<K, MINB, W32><<<grid, kThreads, Gm::kSmemBytes, c.stream>>>(
+        in, len, static_cast<OutT *>(out), tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch,
+        static_cast<ResultPOD *>(res));
   }
   count_launch(2);
   return cudaGetLastError();
@@ -526,30 +613,30 @@ cudaError_t launch_t16(const LaunchCtx &c, const char *in, size_t len, uint16_t 
 }  // namespace
 
 // Workspace, in 8-byte descriptor slots, the two kernels need for an input of `len` bytes.
-size_t utf8_to_utf16_tiles(const void *in, size_t len) {
-  const size_t tiles = tiles16_for(in, len, tuned_k());
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
-}
+size_t utf8_to_utf16_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len, tuned_k())); }
+size_t utf8_to_utf32_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len, 2)); }
 
 cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res) {
   const int k = tuned_k();
-  const size_t tiles = tiles16_for(in, len, k);
-  if (utf8_to_utf16_tiles(in, len) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
+  const size_t tiles = tiles_for(in, len, k);
+  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
   const int mb = tuned_minb16();
   switch (k) {
     case 1:
-      if (mb >= 3) return launch_t16<1, 3>(c, in, len, out, res, tiles);
-      return launch_t16<1, 2>(c, in, len, out, res, tiles);
+      return launch_bp<1, 3, false>(c, in, len, out, res, tiles);
     case 4:
-      if (mb == 1) return launch_t16<4, 1>(c, in, len, out, res, tiles);
-      return launch_t16<4, 2>(c, in, len, out, res, tiles);
+      return launch_bp<4, 2, false>(c, in, len, out, res, tiles);
     default:
-      if (mb == 1) return launch_t16<2, 1>(c, in, len, out, res, tiles);
-      if (mb >= 4) return launch_t16<2, 4>(c, in, len, out, res, tiles);
-      if (mb == 3) return launch_t16<2, 3>(c, in, len, out, res, tiles);
-      return launch_t16<2, 2>(c, in, len, out, res, tiles);
+      if (mb <= 2) return launch_bp<2, 2, false>(c, in, len, out, res, tiles);
+      return launch_bp<2, 3, false>(c, in, len, out, res, tiles);
   }
+}
+
+cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res) {
+  const size_t tiles = tiles_for(in, len, 2);
+  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
+  if (tuned_minb16() <= 1) return launch_bp<2, 1, true>(c, in, len, out, res, tiles);
+  return launch_bp<2, 2, true>(c, in, len, out, res, tiles);
 }
 
 }  // namespace b200

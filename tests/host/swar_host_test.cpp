@@ -186,6 +186,7 @@ static void test_utf8_bitplane(const std::vector<uint8_t> &d, unsigned misalign,
   const oracle_result want = oracle_validate_utf8_with_errors(d.data(), len);
   const bool poison = len > 0 && (d[0] & 0xC0) == 0x80;
   std::vector<uint16_t> out;
+  std::vector<uint32_t> out32;
   uint64_t best_pos = ~0ull; int best_code = 0; bool any_flag = false;
   auto at = [&](uint64_t j) -> uint32_t { return d[j]; };
   auto vbyte = [&](uint64_t pos) -> uint32_t { return (pos >= v.vbeg && pos < v.vend) ? v.mem[pos] : 0u; };
@@ -193,6 +194,7 @@ static void test_utf8_bitplane(const std::vector<uint8_t> &d, unsigned misalign,
   for (uint64_t r = 0; r < nregions; r++) {
     const uint64_t r0 = r * region;
     bp::Carry carry = bp::carry_from_word(v.word((long long)(r0 / 4) - 1));
+    bp::Carry carry32 = carry;
     bp::VCarry vc = bp::vcarry_from_word(v.word((long long)(r0 / 4) - 1));
     uint32_t prev_l4 = carry.l4;
     for (int j = 0; j < K; j++) {
@@ -214,6 +216,13 @@ static void test_utf8_bitplane(const std::vector<uint8_t> &d, unsigned misalign,
       prev_l4 = carry.l4;
       bp::transpose_out16(U);
       for (int p = 0; p < 32; p++) if ((em >> p) & 1) out.push_back((uint16_t)(p < 16 ? U[p] : U[p - 16] >> 16));
+      uint32_t em32 = bp::emit32_mask(B, next_nc) & range_mask32(v, b0);
+      if (poison) em32 = 0;
+      uint32_t C[32];
+      const uint32_t err3 = bp::utf8_to_utf32_block<true>(B, carry32, C);
+      CHECK(err3 == err, "utf32 detector differs");
+      bp::transpose_out21(C);
+      for (int p = 0; p < 32; p++) if ((em32 >> p) & 1) out32.push_back(C[p]);
       bool flagged = err != 0;
       if (b0 < v.vend && v.vend <= b0 + 32 && len > 0) {
         uint32_t b1 = d[len - 1], b2 = len >= 2 ? d[len - 2] : 0, b3 = len >= 3 ? d[len - 3] : 0;
@@ -237,10 +246,14 @@ static void test_utf8_bitplane(const std::vector<uint8_t> &d, unsigned misalign,
     std::vector<uint16_t> w16(2 * len + 8);
     oracle_result r16 = oracle_convert_utf8_to_utf16le_with_errors(d.data(), len, w16.data());
     CHECK(out.size() == r16.count && memcmp(out.data(), w16.data(), 2 * r16.count) == 0, "bitplane utf16 output mis=%u K=%d %s", misalign, K, hex(d).c_str());
+    std::vector<uint32_t> w32(len + 8);
+    oracle_result r32 = oracle_convert_utf8_to_utf32_with_errors(d.data(), len, w32.data());
+    CHECK(out32.size() == r32.count && memcmp(out32.data(), w32.data(), 4 * r32.count) == 0, "bitplane utf32 output mis=%u K=%d %s", misalign, K, hex(d).c_str());
   } else {
     CHECK(best_code == want.error && best_pos == want.count, "bitplane error mismatch got (%d,%llu) want (%d,%llu) mis=%u K=%d %s", best_code,
           (unsigned long long)best_pos, want.error, (unsigned long long)want.count, misalign, K, hex(d).c_str());
   }
+  CHECK(out32.size() <= oracle_count_utf8(d.data(), len), "bitplane utf32 overrun");
   CHECK(out.size() <= oracle_utf16_length_from_utf8(d.data(), len), "bitplane overrun %zu > %llu mis=%u %s", out.size(),
         (unsigned long long)oracle_utf16_length_from_utf8(d.data(), len), misalign, hex(d).c_str());
 }
