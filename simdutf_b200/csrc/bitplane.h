@@ -152,26 +152,37 @@ B200_HD void dswap_z(uint32_t &a, uint32_t &b) {
   b = shr_fma<S>(a) & M0;
   a = a2;
 }
-// 21 planes (u[0..20]; u[21..31] are ignored and treated as zero) of a 21-bit value per position -> 32 words, in
-// place: afterwards u[q] = value of position q.  Five exchange stages; pairs of known-zero words are skipped.
-B200_HD void transpose_out21(uint32_t (&u)[32]) {
+// N planes (u[0..N-1]; u[N..31] are ignored and treated as zero, 16 < N <= 24) of an N-bit value per position
+// -> 32 words, in place: afterwards u[q] = value of position q.  Five exchange stages; pairs of known-zero words
+// are skipped, pairs with one known-zero word take the cheap form.
+template <int N>
+B200_HD void transpose_out_n(uint32_t (&u)[32]) {
+  static_assert(N > 16 && N <= 24, "live planes");
+  constexpr int L1 = (N + 1) / 2 * 2, L2 = (L1 + 3) / 4 * 4, L3 = (L2 + 7) / 8 * 8;
+  static_assert(L3 == 24, "stage 3 assumes words 0..23 live");
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < 20; i += 2) dswap<1, 0x55555555u>(u[i], u[i + 1]);
-  dswap_z<1, 0x55555555u>(u[20], u[21]);  // words 0..21 live
+  for (int i = 0; i < N; i += 2) {
+    if (i + 1 < N) dswap<1, 0x55555555u>(u[i], u[i + 1]);
+    else dswap_z<1, 0x55555555u>(u[i], u[i + 1]);
+  }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < 20; i++)
-    if (!(i & 2)) dswap<2, 0x33333333u>(u[i], u[i + 2]);
-  dswap_z<2, 0x33333333u>(u[20], u[22]);
-  dswap_z<2, 0x33333333u>(u[21], u[23]);  // words 0..23 live
+  for (int i = 0; i < L1; i++) {
+    if (i & 2) continue;
+    if (i + 2 < L1) dswap<2, 0x33333333u>(u[i], u[i + 2]);
+    else dswap_z<2, 0x33333333u>(u[i], u[i + 2]);
+  }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < 24; i++)
-    if (!(i & 4)) dswap<4, 0x0F0F0F0Fu>(u[i], u[i + 4]);
+  for (int i = 0; i < L2; i++) {
+    if (i & 4) continue;
+    if (i + 4 < L2) dswap<4, 0x0F0F0F0Fu>(u[i], u[i + 4]);
+    else dswap_z<4, 0x0F0F0F0Fu>(u[i], u[i + 4]);
+  }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -193,6 +204,38 @@ B200_HD void transpose_out21(uint32_t (&u)[32]) {
     u[i + 16] = prmt(a, b, 0x7632);
   }
 }
+B200_HD void transpose_out21(uint32_t (&u)[32]) { transpose_out_n<21>(u); }
+
+// 32 UTF-16 units (w[i] = units 2i, 2i+1) -> 16 planes, in place.  The planes come out in SPLIT order: bit i of a
+// plane belongs to unit 2i, bit 16+i to unit 2i+1 (i = 0..15) — the exact inverse of transpose_out16, which saves
+// the 16 halfword permutes natural order would need.  split_pos() maps a unit index to its bit.
+B200_HD void transpose_in16(uint32_t (&w)[16]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 8; i++) dswap_bytes(w[i], w[i + 8]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i++)
+    if (!(i & 4)) dswap<4, 0x0F0F0F0Fu>(w[i], w[i + 4]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i++)
+    if (!(i & 2)) dswap<2, 0x33333333u>(w[i], w[i + 2]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; i += 2) dswap<1, 0x55555555u>(w[i], w[i + 1]);
+}
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int split_pos(int unit) { return (unit >> 1) + 16 * (unit & 1); }
+// "The unit before" in split order: odd units look at the even unit of the same word, even units at the odd unit of
+// the word before (the first one at the last unit of the previous block, bit 31 of `prev`).
+B200_HD uint32_t split_prev1(uint32_t prev, uint32_t x) { return (x << 16) | ((x >> 15) & 0xFFFEu) | (prev >> 31); }
 
 // The top four positions (28..31) of the planes of a virtual block whose last word is `pw`; the other bits
 // are unspecified (only the top <= 3 bits are ever shifted into the block that follows).
@@ -420,6 +463,74 @@ B200_HD uint32_t utf8_check_block(const uint32_t (&B)[8], VCarry &c) {
   const uint32_t rng = (pe0 & ~B[5]) | (ped & B[5]) | (pf0 & ~B[5] & ~B[4]) | (pf4 & (B[5] | B[4]));
   c.l2 = l2; c.l3 = l3; c.l4 = l4; c.e0 = e0; c.ed = ed; c.f0 = f0; c.f4 = f4;
   return (must ^ cont) | over2 | big | rng;
+}
+
+// ---------------------------------------------------------------------------------------------
+// UTF-16LE -> UTF-8 (reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153; surrogate rule src/scalar/utf16.h:39-67).
+// Planes W[0..15] of 32 units in split order.  Every unit emits 1..3 bytes on its own: ASCII 1, < 0x800 2, other
+// BMP 3, and each half of a surrogate pair 2 (the high surrogate the first two bytes of the 4-byte sequence, the low
+// surrogate the last two, which need the two low bits of the high surrogate: one unit of look-back).
+// X[0..23] = planes of (byte0 | byte1 << 8 | byte2 << 16) per unit; e1 / e2 = units that emit a second / third byte.
+// The detector plane is set where "previous unit is a high surrogate" != "this unit is a low surrogate".
+// ---------------------------------------------------------------------------------------------
+struct Carry16 {
+  uint32_t his, w0, w1;  // previous block: high-surrogate plane and planes 0, 1 (only bit 31 = its last unit is used)
+};
+B200_HD Carry16 carry16_from_unit(uint32_t pu) {
+  Carry16 c;
+  c.his = ((pu & 0xFC00u) == 0xD800u) ? 0x80000000u : 0u;
+  c.w0 = (pu & 1u) << 31;
+  c.w1 = (pu & 2u) << 30;
+  return c;
+}
+B200_HD uint32_t utf16_to_utf8_block(const uint32_t (&W)[16], Carry16 &c, uint32_t (&X)[32], uint32_t &e1, uint32_t &e2) {
+  const uint32_t ge800 = W[11] | W[12] | W[13] | W[14] | W[15];
+  const uint32_t na = ge800 | W[7] | W[8] | W[9] | W[10];                // not ASCII
+  const uint32_t sur = W[15] & W[14] & ~W[13] & W[12] & W[11];
+  const uint32_t his = sur & ~W[10], los = sur & W[10];
+  const uint32_t three = ge800 & ~sur;
+  const uint32_t two = na & ~ge800;
+  const uint32_t p0 = split_prev1(c.w0, W[0]), p1 = split_prev1(c.w1, W[1]);
+  const uint32_t phis = split_prev1(c.his, his);
+  // t = (high surrogate & 0x3FF) + 0x40 = code point >> 10; bits 0..5 are W[0..5]
+  const uint32_t t6 = ~W[6];
+  const uint32_t c6 = W[6];
+  const uint32_t t7 = W[7] ^ c6, c7 = W[7] & c6;
+  const uint32_t t8 = W[8] ^ c7, c8 = W[8] & c7;
+  const uint32_t t9 = W[9] ^ c8, c9 = W[9] & c8;
+  const uint32_t t10 = c9;
+  // first byte
+  X[7] = na;
+  X[6] = (~na & W[6]) | (na & ~los);
+  X[5] = (~na & W[5]) | three | his | (los & p1);
+  X[4] = (~na & W[4]) | (two & W[10]) | his | (los & p0);
+  X[3] = (~na & W[3]) | (two & W[9]) | (three & W[15]) | (los & W[9]);
+  X[2] = (~na & W[2]) | (two & W[8]) | (three & W[14]) | (his & t10) | (los & W[8]);
+  X[1] = (~na & W[1]) | (two & W[7]) | (three & W[13]) | (his & t9) | (los & W[7]);
+  X[0] = (~na & W[0]) | (two & W[6]) | (three & W[12]) | (his & t8) | (los & W[6]);
+  // second byte: 10xxxxxx with x = W[11..6] (three), t[7..2] (high surrogate), W[5..0] (two, low surrogate)
+  X[15] = 0xFFFFFFFFu;
+  X[14] = 0u;
+  X[13] = (three & W[11]) | (his & t7) | (~three & ~his & W[5]);
+  X[12] = (three & W[10]) | (his & t6) | (~three & ~his & W[4]);
+  X[11] = (three & W[9]) | (his & W[5]) | (~three & ~his & W[3]);
+  X[10] = (three & W[8]) | (his & W[4]) | (~three & ~his & W[2]);
+  X[9] = (three & W[7]) | (his & W[3]) | (~three & ~his & W[1]);
+  X[8] = (three & W[6]) | (his & W[2]) | (~three & ~his & W[0]);
+  // third byte: 10 W[5..0]
+  X[23] = 0xFFFFFFFFu;
+  X[22] = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 6; k++) X[16 + k] = W[k];
+  e1 = na;
+  e2 = three;
+  const uint32_t err = phis ^ los;
+  c.his = his;
+  c.w0 = W[0];
+  c.w1 = W[1];
+  return err;
 }
 
 }  // namespace bp

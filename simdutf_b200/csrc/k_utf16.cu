@@ -1,11 +1,10 @@
 // k_utf16.cu — sm_100a kernels whose input is UTF-16LE:
 //   K5  count_utf16le / utf8_length_from_utf16le   (reference src/scalar/utf16.h:69-94)
 //       validate_utf16le_with_errors                (reference src/scalar/utf16.h:39-67)
-//   K6  convert_utf16le_to_utf8[_with_errors]       (reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153)
+// (convert_utf16le_to_utf8 lives in k_utf16_to_utf8.cu)
 //
 // Same data path as k_utf8.cu: 16-byte granules (8 units) loaded with coalesced 128-bit streaming loads,
-// neighbour unit by warp shuffle, one-pass look-back scan for the output offsets, shared-memory staging,
-// 16-byte coalesced stores.  Surrogate verdicts are exact per unit, so the first error is
+// neighbour unit by warp shuffle.  Surrogate verdicts are exact per unit, so the first error is
 // a plain atomicMin of (unit index << 8 | SURROGATE).
 #include "device_common.cuh"
 #include "launch.h"
@@ -137,91 +136,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K6: UTF-16LE -> UTF-8, validating.
-// ---------------------------------------------------------------------------------------------
-template <int ITEMS>
-struct Convert16Smem {
-  static constexpr uint32_t kTileUnits = kBlock * ITEMS * 8;
-  alignas(16) uint8_t out[kTileUnits * 3 + 16];  // at most 3 bytes per unit
-  uint32_t warp_tot[kWarps];
-  uint32_t tile;
-  unsigned long long excl;
-};
-
-template <int ITEMS>
-__global__ void __launch_bounds__(kBlock) k_convert_utf16_to_utf8(const uint16_t *ptr, size_t len, uint8_t *out,
-                                                                  Scratch *scr, unsigned long long *desc,
-                                                                  uint32_t epoch, uint32_t num_tiles, ResultPOD *res) {
-  __shared__ Convert16Smem<ITEMS> sm;
-  const InView in = make_view16(ptr, len);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-
-  while (true) {
-    if (threadIdx.x == 0) sm.tile = atomicAdd(&scr->ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-    if (tile >= num_tiles) break;
-    const unsigned long long g0 = ((unsigned long long)tile * kWarps + warp) * (32ull * ITEMS);
-
-    uint32_t w[ITEMS][4];
-    bool inside[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
-    uint32_t pw[ITEMS], nw[ITEMS];
-    neighbour_words<ITEMS>(in, g0, w, pw, nw);
-
-    uint32_t valid[ITEMS], cnt[ITEMS], off[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-      valid[j] = inside[j] ? 0xFFu : inrange_units(in, g);
-      uint32_t c = 0;
-#pragma unroll
-      for (int i = 0; i < 8; i++) c += ((valid[j] >> i) & 1u) ? u16_utf8_bytes(u16_unit(w[j], i)) : 0u;
-      cnt[j] = c;
-      check_surrogates(in, scr, g, w[j], pw[j], nw[j], valid[j]);
-    }
-    const uint32_t tile_total = block_exclusive_offsets<ITEMS>(cnt, off, sm.warp_tot);
-
-    if (warp == 0) {
-      unsigned long long excl;
-      uint32_t aux;
-      tile_lookback(desc, epoch, tile, tile_total, 0u, excl, aux);
-      if (lane == 0) {
-        sm.excl = excl;
-        if (tile == num_tiles - 1) st_relaxed_u64(&scr->acc0, excl + tile_total);
-      }
-    }
-    __syncthreads();
-    const unsigned long long excl = sm.excl;
-    uint8_t *gdst = out + excl;
-    const uint32_t shift = staging_shift(gdst);
-
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-      uint32_t o = shift + off[j];
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        if (!((valid[j] >> i) & 1u)) continue;
-        const uint32_t u = u16_unit(w[j], i);
-        const uint32_t pu = i == 0 ? (pw[j] >> 16) : u16_unit(w[j], i - 1);
-        u16_emit8_unit(u, pu, [&](uint8_t b) { sm.out[o++] = b; });
-      }
-    }
-    __syncthreads();
-    copy_out_aligned<uint8_t>(sm.out, gdst, shift, tile_total);
-    __syncthreads();
-  }
-
-  if (grid_last_thread(scr)) {
-    write_result_from_key16(res, ld_relaxed_u64(&scr->err_key), ld_relaxed_u64(&scr->acc0));
-    scratch_reset(scr);
-  }
-}
-
 constexpr int kStreamItems = 4;
-constexpr int kConvItems = 4;  // 8192 units per tile, 24 KiB staging
 
 inline unsigned reduction_grid(const LaunchCtx &c, size_t len_bytes, int items) {
   const unsigned long long chunks = (len_bytes + 16 + 511ull * items) / (512ull * items);
@@ -230,16 +145,7 @@ inline unsigned reduction_grid(const LaunchCtx &c, size_t len_bytes, int items) 
   return (unsigned)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
 }
 
-inline size_t tiles_for(const void *in, size_t len_bytes, int items) {
-  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
-  const size_t gran = (span + 15) / 16;
-  const size_t per_tile = (size_t)kBlock * items;
-  return (gran + per_tile - 1) / per_tile;
-}
-
 }  // namespace
-
-size_t utf16_convert_tiles(const void *in, size_t len) { return tiles_for(in, 2 * len, kConvItems); }
 
 cudaError_t launch_count_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode) {
   const unsigned grid = reduction_grid(c, 2 * len, kStreamItems);
@@ -252,22 +158,6 @@ cudaError_t launch_count_utf16le(const LaunchCtx &c, const uint16_t *in, size_t 
 cudaError_t launch_validate_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, void *res) {
   const unsigned grid = reduction_grid(c, 2 * len, kStreamItems);
   k_scan_utf16<2, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, res);
-  count_launch(1);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_convert_utf16le_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res) {
-  const size_t tiles = tiles_for(in, 2 * len, kConvItems);
-  if (tiles > c.desc_capacity || tiles > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_convert_utf16_to_utf8<kConvItems>, kBlock, 0);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  const size_t cap = (size_t)c.sm_count * per_sm;
-  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-  k_convert_utf16_to_utf8<kConvItems><<<grid, kBlock, 0, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), c.scratch,
-                                                                    c.desc, c.epoch, (uint32_t)tiles,
-                                                                    static_cast<ResultPOD *>(res));
   count_launch(1);
   return cudaGetLastError();
 }

@@ -1,0 +1,399 @@
+// k_utf16_to_utf8.cu — sm_100a kernels K6a/K6b: convert_utf16le_to_utf8[_with_errors]
+// (reference include/simdutf/implementation.h:4038-4080; semantics src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153,
+// surrogate rule src/scalar/utf16.h:39-67).
+//
+// Same shape as the UTF-8 -> UTF-16 transcoder (k_utf8_to_utf16.cu):
+//   K6a  k_utf8len_tile_counts   per warp-tile (32 lanes x 32 units = 2 KiB of input) the number of UTF-8 bytes it
+//        emits — utf8_length_from_utf16le restricted to the tile (reference src/scalar/utf16.h:80-94; every unit
+//        contributes on its own, a surrogate counts 2) — then chunk totals -> exclusive chunk offsets.  16-bit-lane
+//        SWAR + popcount, HBM-bound.
+//   K6b  k_utf16_to_utf8_bp      bit-plane transcoder (bitplane.h: utf16_to_utf8_block): every lane transposes its 32
+//        contiguous units into 16 planes, builds the 24 planes of (byte0, byte1, byte2) of every unit, transposes them
+//        back to one 24-bit word per unit and compacts the 1..3 bytes per unit with predicated byte stores into its
+//        private staging region, which it then streams out as 16-byte vectors.
+// First error = minimum over flagged blocks of the exact surrogate verdict.
+#include <cstdlib>
+
+#include "bitplane.h"
+#include "bp_device.cuh"
+#include "device_common.cuh"
+#include "launch.h"
+
+namespace b200 {
+
+namespace {
+
+using bpd::kChunkTiles;
+using bpd::kThreads;
+using bpd::kWarpsPerCta;
+
+constexpr uint32_t kRegionBytes = 64u;                 // 32 units per lane
+constexpr uint32_t kTileBytes = 32u * kRegionBytes;    // 2 KiB per warp
+constexpr uint32_t kTileGranules = kTileBytes / 16u;   // 128
+constexpr uint32_t kStrideWords = ((96u + 16u) / 4u) | 1u;  // <= 96 bytes + 15 bytes of alignment pad, odd stride
+constexpr uint32_t kSmemBytes = kWarpsPerCta * 32u * kStrideWords * 4u;
+constexpr uint32_t kMaxVec = (96u + 15u) / 16u;
+
+__device__ __forceinline__ InView make_view_u16(const uint16_t *p, size_t len_units) {
+  InView v;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
+  v.vbeg = a & 15u;
+  v.vend = v.vbeg + 2ull * len_units;
+  return v;
+}
+
+// Unit at virtual unit index i (from the aligned base); zero outside the buffer.
+__device__ __forceinline__ uint32_t unit_guarded(const InView &in, long long i) {
+  const long long pos = i * 2;
+  if (pos < (long long)in.vbeg || pos >= (long long)in.vend) return 0u;
+  return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(in.base) + i);
+}
+
+// Exact first bad surrogate among virtual units [lo, hi) (reference src/scalar/utf16.h:44-60).
+static __device__ __noinline__ void u16_locate_error(const uint4 *base, unsigned long long vbeg, unsigned long long vend,
+                                                     Scratch *scr, long long lo, long long hi) {
+  InView in;
+  in.base = base;
+  in.vbeg = vbeg;
+  in.vend = vend;
+  const long long first = (long long)(vbeg >> 1), last = (long long)(vend >> 1);  // vbeg is even: units are 2-byte aligned
+  if (lo < first) lo = first;
+  if (hi > last) hi = last;
+  for (long long i = lo; i < hi; i++) {
+    const uint32_t u = unit_guarded(in, i);
+    if ((u & 0xF800u) != 0xD800u) continue;
+    const bool hp = i > first, hn = i + 1 < last;
+    if (u16_bad(u, hp ? unit_guarded(in, i - 1) : 0u, hp, hn ? unit_guarded(in, i + 1) : 0u, hn)) {
+      report_error(scr, err_key((unsigned long long)(i - first), kSurrogate));
+      return;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6a: per-tile byte counts (granule layout: lane l, item j owns granule g0 + 32 j + l)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t count_tile_utf8len(const InView &in, unsigned long long g0) {
+  const unsigned lane = threadIdx.x & 31u;
+  const bool interior = g0 * 16ull >= in.vbeg && (g0 + kTileGranules) * 16ull <= in.vend;
+  uint32_t cnt = 0;
+  if (interior) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = ldg_stream_v4(in.base + g0 + (unsigned long long)j * 32u + lane);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        // per 16-bit lane: bit 15 of ge80 / ge800 / notsur <=> unit >= 0x80 / >= 0x800 / not in D800..DFFF
+        const uint32_t h = w[k] >> 1;
+        const uint32_t ge80 = (h & 0x7FC07FC0u) + 0x7FC07FC0u;
+        const uint32_t ge800 = (h & 0x7C007C00u) + 0x7C007C00u;
+        const uint32_t z = (w[k] ^ 0xD800D800u) & 0xF800F800u;
+        const uint32_t notsur = (z >> 1) + 0x7C007C00u;
+        const uint32_t mk = (ge80 & 0x80008000u) | ((ge800 & notsur & 0x80008000u) >> 1);
+        m |= mk >> (2 * k);
+      }
+      cnt += 8u + (uint32_t)__popc(m);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+      uint32_t w[4];
+      bool inside;
+      load_granule(in, g, w, inside);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const unsigned long long pos = g * 16ull + 2u * i;
+        if (pos >= in.vbeg && pos < in.vend) cnt += u16_utf8_bytes(u16_unit(w, i));
+      }
+    }
+  }
+  return bpd::warp_sum_u32(cnt);
+}
+
+__global__ void __launch_bounds__(kThreads) k_utf8len_tile_counts(const uint16_t *ptr, size_t len, uint16_t *tile_cnt,
+                                                                   unsigned long long *chunk_off, uint32_t num_tiles,
+                                                                   uint32_t num_chunks, Scratch *scr) {
+  const InView in = make_view_u16(ptr, len);
+  bpd::counts_pass([&](uint32_t t) -> uint32_t { return count_tile_utf8len(in, (unsigned long long)t * kTileGranules); },
+                   tile_cnt, chunk_off, num_tiles, num_chunks, scr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6b: bit-plane transcoder
+// ---------------------------------------------------------------------------------------------
+// Bits (split order) of the units of the 64-byte block at virtual byte offset b0 that lie inside the buffer.
+__device__ __forceinline__ uint32_t range_mask_split(const InView &in, unsigned long long b0) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int s = 0; s < 32; s++) {
+    const unsigned long long pos = b0 + 2ull * s;
+    if (pos >= in.vbeg && pos < in.vend) m |= 1u << bp::split_pos(s);
+  }
+  return m;
+}
+
+// Compaction of one block: unit s (stream order) owns bit split_pos(s) of the masks and word split_pos(s) of X.
+// Four independent store chains (units 0-7, 8-15, 16-23, 24-31) so that no chain waits for its own previous store.
+template <bool ALL>
+__device__ __forceinline__ void compact_block(const uint32_t (&X)[32], uint32_t e0, uint32_t e1, uint32_t e2,
+                                              uint32_t base, uint32_t one) {
+  uint32_t s[4];
+  s[0] = base;
+#pragma unroll
+  for (int c = 1; c < 4; c++) {
+    const uint32_t mk = c == 1 ? 0x000F000Fu : c == 2 ? 0x00FF00FFu : 0x0FFF0FFFu;
+    const uint32_t n0 = ALL ? 8u * c : (uint32_t)__popc(e0 & mk);
+    s[c] = base + n0 + (uint32_t)__popc(e1 & mk) + (uint32_t)__popc(e2 & mk);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int p = bp::split_pos(8 * c + i);
+      const uint32_t x = X[p];
+      if (ALL || (e0 & (1u << p))) {
+        bpd::sts_u8(s[c], x);
+        s[c] = bpd::bump<1>(s[c], one);
+      }
+      if (e1 & (1u << p)) {
+        bpd::sts_u8(s[c], __umulhi(x, 1u << 24));
+        s[c] = bpd::bump<1>(s[c], one);
+      }
+      if (e2 & (1u << p)) {
+        bpd::sts_u8(s[c], __umulhi(x, 1u << 16));
+        s[c] = bpd::bump<1>(s[c], one);
+      }
+    }
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_utf16_to_utf8_bp(const uint16_t *ptr, size_t len, uint8_t *out, const uint16_t *tile_cnt,
+                   const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
+                   ResultPOD *res) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const InView in = make_view_u16(ptr, len);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
+  uint32_t *region_w = smem + (warp * 32u + lane) * kStrideWords;  // this lane's private staging region
+  uint8_t *region = reinterpret_cast<uint8_t *>(region_w);
+  const unsigned long long out_addr = (unsigned long long)reinterpret_cast<uintptr_t>(out);
+  const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (bpd::bump)
+  const long long last_unit = (long long)(in.vend >> 1) - 1;  // virtual index of the buffer's last unit
+
+  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
+    const unsigned long long t0 = (unsigned long long)tile * kTileBytes;
+    const unsigned long long r0 = t0 + (unsigned long long)lane * kRegionBytes;
+    const bool interior = t0 >= in.vbeg + 16ull && t0 + kTileBytes + 2ull <= in.vend;  // never the tile of the last unit
+    if (tile + nwarps < num_tiles) {
+      const char *nx = reinterpret_cast<const char *>(in.base) + r0 + (unsigned long long)nwarps * kTileBytes;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+    }
+    uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
+    const unsigned long long coff = chunk_off[tile / kChunkTiles];
+
+    // ---- this lane's 32 contiguous units and the unit before them ----
+    uint32_t W[16];
+    uint32_t pu;
+    if (interior) {
+      const uint4 *gp = in.base + (r0 >> 4);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint4 v = __ldg(gp + j);
+        W[4 * j] = v.x; W[4 * j + 1] = v.y; W[4 * j + 2] = v.z; W[4 * j + 3] = v.w;
+      }
+      pu = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(in.base) + (r0 >> 1) - 1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        bool ins;
+        load_granule(in, (r0 >> 4) + (unsigned long long)j, &W[4 * j], ins);
+      }
+      pu = unit_guarded(in, (long long)(r0 >> 1) - 1);
+    }
+    before = bpd::warp_sum_u32(before);
+    const unsigned long long goff = coff + before;
+
+    uint32_t hi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) hi |= W[i];
+    hi = (hi & 0xFF80FF80u) | (pu & 0xFF80u);
+    const bool ascii_tile = !__any_sync(kFull, hi != 0u);
+
+    uint32_t e0 = 0xFFFFFFFFu, e1 = 0, e2 = 0, err = 0;
+    uint32_t X[32];
+    if (!interior) e0 = range_mask_split(in, r0);
+    if (!ascii_tile) {
+      bp::transpose_in16(W);
+      bp::Carry16 carry = bp::carry16_from_unit(pu);
+      err = bp::utf16_to_utf8_block(W, carry, X, e1, e2);
+      e1 &= e0;
+      e2 &= e0;
+    }
+    const uint32_t cnt = (uint32_t)__popc(e0) + (uint32_t)__popc(e1) + (uint32_t)__popc(e2);
+    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
+    const unsigned long long G = goff + (incl - cnt);        // global index of this lane's first byte
+    const uint32_t a = (uint32_t)((out_addr + G) & 15ull);   // its offset inside a 16-byte output vector
+
+    // ---- bytes, compaction into the private region ----
+    {
+      const uint32_t spa = (uint32_t)__cvta_generic_to_shared(region + a);
+      if (!ascii_tile) {
+        bp::transpose_out_n<24>(X);
+        if (interior) compact_block<true>(X, e0, e1, e2, spa, one);
+        else compact_block<false>(X, e0, e1, e2, spa, one);
+      } else {
+        uint32_t sp = spa;
+#pragma unroll
+        for (int s = 0; s < 32; s++) {
+          if (e0 & (1u << bp::split_pos(s))) {
+            bpd::sts_u8(sp, W[s >> 1] >> (16 * (s & 1)));
+            sp = bpd::bump<1>(sp, one);
+          }
+        }
+      }
+    }
+    // ---- exact error location (rare) ----
+    {
+      const long long u0 = (long long)(r0 >> 1);
+      bool bad = err != 0u;
+      if (!interior && last_unit >= u0 && last_unit < u0 + 32 && in.vend > in.vbeg) {
+        const uint32_t lu = unit_guarded(in, last_unit);
+        bad = bad || (lu & 0xFC00u) == 0xD800u;  // a high surrogate cut off by the end of the buffer
+      }
+      if (bad) u16_locate_error(in.base, in.vbeg, in.vend, scr, u0 - 1, u0 + 32);
+    }
+    __syncwarp();
+
+    // ---- staging -> global ----
+    {
+      uint8_t *gbase = out + G - a;  // 16-byte aligned
+      const uint32_t end = a + cnt;
+      if (__all_sync(kFull, cnt >= 16u)) {
+        // every lane owns the 16-byte vectors that hold its bytes, except its last partial one (owned by the lane to
+        // its right, which copies the bytes in front of its own first one from this lane's tail; that source starts
+        // on a vector boundary of the region: prev_end = a mod 16)
+        const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
+        if (lane > 0) {
+          const uint32_t *src = region_w - kStrideWords + ((prev_end - a) >> 2);
+#pragma unroll
+          for (uint32_t u = 0; u < 3; u++)
+            if (4u * u + 4u <= a) region_w[u] = src[u];
+          uint32_t i = a & ~3u;
+          if (a & 2u) {
+            *reinterpret_cast<uint16_t *>(region + i) = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(src) + i);
+            i += 2u;
+          }
+          if (a & 1u) region[i] = reinterpret_cast<const uint8_t *>(src)[i];
+        }
+        const uint32_t vfull = end >> 4;
+        uint32_t v0 = 0;
+        if (lane == 0 && a > 0) {  // the tile's first partial vector is shared with the previous tile: 1 + 2 + 4 + 8 bytes
+          uint32_t i = a;
+          if (i & 1u) { gbase[i] = region[i]; i++; }
+          if (i & 2u) { *reinterpret_cast<uint16_t *>(gbase + i) = *reinterpret_cast<const uint16_t *>(region + i); i += 2u; }
+          if (i & 4u) { *reinterpret_cast<uint32_t *>(gbase + i) = region_w[i >> 2]; i += 4u; }
+          if (i == 8u) *reinterpret_cast<uint2 *>(gbase + 8) = make_uint2(region_w[2], region_w[3]);
+          v0 = 1;
+        }
+        if (lane == 31) {  // the tile's last partial vector is shared with the next tile: 8 + 4 + 2 + 1 bytes
+          const uint32_t r = end & 15u;
+          uint32_t i = vfull * 16u;
+          if (r & 8u) { *reinterpret_cast<uint2 *>(gbase + i) = make_uint2(region_w[i >> 2], region_w[(i >> 2) + 1u]); i += 8u; }
+          if (r & 4u) { *reinterpret_cast<uint32_t *>(gbase + i) = region_w[i >> 2]; i += 4u; }
+          if (r & 2u) { *reinterpret_cast<uint16_t *>(gbase + i) = *reinterpret_cast<const uint16_t *>(region + i); i += 2u; }
+          if (r & 1u) gbase[i] = region[i];
+        }
+#pragma unroll
+        for (uint32_t v = 0; v < kMaxVec; v++) {
+          if (v >= v0 && v < vfull) {
+            uint4 x;
+            x.x = region_w[4u * v];
+            x.y = region_w[4u * v + 1u];
+            x.z = region_w[4u * v + 2u];
+            x.w = region_w[4u * v + 3u];
+            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, x);
+          }
+        }
+      } else {
+        // edge tiles: byte by byte
+        for (uint32_t i = a; i < end; i++) gbase[i] = region[i];
+      }
+    }
+    __syncwarp();  // the regions are rewritten by the next tile
+  }
+
+  if (grid_last_thread(scr)) {
+    bpd::write_result_from_key(res, ld_relaxed_u64(&scr->err_key), chunk_off[num_chunks]);
+    scratch_reset(scr);
+  }
+}
+
+inline size_t tiles_for(const void *in, size_t len_bytes) {
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
+  return (span + kTileBytes - 1) / kTileBytes;
+}
+inline size_t workspace_slots(size_t tiles) {
+  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
+  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
+}
+
+template <int MINB>
+cudaError_t launch_u16to8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res, size_t tiles) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k_utf16_to_utf8_bp<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf16_to_utf8_bp<MINB>, kThreads, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    per_sm = n < 1 ? 1 : n;
+  }
+  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
+  unsigned long long *chunk_off = c.desc;
+  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.desc + chunks + 1);
+  {
+    const size_t cap = (size_t)c.sm_count * 8;
+    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+    k_utf8len_tile_counts<<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks,
+                                                          c.scratch);
+  }
+  {
+    const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t cap = (size_t)c.sm_count * per_sm;
+    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
+    k_utf16_to_utf8_bp<MINB><<<grid, kThreads, kSmemBytes, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), tile_cnt,
+                                                                      chunk_off, (uint32_t)tiles, (uint32_t)chunks,
+                                                                      c.scratch, static_cast<ResultPOD *>(res));
+  }
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+inline int tuned_minb() {
+  const char *e = getenv("B200_TUNE_MINB");
+  const int v = (e && *e) ? atoi(e) : 0;
+  return (v >= 1 && v <= 4) ? v : 3;
+}
+
+}  // namespace
+
+size_t utf16_convert_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, 2 * len)); }
+
+cudaError_t launch_convert_utf16le_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res) {
+  const size_t tiles = tiles_for(in, 2 * len);
+  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
+  static const int mb = tuned_minb();
+  if (mb <= 2) return launch_u16to8<2>(c, in, len, out, res, tiles);
+  if (mb == 3) return launch_u16to8<3>(c, in, len, out, res, tiles);
+  return launch_u16to8<4>(c, in, len, out, res, tiles);
+}
+
+}  // namespace b200

@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "bitplane.h"
+#include "bp_device.cuh"
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -30,9 +31,11 @@ namespace b200 {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr uint32_t kChunkTiles = 64;  // warp-tiles per chunk (one chunk total / chunk offset)
+using bpd::kChunkTiles;
+using bpd::kThreads;
+using bpd::kWarpsPerCta;
+using bpd::sts_u16;
+using bpd::sts_u32;
 
 // W32 = false: UTF-16LE output (16-bit units, 8 per 16-byte vector); W32 = true: UTF-32 (4 per vector).
 template <int K, bool W32>
@@ -140,70 +143,15 @@ template <int G, bool W32>
 __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr, size_t len, uint16_t *tile_cnt,
                                                                  unsigned long long *chunk_off, uint32_t num_tiles,
                                                                  uint32_t num_chunks, Scratch *scr) {
-  __shared__ uint32_t s_tot[kWarpsPerCta];
-  __shared__ unsigned long long s_warp_sum[kWarpsPerCta];
-  __shared__ unsigned long long s_carry;
-  __shared__ bool s_last;
   const InView in = make_view16(ptr, len);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const bool poison = starts_with_continuation(in);
-  for (uint32_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-    uint32_t mine = 0;
-    for (uint32_t i = warp; i < kChunkTiles; i += kWarpsPerCta) {
-      const uint32_t t = chunk * kChunkTiles + i;
-      if (t >= num_tiles) break;
-      const unsigned long long g0 = (unsigned long long)t * (32ull * G);
-      uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
-      if (poison) c = 0;
-      if (lane == 0) tile_cnt[t] = (uint16_t)c;
-      mine += c;
-    }
-    if (lane == 0) s_tot[warp] = mine;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t tot = 0;
-#pragma unroll
-      for (int k = 0; k < kWarpsPerCta; k++) tot += s_tot[k];
-      chunk_off[chunk] = tot;  // turned into an exclusive offset below
-    }
-    __syncthreads();
-  }
-  // the CTA that finishes last scans the chunk totals (num_chunks is small: 8 Ki per GiB of input at 2 KiB tiles)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(&scr->done, 1u) == gridDim.x - 1;
-    s_carry = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (uint32_t base = 0; base < num_chunks; base += kThreads) {
-    const uint32_t i = base + threadIdx.x;
-    const unsigned long long v = i < num_chunks ? ld_relaxed_u64(chunk_off + i) : 0ull;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= (unsigned)o) incl += t;
-    }
-    if (lane == 31) s_warp_sum[warp] = incl;
-    __syncthreads();
-    unsigned long long before = s_carry;
-#pragma unroll
-    for (int k = 0; k < kWarpsPerCta; k++)
-      if ((unsigned)k < warp) before += s_warp_sum[k];
-    if (i < num_chunks) chunk_off[i] = before + incl - v;
-    __syncthreads();
-    if (threadIdx.x == kThreads - 1) s_carry = before + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    chunk_off[num_chunks] = s_carry;  // grand total
-    scr->done = 0;
-    __threadfence();
-  }
+  bpd::counts_pass(
+      [&](uint32_t t) -> uint32_t {
+        const unsigned long long g0 = (unsigned long long)t * (32ull * G);
+        const uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
+        return poison ? 0u : c;
+      },
+      tile_cnt, chunk_off, num_tiles, num_chunks, scr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -217,24 +165,6 @@ __device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long
   const uint32_t mhi = hi >= 32 ? 0xFFFFFFFFu : ((1u << (unsigned)hi) - 1u);
   const uint32_t mlo = lo >= 32 ? 0xFFFFFFFFu : ((1u << (unsigned)lo) - 1u);
   return mhi & ~mlo;
-}
-
-// 16-bit shared store of the low half of `v` at a 32-bit shared-space address, and address + 2 on the FMA pipe.
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
-  asm volatile("{ .reg .b16 l, h; mov.b32 {l, h}, %1; st.shared.b16 [%0], l; }" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t bump2(uint32_t addr, uint32_t one) {
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(one), "r"(addr));
-  return r;
-}
-__device__ __forceinline__ uint32_t bump4(uint32_t addr, uint32_t one) {
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(r) : "r"(one), "r"(addr));
-  return r;
 }
 
 template <int K, int MINB, bool W32>
@@ -379,19 +309,19 @@ k_utf8_transcode_bp(const char *ptr, size_t len, typename std::conditional<W32, 
             for (int i = 0; i < 8; i++) {
               if (m & (1u << i)) {
                 sts_u32(s0, C[i]);
-                s0 = bump4(s0, one);
+                s0 = bpd::bump<4>(s0, one);
               }
               if (m & (1u << (8 + i))) {
                 sts_u32(s1, C[8 + i]);
-                s1 = bump4(s1, one);
+                s1 = bpd::bump<4>(s1, one);
               }
               if (m & (1u << (16 + i))) {
                 sts_u32(s2, C[16 + i]);
-                s2 = bump4(s2, one);
+                s2 = bpd::bump<4>(s2, one);
               }
               if (m & (1u << (24 + i))) {
                 sts_u32(s3, C[24 + i]);
-                s3 = bump4(s3, one);
+                s3 = bpd::bump<4>(s3, one);
               }
             }
           } else {
@@ -403,19 +333,19 @@ k_utf8_transcode_bp(const char *ptr, size_t len, typename std::conditional<W32, 
             for (int i = 0; i < 8; i++) {
               if (m & (1u << i)) {
                 sts_u16(s0, U[i]);
-                s0 = bump2(s0, one);
+                s0 = bpd::bump<2>(s0, one);
               }
               if (m & (1u << (8 + i))) {
                 sts_u16(s1, U[8 + i]);
-                s1 = bump2(s1, one);
+                s1 = bpd::bump<2>(s1, one);
               }
               if (m & (1u << (16 + i))) {
                 sts_u16(s2, __umulhi(U[i], 65536u));
-                s2 = bump2(s2, one);
+                s2 = bpd::bump<2>(s2, one);
               }
               if (m & (1u << (24 + i))) {
                 sts_u16(s3, __umulhi(U[8 + i], 65536u));
-                s3 = bump2(s3, one);
+                s3 = bpd::bump<2>(s3, one);
               }
             }
           }
@@ -431,10 +361,10 @@ k_utf8_transcode_bp(const char *ptr, size_t len, typename std::conditional<W32, 
               const uint32_t byte = (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu;
               if (W32) {
                 sts_u32(spa, byte);
-                spa = bump4(spa, one);
+                spa = bpd::bump<4>(spa, one);
               } else {
                 sts_u16(spa, byte);
-                spa = bump2(spa, one);
+                spa = bpd::bump<2>(spa, one);
               }
             }
           }

@@ -294,6 +294,62 @@ static void test_utf16(const std::vector<uint16_t> &u, unsigned misalign_units) 
   }
 }
 
+
+// ---- UTF-16 -> UTF-8 through the bit-plane transcoder (bitplane.h; k_utf16_to_utf8.cu) ------------------------
+static void test_utf16_bitplane(const std::vector<uint16_t> &u, unsigned misalign_units) {
+  const size_t len = u.size();
+  View v(reinterpret_cast<const uint8_t *>(u.data()), 2 * len, 2 * misalign_units);
+  auto vunit = [&](long long idx) -> uint32_t {  // virtual unit index (from the aligned base); zero outside
+    long long pos = idx * 2;
+    if (pos < (long long)v.vbeg || pos >= (long long)v.vend) return 0u;
+    return (uint32_t)v.mem[pos] | ((uint32_t)v.mem[pos + 1] << 8);
+  };
+  std::vector<uint8_t> out;
+  uint64_t bad_pos = ~0ull;
+  const uint64_t nblocks = (v.vend + 63) / 64 + 1;
+  for (uint64_t blk = 0; blk < nblocks; blk++) {
+    const long long u0 = (long long)blk * 32;
+    uint32_t W[16];
+    for (int i = 0; i < 16; i++) W[i] = vunit(u0 + 2 * i) | (vunit(u0 + 2 * i + 1) << 16);
+    bp::transpose_in16(W);
+    for (int k = 0; k < 16; k++) for (int s = 0; s < 32; s++)
+      CHECK(((W[k] >> bp::split_pos(s)) & 1) == ((vunit(u0 + s) >> k) & 1), "transpose_in16 plane %d unit %d", k, s);
+    bp::Carry16 c = bp::carry16_from_unit(vunit(u0 - 1));
+    uint32_t X[32], e1, e2;
+    const uint32_t err = bp::utf16_to_utf8_block(W, c, X, e1, e2);
+    bp::transpose_out_n<24>(X);
+    for (int s = 0; s < 32; s++) {
+      const long long pos = (u0 + s) * 2;
+      if (pos < (long long)v.vbeg || pos >= (long long)v.vend) continue;
+      const int p = bp::split_pos(s);
+      out.push_back((uint8_t)X[p]);
+      if ((e1 >> p) & 1) out.push_back((uint8_t)(X[p] >> 8));
+      if ((e2 >> p) & 1) out.push_back((uint8_t)(X[p] >> 16));
+    }
+    bool flagged = err != 0;
+    // a buffer that ends with a high surrogate and has no filler unit behind it inside this block
+    if (len > 0 && (long long)(v.vend / 2) - 1 >= u0 && (long long)(v.vend / 2) - 1 < u0 + 32 && (u[len - 1] & 0xFC00) == 0xD800) flagged = true;
+    if (flagged) {
+      for (long long i = u0 - 1; i < u0 + 32; i++) {
+        const long long pos = i * 2;
+        if (pos < (long long)v.vbeg || pos >= (long long)v.vend) continue;
+        const uint64_t idx = (uint64_t)(pos - (long long)v.vbeg) / 2;
+        const bool hp = idx > 0, hn = idx + 1 < len;
+        if (u16_bad(u[idx], hp ? u[idx - 1] : 0, hp, hn ? u[idx + 1] : 0, hn)) { if (idx < bad_pos) bad_pos = idx; break; }
+      }
+    }
+  }
+  std::vector<uint8_t> want(3 * len + 8);
+  oracle_result r = oracle_convert_utf16le_to_utf8_with_errors(u.data(), len, want.data());
+  CHECK(out.size() == oracle_utf8_length_from_utf16le(u.data(), len), "utf16 bitplane size %zu vs %llu", out.size(), (unsigned long long)oracle_utf8_length_from_utf16le(u.data(), len));
+  if (r.error == 0) {
+    CHECK(bad_pos == ~0ull, "utf16 bitplane false error at %llu", (unsigned long long)bad_pos);
+    CHECK(out.size() == r.count && memcmp(out.data(), want.data(), r.count) == 0, "utf16 bitplane output");
+  } else {
+    CHECK(bad_pos == r.count, "utf16 bitplane error pos got %llu want %llu", (unsigned long long)bad_pos, (unsigned long long)r.count);
+  }
+}
+
 // ---- base64 --------------------------------------------------------------------------------------------
 static void test_b64(const std::vector<uint8_t> &d, uint64_t options, uint64_t last_chunk) {
   const size_t len = d.size();
@@ -417,6 +473,7 @@ int main(int argc, char **argv) {
     test_utf8_bitplane(d, rnd(16), 1 + rnd(4));
     std::vector<uint16_t> u = gen_utf16(rnd(4) ? rnd(60) : rnd(300));
     test_utf16(u, rnd(8));
+    test_utf16_bitplane(u, rnd(8));
     std::vector<uint8_t> b = gen_b64(rnd(4) ? rnd(100) : rnd(400));
     static const uint64_t opts[] = {0, 1, 2, 3, 4, 5, 8, 12};
     test_b64(b, opts[rnd(8)], rnd(3));
