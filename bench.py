@@ -330,7 +330,7 @@ def main():
                 "parallelism": f"shards x{world}",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_utf16_tile_counts + k_utf8_to_utf16_emit (convert_utf8_to_utf16le_with_errors = two launches)",
+                         "traffic": traffic, "kernel": "k_utf16_tile_counts + k_utf8_transcode_bp (convert_utf8_to_utf16le_with_errors = two launches; bit-plane transcoder)",
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg, "peak_source": peak_src,
                          "length_kernel_ms": sum(len_ms) / len(len_ms),
                          "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9},

@@ -52,6 +52,7 @@ int fail(int code, const char *what) {
 struct StreamWs {
   Scratch *scratch = nullptr;
   unsigned long long *desc = nullptr;
+  unsigned long long *cnt = nullptr;
   size_t desc_cap = 0;
   uint32_t epoch = 0;
   void *h_slot = nullptr;  // 64 B pinned + mapped: kernels write results straight into host memory
@@ -164,10 +165,13 @@ int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, Strea
     if (w.desc) {
       B200_CUDA(cudaStreamSynchronize(stream));
       B200_CUDA(cudaFree(w.desc));
+      B200_CUDA(cudaFree(w.cnt));
       w.desc = nullptr;
+      w.cnt = nullptr;
       w.desc_cap = 0;
     }
     B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&w.desc), cap * sizeof(unsigned long long)));
+    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&w.cnt), cap * sizeof(unsigned long long)));
     B200_CUDA(cudaMemsetAsync(w.desc, 0, cap * sizeof(unsigned long long), stream));
     w.desc_cap = cap;
     w.epoch = 0;
@@ -181,6 +185,7 @@ int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, Strea
   }
   lc->scratch = w.scratch;
   lc->desc = w.desc;
+  lc->cnt = w.cnt;
   lc->desc_capacity = w.desc_cap;
   lc->epoch = w.epoch;
   lc->sm_count = c->sm_count;

@@ -220,7 +220,9 @@ __device__ __forceinline__ void tile_lookback(unsigned long long *desc, uint32_t
     unsigned long long d;
     if (idx >= 0) {
       d = ld_relaxed_u64(desc + idx);
-      while (desc_epoch(d) != epoch || desc_status(d) == 0) {
+      // every predecessor was handed out earlier by the ticket, so this wait is short; the cap only keeps a logic
+      // error from hanging the device (the result is then wrong, never silent: callers check the prefix status)
+      for (uint32_t spins = 0; (desc_epoch(d) != epoch || desc_status(d) == 0) && spins < (1u << 24); spins++) {
         __nanosleep(32);
         d = ld_relaxed_u64(desc + idx);
       }

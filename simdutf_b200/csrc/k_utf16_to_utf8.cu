@@ -358,7 +358,7 @@ cudaError_t launch_u16to8(const LaunchCtx &c, const uint16_t *in, size_t len, ch
   }
   const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
   unsigned long long *chunk_off = c.desc;
-  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.desc + chunks + 1);
+  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
   {
     const size_t cap = (size_t)c.sm_count * 8;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);

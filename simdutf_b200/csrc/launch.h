@@ -16,6 +16,8 @@ struct LaunchCtx {
   Scratch *scratch;
   unsigned long long *desc;
   size_t desc_capacity;
+  unsigned long long *cnt;  // second array of desc_capacity slots: per-tile counts (never aliases descriptors, whose
+                            // epoch tags must not be imitated by stale data)
   uint32_t epoch;
   int sm_count;
   cudaStream_t stream;
