@@ -139,6 +139,44 @@ __device__ __forceinline__ uint32_t count_tile(const InView &in, unsigned long l
   return cnt;
 }
 
+// Interior tiles (all bytes and the 16 bytes on either side inside the buffer): the emission count is separable,
+//   #positions p in tile with noncont(p + 1)  =  #noncont in tile - noncont(t0) + noncont(t1)
+//   #positions p in tile with byte(p - 2) >= 0xF0  =  #(>= 0xF0) in tile + [t0-2] + [t0-1] - [t1-2] - [t1-1]
+// so the tile needs two plain popcounts (one packed popc per granule) and a 4-word boundary correction instead of
+// shifted masks.  For valid input the two position sets are disjoint and this equals the transcoder's count; for
+// invalid input it can only be larger (gaps in an output that is unspecified anyway, never an overlap), and the grand
+// total still never exceeds utf16_length_from_utf8 / count_utf8.
+template <int G, bool W32>
+__device__ __forceinline__ uint32_t count_tile_interior(const InView &in, unsigned long long g0) {
+  const unsigned lane = threadIdx.x & 31u;
+  uint4 v[G];
+#pragma unroll
+  for (int j = 0; j < G; j++) v[j] = ldg_stream_v4(in.base + g0 + (unsigned long long)j * 32u + lane);
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(in.base);
+  const unsigned long long t0w = g0 * 4ull, t1w = (g0 + 32ull * G) * 4ull;
+  const uint32_t wa = __ldg(wp + t0w - 1), wb = __ldg(wp + t0w), wc = __ldg(wp + t1w - 1), wd = __ldg(wp + t1w);
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int j = 0; j < G; j++) {
+    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t mk = u8_noncont(w[k]);               // bit 7 of every byte
+      if (!W32) mk |= u8_ge_f0(w[k]) >> 1;          // bit 6
+      m |= mk >> (2 * (3 - k));
+    }
+    cnt += (uint32_t)__popc(m);
+  }
+  cnt = bpd::warp_sum_u32(cnt);
+  cnt += (u8_noncont(wd) >> 7 & 1u) - (u8_noncont(wb) >> 7 & 1u);
+  if (!W32) {
+    const uint32_t fa = u8_ge_f0(wa), fc = u8_ge_f0(wc);
+    cnt += (fa >> 23 & 1u) + (fa >> 31) - (fc >> 23 & 1u) - (fc >> 31);
+  }
+  return cnt;
+}
+
 template <int G, bool W32>
 __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr, size_t len, uint16_t *tile_cnt,
                                                                  unsigned long long *chunk_off, uint32_t num_tiles,
@@ -148,7 +186,9 @@ __global__ void __launch_bounds__(kThreads) k_utf16_tile_counts(const char *ptr,
   bpd::counts_pass(
       [&](uint32_t t) -> uint32_t {
         const unsigned long long g0 = (unsigned long long)t * (32ull * G);
-        const uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
+        const unsigned long long lo = g0 * 16ull, hi = (g0 + 32ull * G) * 16ull;
+        const bool deep = lo >= in.vbeg + 16ull && hi + 16ull <= in.vend;
+        const uint32_t c = deep ? count_tile_interior<G, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
         return poison ? 0u : c;
       },
       tile_cnt, chunk_off, num_tiles, num_chunks, scr);
@@ -527,7 +567,9 @@ k_utf8_transcode_fused(const char *ptr, size_t len, typename std::conditional<W3
         const uint32_t tile = chunk * kChunkTiles + i * kWarpsPerCta + warp;
         if (tile >= num_tiles) break;
         const unsigned long long g0 = (unsigned long long)tile * (32ull * G);
-        uint32_t c = granules_interior<G>(in, g0) ? count_tile<G, false, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
+        const unsigned long long lo = g0 * 16ull, hi = (g0 + 32ull * G) * 16ull;
+        const bool deep = lo >= in.vbeg + 16ull && hi + 16ull <= in.vend;
+        uint32_t c = deep ? count_tile_interior<G, W32>(in, g0) : count_tile<G, true, W32>(in, g0);
         if (poison) c = 0;
         if (lane == 0) tile_cnt[tile] = (uint16_t)c;
         mine += c;

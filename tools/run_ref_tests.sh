@@ -9,5 +9,5 @@ for t in $(ls $D | grep -vE '\.(o|a|so|inc|cpp)$'); do
   timeout 600 $D/$t -a b200 > "$OUT/$t.log" 2>&1
   rc=$?
   end=$(date +%s.%N)
-  printf "%-50s rc=%d %.1fs  %s\n" "$t" "$rc" "$(echo "$end - $start" | bc)" "$(grep -c OK "$OUT/$t.log") OK lines; last: $(tail -n 1 "$OUT/$t.log" | cut -c1-80)"
+  printf "%-50s rc=%d %s\n" "$t" "$rc" "$(grep -c OK "$OUT/$t.log") OK lines; last: $(tail -n 1 "$OUT/$t.log" | cut -c1-80)"
 done
