@@ -149,14 +149,34 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there) must not add to
+    it: keep a private handle to the real stdout and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -196,13 +216,17 @@ def main():
     units = b.utf16_length_from_utf8(d_in)
     d_out = torch.empty(units, dtype=torch.int16, device=device)
     d_cnt = torch.zeros(1, dtype=torch.int64, device=device)
-    d_res = torch.zeros(2, dtype=torch.int64, device=device)  # b200_result {int32 error; pad; uint64 count}
+    # [n, b200_result {int32 error; pad; uint64 count}]: the kernels write the result straight into the buffer that is
+    # all-gathered, so the multi-GPU step adds no copy and no host->device traffic
+    gather_in = torch.zeros(3, dtype=torch.int64, device=device)
+    gather_in[0] = n
+    d_res = gather_in[1:3]
     stream = torch.cuda.current_stream(device)
     sp = ctypes.c_void_p(stream.cuda_stream)
     in_p, out_p = ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr())
     cnt_p, res_p = ctypes.c_void_p(d_cnt.data_ptr()), ctypes.c_void_p(d_res.data_ptr())
-    gather_in = torch.zeros(2, dtype=torch.int64, device=device)
-    gather_out = torch.zeros(2 * world, dtype=torch.int64, device=device)
+    gather_out = torch.zeros(3 * world, dtype=torch.int64, device=device)
+    no_key = torch.full((1,), sharded.NO_ERROR_KEY, dtype=torch.int64, device=device)
     key = torch.zeros(1, dtype=torch.int64, device=device)
 
     def step(ev=None):
@@ -217,11 +241,9 @@ def main():
         if st:
             raise RuntimeError("b200 launch failed: " + lib.b200_last_error().decode())
         if world > 1:  # the sharded path's two collectives, fed from the device-side results (no host sync)
-            gather_in[0] = n
-            gather_in[1] = d_res[1]
             dist.all_gather_into_tensor(gather_out, gather_in)
-            key.copy_(torch.where(d_res[0:1] & 0xFFFFFFFF != 0, (d_res[1:2] << 8) | (d_res[0:1] & 0xFF),
-                                  torch.full_like(key, sharded.NO_ERROR_KEY)))
+            err = d_res[0:1] & 0xFF
+            torch.where(err != 0, (d_res[1:2] << 8) | err, no_key, out=key)
             dist.all_reduce(key, op=dist.ReduceOp.MIN)
 
     # nvidia-smi samples every 200 ms and a step takes ~2 ms: start sampling before the warm-up and keep the GPU
@@ -308,11 +330,11 @@ def main():
     del h_in, h_out
 
     extras = {}
-    if not args.no_extras and rank == 0:
+    if not args.no_extras and rank == 0 and world == 1:
         extras = side_measurements(b, lib, synth, torch, device, stream, sp, peak, K)
 
-    cpu = None
-    if rank == 0:
+    cpu = cpu1 = None
+    if rank == 0 and world == 1:  # the CPU baseline is reported at N = 1 only
         cpu = cpu_reference_run(args.cpu_sample_bytes, os.cpu_count() or 1, 3, 1)
         cpu1 = cpu_reference_run(min(args.cpu_sample_bytes, 128 << 20), 1, 2, 1)
     if rank == 0:
@@ -334,8 +356,8 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg, "peak_source": peak_src,
                          "length_kernel_ms": sum(len_ms) / len(len_ms),
                          "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9},
-            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "cpu_baseline_1thread": {k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "cpu_baseline_1thread": ({k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu1 else None),
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 2 * units + 24,
                     "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers)",
                     "ms_per_step": float(te.item()) * 1e3},
@@ -343,7 +365,7 @@ def main():
             "clocks": clocks,
             "extra": extras,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
