@@ -533,5 +533,88 @@ B200_HD uint32_t utf16_to_utf8_block(const uint32_t (&W)[16], Carry16 &c, uint32
   return err;
 }
 
+// ---------------------------------------------------------------------------------------------
+// base64 (reference src/tables/base64_tables.h:791-849 for the classes, src/scalar/base64.h:33-216 for the decode):
+// planes B[0..7] of 32 characters -> `valid` (the character is a sextet of the selected alphabet), `ws` (ASCII
+// whitespace ' ' \t \n \f \r), and the six planes of the sextet value.  Everything else is an invalid character.
+//   plus_ok / slash_ok select the default alphabet's "+" "/" ; minus_ok / under_ok the URL alphabet's "-" "_"
+//   (all-ones or zero words, uniform for the call; base64_default_or_url sets all four).
+// ---------------------------------------------------------------------------------------------
+struct B64Class {
+  uint32_t valid, ws;
+};
+template <bool VALUES>
+B200_HD B64Class base64_classify(const uint32_t (&B)[8], uint32_t plus_ok, uint32_t slash_ok, uint32_t minus_ok,
+                                 uint32_t under_ok, uint32_t (&S)[6]) {
+  const uint32_t b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7];
+  const uint32_t lo5_nz = b4 | b3 | b2 | b1 | b0;
+  const uint32_t lo5_ge27 = b4 & b3 & (b2 | (b1 & b0));
+  const uint32_t letter = ~b7 & b6 & lo5_nz & ~lo5_ge27;         // 41..5A, 61..7A
+  const uint32_t row2 = ~b7 & ~b6 & b5;                          // 20..3F
+  const uint32_t digit = row2 & b4 & ~(b3 & (b2 | b1));          // 30..39
+  const uint32_t p2 = row2 & ~b4 & b3 & b0;                      // 29, 2B, 2D, 2F
+  const uint32_t plus = p2 & ~b2 & b1;                           // 2B
+  const uint32_t slash = p2 & b2 & b1;                           // 2F
+  const uint32_t minus = p2 & b2 & ~b1;                          // 2D
+  const uint32_t under = ~b7 & b6 & ~b5 & b4 & b3 & b2 & b1 & b0;  // 5F
+  const uint32_t space = row2 & ~(b4 | b3 | b2 | b1 | b0);       // 20
+  const uint32_t ctl = ~(b7 | b6 | b5 | b4) & b3;                // 08..0F
+  const uint32_t wsc = ctl & ((~b2 & (b1 ^ b0)) | (b2 & ~b1));   // 09, 0A, 0C, 0D
+  const uint32_t c62 = (plus & plus_ok) | (minus & minus_ok);
+  const uint32_t c63 = (slash & slash_ok) | (under & under_ok);
+  B64Class c;
+  c.valid = letter | digit | c62 | c63;
+  c.ws = space | wsc;
+  if (VALUES) {
+    const uint32_t upper = letter & ~b5, lower = letter & b5;
+    // d = low5 - 1 (upper: 0..25)
+    const uint32_t d0 = ~b0, r0 = ~b0;
+    const uint32_t d1 = b1 ^ r0, r1 = ~b1 & r0;
+    const uint32_t d2 = b2 ^ r1, r2 = ~b2 & r1;
+    const uint32_t d3 = b3 ^ r2, r3 = ~b3 & r2;
+    const uint32_t d4 = b4 ^ r3;
+    // s = d + 26 (lower: 26..51); 26 = 011010b
+    const uint32_t s0 = d0;
+    const uint32_t s1 = ~d1, k1 = d1;
+    const uint32_t s2 = d2 ^ k1, k2 = d2 & k1;
+    const uint32_t s3 = ~(d3 ^ k2), k3 = d3 | k2;
+    const uint32_t s4 = ~(d4 ^ k3), k4 = d4 | k3;
+    const uint32_t s5 = k4;
+    // g = low4 + 52 (digit: 52..61): 110100b + n, n <= 9
+    const uint32_t g2 = ~b2, g3 = b3 | b2;
+    const uint32_t hi = digit | c62 | c63;  // values >= 52 have bits 5 and 4 set
+    S[0] = (upper & d0) | (lower & s0) | (digit & b0) | c63;
+    S[1] = (upper & d1) | (lower & s1) | (digit & b1) | c62 | c63;
+    S[2] = (upper & d2) | (lower & s2) | (digit & g2) | c62 | c63;
+    S[3] = (upper & d3) | (lower & s3) | (digit & g3) | c62 | c63;
+    S[4] = (upper & d4) | (lower & s4) | hi;
+    S[5] = (lower & s5) | hi;
+  }
+  return c;
+}
+
+// 8 planes (u[k] = plane k of a byte per position; planes that are zero cost the same) -> 32 bytes, in place:
+// afterwards u[i] = bytes 4i..4i+3.  The exact inverse of transpose_in.
+B200_HD void transpose_out8(uint32_t (&u)[8]) {
+  uint32_t e0 = u[0], e1 = u[1], e2 = u[2], e3 = u[3];
+  uint32_t o0 = u[4], o1 = u[5], o2 = u[6], o3 = u[7];
+  dswap<1, 0x55555555u>(e0, e1);
+  dswap<1, 0x55555555u>(e2, e3);
+  dswap<1, 0x55555555u>(o0, o1);
+  dswap<1, 0x55555555u>(o2, o3);
+  dswap<2, 0x33333333u>(e0, e2);
+  dswap<2, 0x33333333u>(e1, e3);
+  dswap<2, 0x33333333u>(o0, o2);
+  dswap<2, 0x33333333u>(o1, o3);
+  dswap<4, 0x0F0F0F0Fu>(e0, o0);
+  dswap<4, 0x0F0F0F0Fu>(e1, o1);
+  dswap<4, 0x0F0F0F0Fu>(e2, o2);
+  dswap<4, 0x0F0F0F0Fu>(e3, o3);
+  tr4x4(e0, e1, e2, e3);
+  tr4x4(o0, o1, o2, o3);
+  u[0] = e0; u[2] = e1; u[4] = e2; u[6] = e3;
+  u[1] = o0; u[3] = o1; u[5] = o2; u[7] = o3;
+}
+
 }  // namespace bp
 }  // namespace b200

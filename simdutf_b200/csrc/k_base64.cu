@@ -3,18 +3,22 @@
 //   last_chunk_handling_options value (reference src/generic/base64.h:40-246, src/scalar/base64.h:33-216,
 //   src/tables/base64_tables.h:791-849).
 //
-// One launch, one pass over HBM:
-//   1. each thread classifies its 16-byte granules through a 256-entry class table in shared memory
-//      (built by the CTA from swar.h:b64_class — 0..63 sextet, 64 whitespace, 255 invalid);
-//   2. valid characters are counted, block-scanned, and their sextets compacted into shared memory
-//      (this is where whitespace disappears);
-//   3. the tile's sextet count goes through the decoupled look-back scan, which also carries the last
-//      sextet seen so far (descriptor `aux`), so a 4-sextet quantum may straddle any number of tiles;
-//   4. output byte b of the stream is made of sextets r = 4*(b/3) + b%3 and r+1; the tile that owns sextet
-//      r+1 writes it — with 16-byte coalesced stores through the same staging scheme as the transcoders;
-//   5. the first invalid character is an atomicMin on its index; the CTA that finishes last strips the
-//      trailing whitespace / '=' (block-cooperative backward scan), fetches the last <= 3 sextet
-//      characters and applies the last-chunk and padding rules (swar.h:b64_finish).
+// Two streaming kernels of independent warps, same shape as the UTF transcoders:
+//   K7a  k_b64_tile_counts   per warp-tile (32 lanes x 64 characters) the number of sextet characters, in bit-plane
+//        form (bitplane.h: base64_classify, ~45 bitwise instructions per 32 characters instead of a table lookup
+//        per character); chunk totals -> exclusive chunk offsets by the CTA that finishes last.
+//   K7b  k_b64_decode_bp     classifies again, builds the six planes of the sextet value, transposes them back to
+//        one byte per character and compacts the sextets (this is where whitespace disappears) into the warp's
+//        staging region at their rank modulo the tile; the <= 3 sextets in front of the tile that complete its
+//        first 4-sextet quantum are fetched by scanning the input backwards.  A quantum belongs to the tile that
+//        holds its last sextet; lanes pack one quantum (4 sextets -> 3 bytes) each into the warp's output staging
+//        region, laid out so that its 16-byte vectors coincide with 16-byte-aligned output addresses, and the warp
+//        streams the vectors out.
+//   The first invalid character is an atomicMin on its index; the CTA that finishes last strips the trailing
+//   whitespace / '=' (block-cooperative backward scan), fetches the last <= 3 sextet characters and applies the
+//   last-chunk and padding rules (swar.h:b64_finish).
+#include "bitplane.h"
+#include "bp_device.cuh"
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -22,17 +26,17 @@ namespace b200 {
 
 namespace {
 
-constexpr int kItems = 4;                          // 16 KiB of text per tile
-constexpr uint32_t kTileChars = kBlock * kItems * 16;
+using bpd::kChunkTiles;
+using bpd::kWarpsPerCta;
+
+constexpr uint32_t kTileChars = 32u * 64u;                 // 2 KiB of text per warp-tile, 64 characters per lane
+constexpr uint32_t kSxBytes = kTileChars + 16u;           // sextet staging: <= 3 carried + 2048 + slack
+constexpr uint32_t kOutBytes = kTileChars / 4u * 3u + 48u;  // output staging: <= 15 of alignment + 1536 + 2 + slack
 
 struct B64Smem {
-  alignas(16) uint8_t sx[kTileChars + 16];         // sx[0] = carry-in sextet, sx[1+k] = k-th sextet of the tile
-  alignas(16) uint8_t out[kTileChars / 4 * 3 + 48];
+  alignas(16) uint8_t sx[kWarpsPerCta][kSxBytes];
+  alignas(16) uint8_t out[kWarpsPerCta][kOutBytes];
   uint8_t lut[256];
-  uint32_t warp_tot[kWarps];
-  uint32_t tile;
-  uint32_t carry;
-  unsigned long long excl;
   unsigned long long found;  // 1 + index, 0 = none
   int is_last;
 };
@@ -69,106 +73,208 @@ __device__ long long block_find_last(const uint8_t *p, long long end, bool sexte
   return -1;
 }
 
-__global__ void __launch_bounds__(kBlock) k_base64_decode(const char *ptr, size_t len, uint8_t *out, Scratch *scr,
-                                                          unsigned long long *desc, uint32_t epoch,
-                                                          uint32_t num_tiles, uint32_t opt_url, uint32_t opt_both,
-                                                          uint32_t opt_garbage, unsigned long long last_chunk,
-                                                          FullResultPOD *res) {
+// Planes of the 32 characters at virtual byte offset b0 (zero filler outside the buffer).
+template <bool INTERIOR>
+__device__ __forceinline__ void load_block32(const InView &in, unsigned long long b0, uint32_t (&B)[8]) {
+  if (INTERIOR) {
+    const uint4 *gp = in.base + (b0 >> 4);
+    const uint4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
+    B[0] = v0.x; B[1] = v0.y; B[2] = v0.z; B[3] = v0.w;
+    B[4] = v1.x; B[5] = v1.y; B[6] = v1.z; B[7] = v1.w;
+  } else {
+    bool ins;
+    load_granule(in, b0 >> 4, &B[0], ins);
+    load_granule(in, (b0 >> 4) + 1ull, &B[4], ins);
+  }
+}
+__device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long long b0) {
+  long long lo = (long long)in.vbeg - (long long)b0, hi = (long long)in.vend - (long long)b0;
+  lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
+  hi = hi < 0 ? 0 : (hi > 32 ? 32 : hi);
+  const uint32_t mhi = hi >= 32 ? 0xFFFFFFFFu : ((1u << (unsigned)hi) - 1u);
+  const uint32_t mlo = lo >= 32 ? 0xFFFFFFFFu : ((1u << (unsigned)lo) - 1u);
+  return mhi & ~mlo;
+}
+
+struct B64Opts {
+  uint32_t plus_ok, slash_ok, minus_ok, under_ok;  // all-ones / zero words
+};
+
+// ---------------------------------------------------------------------------------------------
+// K7a: sextet characters per tile
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_b64_tile_counts(const char *ptr, size_t len, uint16_t *tile_cnt,
+                                                             unsigned long long *chunk_off, uint32_t num_tiles,
+                                                             uint32_t num_chunks, B64Opts o, Scratch *scr) {
+  const InView in = make_view(ptr, len);
+  const unsigned lane = threadIdx.x & 31u;
+  bpd::counts_pass(
+      [&](uint32_t t) -> uint32_t {
+        const unsigned long long t0 = (unsigned long long)t * kTileChars, r0 = t0 + lane * 64ull;
+        const bool interior = t0 >= in.vbeg && t0 + kTileChars <= in.vend;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          uint32_t B[8], S[6];
+          if (interior) load_block32<true>(in, r0 + 32ull * j, B);
+          else load_block32<false>(in, r0 + 32ull * j, B);
+          bp::transpose_in(B);
+          uint32_t v = bp::base64_classify<false>(B, o.plus_ok, o.slash_ok, o.minus_ok, o.under_ok, S).valid;
+          if (!interior) v &= range_mask32(in, r0 + 32ull * j);
+          cnt += (uint32_t)__popc(v);
+        }
+        return bpd::warp_sum_u32(cnt);
+      },
+      tile_cnt, chunk_off, num_tiles, num_chunks, scr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7b: decode
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 3) k_b64_decode_bp(const char *ptr, size_t len, uint8_t *out, Scratch *scr,
+                                                             const uint16_t *tile_cnt,
+                                                             const unsigned long long *chunk_off, uint32_t num_tiles,
+                                                             uint32_t num_chunks, B64Opts o, uint32_t opt_url,
+                                                             uint32_t opt_both, uint32_t opt_garbage,
+                                                             unsigned long long last_chunk, FullResultPOD *res) {
   __shared__ B64Smem sm;
   const InView in = make_view(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   sm.lut[threadIdx.x] = (uint8_t)b64_class(threadIdx.x, opt_url != 0, opt_both != 0);
   __syncthreads();
+  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
+  const uint32_t one = blockDim.x >> 8;  // 1, opaque to the assembler (bpd::bump)
+  uint8_t *sx = sm.sx[warp];
+  uint8_t *so = sm.out[warp];
+  const unsigned long long V_total = chunk_off[num_chunks];  // written by the counts pass
 
-  while (true) {
-    if (threadIdx.x == 0) sm.tile = atomicAdd(&scr->ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-    if (tile >= num_tiles) break;
-    const unsigned long long g0 = ((unsigned long long)tile * kWarps + warp) * (32ull * kItems);
+  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
+    const unsigned long long t0 = (unsigned long long)tile * kTileChars, r0 = t0 + lane * 64ull;
+    const bool interior = t0 >= in.vbeg && t0 + kTileChars <= in.vend;
+    if (tile + nwarps < num_tiles) {
+      const char *nx = reinterpret_cast<const char *>(in.base) + r0 + (unsigned long long)nwarps * kTileChars;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+    }
+    const uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
+    const unsigned long long coff = chunk_off[tile / kChunkTiles];
 
-    uint32_t w[kItems][4];
-    bool inside[kItems];
+    // ---- classify, sextet planes, counts ----
+    uint32_t S[2][8], V[2];
+    uint32_t cnt = 0;
 #pragma unroll
-    for (int j = 0; j < kItems; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
-
-    // ---- classify: per granule a 16-bit "is sextet" mask, the sextet values overwrite w ---------
-    uint32_t vmask[kItems], cnt[kItems], off[kItems];
-#pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-      uint32_t valid = 0, badm = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        uint32_t cls = 0;
-#pragma unroll
-        for (int b = 0; b < 4; b++) cls |= (uint32_t)sm.lut[(w[j][k] >> (8 * b)) & 0xFFu] << (8 * b);
-        w[j][k] = cls;
-        // class <= 63 <=> bits 6,7 clear ; class == 255 <=> bit 7 set
-        const uint32_t is_sx = ~(cls | (cls << 1)) & kH;
-        valid |= mask4(is_sx) << (4 * k);
-        badm |= mask4(cls & kH) << (4 * k);
+    for (int j = 0; j < 2; j++) {
+      uint32_t B[8], Sv[6];
+      if (interior) load_block32<true>(in, r0 + 32ull * j, B);
+      else load_block32<false>(in, r0 + 32ull * j, B);
+      bp::transpose_in(B);
+      const bp::B64Class c = bp::base64_classify<true>(B, o.plus_ok, o.slash_ok, o.minus_ok, o.under_ok, Sv);
+      uint32_t v = c.valid, bad = ~(c.valid | c.ws);
+      if (!interior) {
+        const uint32_t r = range_mask32(in, r0 + 32ull * j);
+        v &= r;
+        bad &= r;
       }
-      if (!inside[j]) {
-        uint32_t r = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) r |= mask4(inrange_mask_word(in, g, k)) << (4 * k);
-        valid &= r;
-        badm &= r;
-      }
-      vmask[j] = valid;
-      cnt[j] = (uint32_t)__popc(valid);
-      if (badm && !opt_garbage) {
-        const unsigned long long pos = g * 16ull + (unsigned)(__ffs((int)badm) - 1) - in.vbeg;
+      if (bad && !opt_garbage) {
+        const unsigned long long pos = r0 + 32ull * j + (unsigned)(__ffs((int)bad) - 1) - in.vbeg;
         const unsigned long long key = err_key(pos, kInvalidBase64Character);
         if (key < ld_relaxed_u64(&scr->err_key)) report_error(scr, key);
       }
+#pragma unroll
+      for (int k = 0; k < 6; k++) S[j][k] = Sv[k];
+      S[j][6] = 0u;
+      S[j][7] = 0u;
+      V[j] = v;
+      cnt += (uint32_t)__popc(v);
     }
-    const uint32_t tile_total = block_exclusive_offsets<kItems>(cnt, off, sm.warp_tot);
+    const unsigned long long goff = coff + bpd::warp_sum_u32(before);  // rank of the tile's first sextet
+    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    const uint32_t pad = (uint32_t)(goff & 3ull);  // sextets of the tile's first quantum that precede the tile
 
-    // ---- compact the sextets of this tile -------------------------------------------------------
+    // ---- compact the sextets: sx[i] = sextet of rank 4 * (goff / 4) + i ----
+    {
+      uint32_t spa = (uint32_t)__cvta_generic_to_shared(sx) + pad + (incl - cnt);
 #pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      uint32_t o = 1u + off[j];
+      for (int j = 0; j < 2; j++) {
+        bp::transpose_out8(S[j]);  // S[j][w] = sextets of characters 4w..4w+3, one per byte
+        const uint32_t m = V[j];
+        uint32_t s[4];
+        s[0] = spa;
+        s[1] = spa + (uint32_t)__popc(m & 0xFFu);
+        s[2] = spa + (uint32_t)__popc(m & 0xFFFFu);
+        s[3] = spa + (uint32_t)__popc(m & 0xFFFFFFu);
 #pragma unroll
-      for (int p = 0; p < 16; p++) {
-        if ((vmask[j] >> p) & 1u) sm.sx[o++] = (uint8_t)((w[j][p >> 2] >> (8 * (p & 3))) & 0x3Fu);
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int p = 8 * c + i;
+            if (m & (1u << p)) {
+              const uint32_t w = S[j][p >> 2];
+              const uint32_t b = (p & 3) == 0 ? w : __umulhi(w, 1u << (32 - 8 * (p & 3)));
+              bpd::sts_u8(s[c], b);
+              s[c] = bpd::bump<1>(s[c], one);
+            }
+          }
+        }
+        spa += (uint32_t)__popc(m);
       }
     }
-    __syncthreads();
-
-    // ---- look-back: global rank of the tile's first sextet + the sextet just before it ----------
-    if (warp == 0) {
-      unsigned long long excl;
-      uint32_t aux;
-      const uint32_t my_last = tile_total ? sm.sx[tile_total] : 0u;
-      tile_lookback(desc, epoch, tile, tile_total, my_last, excl, aux);
-      if (lane == 0) {
-        sm.excl = excl;
-        sm.sx[0] = (uint8_t)aux;
-        if (tile == num_tiles - 1) st_relaxed_u64(&scr->acc0, excl + tile_total);
+    if (lane == 0 && pad) {  // the sextets just before the tile: scan the input backwards (whitespace is skipped)
+      uint32_t need = pad;
+      const uint8_t *p8 = reinterpret_cast<const uint8_t *>(in.base);
+      for (long long pos = (long long)t0 - 1; need && pos >= (long long)in.vbeg; pos--) {
+        const uint32_t cls = sm.lut[p8[pos]];
+        if (cls <= 63u) sx[--need] = (uint8_t)cls;
       }
     }
-    __syncthreads();
-    const unsigned long long R0 = sm.excl;
-    const unsigned long long B0 = b64_bytes_from_sextets(R0);
-    const uint32_t nbytes = (uint32_t)(b64_bytes_from_sextets(R0 + tile_total) - B0);
-    uint8_t *gdst = out + B0;
-    const uint32_t shift = staging_shift(gdst);
-    const uint32_t m0 = (uint32_t)(R0 & 3ull);
-    const uint32_t b0m = m0 ? m0 - 1u : 0u;
+    __syncwarp();
 
-    // ---- pack: output byte t of this tile = sextets (k, k+1), k = 4*((b0m+t)/3) + (b0m+t)%3 - m0 ----
-    for (uint32_t t = threadIdx.x; t < nbytes; t += kBlock) {
-      const uint32_t a = b0m + t;
-      const uint32_t q = a / 3u, m = a - 3u * q;
-      const uint32_t k1 = 4u * q + m + 1u - m0;  // index into sx of the first sextet (sx[0] is rank R0-1)
-      const uint32_t s0 = sm.sx[k1], s1 = sm.sx[k1 + 1u];
-      sm.out[shift + t] = (uint8_t)((s0 << (2u + 2u * m)) | (s1 >> (4u - 2u * m)));
+    // ---- pack: one quantum (4 sextets -> 3 bytes) per lane and round ----
+    const unsigned long long q0 = goff >> 2;
+    const uint32_t have = pad + total;
+    const uint32_t nq = have >> 2;
+    // the tile that holds the stream's last sextet also emits the 1 or 2 bytes of a trailing partial quantum
+    const bool is_last = total > 0u && goff + total == V_total;
+    const uint32_t xb = (is_last && (have & 3u) >= 2u) ? (have & 3u) - 1u : 0u;
+    const uint32_t nb = 3u * nq + xb;                       // output bytes of this tile
+    uint8_t *gdst = out + 3ull * q0;                        // where they go
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+    {
+      const uint32_t *sx32 = reinterpret_cast<const uint32_t *>(sx);
+      const uint32_t so_a = (uint32_t)__cvta_generic_to_shared(so) + mis;
+      for (uint32_t j = lane; j < nq + (xb ? 1u : 0u); j += 32u) {
+        const uint32_t w = sx32[j] & 0x3F3F3F3Fu;
+        const uint32_t t1 = ((w & 0x00FF00FFu) << 6) + ((w >> 8) & 0x00FF00FFu);  // s0:s1 | s2:s3, 12 bits each
+        const uint32_t x = ((t1 & 0xFFFFu) << 12) | (t1 >> 16);                   // 24 bits
+        const uint32_t a = so_a + 3u * j;
+        const uint32_t lim = j < nq ? 3u : xb;
+        bpd::sts_u8(a, x >> 16);
+        if (lim > 1u) bpd::sts_u8(a + 1u, x >> 8);
+        if (lim > 2u) bpd::sts_u8(a + 2u, x);
+      }
     }
-    __syncthreads();
-    copy_out_aligned<uint8_t>(sm.out, gdst, shift, nbytes);
-    __syncthreads();
+    __syncwarp();
+
+    // ---- staging -> global: vector v of the staging region is vector v of the 16-byte-aligned destination ----
+    {
+      uint8_t *gbase = gdst - mis;
+      const uint32_t end = mis + nb;
+      const uint32_t nvec = (end + 15u) >> 4;
+      const uint4 *sv = reinterpret_cast<const uint4 *>(so);
+      for (uint32_t v = lane; v < nvec; v += 32u) {
+        const bool full = (v > 0u || mis == 0u) && 16u * v + 16u <= end;
+        if (full) {
+          stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, sv[v]);
+        } else {
+#pragma unroll
+          for (uint32_t t = 0; t < 16u; t++) {
+            const uint32_t e = 16u * v + t;
+            if (e >= mis && e < end) gbase[e] = so[e];
+          }
+        }
+      }
+    }
+    __syncwarp();  // the staging regions are rewritten by the next tile
   }
 
   // ---- epilogue by the CTA that finishes last -----------------------------------------------------
@@ -201,7 +307,7 @@ __global__ void __launch_bounds__(kBlock) k_base64_decode(const char *ptr, size_
     }
   }
   const unsigned long long key = ld_relaxed_u64(&scr->err_key);
-  const unsigned long long V = ld_relaxed_u64(&scr->acc0);
+  const unsigned long long V = V_total;
   const bool invalid = key != kNoError && (key >> 8) < srclen;
   uint32_t tail_val[3] = {0, 0, 0};
   uint64_t tail_pos[3] = {0, 0, 0};
@@ -238,33 +344,53 @@ __global__ void __launch_bounds__(kBlock) k_base64_decode(const char *ptr, size_
 
 inline size_t tiles_for(const void *in, size_t len_bytes) {
   const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
-  const size_t gran = (span + 15) / 16;
-  const size_t per_tile = (size_t)kBlock * kItems;
-  return (gran + per_tile - 1) / per_tile;
+  return (span + kTileChars - 1) / kTileChars;
+}
+inline size_t workspace_slots(size_t tiles) {
+  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
+  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
 }
 
 }  // namespace
 
-size_t base64_tiles(const void *in, size_t len) { return tiles_for(in, len); }
+size_t base64_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len)); }
 
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
                                     uint64_t last_chunk, void *full_res) {
   const size_t tiles = tiles_for(in, len);
-  if (tiles > c.desc_capacity || tiles > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_base64_decode, kBlock, 0);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  const size_t cap = (size_t)c.sm_count * per_sm;
-  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_b64_decode_bp, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    per_sm = n < 1 ? 1 : n;
+  }
   // reference include/simdutf/implementation.h:2782-2800 and src/scalar/base64.h:66-69
   const uint32_t url = (options & 1u) ? 1u : 0u;
   const uint32_t both = (options & 8u) ? 1u : 0u;
   const uint32_t garbage = (options == 4u || options == 5u || options == 12u) ? 1u : 0u;
-  k_base64_decode<<<grid, kBlock, 0, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), c.scratch, c.desc, c.epoch,
-                                                 (uint32_t)tiles, url, both, garbage, last_chunk,
-                                                 static_cast<FullResultPOD *>(full_res));
-  count_launch(1);
+  B64Opts o;
+  o.plus_ok = o.slash_ok = (both || !url) ? 0xFFFFFFFFu : 0u;
+  o.minus_ok = o.under_ok = (both || url) ? 0xFFFFFFFFu : 0u;
+  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
+  unsigned long long *chunk_off = c.desc;
+  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
+  {
+    const size_t cap = (size_t)c.sm_count * 8;
+    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+    k_b64_tile_counts<<<grid, kBlock, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, o,
+                                                    c.scratch);
+  }
+  {
+    const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t cap = (size_t)c.sm_count * per_sm;
+    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
+    k_b64_decode_bp<<<grid, kBlock, 0, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), c.scratch, tile_cnt, chunk_off,
+                                                  (uint32_t)tiles, (uint32_t)chunks, o, url, both, garbage, last_chunk,
+                                                  static_cast<FullResultPOD *>(full_res));
+  }
+  count_launch(2);
   return cudaGetLastError();
 }
 

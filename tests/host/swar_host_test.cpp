@@ -401,6 +401,32 @@ static void test_b64(const std::vector<uint8_t> &d, uint64_t options, uint64_t l
         (unsigned long long)in_count, (unsigned long long)out_count, r.error, (unsigned long long)r.input_count, (unsigned long long)r.output_count, hex(d).c_str());
 }
 
+
+// ---- base64 classification / sextet values in bit-plane form (bitplane.h; k_base64.cu) -------------------------
+static void test_b64_bitplane(const std::vector<uint8_t> &d, uint64_t options) {
+  const bool url = options & 1, both = options & 8;
+  const uint32_t plus_ok = (both || !url) ? ~0u : 0u, minus_ok = (both || url) ? ~0u : 0u;
+  for (size_t b0 = 0; b0 < d.size(); b0 += 32) {
+    uint32_t B[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint8_t raw[32] = {0};
+    for (size_t i = 0; i < 32 && b0 + i < d.size(); i++) raw[i] = d[b0 + i];
+    memcpy(B, raw, 32);
+    bp::transpose_in(B);
+    uint32_t S[6];
+    const bp::B64Class c = bp::base64_classify<true>(B, plus_ok, plus_ok, minus_ok, minus_ok, S);
+    uint32_t U[8] = {S[0], S[1], S[2], S[3], S[4], S[5], 0, 0};
+    bp::transpose_out8(U);
+    uint8_t sx[32];
+    memcpy(sx, U, 32);
+    for (int p = 0; p < 32; p++) {
+      const uint32_t cls = b64_class(raw[p], url, both);
+      CHECK(((c.valid >> p) & 1) == (cls <= 63), "b64 plane valid byte %02x opt %llu", raw[p], (unsigned long long)options);
+      CHECK(((c.ws >> p) & 1) == (cls == 64), "b64 plane ws byte %02x", raw[p]);
+      if (cls <= 63) CHECK(sx[p] == cls, "b64 plane value byte %02x got %u want %u", raw[p], sx[p], cls);
+    }
+  }
+}
+
 // ---- generators ----------------------------------------------------------------------------------------
 static const uint8_t kSpecial[] = {0x20, 0x41, 0x7F, 0x80, 0x8F, 0x90, 0x9F, 0xA0, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1, 0xF3, 0xF4, 0xF5, 0xF7, 0xF8, 0xFF};
 static void push_cp(std::vector<uint8_t> &o, uint32_t cp) {
@@ -477,6 +503,8 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> b = gen_b64(rnd(4) ? rnd(100) : rnd(400));
     static const uint64_t opts[] = {0, 1, 2, 3, 4, 5, 8, 12};
     test_b64(b, opts[rnd(8)], rnd(3));
+    test_b64_bitplane(b, opts[rnd(8)]);
+    if (it < 256) { std::vector<uint8_t> all(256); for (int i = 0; i < 256; i++) all[i] = (uint8_t)(i + it); test_b64_bitplane(all, opts[it & 7]); }
     if (failures > 50) break;
   }
   // known-answer edge cases
