@@ -240,38 +240,67 @@ __global__ void __launch_bounds__(kBlock, 3) k_b64_decode_bp(const char *ptr, si
     uint8_t *gdst = out + 3ull * q0;                        // where they go
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
     {
-      const uint32_t *sx32 = reinterpret_cast<const uint32_t *>(sx);
-      const uint32_t so_a = (uint32_t)__cvta_generic_to_shared(so) + mis;
-      for (uint32_t j = lane; j < nq + (xb ? 1u : 0u); j += 32u) {
-        const uint32_t w = sx32[j] & 0x3F3F3F3Fu;
-        const uint32_t t1 = ((w & 0x00FF00FFu) << 6) + ((w >> 8) & 0x00FF00FFu);  // s0:s1 | s2:s3, 12 bits each
-        const uint32_t x = ((t1 & 0xFFFFu) << 12) | (t1 >> 16);                   // 24 bits
-        const uint32_t a = so_a + 3u * j;
-        const uint32_t lim = j < nq ? 3u : xb;
-        bpd::sts_u8(a, x >> 16);
-        if (lim > 1u) bpd::sts_u8(a + 1u, x >> 8);
-        if (lim > 2u) bpd::sts_u8(a + 2u, x);
+      // four quanta per lane and round: 16 sextets (one 128-bit load) -> 12 bytes (three 32-bit stores); staging byte
+      // 3 j + k is byte k of quantum j; whatever is packed beyond `nb` bytes is never copied out
+      const uint4 *sx128 = reinterpret_cast<const uint4 *>(sx);
+      uint32_t *so32 = reinterpret_cast<uint32_t *>(so);
+      const uint32_t ngroups = (nq + (xb ? 1u : 0u) + 3u) >> 2;
+      for (uint32_t g = lane; g < ngroups; g += 32u) {
+        const uint4 q = sx128[g];
+        // (& 0x3F: the sextets past the end of a trailing partial quantum are stale staging bytes)
+        const uint32_t w[4] = {q.x & 0x3F3F3F3Fu, q.y & 0x3F3F3F3Fu, q.z & 0x3F3F3F3Fu, q.w & 0x3F3F3F3Fu};
+        uint32_t y[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t t1 = (w[k] & 0x00FF00FFu) * 64u + ((w[k] >> 8) & 0x00FF00FFu);  // s0:s1 | s2:s3, 12 bits each
+          const uint32_t x = (t1 & 0xFFFFu) * 4096u + (t1 >> 16);                       // 24 bits, first byte on top
+          y[k] = __byte_perm(x, 0u, 0x4012);                                             // first byte lowest
+        }
+        so32[3u * g] = __byte_perm(y[0], y[1], 0x4210);
+        so32[3u * g + 1u] = __byte_perm(y[1], y[2], 0x5421);
+        so32[3u * g + 2u] = __byte_perm(y[2], y[3], 0x6542);
       }
     }
     __syncwarp();
 
-    // ---- staging -> global: vector v of the staging region is vector v of the 16-byte-aligned destination ----
+    // ---- staging -> global.  Destination coordinates e are relative to gbase = gdst - mis (16-byte aligned): the
+    // data occupies [mis, end); full vectors are funnel-shifted out of the staging words, the partial first and
+    // last vectors are written bytewise by lanes 0-15 and 16-31.
     {
       uint8_t *gbase = gdst - mis;
       const uint32_t end = mis + nb;
-      const uint32_t nvec = (end + 15u) >> 4;
+      const uint32_t v_lo = (mis + 15u) >> 4, v_hi = end >> 4;
+      const uint32_t sh = (16u - mis) & 15u;            // staging byte offset of destination vector v is 16 v - mis
+      const uint32_t wsel = sh >> 2;                    // = 16 (v - 1) + sh for v >= 1
+      const uint32_t psel = 0x3210u + 0x1111u * (sh & 3u);
       const uint4 *sv = reinterpret_cast<const uint4 *>(so);
-      for (uint32_t v = lane; v < nvec; v += 32u) {
-        const bool full = (v > 0u || mis == 0u) && 16u * v + 16u <= end;
-        if (full) {
-          stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, sv[v]);
+      for (uint32_t v = v_lo + lane; v < v_hi; v += 32u) {
+        uint4 o;
+        if (mis == 0u) {
+          o = sv[v];
         } else {
-#pragma unroll
-          for (uint32_t t = 0; t < 16u; t++) {
-            const uint32_t e = 16u * v + t;
-            if (e >= mis && e < end) gbase[e] = so[e];
+          const uint4 lo = sv[v - 1u], hi = sv[v];
+          uint32_t t0, t1, t2, t3, t4;
+          switch (wsel) {  // warp-uniform
+            case 0: t0 = lo.x; t1 = lo.y; t2 = lo.z; t3 = lo.w; t4 = hi.x; break;
+            case 1: t0 = lo.y; t1 = lo.z; t2 = lo.w; t3 = hi.x; t4 = hi.y; break;
+            case 2: t0 = lo.z; t1 = lo.w; t2 = hi.x; t3 = hi.y; t4 = hi.z; break;
+            default: t0 = lo.w; t1 = hi.x; t2 = hi.y; t3 = hi.z; t4 = hi.w; break;
           }
+          o.x = __byte_perm(t0, t1, psel);
+          o.y = __byte_perm(t1, t2, psel);
+          o.z = __byte_perm(t2, t3, psel);
+          o.w = __byte_perm(t3, t4, psel);
         }
+        stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, o);
+      }
+      const uint32_t head_end = 16u * v_lo < end ? 16u * v_lo : end;
+      if (lane < 16u) {
+        const uint32_t e = mis + lane;
+        if (e < head_end) gbase[e] = so[lane];
+      } else if (v_hi >= v_lo) {
+        const uint32_t e = 16u * v_hi + (lane - 16u);
+        if (e >= mis && e < end) gbase[e] = so[e - mis];
       }
     }
     __syncwarp();  // the staging regions are rewritten by the next tile
