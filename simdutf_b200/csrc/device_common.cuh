@@ -1,6 +1,6 @@
 // device_common.cuh — sm_100a building blocks shared by the kernels: guarded 16-byte streaming loads,
-// warp/block scans, the single-pass decoupled look-back tile scan, the first-error key, coalesced
-// copy-out of a shared-memory staging buffer, and the "last CTA finalises" epilogue.
+// warp reductions, the single-pass decoupled look-back scan over epoch-tagged descriptors, the first-error key,
+// and the "last CTA finalises" epilogue.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -144,44 +144,6 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
-// Exclusive offsets, in element order (warp, item, lane), of per-thread per-item counts c[j] <= 2047.
-// Returns the tile total.  `s_warp` is kWarps uint32 of shared memory.  Contains two __syncthreads().
-template <int ITEMS>
-__device__ __forceinline__ uint32_t block_exclusive_offsets(const uint32_t (&c)[ITEMS], uint32_t (&off)[ITEMS],
-                                                            uint32_t *s_warp) {
-  static_assert(ITEMS % 2 == 0, "ITEMS must be even");
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t run = 0;  // sum of the totals of items < j in this warp
-#pragma unroll
-  for (int j = 0; j < ITEMS; j += 2) {
-    uint32_t packed = c[j] | (c[j + 1] << 16);  // two 16-bit lanes; 32 lanes * 2047 < 65536
-    uint32_t incl = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= (unsigned)o) incl += t;
-    }
-    const uint32_t tot = __shfl_sync(kFull, incl, 31);
-    off[j] = run + (incl & 0xFFFFu) - c[j];
-    run += tot & 0xFFFFu;
-    off[j + 1] = run + (incl >> 16) - c[j + 1];
-    run += tot >> 16;
-  }
-  if (lane == 0) s_warp[warp] = run;
-  __syncthreads();
-  uint32_t base = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; w++) {
-    const uint32_t t = s_warp[w];
-    if ((unsigned)w < warp) base += t;
-    total += t;
-  }
-#pragma unroll
-  for (int j = 0; j < ITEMS; j++) off[j] += base;
-  __syncthreads();  // s_warp may be reused by the caller
-  return total;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Single-pass chained scan with decoupled look-back over tile descriptors.
 //   descriptor = epoch:12 | status:2 | aux:6 | value:44   (one 64-bit word -> single-copy atomic)
@@ -245,34 +207,6 @@ __device__ __forceinline__ void tile_lookback(unsigned long long *desc, uint32_t
   excl = sum;
   excl_aux = aux;
   if (lane == 0) st_relaxed_u64(desc + tile, desc_pack(epoch, kStatusPrefix, agg ? agg_aux : aux, sum + agg));
-}
-
-// ---------------------------------------------------------------------------------------------
-// Coalesced copy-out of `n` elements staged in shared memory at s[shift .. shift+n) to global
-// g[0 .. n), where shift = (address of g[0] / sizeof(T)) mod (16/sizeof(T)) so that 16-byte vectors
-// of the staging buffer line up with 16-byte-aligned global addresses.  s must be 16-byte aligned.
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ uint32_t staging_shift(const T *g) {
-  return (uint32_t)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) % (16 / sizeof(T)));
-}
-template <typename T>
-__device__ __forceinline__ void copy_out_aligned(const T *s, T *g, uint32_t shift, uint32_t n) {
-  constexpr uint32_t EPV = 16 / sizeof(T);
-  const uint32_t nvec = (shift + n + EPV - 1) / EPV;
-  T *gbase = g - shift;  // 16-byte aligned by construction
-  for (uint32_t v = threadIdx.x; v < nvec; v += kBlock) {
-    const uint32_t e0 = v * EPV;
-    if (e0 >= shift && e0 + EPV <= shift + n) {
-      stg_stream_v4(reinterpret_cast<uint4 *>(gbase + e0), *reinterpret_cast<const uint4 *>(s + e0));
-    } else {
-#pragma unroll
-      for (uint32_t e = 0; e < EPV; e++) {
-        const uint32_t i = e0 + e;
-        if (i >= shift && i < shift + n) gbase[i] = s[i];
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
