@@ -349,6 +349,56 @@ def test_base64_large_with_whitespace(b, oracle):
         run_b64(b, oracle, cand, options=1 if url else 0, host_too=False)
 
 
+def test_bitplane_edge_paths(b, oracle):
+    """Paths the bit-plane kernels take only on unusual inputs: all-ASCII tiles next to non-ASCII ones, lanes that
+    emit fewer than one vector (unit-by-unit copy-out), a buffer that starts with a continuation byte, UTF-16
+    buffers that end with a high surrogate exactly at a tile edge, base64 tiles that are all whitespace (the
+    backward carry scan crosses them) or hold 1-3 sextets."""
+    rng = random.Random(77)
+    # UTF-8: ASCII runs of tile size glued to mixed text, at every alignment class
+    for it in range(12):
+        parts = []
+        for _ in range(6):
+            parts.append(bytes(rng.randrange(0x20, 0x7f) for _ in range(rng.choice([1, 63, 64, 2047, 2048, 2049, 4100]))))
+            parts.append(rand_text(rng, rng.choice([1, 5, 700, 3000])))
+        run_utf8(b, oracle, b"".join(parts), misalign=rng.randrange(16), host_too=(it == 0))
+    # invalid from the first byte / nothing but continuation bytes / long runs of them inside valid text
+    run_utf8(b, oracle, b"\x80" + rand_text(rng, 5000), misalign=1, host_too=False)
+    run_utf8(b, oracle, b"\x80" * 10000, misalign=7, host_too=False)
+    run_utf8(b, oracle, b"\xbf" * 3 + b"abc", host_too=False)
+    t = bytearray(rand_text(rng, 9000))
+    t[5000:9000] = b"\x80" * 4000
+    run_utf8(b, oracle, bytes(t), misalign=9, host_too=False)
+    run_utf8(b, oracle, rand_text(rng, 3000) + b"\xf0\x9f\x98", misalign=2, host_too=False)
+    # 4-byte characters only (two units per character), 3-byte only, 2-byte only: regular strides
+    for ch in ("\U0001F600", "\u4e2d", "\u00e9", "a"):
+        run_utf8(b, oracle, (ch * 9001).encode(), misalign=rng.randrange(16), host_too=False)
+    # UTF-16: ASCII tiles, pairs only, a high surrogate as the very last unit at / around a 1024-unit tile edge
+    for n in (1023, 1024, 1025, 2048, 4096):
+        for mis in (0, 3):
+            u = np.array([rng.randrange(0x20, 0x7f) for _ in range(n)], dtype=np.uint16)
+            run_utf16(b, oracle, u, misalign=mis, host_too=False)
+            u2 = u.copy(); u2[-1] = 0xD83D
+            run_utf16(b, oracle, u2, misalign=mis, host_too=False)
+            u3 = u.copy(); u3[0] = 0xDC00
+            run_utf16(b, oracle, u3, misalign=mis, host_too=False)
+    pairs = np.array([0xD83D, 0xDE00] * 3000, dtype=np.uint16)
+    run_utf16(b, oracle, pairs, misalign=1, host_too=False)
+    run_utf16(b, oracle, np.array([0x4E2D] * 5000, dtype=np.uint16), misalign=5, host_too=False)
+    # base64: whitespace deserts between sextets, sextets sprinkled one per tile, whitespace only
+    for opt in (0, 1, 4):
+        for lc in (0, 1, 2):
+            d = b"QUJD" + b" " * 9000 + b"R" + b"\n" * 5000 + b"EVG" + b"\r\n" * 3000 + b"R0g="
+            run_b64(b, oracle, d, opt, lc, misalign=rng.randrange(16), host_too=False)
+            run_b64(b, oracle, b" \t\r\n" * 3000, opt, lc, host_too=False)
+            sparse = bytearray(b" " * 20000)
+            for k, q in enumerate(range(100, 20000, 2100)):
+                sparse[q] = ABC[k % 62]
+            run_b64(b, oracle, bytes(sparse), opt, lc, misalign=3, host_too=False)
+            dense = bytes(rng.choice(ABC[:62]) for _ in range(8190)) + rng.choice([b"", b"A", b"AA", b"AA=", b"A=="])
+            run_b64(b, oracle, dense, opt, lc, misalign=rng.randrange(16), host_too=False)
+
+
 def test_repeated_calls_and_epoch_wrap(b, oracle):
     """More than 4096 scan launches on one stream: the 12-bit descriptor epoch wraps and must be handled."""
     from simdutf_b200 import synth
