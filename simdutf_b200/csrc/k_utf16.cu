@@ -107,12 +107,35 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size
 #pragma unroll
       for (int j = 0; j < ITEMS; j++) {
         const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-        const uint32_t valid = inside[j] ? 0xFFu : inrange_units(in, g);
+        if (inside[j]) {
+          // 16-bit-lane SWAR: bit 15 of a lane <=> the predicate holds for that unit; the four words of the granule
+          // share one popcount (POPC issues at a quarter of the logic rate: one per word made the kernel POPC-bound)
+          uint32_t m = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const uint32_t u = u16_unit(w[j], i);
-          const uint32_t c = MODE == 0 ? (uint32_t)((u & 0xFC00u) != 0xDC00u) : u16_utf8_bytes(u);
-          cnt += ((valid >> i) & 1u) ? c : 0u;
+          for (int k = 0; k < 4; k++) {
+            const uint32_t x = w[j][k];
+            if (MODE == 0) {
+              const uint32_t z = (x ^ 0xDC00DC00u) & 0xFC00FC00u;         // zero lane <=> low surrogate
+              const uint32_t notlow = (z >> 1) + 0x7E007E00u;
+              m |= (notlow & 0x80008000u) >> k;
+            } else {
+              const uint32_t h = x >> 1;
+              const uint32_t ge80 = (h & 0x7FC07FC0u) + 0x7FC07FC0u;
+              const uint32_t ge800 = (h & 0x7C007C00u) + 0x7C007C00u;
+              const uint32_t z = (x ^ 0xD800D800u) & 0xF800F800u;         // zero lane <=> surrogate
+              const uint32_t notsur = (z >> 1) + 0x7C007C00u;
+              m |= ((ge80 & 0x80008000u) | ((ge800 & notsur & 0x80008000u) >> 1)) >> (2 * k);
+            }
+          }
+          cnt += (MODE == 0 ? 0u : 8u) + (uint32_t)__popc(m);
+        } else {
+          const uint32_t valid = inrange_units(in, g);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const uint32_t u = u16_unit(w[j], i);
+            const uint32_t c = MODE == 0 ? (uint32_t)((u & 0xFC00u) != 0xDC00u) : u16_utf8_bytes(u);
+            cnt += ((valid >> i) & 1u) ? c : 0u;
+          }
         }
       }
       total += cnt;

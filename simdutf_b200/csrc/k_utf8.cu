@@ -156,15 +156,26 @@ __global__ void __launch_bounds__(kBlock) k_count_utf8(const char *ptr, size_t l
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
       const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+      if (inside[j]) {
+        // the masks of the four words share one popcount: word k's bits move down by 2 (3 - k) (MODE 1: bits 7 and 6
+        // of every byte are in use) or by (3 - k) (MODE 0: bit 7 only)
+        uint32_t m = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        uint32_t m = u8_noncont(w[j][k]);
-        if (MODE == 1) m |= u8_ge_f0(w[j][k]) >> 1;  // bit 6 of the same byte: one popc counts both
-        if (!inside[j]) {
-          const uint32_t r = inrange_mask_word(in, g, k);
-          m &= r | (r >> 1);
+        for (int k = 0; k < 4; k++) {
+          uint32_t mk = u8_noncont(w[j][k]);
+          if (MODE == 1) mk |= u8_ge_f0(w[j][k]) >> 1;
+          m |= mk >> ((MODE == 1 ? 2 : 1) * (3 - k));
         }
         cnt += (uint32_t)__popc(m);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint32_t m = u8_noncont(w[j][k]);
+          if (MODE == 1) m |= u8_ge_f0(w[j][k]) >> 1;  // bit 6 of the same byte: one popc counts both
+          const uint32_t r = inrange_mask_word(in, g, k);
+          m &= r | (r >> 1);
+          cnt += (uint32_t)__popc(m);
+        }
       }
     }
     total += cnt;
