@@ -1,4 +1,2 @@
-python tools/sanitize_smoke.py 2>&1 | tail -2
-for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|error" gpurun_out/sanitizer_$tool.log | head -8
-done
+for mb in 3; do echo "K=2 MINB=$mb: $(B200_TUNE_K=2 B200_TUNE_MINB=$mb python tools/prof_one.py convert16 1073741824 5 2>&1 | tail -n 1)"; done
+python tools/prof_one.py convert32 1073741824 5 2>&1 | tail -n 1
