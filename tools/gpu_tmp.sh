@@ -1,2 +1,2 @@
-for mb in 3; do echo "K=2 MINB=$mb: $(B200_TUNE_K=2 B200_TUNE_MINB=$mb python tools/prof_one.py convert16 1073741824 5 2>&1 | tail -n 1)"; done
-python tools/prof_one.py convert32 1073741824 5 2>&1 | tail -n 1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_" -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-extras --e2e-steps 1 --cpu-sample-bytes 33554432 > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+wc -l gpurun_out/launches.csv; tail -3 gpurun_out/ncu_bench.log
