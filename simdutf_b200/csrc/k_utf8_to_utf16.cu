@@ -364,6 +364,26 @@ __device__ __forceinline__ void transcode_tile(const InView &in, typename std::c
       cnt += (uint32_t)__popc(m);
     }
     lane_offsets();
+    if (interior && !poison && a == 0u) {
+      // every lane emits exactly 32K elements and the tile's output is vector-aligned (a is the same in all lanes:
+      // 32K is a multiple of the vector size): widen in registers and store straight to global memory
+      uint4 *gv = reinterpret_cast<uint4 *>(out + G);
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t w = B[j][k];
+          if (W32) {
+            stg_stream_v4(gv + 8 * j + k, make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24));
+          } else if ((k & 1) == 0) {
+            const uint32_t w1 = B[j][k + 1];
+            stg_stream_v4(gv + 4 * j + (k >> 1), make_uint4(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342),
+                                                             __byte_perm(w1, 0u, 0x4140), __byte_perm(w1, 0u, 0x4342)));
+          }
+        }
+      }
+      return;  // warp-uniform; nothing staged, no errors possible in an all-ASCII interior tile
+    }
     uint32_t spa = (uint32_t)__cvta_generic_to_shared(region + a);
 #pragma unroll
     for (int j = 0; j < K; j++) {

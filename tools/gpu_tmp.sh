@@ -1,2 +1,3 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_" -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-extras --e2e-steps 1 --cpu-sample-bytes 33554432 > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
-wc -l gpurun_out/launches.csv; tail -3 gpurun_out/ncu_bench.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "utf8 or golden or config2 or repeated or edge" 2>&1 | tail -3
+python tools/prof_texts.py 2>&1 | head -2
+python tools/prof_one.py convert16 1073741824 5 2>&1 | tail -n 1
