@@ -132,6 +132,37 @@ def cpu_reference_run(sample_bytes: int, threads: int, steps: int, warmup: int, 
             "ms_per_step": sec * 1e3, "bytes": n}
 
 
+def threaded_cpp_run(sample_bytes: int, seed: int = 2):
+    """The reference's own benchmarks/threaded.cpp, compiled as is into oracle/_ref/threaded (oracle/Makefile), on a
+    file dump of the config-2 sample: convert_utf8_to_utf16le on one thread and split over two (its hard-wired
+    design, reference benchmarks/threaded.cpp:36-94).  Returns None when the binary is absent."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "threaded")
+    if not os.path.exists(exe):
+        return None
+    import tempfile
+    import torch
+    from simdutf_b200 import synth
+    data = synth.mixed_utf8(sample_bytes, seed=seed, device=torch.device("cpu")).numpy()
+    n = int(data.size)
+    with tempfile.NamedTemporaryFile(suffix=".utf8", delete=False) as f:
+        f.write(data.tobytes())
+        path = f.name
+    try:
+        p = subprocess.run([exe, path], capture_output=True, text=True, timeout=300)
+    finally:
+        os.unlink(path)
+    ns = {}
+    for line in p.stdout.splitlines():
+        for key in ("singlethread", "doublethread"):
+            if line.startswith(key + ":"):
+                ns[key] = float(line.split(":")[1])
+    if len(ns) != 2:
+        return None
+    return {"single_thread_gbs": n / ns["singlethread"], "two_threads_gbs": n / ns["doublethread"], "unit": "GB/s",
+            "kind": "reference", "what": "benchmarks/threaded.cpp as is: convert_utf8_to_utf16le only (no length query)",
+            "sample": f"{n} bytes of the config-2 mixed UTF-8 distribution (seed {seed}) from a file"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -333,10 +364,11 @@ def main():
     if not args.no_extras and rank == 0 and world == 1:
         extras = side_measurements(b, lib, synth, torch, device, stream, sp, peak, K)
 
-    cpu = cpu1 = None
+    cpu = cpu1 = cpu_thr = None
     if rank == 0 and world == 1:  # the CPU baseline is reported at N = 1 only
         cpu = cpu_reference_run(args.cpu_sample_bytes, os.cpu_count() or 1, 3, 1)
         cpu1 = cpu_reference_run(min(args.cpu_sample_bytes, 128 << 20), 1, 2, 1)
+        cpu_thr = threaded_cpp_run(min(args.cpu_sample_bytes, 64 << 20))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -353,11 +385,14 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_utf16_tile_counts + k_utf8_transcode_bp (convert_utf8_to_utf16le_with_errors = two launches; bit-plane transcoder)",
-                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg,
+                         "best_launch_ms": min(conv_ms), "median_launch_ms": statistics.median(conv_ms),
+                         "peak_source": peak_src,
                          "length_kernel_ms": sum(len_ms) / len(len_ms),
                          "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cpu_baseline_1thread": ({k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu1 else None),
+            "cpu_baseline_threaded_cpp": cpu_thr,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 2 * units + 24,
                     "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers)",
                     "ms_per_step": float(te.item()) * 1e3},
