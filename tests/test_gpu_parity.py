@@ -485,6 +485,46 @@ def test_config2_mixed_1gib_roundtrip(b, oracle):
     check_guard(out, units_bad)
 
 
+def test_beyond_4gib_offsets(b, oracle):
+    """5 GiB of mixed UTF-8 on one GPU (config 5 gives one GPU up to 16 GiB): input offsets beyond 2^32 bytes, more
+    than 2^31 output units, tile indices beyond 2^21.  Checked through size-independent properties: counts agree
+    across encodings, the round trip gives the input back, the tail agrees with the oracle, an error planted past
+    4 GiB is located exactly."""
+    from simdutf_b200 import synth
+    base = synth.mixed_utf8(1 << 30, seed=9, device="cuda")  # ends on a character boundary
+    reps = 5
+    d = base.repeat(reps)
+    n = d.numel()
+    assert n > (1 << 32)
+    assert b.validate_utf8_with_errors(d) == (0, n)
+    units = b.utf16_length_from_utf8(d)
+    assert units == reps * b.utf16_length_from_utf8(base) and units > (1 << 31)
+    out = torch.empty(units + 64, dtype=torch.int16, device="cuda")
+    out[units:] = 0x5A5A
+    assert b.convert_utf8_to_utf16le_with_errors(d, out) == (0, units)
+    assert bool((out[units:] == 0x5A5A).all())
+    u16 = out[:units]
+    per = units // reps
+    assert torch.equal(u16[:per], u16[(reps - 1) * per:])  # every repetition transcodes identically
+    assert b.utf8_length_from_utf16le(u16) == n and b.count_utf16le(u16) == reps * b.count_utf8(base)
+    back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert b.convert_utf16le_to_utf8_with_errors(u16, back) == (0, n)
+    assert torch.equal(back, d)
+    tail = base[-(1 << 20):].cpu().numpy().tobytes()
+    k = 0
+    while (tail[k] & 0xC0) == 0x80:
+        k += 1
+    (e, c), o = oracle.convert_utf8_to_utf16le_with_errors(tail[k:])
+    assert e == 0 and u16[units - c:].cpu().numpy().view(np.uint16).tobytes() == o.tobytes()
+    del back
+    p = (1 << 32) + (1 << 29) + 777
+    while (int(d[p].item()) & 0xC0) == 0x80:
+        p -= 1
+    d[p] = 0xF8
+    assert b.validate_utf8_with_errors(d) == (1, p)
+    assert b.convert_utf8_to_utf16le_with_errors(d, out)[:2] == (1, p)
+
+
 def test_config3_utf16_2gib(b, oracle):
     from simdutf_b200 import synth
     u = synth.mixed_utf16le(1 << 30, seed=3, device="cuda")
