@@ -6,6 +6,7 @@
 // (reference CMakeLists.txt:173-214 forbids it for anything linked into libsimdutf).
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -341,7 +342,12 @@ size_t out_elem_bytes(Op op) {
 // kernels; their results are combined exactly like the shards of the multi-GPU path (first error in buffer
 // order wins, counts add up).
 // ---------------------------------------------------------------------------------------------
-constexpr size_t kSegmentBytes = size_t(32) << 20;
+// B200_TUNE_SEG_MB overrides the segment size for experiments (tools/).
+static const size_t kSegmentBytes = [] {
+  const char *e = getenv("B200_TUNE_SEG_MB");
+  const long v = (e && *e) ? atol(e) : 0;
+  return size_t(v >= 1 && v <= 1024 ? v : 32) << 20;
+}();
 
 bool op_streams(Op op) { return op != kOpBase64; }  // base64 quanta straddle any cut: single shot
 
