@@ -185,6 +185,34 @@ SIMDUTF_B200_API int b200_convert_utf16le_to_utf8(const uint16_t *d_in, size_t l
 SIMDUTF_B200_API int b200_host_convert_utf16le_to_utf8(const uint16_t *h_in, size_t len, char *h_out, b200_result *h_res);
 
 /* ------------------------------------------------------------------------- */
+/* UTF-16BE twins: the same kernels reading / writing   */
+/* big-endian units.  implementation::convert_utf8_to_utf16be[_with_errors]    */
+/* (reference include/simdutf/implementation.h:3727-3760), ::count_utf16be     */
+/* (:4783) == utf32_length_from_utf16be, ::utf8_length_from_utf16be (:4299),   */
+/* ::validate_utf16be_with_errors (:3499), ::convert_utf16be_to_utf8           */
+/* [_with_errors] (:4058-4101), ::change_endianness_utf16 (:4567-4584; its     */
+/* b200_result is {SUCCESS, len}).  Same result conventions as the LE entries. */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_convert_utf8_to_utf16be_async(const char *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf8_to_utf16be(const char *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf8_to_utf16be(const char *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_count_utf16be_async(const uint16_t *d_in, size_t len, uint64_t *d_count, void *stream);
+SIMDUTF_B200_API int b200_count_utf16be(const uint16_t *d_in, size_t len, uint64_t *h_count, void *stream);
+SIMDUTF_B200_API int b200_host_count_utf16be(const uint16_t *h_in, size_t len, uint64_t *h_count);
+SIMDUTF_B200_API int b200_utf8_length_from_utf16be_async(const uint16_t *d_in, size_t len, uint64_t *d_count, void *stream);
+SIMDUTF_B200_API int b200_utf8_length_from_utf16be(const uint16_t *d_in, size_t len, uint64_t *h_count, void *stream);
+SIMDUTF_B200_API int b200_host_utf8_length_from_utf16be(const uint16_t *h_in, size_t len, uint64_t *h_count);
+SIMDUTF_B200_API int b200_validate_utf16be_with_errors_async(const uint16_t *d_in, size_t len, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_validate_utf16be_with_errors(const uint16_t *d_in, size_t len, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_validate_utf16be_with_errors(const uint16_t *h_in, size_t len, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf16be_to_utf8_async(const uint16_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf16be_to_utf8(const uint16_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf16be_to_utf8(const uint16_t *h_in, size_t len, char *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_change_endianness_utf16_async(const uint16_t *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_change_endianness_utf16(const uint16_t *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_change_endianness_utf16(const uint16_t *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+
+/* ------------------------------------------------------------------------- */
 /* WHATWG forgiving base64 decode — implementation::base64_to_binary_details   */
 /* (:4902-4906) and ::base64_to_binary (:4866-4870; result derived from the    */
 /* full_result as in include/simdutf/error.h:66-73).  Semantics                */

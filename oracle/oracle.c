@@ -131,19 +131,26 @@ uint64_t oracle_convert_utf8_to_utf32(const uint8_t *in, size_t len, uint32_t *o
 }
 
 /* ------------------------------------------------------------------------- */
-/* UTF-16LE                                                                   */
+/* UTF-16 (LE and BE)                                                         */
+/* The reference's scalar routines are templates on the endianness that read  */
+/* every unit through `!match_system(big_endian) ? u16_swap_bytes(w) : w`     */
+/* (src/scalar/utf16.h:44, :73, :85; src/scalar/utf16_to_utf8/utf16_to_utf8.h */
+/* :93; src/scalar/utf8_to_utf16/utf8_to_utf16.h:143-146 for the stores); the */
+/* host is little-endian, so `be` means "swap".                               */
 /* ------------------------------------------------------------------------- */
 static int is_high(uint16_t w) { return (w & 0xFC00) == 0xD800; }
 static int is_low(uint16_t w) { return (w & 0xFC00) == 0xDC00; }
+static uint16_t swap16(uint16_t w) { return (uint16_t)((w >> 8) | (w << 8)); }
+static uint16_t ld16(const uint16_t *in, size_t i, int be) { return be ? swap16(in[i]) : in[i]; }
 
 /* reference src/scalar/utf16.h:39-67 */
-oracle_result oracle_validate_utf16le_with_errors(const uint16_t *in, size_t len) {
+static oracle_result validate_utf16_impl(const uint16_t *in, size_t len, int be) {
   oracle_result r;
   size_t pos = 0;
   while (pos < len) {
-    uint16_t w = in[pos];
+    uint16_t w = ld16(in, pos, be);
     if ((w & 0xF800) == 0xD800) {
-      if (!is_high(w) || pos + 1 >= len || !is_low(in[pos + 1])) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+      if (!is_high(w) || pos + 1 >= len || !is_low(ld16(in, pos + 1, be))) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
       pos += 2;
     } else {
       pos += 1;
@@ -152,33 +159,40 @@ oracle_result oracle_validate_utf16le_with_errors(const uint16_t *in, size_t len
   r.error = ORACLE_SUCCESS; r.count = len;
   return r;
 }
+oracle_result oracle_validate_utf16le_with_errors(const uint16_t *in, size_t len) { return validate_utf16_impl(in, len, 0); }
+oracle_result oracle_validate_utf16be_with_errors(const uint16_t *in, size_t len) { return validate_utf16_impl(in, len, 1); }
 
 /* reference src/scalar/utf16.h:69-78 */
-uint64_t oracle_count_utf16le(const uint16_t *in, size_t len) {
+static uint64_t count_utf16_impl(const uint16_t *in, size_t len, int be) {
   uint64_t n = 0;
-  for (size_t i = 0; i < len; i++) n += !is_low(in[i]);
+  for (size_t i = 0; i < len; i++) n += !is_low(ld16(in, i, be));
   return n;
 }
+uint64_t oracle_count_utf16le(const uint16_t *in, size_t len) { return count_utf16_impl(in, len, 0); }
+uint64_t oracle_count_utf16be(const uint16_t *in, size_t len) { return count_utf16_impl(in, len, 1); }
 
 /* reference src/scalar/utf16.h:80-94 — every surrogate unit counts 2 */
-uint64_t oracle_utf8_length_from_utf16le(const uint16_t *in, size_t len) {
+static uint64_t utf8_length_from_utf16_impl(const uint16_t *in, size_t len, int be) {
   uint64_t n = 0;
   for (size_t i = 0; i < len; i++) {
-    uint16_t w = in[i];
+    uint16_t w = ld16(in, i, be);
     n += 1 + (w > 0x7F) + ((w > 0x7FF && w <= 0xD7FF) || w >= 0xE000);
   }
   return n;
 }
+uint64_t oracle_utf8_length_from_utf16le(const uint16_t *in, size_t len) { return utf8_length_from_utf16_impl(in, len, 0); }
+uint64_t oracle_utf8_length_from_utf16be(const uint16_t *in, size_t len) { return utf8_length_from_utf16_impl(in, len, 1); }
 
 /* reference src/scalar/utf16.h:96-105 */
 uint64_t oracle_utf32_length_from_utf16le(const uint16_t *in, size_t len) { return oracle_count_utf16le(in, len); }
+uint64_t oracle_utf32_length_from_utf16be(const uint16_t *in, size_t len) { return oracle_count_utf16be(in, len); }
 
 /* reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153 */
-oracle_result oracle_convert_utf16le_to_utf8_with_errors(const uint16_t *in, size_t len, uint8_t *out) {
+static oracle_result convert_utf16_to_utf8_impl(const uint16_t *in, size_t len, uint8_t *out, int be) {
   oracle_result r;
   size_t pos = 0; uint64_t w = 0;
   while (pos < len) {
-    uint32_t u = in[pos];
+    uint32_t u = ld16(in, pos, be);
     if (u < 0x80) {
       out[w++] = (uint8_t)u; pos++;
     } else if (u < 0x800) {
@@ -189,10 +203,10 @@ oracle_result oracle_convert_utf16le_to_utf8_with_errors(const uint16_t *in, siz
       out[w++] = (uint8_t)(0x80 | ((u >> 6) & 0x3F));
       out[w++] = (uint8_t)(0x80 | (u & 0x3F)); pos++;
     } else {
-      if (pos + 1 >= len || !is_high((uint16_t)u) || !is_low(in[pos + 1])) {
+      if (pos + 1 >= len || !is_high((uint16_t)u) || !is_low(ld16(in, pos + 1, be))) {
         r.error = ORACLE_SURROGATE; r.count = pos; return r;
       }
-      uint32_t cp = 0x10000 + ((u - 0xD800) << 10) + (in[pos + 1] - 0xDC00u);
+      uint32_t cp = 0x10000 + ((u - 0xD800) << 10) + (ld16(in, pos + 1, be) - 0xDC00u);
       out[w++] = (uint8_t)(0xF0 | (cp >> 18));
       out[w++] = (uint8_t)(0x80 | ((cp >> 12) & 0x3F));
       out[w++] = (uint8_t)(0x80 | ((cp >> 6) & 0x3F));
@@ -202,11 +216,32 @@ oracle_result oracle_convert_utf16le_to_utf8_with_errors(const uint16_t *in, siz
   r.error = ORACLE_SUCCESS; r.count = w;
   return r;
 }
+oracle_result oracle_convert_utf16le_to_utf8_with_errors(const uint16_t *in, size_t len, uint8_t *out) {
+  return convert_utf16_to_utf8_impl(in, len, out, 0);
+}
+oracle_result oracle_convert_utf16be_to_utf8_with_errors(const uint16_t *in, size_t len, uint8_t *out) {
+  return convert_utf16_to_utf8_impl(in, len, out, 1);
+}
 
 /* reference src/scalar/utf16_to_utf8/utf16_to_utf8.h:9-80: bytes written, 0 on error */
 uint64_t oracle_convert_utf16le_to_utf8(const uint16_t *in, size_t len, uint8_t *out) {
   oracle_result r = oracle_convert_utf16le_to_utf8_with_errors(in, len, out);
   return r.error ? 0 : r.count;
+}
+
+/* reference src/scalar/utf8_to_utf16/utf8_to_utf16.h:128-255 with big_endian stores (:143-146, :186-189, :228-235):
+ * the same units, byte-swapped.  On error the units written so far are swapped too. */
+oracle_result oracle_convert_utf8_to_utf16be_with_errors(const uint8_t *in, size_t len, uint16_t *out) {
+  /* units written before the error position = utf16 length of the valid prefix */
+  oracle_result r = oracle_convert_utf8_to_utf16le_with_errors(in, len, out);
+  uint64_t n = r.error ? oracle_utf16_length_from_utf8(in, r.count) : r.count;
+  for (uint64_t i = 0; i < n; i++) out[i] = swap16(out[i]);
+  return r;
+}
+
+/* reference src/scalar/utf16.h:107-112 (change_endianness_utf16) */
+void oracle_change_endianness_utf16(const uint16_t *in, size_t len, uint16_t *out) {
+  for (size_t i = 0; i < len; i++) out[i] = swap16(in[i]);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -67,6 +67,15 @@ uint64_t oracle_utf32_length_from_utf16le(const uint16_t *in, size_t len);
 oracle_result oracle_convert_utf16le_to_utf8_with_errors(const uint16_t *in, size_t len, uint8_t *out);
 uint64_t oracle_convert_utf16le_to_utf8(const uint16_t *in, size_t len, uint8_t *out);
 
+/* UTF-16BE twins: same routines, units byte-swapped on the way in / out */
+oracle_result oracle_validate_utf16be_with_errors(const uint16_t *in, size_t len);
+uint64_t oracle_count_utf16be(const uint16_t *in, size_t len);
+uint64_t oracle_utf8_length_from_utf16be(const uint16_t *in, size_t len);
+uint64_t oracle_utf32_length_from_utf16be(const uint16_t *in, size_t len);
+oracle_result oracle_convert_utf16be_to_utf8_with_errors(const uint16_t *in, size_t len, uint8_t *out);
+oracle_result oracle_convert_utf8_to_utf16be_with_errors(const uint8_t *in, size_t len, uint16_t *out);
+void oracle_change_endianness_utf16(const uint16_t *in, size_t len, uint16_t *out);
+
 uint64_t oracle_maximal_binary_length_from_base64(const uint8_t *in, size_t len);
 oracle_full_result oracle_base64_to_binary_details(const uint8_t *in, size_t len, uint8_t *out,
                                                    uint64_t options, uint64_t last_chunk);

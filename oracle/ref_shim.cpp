@@ -113,6 +113,34 @@ int64_t ref_convert_utf16le_to_utf8(const char *impl, const char16_t *in, size_t
   auto *i = pick(impl); if (!i) return -1;
   return int64_t(i->convert_utf16le_to_utf8(in, len, dst));
 }
+// UTF-16BE twins
+int64_t ref_count_utf16be(const char *impl, const char16_t *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->count_utf16be(in, len));
+}
+int64_t ref_utf8_length_from_utf16be(const char *impl, const char16_t *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->utf8_length_from_utf16be(in, len));
+}
+int ref_validate_utf16be_with_errors(const char *impl, const char16_t *in, size_t len, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->validate_utf16be_with_errors(in, len);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_convert_utf16be_to_utf8_with_errors(const char *impl, const char16_t *in, size_t len, char *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->convert_utf16be_to_utf8_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_convert_utf8_to_utf16be_with_errors(const char *impl, const char *in, size_t len, char16_t *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->convert_utf8_to_utf16be_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_change_endianness_utf16(const char *impl, const char16_t *in, size_t len, char16_t *dst) {
+  auto *i = pick(impl); if (!i) return -1;
+  i->change_endianness_utf16(in, len, dst); return 0;
+}
 int64_t ref_maximal_binary_length_from_base64(const char *in, size_t len) {
   return int64_t(simdutf::maximal_binary_length_from_base64(in, len));
 }

@@ -84,11 +84,13 @@ SYMBOLS = {
 }
 for _name, _res in [("validate_utf8_with_errors", _pres), ("count_utf8", _pu64), ("utf16_length_from_utf8", _pu64),
                     ("count_utf16le", _pu64), ("utf8_length_from_utf16le", _pu64),
-                    ("validate_utf16le_with_errors", _pres)]:
+                    ("validate_utf16le_with_errors", _pres), ("count_utf16be", _pu64), ("utf8_length_from_utf16be", _pu64),
+                    ("validate_utf16be_with_errors", _pres)]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _res, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _res])
-for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16le_to_utf8"]:
+for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16le_to_utf8", "convert_utf8_to_utf16be",
+              "convert_utf16be_to_utf8", "change_endianness_utf16"]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _vp, _pres, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _vp, _pres])
@@ -257,6 +259,38 @@ def convert_utf16le_to_utf8_with_errors(data, out):
 def convert_utf16le_to_utf8(data, out) -> int:
     err, count = convert_utf16le_to_utf8_with_errors(data, out)
     return 0 if err else count
+
+
+# ---- UTF-16BE twins: `data` / `out` hold big-endian 16-bit units ------------------------------
+def count_utf16be(data) -> int:
+    return int(_reduce_op("count_utf16be", data, 2, ctypes.c_uint64()).value)
+
+
+def utf32_length_from_utf16be(data) -> int:
+    return count_utf16be(data)
+
+
+def utf8_length_from_utf16be(data) -> int:
+    return int(_reduce_op("utf8_length_from_utf16be", data, 2, ctypes.c_uint64()).value)
+
+
+def validate_utf16be_with_errors(data):
+    return _reduce_op("validate_utf16be_with_errors", data, 2, Result()).astuple()
+
+
+def convert_utf8_to_utf16be_with_errors(data, out):
+    return _convert_op("convert_utf8_to_utf16be", data, 1, out)
+
+
+def convert_utf16be_to_utf8_with_errors(data, out):
+    return _convert_op("convert_utf16be_to_utf8", data, 2, out)
+
+
+def change_endianness_utf16(data, out) -> None:
+    """simdutf::change_endianness_utf16: out[i] = byteswap(data[i])."""
+    err, _n = _convert_op("change_endianness_utf16", data, 2, out)
+    if err:
+        raise B200Error("change_endianness_utf16 failed")
 
 
 def base64_to_binary_details(data, out, options: int = base64_default, last_chunk: int = loose):

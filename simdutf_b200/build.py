@@ -92,6 +92,9 @@ REF_TESTS = [
     "convert_valid_utf8_to_utf32_tests", "convert_utf16le_to_utf8_tests", "convert_utf16le_to_utf8_with_errors_tests",
     "convert_valid_utf16le_to_utf8_tests", "count_utf8", "count_utf16le", "utf8_length_from_utf16_tests",
     "validate_utf16le_basic_tests", "validate_utf16le_with_errors_tests", "base64_tests", "select_implementation",
+    "convert_utf8_to_utf16be_tests", "convert_utf8_to_utf16be_with_errors_tests", "convert_valid_utf8_to_utf16be_tests",
+    "convert_utf16be_to_utf8_tests", "convert_utf16be_to_utf8_with_errors_tests", "convert_valid_utf16be_to_utf8_tests",
+    "count_utf16be", "validate_utf16be_basic_tests", "validate_utf16be_with_errors_tests",
     "null_safety_tests", "random_fuzzer",
 ]
 WITH_B200 = os.path.join(OBJ, "with_b200")

@@ -114,6 +114,58 @@ size_t implementation::convert_valid_utf16le_to_utf8(const char16_t *input, size
   return convert_utf16le_to_utf8(input, length, utf8_buffer);
 }
 
+// ---- UTF-16BE twins (reference include/simdutf/implementation.h:3443-3569, 3727-3760,
+//      4058-4101, 4299-4368, 4567-4584, 4783-4800): the same kernels with big-endian units ----
+size_t implementation::count_utf16be(const char16_t *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_count_utf16be(u16(input), length, &n) == 0 ? size_t(n) : 0;
+}
+size_t implementation::utf32_length_from_utf16be(const char16_t *input, size_t length) const noexcept {
+  return count_utf16be(input, length);
+}
+size_t implementation::utf8_length_from_utf16be(const char16_t *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_utf8_length_from_utf16be(u16(input), length, &n) == 0 ? size_t(n) : 0;
+}
+bool implementation::validate_utf16be(const char16_t *buf, size_t len) const noexcept {
+  b200_result r;
+  return b200_host_validate_utf16be_with_errors(u16(buf), len, &r) == 0 && r.error == B200_SUCCESS;
+}
+result implementation::validate_utf16be_with_errors(const char16_t *buf, size_t len) const noexcept {
+  b200_result r;
+  return to_result(b200_host_validate_utf16be_with_errors(u16(buf), len, &r), r);
+}
+result implementation::convert_utf8_to_utf16be_with_errors(const char *input, size_t length,
+                                                           char16_t *utf16_output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf8_to_utf16be(input, length, reinterpret_cast<uint16_t *>(utf16_output), &r), r);
+}
+size_t implementation::convert_utf8_to_utf16be(const char *input, size_t length, char16_t *utf16_output) const noexcept {
+  const result r = convert_utf8_to_utf16be_with_errors(input, length, utf16_output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf8_to_utf16be(const char *input, size_t length,
+                                                     char16_t *utf16_buffer) const noexcept {
+  return convert_utf8_to_utf16be(input, length, utf16_buffer);
+}
+result implementation::convert_utf16be_to_utf8_with_errors(const char16_t *input, size_t length,
+                                                           char *utf8_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf16be_to_utf8(u16(input), length, utf8_buffer, &r), r);
+}
+size_t implementation::convert_utf16be_to_utf8(const char16_t *input, size_t length, char *utf8_buffer) const noexcept {
+  const result r = convert_utf16be_to_utf8_with_errors(input, length, utf8_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf16be_to_utf8(const char16_t *input, size_t length,
+                                                     char *utf8_buffer) const noexcept {
+  return convert_utf16be_to_utf8(input, length, utf8_buffer);
+}
+void implementation::change_endianness_utf16(const char16_t *input, size_t length, char16_t *output) const noexcept {
+  b200_result r;
+  (void)b200_host_change_endianness_utf16(u16(input), length, reinterpret_cast<uint16_t *>(output), &r);
+}
+
 // ---- base64 decode, char input (:4866-4870, :4902-4906); result derived as in include/simdutf/error.h:66-73 ----
 full_result implementation::base64_to_binary_details(const char *input, size_t length, char *output,
                                                      base64_options options,

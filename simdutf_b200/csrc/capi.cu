@@ -226,14 +226,21 @@ enum Op {
   kOpUtf8LenFromUtf16,
   kOpValidateUtf16,
   kOpUtf16ToUtf8,
-  kOpBase64
+  kOpBase64,
+  // UTF-16BE twins and change_endianness_utf16
+  kOpUtf8ToUtf16BE,
+  kOpCountUtf16BE,
+  kOpUtf8LenFromUtf16BE,
+  kOpValidateUtf16BE,
+  kOpUtf16BEToUtf8,
+  kOpSwapUtf16
 };
 
 size_t tiles_needed(Op op, const void *in, size_t len) {
   switch (op) {
-    case kOpUtf8ToUtf16: return utf8_to_utf16_tiles(in, len);
+    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: return utf8_to_utf16_tiles(in, len);
     case kOpUtf8ToUtf32: return utf8_to_utf32_tiles(in, len);
-    case kOpUtf16ToUtf8: return utf16_convert_tiles(in, len);
+    case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return utf16_convert_tiles(in, len);
     case kOpBase64: return base64_tiles(in, len);
     default: return 0;
   }
@@ -244,6 +251,7 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
   if (len == 0) {  // reference: empty input is SUCCESS / 0 everywhere on the hot path
     switch (op) {
       case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
+      case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE:
         B200_CUDA(launch_write_u64(static_cast<unsigned long long *>(res), 0, lc.stream));
         return 0;
       case kOpBase64:
@@ -258,12 +266,21 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
     case kOpValidateUtf8: B200_CUDA(launch_validate_utf8(lc, static_cast<const char *>(in), len, res)); break;
     case kOpCountUtf8: B200_CUDA(launch_count_utf8(lc, static_cast<const char *>(in), len, static_cast<unsigned long long *>(res), 0)); break;
     case kOpUtf16LenFromUtf8: B200_CUDA(launch_count_utf8(lc, static_cast<const char *>(in), len, static_cast<unsigned long long *>(res), 1)); break;
-    case kOpUtf8ToUtf16: B200_CUDA(launch_convert_utf8_to_utf16le(lc, static_cast<const char *>(in), len, static_cast<uint16_t *>(out), res)); break;
+    case kOpUtf8ToUtf16: B200_CUDA(launch_convert_utf8_to_utf16(lc, static_cast<const char *>(in), len, static_cast<uint16_t *>(out), res, false)); break;
+    case kOpUtf8ToUtf16BE: B200_CUDA(launch_convert_utf8_to_utf16(lc, static_cast<const char *>(in), len, static_cast<uint16_t *>(out), res, true)); break;
     case kOpUtf8ToUtf32: B200_CUDA(launch_convert_utf8_to_utf32(lc, static_cast<const char *>(in), len, static_cast<uint32_t *>(out), res)); break;
-    case kOpCountUtf16: B200_CUDA(launch_count_utf16le(lc, static_cast<const uint16_t *>(in), len, static_cast<unsigned long long *>(res), 0)); break;
-    case kOpUtf8LenFromUtf16: B200_CUDA(launch_count_utf16le(lc, static_cast<const uint16_t *>(in), len, static_cast<unsigned long long *>(res), 1)); break;
-    case kOpValidateUtf16: B200_CUDA(launch_validate_utf16le(lc, static_cast<const uint16_t *>(in), len, res)); break;
-    case kOpUtf16ToUtf8: B200_CUDA(launch_convert_utf16le_to_utf8(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res)); break;
+    case kOpCountUtf16: B200_CUDA(launch_count_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<unsigned long long *>(res), 0, false)); break;
+    case kOpUtf8LenFromUtf16: B200_CUDA(launch_count_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<unsigned long long *>(res), 1, false)); break;
+    case kOpValidateUtf16: B200_CUDA(launch_validate_utf16(lc, static_cast<const uint16_t *>(in), len, res, false)); break;
+    case kOpUtf16ToUtf8: B200_CUDA(launch_convert_utf16_to_utf8(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res, false)); break;
+    case kOpCountUtf16BE: B200_CUDA(launch_count_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<unsigned long long *>(res), 0, true)); break;
+    case kOpUtf8LenFromUtf16BE: B200_CUDA(launch_count_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<unsigned long long *>(res), 1, true)); break;
+    case kOpValidateUtf16BE: B200_CUDA(launch_validate_utf16(lc, static_cast<const uint16_t *>(in), len, res, true)); break;
+    case kOpUtf16BEToUtf8: B200_CUDA(launch_convert_utf16_to_utf8(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res, true)); break;
+    case kOpSwapUtf16:
+      B200_CUDA(launch_change_endianness_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<uint16_t *>(out)));
+      B200_CUDA(launch_write_result(res, B200_SUCCESS, len, lc.stream));
+      break;
     case kOpBase64: B200_CUDA(launch_base64_to_binary(lc, static_cast<const char *>(in), len, static_cast<char *>(out), opt, lastc, res)); break;
   }
   return 0;
@@ -271,7 +288,8 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
 
 size_t result_bytes(Op op) {
   switch (op) {
-    case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16: return 8;
+    case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
+    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: return 8;
     case kOpBase64: return sizeof(b200_full_result);
     default: return sizeof(b200_result);
   }
@@ -311,22 +329,24 @@ int run_sync(Op op, const void *d_in, size_t len, void *d_out, void *h_res, void
 // buffer of the host path; the caller's own buffer is only ever written up to the returned count).
 size_t max_out_bytes(Op op, size_t len) {
   switch (op) {
-    case kOpUtf8ToUtf16: return 2 * len;       // <= 1 unit per input byte
+    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: return 2 * len;       // <= 1 unit per input byte
     case kOpUtf8ToUtf32: return 4 * len;
-    case kOpUtf16ToUtf8: return 3 * len;       // <= 3 bytes per unit
+    case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return 3 * len;       // <= 3 bytes per unit
+    case kOpSwapUtf16: return 2 * len;
     case kOpBase64: return len / 4 * 3 + 3;
     default: return 0;
   }
 }
 size_t in_elem_bytes(Op op) {
   switch (op) {
-    case kOpCountUtf16: case kOpUtf8LenFromUtf16: case kOpValidateUtf16: case kOpUtf16ToUtf8: return 2;
+    case kOpCountUtf16: case kOpUtf8LenFromUtf16: case kOpValidateUtf16: case kOpUtf16ToUtf8:
+    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpSwapUtf16: return 2;
     default: return 1;
   }
 }
 size_t out_elem_bytes(Op op) {
   switch (op) {
-    case kOpUtf8ToUtf16: return 2;
+    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: case kOpSwapUtf16: return 2;
     case kOpUtf8ToUtf32: return 4;
     default: return 1;
   }
@@ -357,7 +377,7 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
   size_t cut = beg + per;
   if (cut >= len) return len;
   switch (op) {
-    case kOpValidateUtf8: case kOpUtf8ToUtf16: case kOpUtf8ToUtf32: {
+    case kOpValidateUtf8: case kOpUtf8ToUtf16: case kOpUtf8ToUtf32: case kOpUtf8ToUtf16BE: {
       const unsigned char *p = static_cast<const unsigned char *>(h_in);
       for (int k = 0; k < 3 && cut > beg + 1 && (p[cut] & 0xC0) == 0x80; k++) cut--;
       return cut;
@@ -367,7 +387,12 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
       if ((p[cut] & 0xFC00u) == 0xDC00u && (p[cut - 1] & 0xFC00u) == 0xD800u) cut--;
       return cut;
     }
-    default: return cut;  // the counts are sums over any partition
+    case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: {  // the same rule on byte-swapped units
+      const uint16_t *p = static_cast<const uint16_t *>(h_in);
+      if ((p[cut] & 0x00FCu) == 0x00DCu && (p[cut - 1] & 0x00FCu) == 0x00D8u) cut--;
+      return cut;
+    }
+    default: return cut;  // the counts are sums over any partition; change_endianness is a map
   }
 }
 
@@ -585,6 +610,9 @@ B200_DEFINE_RESULT_OP(utf16_length_from_utf8, kOpUtf16LenFromUtf8, char, uint64_
 B200_DEFINE_RESULT_OP(count_utf16le, kOpCountUtf16, uint16_t, uint64_t)
 B200_DEFINE_RESULT_OP(utf8_length_from_utf16le, kOpUtf8LenFromUtf16, uint16_t, uint64_t)
 B200_DEFINE_RESULT_OP(validate_utf16le_with_errors, kOpValidateUtf16, uint16_t, b200_result)
+B200_DEFINE_RESULT_OP(count_utf16be, kOpCountUtf16BE, uint16_t, uint64_t)
+B200_DEFINE_RESULT_OP(utf8_length_from_utf16be, kOpUtf8LenFromUtf16BE, uint16_t, uint64_t)
+B200_DEFINE_RESULT_OP(validate_utf16be_with_errors, kOpValidateUtf16BE, uint16_t, b200_result)
 
 #define B200_DEFINE_CONVERT_OP(NAME, OP, INTYPE, OUTTYPE)                                                          \
   int b200_##NAME##_async(const INTYPE *d_in, size_t len, OUTTYPE *d_out, b200_result *d_res, void *stream) {      \
@@ -600,6 +628,9 @@ B200_DEFINE_RESULT_OP(validate_utf16le_with_errors, kOpValidateUtf16, uint16_t, 
 B200_DEFINE_CONVERT_OP(convert_utf8_to_utf16le, kOpUtf8ToUtf16, char, uint16_t)
 B200_DEFINE_CONVERT_OP(convert_utf8_to_utf32, kOpUtf8ToUtf32, char, uint32_t)
 B200_DEFINE_CONVERT_OP(convert_utf16le_to_utf8, kOpUtf16ToUtf8, uint16_t, char)
+B200_DEFINE_CONVERT_OP(convert_utf8_to_utf16be, kOpUtf8ToUtf16BE, char, uint16_t)
+B200_DEFINE_CONVERT_OP(convert_utf16be_to_utf8, kOpUtf16BEToUtf8, uint16_t, char)
+B200_DEFINE_CONVERT_OP(change_endianness_utf16, kOpSwapUtf16, uint16_t, uint16_t)
 
 static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
   return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;

@@ -77,7 +77,11 @@ __device__ __forceinline__ void write_result_from_key16(ResultPOD *res, unsigned
 // ---------------------------------------------------------------------------------------------
 // K5: MODE 0 count_utf16le, MODE 1 utf8_length_from_utf16le, MODE 2 validate_utf16le_with_errors.
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int ITEMS>
+// BE = true: the units are big-endian (UTF-16BE twins, reference include/simdutf/implementation.h:3443-3569,
+// 4299-4368, 4783-4800): every loaded word is byte-swapped within its halves (one PRMT) and the rest is unchanged.
+__device__ __forceinline__ uint32_t swap16x2(uint32_t w) { return __byte_perm(w, 0u, 0x2301); }
+
+template <int MODE, int ITEMS, bool BE>
 __global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size_t len, Scratch *scr, void *out) {
   __shared__ unsigned long long s_part[kWarps];
   const InView in = make_view16(ptr, len);
@@ -93,9 +97,25 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size
     bool inside[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    if (BE && MODE != 2) {
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[j][k] = swap16x2(w[j][k]);
+      }
+    }
     if (MODE == 2) {
       uint32_t pw[ITEMS], nw[ITEMS];
       neighbour_words<ITEMS>(in, g0, w, pw, nw);
+      if (BE) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) w[j][k] = swap16x2(w[j][k]);
+          pw[j] = swap16x2(pw[j]);
+          nw[j] = swap16x2(nw[j]);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < ITEMS; j++) {
         const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
@@ -170,17 +190,56 @@ inline unsigned reduction_grid(const LaunchCtx &c, size_t len_bytes, int items) 
 
 }  // namespace
 
-cudaError_t launch_count_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode) {
+cudaError_t launch_count_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode,
+                               bool big_endian) {
   const unsigned grid = reduction_grid(c, 2 * len, kStreamItems);
-  if (mode == 0) k_scan_utf16<0, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
-  else k_scan_utf16<1, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  if (mode == 0) {
+    if (big_endian) k_scan_utf16<0, kStreamItems, true><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+    else k_scan_utf16<0, kStreamItems, false><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  } else {
+    if (big_endian) k_scan_utf16<1, kStreamItems, true><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+    else k_scan_utf16<1, kStreamItems, false><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, count);
+  }
   count_launch(1);
   return cudaGetLastError();
 }
 
-cudaError_t launch_validate_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, void *res) {
+cudaError_t launch_validate_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, void *res, bool big_endian) {
   const unsigned grid = reduction_grid(c, 2 * len, kStreamItems);
-  k_scan_utf16<2, kStreamItems><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, res);
+  if (big_endian) k_scan_utf16<2, kStreamItems, true><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, res);
+  else k_scan_utf16<2, kStreamItems, false><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, res);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+// change_endianness_utf16 (reference include/simdutf/implementation.h:4567-4584): out[i] = byteswap(in[i]).
+// Pure streaming: 16-byte vectors where both pointers allow it, units at the ragged ends.
+__global__ void __launch_bounds__(kBlock) k_swap_utf16(const uint16_t *in, size_t len, uint16_t *out) {
+  const size_t tid = (size_t)blockIdx.x * kBlock + threadIdx.x, nthreads = (size_t)gridDim.x * kBlock;
+  const uintptr_t ai = reinterpret_cast<uintptr_t>(in), ao = reinterpret_cast<uintptr_t>(out);
+  if (((ai ^ ao) & 15u) == 0) {  // same misalignment: a common 16-byte grid exists
+    size_t head = ((16u - (ai & 15u)) & 15u) >> 1;
+    if (head > len) head = len;
+    const size_t nvec = (len - head) >> 3;
+    const uint4 *vi = reinterpret_cast<const uint4 *>(in + head);
+    uint4 *vo = reinterpret_cast<uint4 *>(out + head);
+    for (size_t v = tid; v < nvec; v += nthreads) {
+      uint4 x = ldg_stream_v4(vi + v);
+      x.x = swap16x2(x.x); x.y = swap16x2(x.y); x.z = swap16x2(x.z); x.w = swap16x2(x.w);
+      stg_stream_v4(vo + v, x);
+    }
+    const size_t done = head + nvec * 8;
+    for (size_t i = tid; i < head; i += nthreads) out[i] = (uint16_t)((in[i] >> 8) | (in[i] << 8));
+    for (size_t i = done + tid; i < len; i += nthreads) out[i] = (uint16_t)((in[i] >> 8) | (in[i] << 8));
+  } else {
+    for (size_t i = tid; i < len; i += nthreads) out[i] = (uint16_t)((in[i] >> 8) | (in[i] << 8));
+  }
+}
+
+cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, uint16_t *out) {
+  const unsigned long long want = (len / 8 + kBlock - 1) / kBlock + 1;
+  const unsigned long long cap = (unsigned long long)c.sm_count * 16;
+  k_swap_utf16<<<(unsigned)(want < cap ? want : cap), kBlock, 0, c.stream>>>(in, len, out);
   count_launch(1);
   return cudaGetLastError();
 }

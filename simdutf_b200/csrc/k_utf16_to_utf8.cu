@@ -43,16 +43,20 @@ __device__ __forceinline__ InView make_view_u16(const uint16_t *p, size_t len_un
   return v;
 }
 
-// Unit at virtual unit index i (from the aligned base); zero outside the buffer.
-__device__ __forceinline__ uint32_t unit_guarded(const InView &in, long long i) {
+__device__ __forceinline__ uint32_t swap16x2(uint32_t w) { return __byte_perm(w, 0u, 0x2301); }
+
+// Unit at virtual unit index i (from the aligned base), in host order; zero outside the buffer.
+// `be`: the buffer holds big-endian units (the UTF-16BE twins of the reference API).
+__device__ __forceinline__ uint32_t unit_guarded(const InView &in, long long i, bool be) {
   const long long pos = i * 2;
   if (pos < (long long)in.vbeg || pos >= (long long)in.vend) return 0u;
-  return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(in.base) + i);
+  const uint32_t u = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(in.base) + i);
+  return be ? ((u >> 8) | ((u & 0xFFu) << 8)) : u;
 }
 
 // Exact first bad surrogate among virtual units [lo, hi) (reference src/scalar/utf16.h:44-60).
 static __device__ __noinline__ void u16_locate_error(const uint4 *base, unsigned long long vbeg, unsigned long long vend,
-                                                     Scratch *scr, long long lo, long long hi) {
+                                                     Scratch *scr, long long lo, long long hi, bool be) {
   InView in;
   in.base = base;
   in.vbeg = vbeg;
@@ -61,10 +65,10 @@ static __device__ __noinline__ void u16_locate_error(const uint4 *base, unsigned
   if (lo < first) lo = first;
   if (hi > last) hi = last;
   for (long long i = lo; i < hi; i++) {
-    const uint32_t u = unit_guarded(in, i);
+    const uint32_t u = unit_guarded(in, i, be);
     if ((u & 0xF800u) != 0xD800u) continue;
     const bool hp = i > first, hn = i + 1 < last;
-    if (u16_bad(u, hp ? unit_guarded(in, i - 1) : 0u, hp, hn ? unit_guarded(in, i + 1) : 0u, hn)) {
+    if (u16_bad(u, hp ? unit_guarded(in, i - 1, be) : 0u, hp, hn ? unit_guarded(in, i + 1, be) : 0u, hn)) {
       report_error(scr, err_key((unsigned long long)(i - first), kSurrogate));
       return;
     }
@@ -74,6 +78,7 @@ static __device__ __noinline__ void u16_locate_error(const uint4 *base, unsigned
 // ---------------------------------------------------------------------------------------------
 // K6a: per-tile byte counts (granule layout: lane l, item j owns granule g0 + 32 j + l)
 // ---------------------------------------------------------------------------------------------
+template <bool BE>
 __device__ __forceinline__ uint32_t count_tile_utf8len(const InView &in, unsigned long long g0) {
   const unsigned lane = threadIdx.x & 31u;
   const bool interior = g0 * 16ull >= in.vbeg && (g0 + kTileGranules) * 16ull <= in.vend;
@@ -84,7 +89,11 @@ __device__ __forceinline__ uint32_t count_tile_utf8len(const InView &in, unsigne
     for (int j = 0; j < 4; j++) v[j] = ldg_stream_v4(in.base + g0 + (unsigned long long)j * 32u + lane);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      if (BE) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = swap16x2(w[k]);
+      }
       uint32_t m = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -106,6 +115,10 @@ __device__ __forceinline__ uint32_t count_tile_utf8len(const InView &in, unsigne
       uint32_t w[4];
       bool inside;
       load_granule(in, g, w, inside);
+      if (BE) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = swap16x2(w[k]);
+      }
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const unsigned long long pos = g * 16ull + 2u * i;
@@ -116,11 +129,12 @@ __device__ __forceinline__ uint32_t count_tile_utf8len(const InView &in, unsigne
   return bpd::warp_sum_u32(cnt);
 }
 
+template <bool BE>
 __global__ void __launch_bounds__(kThreads) k_utf8len_tile_counts(const uint16_t *ptr, size_t len, uint16_t *tile_cnt,
                                                                    unsigned long long *chunk_off, uint32_t num_tiles,
                                                                    uint32_t num_chunks, Scratch *scr) {
   const InView in = make_view_u16(ptr, len);
-  bpd::counts_pass([&](uint32_t t) -> uint32_t { return count_tile_utf8len(in, (unsigned long long)t * kTileGranules); },
+  bpd::counts_pass([&](uint32_t t) -> uint32_t { return count_tile_utf8len<BE>(in, (unsigned long long)t * kTileGranules); },
                    tile_cnt, chunk_off, num_tiles, num_chunks, scr);
 }
 
@@ -173,7 +187,7 @@ __device__ __forceinline__ void compact_block(const uint32_t (&X)[32], uint32_t 
   }
 }
 
-template <int MINB>
+template <int MINB, bool BE>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_utf16_to_utf8_bp(const uint16_t *ptr, size_t len, uint8_t *out, const uint16_t *tile_cnt,
                    const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
@@ -209,14 +223,18 @@ k_utf16_to_utf8_bp(const uint16_t *ptr, size_t len, uint8_t *out, const uint16_t
         const uint4 v = __ldg(gp + j);
         W[4 * j] = v.x; W[4 * j + 1] = v.y; W[4 * j + 2] = v.z; W[4 * j + 3] = v.w;
       }
-      pu = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(in.base) + (r0 >> 1) - 1);
+      pu = unit_guarded(in, (long long)(r0 >> 1) - 1, BE);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         bool ins;
         load_granule(in, (r0 >> 4) + (unsigned long long)j, &W[4 * j], ins);
       }
-      pu = unit_guarded(in, (long long)(r0 >> 1) - 1);
+      pu = unit_guarded(in, (long long)(r0 >> 1) - 1, BE);
+    }
+    if (BE) {  // host order from here on
+#pragma unroll
+      for (int i = 0; i < 16; i++) W[i] = swap16x2(W[i]);
     }
     before = bpd::warp_sum_u32(before);
     const unsigned long long goff = coff + before;
@@ -265,10 +283,10 @@ k_utf16_to_utf8_bp(const uint16_t *ptr, size_t len, uint8_t *out, const uint16_t
       const long long u0 = (long long)(r0 >> 1);
       bool bad = err != 0u;
       if (!interior && last_unit >= u0 && last_unit < u0 + 32 && in.vend > in.vbeg) {
-        const uint32_t lu = unit_guarded(in, last_unit);
+        const uint32_t lu = unit_guarded(in, last_unit, BE);
         bad = bad || (lu & 0xFC00u) == 0xD800u;  // a high surrogate cut off by the end of the buffer
       }
-      if (bad) u16_locate_error(in.base, in.vbeg, in.vend, scr, u0 - 1, u0 + 32);
+      if (bad) u16_locate_error(in.base, in.vbeg, in.vend, scr, u0 - 1, u0 + 32, BE);
     }
     __syncwarp();
 
@@ -345,14 +363,14 @@ inline size_t workspace_slots(size_t tiles) {
   return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
 }
 
-template <int MINB>
+template <int MINB, bool BE>
 cudaError_t launch_u16to8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res, size_t tiles) {
   static int per_sm = 0;
   if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_utf16_to_utf8_bp<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_utf16_to_utf8_bp<MINB, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf16_to_utf8_bp<MINB>, kThreads, kSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf16_to_utf8_bp<MINB, BE>, kThreads, kSmemBytes);
     if (e != cudaSuccess) return e;
     per_sm = n < 1 ? 1 : n;
   }
@@ -362,14 +380,14 @@ cudaError_t launch_u16to8(const LaunchCtx &c, const uint16_t *in, size_t len, ch
   {
     const size_t cap = (size_t)c.sm_count * 8;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_utf8len_tile_counts<<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks,
+    k_utf8len_tile_counts<BE><<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks,
                                                           c.scratch);
   }
   {
     const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t cap = (size_t)c.sm_count * per_sm;
     const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_utf16_to_utf8_bp<MINB><<<grid, kThreads, kSmemBytes, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), tile_cnt,
+    k_utf16_to_utf8_bp<MINB, BE><<<grid, kThreads, kSmemBytes, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), tile_cnt,
                                                                       chunk_off, (uint32_t)tiles, (uint32_t)chunks,
                                                                       c.scratch, static_cast<ResultPOD *>(res));
   }
@@ -387,13 +405,15 @@ inline int tuned_minb() {
 
 size_t utf16_convert_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, 2 * len)); }
 
-cudaError_t launch_convert_utf16le_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res) {
+cudaError_t launch_convert_utf16_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res,
+                                         bool big_endian) {
   const size_t tiles = tiles_for(in, 2 * len);
   if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
   static const int mb = tuned_minb();
-  if (mb <= 2) return launch_u16to8<2>(c, in, len, out, res, tiles);
-  if (mb == 3) return launch_u16to8<3>(c, in, len, out, res, tiles);
-  return launch_u16to8<4>(c, in, len, out, res, tiles);
+  if (big_endian) return launch_u16to8<3, true>(c, in, len, out, res, tiles);
+  if (mb <= 2) return launch_u16to8<2, false>(c, in, len, out, res, tiles);
+  if (mb == 3) return launch_u16to8<3, false>(c, in, len, out, res, tiles);
+  return launch_u16to8<4, false>(c, in, len, out, res, tiles);
 }
 
 }  // namespace b200

@@ -209,7 +209,9 @@ __device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long
 
 // One warp-tile: 32 lanes x K blocks x 32 bytes of input at virtual byte offset tile * kTileBytes.  The tile's output
 // starts at element index coff + (warp sum of before_partial).  Must be called by all 32 lanes.
-template <int K, bool W32>
+// BE (UTF-16 only): big-endian units — the low and high byte planes of the unit trade places before the transposition
+// back (free), the ASCII paths put the byte into the upper half.
+template <int K, bool W32, bool BE = false>
 __device__ __forceinline__ void transcode_tile(const InView &in, typename std::conditional<W32, uint32_t, uint16_t>::type *out,
                                                unsigned long long out_units, uint32_t tile, uint32_t before_partial,
                                                unsigned long long coff, uint32_t *region_w, bool poison, uint32_t one,
@@ -331,6 +333,14 @@ __device__ __forceinline__ void transcode_tile(const InView &in, typename std::c
         uint32_t U[16];
         const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
         if (err) badblocks |= 1u << j;
+        if (BE) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint32_t t = U[k];
+            U[k] = U[k + 8];
+            U[k + 8] = t;
+          }
+        }
         bp::transpose_out16(U);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -377,8 +387,9 @@ __device__ __forceinline__ void transcode_tile(const InView &in, typename std::c
             stg_stream_v4(gv + 8 * j + k, make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24));
           } else if ((k & 1) == 0) {
             const uint32_t w1 = B[j][k + 1];
-            stg_stream_v4(gv + 4 * j + (k >> 1), make_uint4(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342),
-                                                             __byte_perm(w1, 0u, 0x4140), __byte_perm(w1, 0u, 0x4342)));
+            constexpr uint32_t s01 = BE ? 0x1404u : 0x4140u, s23 = BE ? 0x3424u : 0x4342u;
+            stg_stream_v4(gv + 4 * j + (k >> 1), make_uint4(__byte_perm(w, 0u, s01), __byte_perm(w, 0u, s23),
+                                                             __byte_perm(w1, 0u, s01), __byte_perm(w1, 0u, s23)));
           }
         }
       }
@@ -396,7 +407,7 @@ __device__ __forceinline__ void transcode_tile(const InView &in, typename std::c
             sts_u32(spa, byte);
             spa = bpd::bump<4>(spa, one);
           } else {
-            sts_u16(spa, byte);
+            sts_u16(spa, BE ? byte << 8 : byte);
             spa = bpd::bump<2>(spa, one);
           }
         }
@@ -493,7 +504,7 @@ __device__ __forceinline__ void transcode_tile(const InView &in, typename std::c
   }
 }
 
-template <int K, int MINB, bool W32>
+template <int K, int MINB, bool W32, bool BE = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_utf8_transcode_bp(const char *ptr, size_t len, typename std::conditional<W32, uint32_t, uint16_t>::type *out,
                     const uint16_t *tile_cnt, const unsigned long long *chunk_off, uint32_t num_tiles,
@@ -518,7 +529,7 @@ k_utf8_transcode_bp(const char *ptr, size_t len, typename std::conditional<W32, 
     // where the tile's elements go: chunk offset + counts of the chunk's earlier tiles
     const uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
     const unsigned long long coff = chunk_off[tile / kChunkTiles];
-    transcode_tile<K, W32>(in, out, out_units, tile, before, coff, region_w, poison, one, scr);
+    transcode_tile<K, W32, BE>(in, out, out_units, tile, before, coff, region_w, poison, one, scr);
     __syncwarp();  // the regions are rewritten by the next tile
   }
 
@@ -681,7 +692,7 @@ inline uint32_t tuned_lead() {
   return (uint32_t)v;
 }
 
-template <int K, int MINB, bool W32>
+template <int K, int MINB, bool W32, bool BE = false>
 cudaError_t launch_bp(const LaunchCtx &c, const char *in, size_t len, void *out, void *res, size_t tiles) {
   using Gm = Geom<K, W32>;
   using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
@@ -690,7 +701,7 @@ cudaError_t launch_bp(const LaunchCtx &c, const char *in, size_t len, void *out,
   // per tile
   unsigned long long *chunk_off = c.desc;
   uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
-  if (tuned_fused()) {
+  if (tuned_fused() && !BE) {
     static int per_sm = 0;
     if (per_sm == 0) {
       cudaError_t e = cudaFuncSetAttribute(k_utf8_transcode_fused<K, MINB, W32>,
@@ -713,11 +724,11 @@ cudaError_t launch_bp(const LaunchCtx &c, const char *in, size_t len, void *out,
   }
   static int per_sm_emit = 0;
   if (per_sm_emit == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_utf8_transcode_bp<K, MINB, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_utf8_transcode_bp<K, MINB, W32, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Gm::kSmemBytes);
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf8_transcode_bp<K, MINB, W32>, kThreads, Gm::kSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf8_transcode_bp<K, MINB, W32, BE>, kThreads, Gm::kSmemBytes);
     if (e != cudaSuccess) return e;
     per_sm_emit = n < 1 ? 1 : n;
   }
@@ -731,7 +742,7 @@ cudaError_t launch_bp(const LaunchCtx &c, const char *in, size_t len, void *out,
     const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t cap = (size_t)c.sm_count * per_sm_emit;
     const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_utf8_transcode_bp<K, MINB, W32><<<grid, kThreads, Gm::kSmemBytes, c.stream>>>(
+    k_utf8_transcode_bp<K, MINB, W32, BE><<<grid, kThreads, Gm::kSmemBytes, c.stream>>>(
         in, len, static_cast<OutT *>(out), tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch,
         static_cast<ResultPOD *>(res));
   }
@@ -742,10 +753,16 @@ cudaError_t launch_bp(const LaunchCtx &c, const char *in, size_t len, void *out,
 }  // namespace
 
 // Workspace, in 8-byte descriptor slots, the two kernels need for an input of `len` bytes.
-size_t utf8_to_utf16_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len, tuned_k())); }
+size_t utf8_to_utf16_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len, tuned_k() < 2 ? tuned_k() : 2)); }
 size_t utf8_to_utf32_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len, 2)); }
 
-cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res) {
+cudaError_t launch_convert_utf8_to_utf16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res,
+                                         bool big_endian) {
+  if (big_endian) {
+    const size_t tiles_be = tiles_for(in, len, 2);
+    if (workspace_slots(tiles_be) > c.desc_capacity || tiles_be > 0xFFFFFF00ull) return cudaErrorInvalidValue;
+    return launch_bp<2, 3, false, true>(c, in, len, out, res, tiles_be);
+  }
   const int k = tuned_k();
   const size_t tiles = tiles_for(in, len, k);
   if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;

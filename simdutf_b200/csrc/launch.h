@@ -38,12 +38,17 @@ cudaError_t launch_scratch_init(Scratch *scr, cudaStream_t stream);
 
 cudaError_t launch_validate_utf8(const LaunchCtx &c, const char *in, size_t len, void *res);
 cudaError_t launch_count_utf8(const LaunchCtx &c, const char *in, size_t len, unsigned long long *count, int mode);
-cudaError_t launch_convert_utf8_to_utf16le(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res);
+cudaError_t launch_convert_utf8_to_utf16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res,
+                                         bool big_endian);
 cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res);
 
-cudaError_t launch_count_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode);
-cudaError_t launch_validate_utf16le(const LaunchCtx &c, const uint16_t *in, size_t len, void *res);
-cudaError_t launch_convert_utf16le_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res);
+// UTF-16 operations take the byte order of the units (big_endian = false: UTF-16LE).
+cudaError_t launch_count_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, unsigned long long *count, int mode,
+                               bool big_endian);
+cudaError_t launch_validate_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, void *res, bool big_endian);
+cudaError_t launch_convert_utf16_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res,
+                                         bool big_endian);
+cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, uint16_t *out);
 
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
                                     uint64_t last_chunk, void *full_res);

@@ -48,13 +48,16 @@ class Oracle:
         L = ctypes.CDLL(ORACLE_SO)
         for f in ("oracle_validate_utf8_with_errors", "oracle_convert_utf8_to_utf16le_with_errors",
                   "oracle_convert_utf8_to_utf32_with_errors", "oracle_convert_utf16le_to_utf8_with_errors",
-                  "oracle_validate_utf16le_with_errors", "oracle_base64_to_binary"):
+                  "oracle_validate_utf16le_with_errors", "oracle_base64_to_binary",
+                  "oracle_validate_utf16be_with_errors", "oracle_convert_utf16be_to_utf8_with_errors",
+                  "oracle_convert_utf8_to_utf16be_with_errors"):
             getattr(L, f).restype = Res
         L.oracle_base64_to_binary_details.restype = Full
         for f in ("oracle_count_utf8", "oracle_utf16_length_from_utf8", "oracle_utf32_length_from_utf8",
                   "oracle_count_utf16le", "oracle_utf8_length_from_utf16le", "oracle_utf32_length_from_utf16le",
                   "oracle_maximal_binary_length_from_base64", "oracle_trim_partial_utf8", "oracle_trim_partial_utf16le",
-                  "oracle_base64_length_from_binary", "oracle_binary_to_base64"):
+                  "oracle_base64_length_from_binary", "oracle_binary_to_base64", "oracle_count_utf16be",
+                  "oracle_utf8_length_from_utf16be", "oracle_utf32_length_from_utf16be"):
             getattr(L, f).restype = ctypes.c_uint64
         self.L = L
 
@@ -103,6 +106,38 @@ class Oracle:
         out = np.zeros(3 * a.size + 8, dtype=np.uint8)
         r = self.L.oracle_convert_utf16le_to_utf8_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out))
         return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    # --- UTF-16BE twins: arrays hold big-endian units (i.e. byte-swapped values on this little-endian host) ---
+    def validate_utf16be_with_errors(self, data):
+        a = _u16(data)
+        r = self.L.oracle_validate_utf16be_with_errors(_p(a), ctypes.c_size_t(a.size))
+        return (r.error, r.count)
+
+    def count_utf16be(self, data):
+        a = _u16(data)
+        return int(self.L.oracle_count_utf16be(_p(a), ctypes.c_size_t(a.size)))
+
+    def utf8_length_from_utf16be(self, data):
+        a = _u16(data)
+        return int(self.L.oracle_utf8_length_from_utf16be(_p(a), ctypes.c_size_t(a.size)))
+
+    def convert_utf16be_to_utf8_with_errors(self, data):
+        a = _u16(data)
+        out = np.zeros(3 * a.size + 8, dtype=np.uint8)
+        r = self.L.oracle_convert_utf16be_to_utf8_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf8_to_utf16be_with_errors(self, data):
+        a = _u8(data)
+        out = np.zeros(a.size + 8, dtype=np.uint16)
+        r = self.L.oracle_convert_utf8_to_utf16be_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def change_endianness_utf16(self, data):
+        a = _u16(data)
+        out = np.zeros(a.size, dtype=np.uint16)
+        self.L.oracle_change_endianness_utf16(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return out
 
     # --- base64 ---
     def maximal_binary_length_from_base64(self, data):
@@ -198,6 +233,40 @@ class Reference:
         out = np.zeros(3 * a.size + 64, dtype=np.uint8)
         assert self.L.ref_convert_utf16le_to_utf8_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
         return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def has_be(self):
+        return hasattr(self.L, "ref_count_utf16be")
+
+    def count_utf16be(self, impl, data):
+        a = _u16(data)
+        return int(self.L.ref_count_utf16be(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def utf8_length_from_utf16be(self, impl, data):
+        a = _u16(data)
+        return int(self.L.ref_utf8_length_from_utf16be(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def validate_utf16be_with_errors(self, impl, data):
+        a = _u16(data); r = Res()
+        assert self.L.ref_validate_utf16be_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), ctypes.byref(r)) == 0
+        return (r.error, r.count)
+
+    def convert_utf16be_to_utf8_with_errors(self, impl, data):
+        a = _u16(data); r = Res()
+        out = np.zeros(3 * a.size + 64, dtype=np.uint8)
+        assert self.L.ref_convert_utf16be_to_utf8_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf8_to_utf16be_with_errors(self, impl, data):
+        a = _u8(data); r = Res()
+        out = np.zeros(a.size + 64, dtype=np.uint16)
+        assert self.L.ref_convert_utf8_to_utf16be_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def change_endianness_utf16(self, impl, data):
+        a = _u16(data)
+        out = np.zeros(a.size, dtype=np.uint16)
+        assert self.L.ref_change_endianness_utf16(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out)) == 0
+        return out
 
     def base64_to_binary_details(self, impl, data, options=0, last_chunk=0):
         a = _u8(data); r = Full()

@@ -399,6 +399,83 @@ def test_bitplane_edge_paths(b, oracle):
             run_b64(b, oracle, dense, opt, lc, misalign=rng.randrange(16), host_too=False)
 
 
+def test_utf16be_twins(b, oracle):
+    """the UTF-16BE twins and change_endianness_utf16 against the oracle — random text, every
+    misalignment class, surrogate errors at tile edges, the host path."""
+    rng = random.Random(2024)
+    for it in range(60):
+        n = rng.choice([0, 1, 2, 7, 8, 9, 31, 32, 33, 1023, 1024, 1025, 5000, 70000])
+        d = rand_text(rng, n // 2 + 1) if it % 3 else bytes(rng.choice(SPECIAL) for _ in range(n))
+        mis = rng.randrange(16)
+        want, wout = oracle.convert_utf8_to_utf16be_with_errors(d)
+        n16 = oracle.utf16_length_from_utf8(d)
+        dd = dev(d, misalign=mis)
+        _, v16 = out_buf(n16, torch.int16, misalign=mis % 8)
+        assert b.convert_utf8_to_utf16be_with_errors(dd, v16) == want, (d[:64].hex(), len(d), mis)
+        if want[0] == 0:
+            assert v16[:want[1]].cpu().numpy().view(np.uint16).tobytes() == wout.tobytes()
+            check_guard(v16, want[1], 0x5A5A)
+            if it % 5 == 0:
+                h = np.zeros(n16 + 4, dtype=np.uint16)
+                assert b.convert_utf8_to_utf16be_with_errors(d, h) == want and h[:want[1]].tobytes() == wout.tobytes()
+    for it in range(60):
+        n = rng.choice([0, 1, 2, 7, 8, 9, 1023, 1024, 1025, 4096, 9000, 40000])
+        u = rand_units(rng, n, it % 3)
+        if it % 4 == 0 and n:
+            u[-1] = 0xD800 + rng.randrange(0x400)  # ends with a high surrogate
+        be = u.byteswap()
+        mis = rng.randrange(8)
+        want, wout = oracle.convert_utf16be_to_utf8_with_errors(be)
+        dd = dev(be.view(np.uint8), dtype=torch.uint8, misalign=2 * mis).view(torch.int16)
+        assert b.count_utf16be(dd) == oracle.count_utf16be(be)
+        assert b.utf8_length_from_utf16be(dd) == oracle.utf8_length_from_utf16be(be)
+        assert b.validate_utf16be_with_errors(dd) == oracle.validate_utf16be_with_errors(be)
+        n8 = oracle.utf8_length_from_utf16be(be)
+        _, v8 = out_buf(n8, torch.uint8, misalign=mis)
+        assert b.convert_utf16be_to_utf8_with_errors(dd, v8) == want, (u[:16], len(u), mis)
+        if want[0] == 0:
+            assert v8[:want[1]].cpu().numpy().tobytes() == wout.tobytes()
+            check_guard(v8, want[1], 0x5A)
+        for omis in (0, mis, (mis + 3) % 8):
+            _, sw = out_buf(len(be), torch.int16, misalign=omis)
+            b.change_endianness_utf16(dd, sw)
+            assert sw[:len(be)].cpu().numpy().view(np.uint16).tobytes() == u.tobytes()
+            check_guard(sw, len(be), 0x5A5A)
+        if it % 6 == 0:
+            assert b.count_utf16be(be) == oracle.count_utf16be(be)
+            h8 = np.zeros(n8 + 4, dtype=np.uint8)
+            assert b.convert_utf16be_to_utf8_with_errors(be, h8) == want
+            hs = np.zeros(len(be) + 1, dtype=np.uint16)
+            b.change_endianness_utf16(be, hs)
+            assert hs[:len(be)].tobytes() == u.tobytes()
+    # a lone surrogate planted at tile edges of a multi-tile buffer
+    base = rand_units(rng, 6000, 1)
+    for pos in (0, 1023, 1024, 1025, 2047, 2048, len(base) - 1):
+        for planted in (0xDC00, 0xD800):
+            u = base.copy()
+            u[pos] = planted
+            be = u.byteswap()
+            dd = dev(be.view(np.uint8), dtype=torch.uint8, misalign=2 * (pos % 8)).view(torch.int16)
+            assert b.validate_utf16be_with_errors(dd) == oracle.validate_utf16be_with_errors(be)
+            _, v8 = out_buf(oracle.utf8_length_from_utf16be(be), torch.uint8)
+            assert b.convert_utf16be_to_utf8_with_errors(dd, v8) == oracle.convert_utf16be_to_utf8_with_errors(be)[0]
+    # 256 MiB round trip: UTF-8 -> UTF-16BE -> swap == UTF-16LE, UTF-16BE -> UTF-8 == input
+    from simdutf_b200 import synth
+    d = synth.mixed_utf8(1 << 28, seed=12, device="cuda")
+    units = b.utf16_length_from_utf8(d)
+    ube = torch.empty(units, dtype=torch.int16, device="cuda")
+    ule = torch.empty(units, dtype=torch.int16, device="cuda")
+    assert b.convert_utf8_to_utf16be_with_errors(d, ube) == (0, units)
+    assert b.convert_utf8_to_utf16le_with_errors(d, ule) == (0, units)
+    sw = torch.empty_like(ube)
+    b.change_endianness_utf16(ube, sw)
+    assert torch.equal(sw, ule)
+    assert b.count_utf16be(ube) == b.count_utf16le(ule) and b.utf8_length_from_utf16be(ube) == d.numel()
+    back = torch.empty_like(d)
+    assert b.convert_utf16be_to_utf8_with_errors(ube, back) == (0, d.numel())
+    assert torch.equal(back, d)
+
+
 def test_repeated_calls_and_epoch_wrap(b, oracle):
     """More than 4096 scan launches on one stream: the 12-bit descriptor epoch wraps and must be handled."""
     from simdutf_b200 import synth

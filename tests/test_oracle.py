@@ -107,6 +107,12 @@ def test_against_reference_library(oracle, ref):
             assert r == w16[0] and o.tobytes() == w16[1].tobytes(), (im, d.hex())
             r, o = ref.convert_utf8_to_utf32_with_errors(im, d)
             assert r == w32[0] and o.tobytes() == w32[1].tobytes(), (im, d.hex())
+        w16be = oracle.convert_utf8_to_utf16be_with_errors(d)
+        assert w16be[0] == w16[0] and w16be[1].tobytes() == w16[1].byteswap().tobytes()
+        if ref.has_be():
+            for im in impls:
+                r, o = ref.convert_utf8_to_utf16be_with_errors(im, d)
+                assert r == w16be[0] and o.tobytes() == w16be[1].tobytes(), (im, d.hex())
     for _ in range(2000):
         n = rng.randrange(0, 80)
         u = []
@@ -126,6 +132,22 @@ def test_against_reference_library(oracle, ref):
             assert ref.validate_utf16le_with_errors(im, a) == oracle.validate_utf16le_with_errors(a)
             r, o = ref.convert_utf16le_to_utf8_with_errors(im, a)
             assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, u)
+        # the UTF-16BE twins on the byte-swapped buffer: same answers, pinned against the reference as well
+        be = a.byteswap()
+        assert oracle.count_utf16be(be) == oracle.count_utf16le(a)
+        assert oracle.utf8_length_from_utf16be(be) == oracle.utf8_length_from_utf16le(a)
+        assert oracle.validate_utf16be_with_errors(be) == oracle.validate_utf16le_with_errors(a)
+        wbe = oracle.convert_utf16be_to_utf8_with_errors(be)
+        assert wbe[0] == want[0] and wbe[1].tobytes() == want[1].tobytes()
+        assert oracle.change_endianness_utf16(a).tobytes() == be.tobytes()
+        if ref.has_be():
+            for im in impls:
+                assert ref.count_utf16be(im, be) == oracle.count_utf16be(be)
+                assert ref.utf8_length_from_utf16be(im, be) == oracle.utf8_length_from_utf16be(be)
+                assert ref.validate_utf16be_with_errors(im, be) == oracle.validate_utf16be_with_errors(be)
+                r, o = ref.convert_utf16be_to_utf8_with_errors(im, be)
+                assert r == wbe[0] and o.tobytes() == wbe[1].tobytes(), (im, u)
+                assert ref.change_endianness_utf16(im, a).tobytes() == be.tobytes()
     abc = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/-_"
     simd = [i for i in impls if i != "fallback"] or impls
     for it in range(1500):

@@ -39,6 +39,15 @@ HOT = {
     ("convert_utf16le_to_utf8", "const char16_t *"), ("convert_utf16le_to_utf8_with_errors", "const char16_t *"),
     ("convert_valid_utf16le_to_utf8", "const char16_t *"),
     ("base64_to_binary", "const char *"), ("base64_to_binary_details", "const char *"),
+    # UTF-16BE twins + change_endianness_utf16
+    ("count_utf16be", "const char16_t *"), ("utf32_length_from_utf16be", "const char16_t *"),
+    ("utf8_length_from_utf16be", "const char16_t *"),
+    ("validate_utf16be", "const char16_t *"), ("validate_utf16be_with_errors", "const char16_t *"),
+    ("convert_utf8_to_utf16be", "const char *"), ("convert_utf8_to_utf16be_with_errors", "const char *"),
+    ("convert_valid_utf8_to_utf16be", "const char *"),
+    ("convert_utf16be_to_utf8", "const char16_t *"), ("convert_utf16be_to_utf8_with_errors", "const char16_t *"),
+    ("convert_valid_utf16be_to_utf8", "const char16_t *"),
+    ("change_endianness_utf16", "const char16_t *"),
 }
 
 hdr = open(os.path.join(ref, "include/simdutf/implementation.h")).read()
