@@ -446,7 +446,13 @@ def side_measurements(b, lib, synth, torch, device, stream, sp, peak, K):
     o32 = torch.empty(chars, dtype=torch.int32, device=device)
     ms = timeit(lambda: lib.b200_convert_utf8_to_utf32_async(mp, n, ctypes.c_void_p(o32.data_ptr()), res_p, sp), max(3, K // 2))
     out["convert_utf8_to_utf32_mixed_1GiB"] = {"input_gbs": n / ms / 1e6, "ms": ms, "frac_of_peak": (n + 4 * chars) / ms / 1e6 / peak}
-    del m, o32
+    # §8f rank 1: UTF-8 -> UTF-16BE (same kernel, byte planes swapped)
+    units = b.utf16_length_from_utf8(m)
+    o16 = torch.empty(units, dtype=torch.int16, device=device)
+    ms = timeit(lambda: lib.b200_convert_utf8_to_utf16be_async(mp, n, ctypes.c_void_p(o16.data_ptr()), res_p, sp), max(3, K // 2))
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == units
+    out["next_convert_utf8_to_utf16be_mixed_1GiB"] = {"input_gbs": n / ms / 1e6, "ms": ms, "frac_of_peak": (n + 2 * units) / ms / 1e6 / peak}
+    del m, o32, o16
     # config 3: UTF-16LE -> UTF-8, 2 GiB
     u = synth.mixed_utf16le(GIB, seed=3, device=device)
     nu = int(u.numel())
@@ -458,7 +464,17 @@ def side_measurements(b, lib, synth, torch, device, stream, sp, peak, K):
     out["config3_convert_utf16le_to_utf8_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": (2 * nu + nb) / ms / 1e6 / peak}
     ms = timeit(lambda: lib.b200_count_utf16le_async(up, nu, res_p, sp), K)
     out["config3_count_utf16le_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": 2 * nu / ms / 1e6 / peak}
-    del u, o8
+    ms = timeit(lambda: lib.b200_utf8_length_from_utf16le_async(up, nu, res_p, sp), K)
+    out["config3_utf8_length_from_utf16le_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": 2 * nu / ms / 1e6 / peak}
+    # §8f rank 1: change_endianness_utf16, then UTF-16BE -> UTF-8 on the swapped buffer
+    ube = torch.empty_like(u)
+    ubp = ctypes.c_void_p(ube.data_ptr())
+    ms = timeit(lambda: lib.b200_change_endianness_utf16_async(up, nu, ubp, res_p, sp), K)
+    out["next_change_endianness_utf16_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": 4 * nu / ms / 1e6 / peak}
+    ms = timeit(lambda: lib.b200_convert_utf16be_to_utf8_async(ubp, nu, ctypes.c_void_p(o8.data_ptr()), res_p, sp), max(3, K // 2))
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == nb
+    out["next_convert_utf16be_to_utf8_2GiB"] = {"input_gbs": 2 * nu / ms / 1e6, "ms": ms, "frac_of_peak": (2 * nu + nb) / ms / 1e6 / peak}
+    del u, o8, ube
     # config 4: base64 decode, 2 GiB of text with CRLF every 76 + sparse whitespace
     text, payload = synth.base64_text(2 * GIB, seed=4, device=device)
     nt = int(text.numel())
