@@ -219,7 +219,7 @@ __device__ __forceinline__ void report_error(Scratch *scr, unsigned long long ke
 
 // Exact UTF-8 first-error search over byte positions [lo, hi) (virtual positions, clipped to the buffer),
 // reading the bytes straight from global memory.  Called only by threads whose granule tripped
-// u8_check_granule / the truncated-tail check.  Skips the work if an earlier error is already recorded.
+// bit-plane detector / the truncated-tail check.  Skips the work if an earlier error is already recorded.
 static __device__ __noinline__ void u8_locate_error_impl(const uint4 *base, unsigned long long vbeg,
                                                          unsigned long long vend, Scratch *scr, long long lo,
                                                          long long hi) {
