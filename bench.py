@@ -143,6 +143,15 @@ def threaded_cpp_run(sample_bytes: int, seed: int = 2):
     import torch
     from simdutf_b200 import synth
     data = synth.mixed_utf8(sample_bytes, seed=seed, device=torch.device("cpu")).numpy()
+    # threaded.cpp:70-73 backs its midpoint up only over continuation bytes 0x80..0x9F; give it a file whose midpoint
+    # is a character start (drop a few trailing characters until it is) so that both halves are valid UTF-8
+    for _ in range(64):
+        if (int(data[data.size // 2]) & 0xC0) != 0x80:
+            break
+        cut = data.size - 1
+        while (int(data[cut]) & 0xC0) == 0x80:
+            cut -= 1
+        data = data[:cut]
     n = int(data.size)
     with tempfile.NamedTemporaryFile(suffix=".utf8", delete=False) as f:
         f.write(data.tobytes())
@@ -157,7 +166,7 @@ def threaded_cpp_run(sample_bytes: int, seed: int = 2):
             if line.startswith(key + ":"):
                 ns[key] = float(line.split(":")[1])
     if len(ns) != 2:
-        return None
+        return {"unavailable": (p.stderr or p.stdout)[-200:].strip().replace("\n", " | ")}
     return {"single_thread_gbs": n / ns["singlethread"], "two_threads_gbs": n / ns["doublethread"], "unit": "GB/s",
             "kind": "reference", "what": "benchmarks/threaded.cpp as is: convert_utf8_to_utf16le only (no length query)",
             "sample": f"{n} bytes of the config-2 mixed UTF-8 distribution (seed {seed}) from a file"}
