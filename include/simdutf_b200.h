@@ -225,6 +225,14 @@ SIMDUTF_B200_API int b200_base64_to_binary(const char *d_in, size_t len, char *d
                           b200_full_result *h_res, void *stream);
 SIMDUTF_B200_API int b200_host_base64_to_binary(const char *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
                                b200_full_result *h_res);
+/* binary_to_base64 — implementation::binary_to_base64 (reference
+ * include/simdutf/implementation.h:4941-4960; semantics src/scalar/base64.h:435-491).  options: base64_default (0),
+ * base64_url (1), and the reverse-padding variants (2, 3).  d_out must hold base64_length_from_binary(len, options)
+ * characters (src/scalar/base64.h:515-533); result = {SUCCESS, characters written}. */
+SIMDUTF_B200_API int b200_binary_to_base64_async(const char *d_in, size_t len, char *d_out, uint64_t options, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_binary_to_base64(const char *d_in, size_t len, char *d_out, uint64_t options, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_binary_to_base64(const char *h_in, size_t len, char *h_out, uint64_t options, b200_result *h_res);
+SIMDUTF_B200_API size_t b200_base64_length_from_binary(size_t len, uint64_t options);
 /* implementation::maximal_binary_length_from_base64 (reference src/implementation.cpp:87-90 ->
  * src/scalar/base64.h:493-513): O(1), looks at the last two characters only; host pointer. */
 SIMDUTF_B200_API size_t b200_host_maximal_binary_length_from_base64(const char *h_in, size_t len);

@@ -94,6 +94,10 @@ for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _vp, _pres, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _vp, _pres])
+SYMBOLS["b200_binary_to_base64_async"] = (_I, [_vp, _sz, _vp, _u64, _vp, _vp])
+SYMBOLS["b200_binary_to_base64"] = (_I, [_vp, _sz, _vp, _u64, _pres, _vp])
+SYMBOLS["b200_host_binary_to_base64"] = (_I, [_vp, _sz, _vp, _u64, _pres])
+SYMBOLS["b200_base64_length_from_binary"] = (_sz, [_sz, _u64])
 SYMBOLS["b200_base64_to_binary_async"] = (_I, [_vp, _sz, _vp, _u64, _u64, _vp, _vp])
 SYMBOLS["b200_base64_to_binary"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull, _vp])
 SYMBOLS["b200_host_base64_to_binary"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull])
@@ -291,6 +295,26 @@ def change_endianness_utf16(data, out) -> None:
     err, _n = _convert_op("change_endianness_utf16", data, 2, out)
     if err:
         raise B200Error("change_endianness_utf16 failed")
+
+
+def base64_length_from_binary(length: int, options: int = 0) -> int:
+    return int(load().b200_base64_length_from_binary(length, options))
+
+
+def binary_to_base64(data, out, options: int = 0) -> int:
+    """simdutf::binary_to_base64 -> characters written (out must hold base64_length_from_binary(len, options))."""
+    lib = load()
+    res = Result()
+    if _is_cuda_tensor(data):
+        ptr, n = _dev_view(data, 1)
+        if not _is_cuda_tensor(out):
+            raise B200Error("device input needs a device output buffer")
+        _check(lib.b200_binary_to_base64(ptr, n, int(out.data_ptr()), options, ctypes.byref(res), _stream_of(data)), "binary_to_base64")
+    else:
+        ptr, n, _keep = _host_view(data, 1)
+        optr, _on, _okeep = _host_view(out, 1)
+        _check(lib.b200_host_binary_to_base64(ptr, n, optr, options, ctypes.byref(res)), "binary_to_base64")
+    return int(res.count)
 
 
 def base64_to_binary_details(data, out, options: int = base64_default, last_chunk: int = loose):

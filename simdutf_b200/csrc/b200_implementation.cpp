@@ -181,6 +181,14 @@ result implementation::base64_to_binary(const char *input, size_t length, char *
   return base64_to_binary_details(input, length, output, options, last_chunk_options);
 }
 
+// ---- binary_to_base64 (:4941-4960) ----
+size_t implementation::binary_to_base64(const char *input, size_t length, char *output,
+                                        base64_options options) const noexcept {
+  b200_result r;
+  if (b200_host_binary_to_base64(input, length, output, uint64_t(options) & 3u, &r) != 0) return 0;
+  return size_t(r.count);
+}
+
 // ---- everything outside the hot path: the reference's "unsupported" answers (generated) ----
 #include "b200_stubs.inc"
 

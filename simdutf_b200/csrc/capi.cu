@@ -233,7 +233,8 @@ enum Op {
   kOpUtf8LenFromUtf16BE,
   kOpValidateUtf16BE,
   kOpUtf16BEToUtf8,
-  kOpSwapUtf16
+  kOpSwapUtf16,
+  kOpBase64Encode  // binary_to_base64
 };
 
 size_t tiles_needed(Op op, const void *in, size_t len) {
@@ -280,6 +281,10 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
     case kOpSwapUtf16:
       B200_CUDA(launch_change_endianness_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<uint16_t *>(out)));
       B200_CUDA(launch_write_result(res, B200_SUCCESS, len, lc.stream));
+      break;
+    case kOpBase64Encode:
+      B200_CUDA(launch_binary_to_base64(lc, static_cast<const char *>(in), len, static_cast<char *>(out), opt));
+      B200_CUDA(launch_write_result(res, B200_SUCCESS, base64_length_from_binary(len, opt), lc.stream));
       break;
     case kOpBase64: B200_CUDA(launch_base64_to_binary(lc, static_cast<const char *>(in), len, static_cast<char *>(out), opt, lastc, res)); break;
   }
@@ -333,6 +338,7 @@ size_t max_out_bytes(Op op, size_t len) {
     case kOpUtf8ToUtf32: return 4 * len;
     case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return 3 * len;       // <= 3 bytes per unit
     case kOpSwapUtf16: return 2 * len;
+    case kOpBase64Encode: return (len + 2) / 3 * 4;
     case kOpBase64: return len / 4 * 3 + 3;
     default: return 0;
   }
@@ -392,6 +398,7 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
       if ((p[cut] & 0x00FCu) == 0x00DCu && (p[cut - 1] & 0x00FCu) == 0x00D8u) cut--;
       return cut;
     }
+    case kOpBase64Encode: return beg + per / 3 * 3;  // whole 3-byte groups: only the last segment pads
     default: return cut;  // the counts are sums over any partition; change_endianness is a map
   }
 }
@@ -631,6 +638,20 @@ B200_DEFINE_CONVERT_OP(convert_utf16le_to_utf8, kOpUtf16ToUtf8, uint16_t, char)
 B200_DEFINE_CONVERT_OP(convert_utf8_to_utf16be, kOpUtf8ToUtf16BE, char, uint16_t)
 B200_DEFINE_CONVERT_OP(convert_utf16be_to_utf8, kOpUtf16BEToUtf8, uint16_t, char)
 B200_DEFINE_CONVERT_OP(change_endianness_utf16, kOpSwapUtf16, uint16_t, uint16_t)
+
+int b200_binary_to_base64_async(const char *d_in, size_t len, char *d_out, uint64_t options, b200_result *d_res, void *stream) {
+  if (options > 3) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  return run_async(kOpBase64Encode, d_in, len, d_out, d_res, stream, options, 0);
+}
+int b200_binary_to_base64(const char *d_in, size_t len, char *d_out, uint64_t options, b200_result *h_res, void *stream) {
+  if (options > 3) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  return run_sync(kOpBase64Encode, d_in, len, d_out, h_res, stream, options, 0);
+}
+int b200_host_binary_to_base64(const char *h_in, size_t len, char *h_out, uint64_t options, b200_result *h_res) {
+  if (options > 3) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  return run_host(kOpBase64Encode, h_in, len, h_out, h_res, options, 0);
+}
+size_t b200_base64_length_from_binary(size_t len, uint64_t options) { return base64_length_from_binary(len, options); }
 
 static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
   return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;

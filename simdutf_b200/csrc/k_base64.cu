@@ -380,6 +380,83 @@ inline size_t workspace_slots(size_t tiles) {
   return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// binary_to_base64 (reference include/simdutf/implementation.h:4941-4960, semantics
+// src/scalar/base64.h:435-491): a fixed 3 -> 4 map, no scan.  A thread takes 48 input bytes (three 128-bit loads) to
+// 64 characters (four 128-bit stores) when both pointers are 16-byte aligned; the value -> character map is
+// arithmetic on four sextets per word (+65, +6 from 26, -75 from 52, then the two alphabet-dependent symbols).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t b64_chars4(uint32_t v, uint32_t d62, uint32_t d63) {
+  // v: four sextets, one per byte.  (v + k) & 0x80 <=> sextet >= 128 - k; no carries between bytes (v <= 63)
+  const uint32_t m26 = ((v + 0x66666666u) >> 7) & 0x01010101u;
+  const uint32_t m52 = ((v + 0x4C4C4C4Cu) >> 7) & 0x01010101u;
+  const uint32_t m62 = ((v + 0x42424242u) >> 7) & 0x01010101u;
+  const uint32_t m63 = ((v + 0x41414141u) >> 7) & 0x01010101u;
+  // every intermediate byte stays in 0..255, so the word-wide adds and subtracts never cross a byte
+  return v + 0x41414141u + m26 * 6u - m52 * 75u - m62 * d62 + m63 * d63;
+}
+__device__ __forceinline__ uint32_t b64_spread(uint32_t t) {  // 24-bit group (first byte on top) -> four sextets
+  return ((t >> 18) & 0x3Fu) | ((t >> 4) & 0x3F00u) | ((t << 10) & 0x3F0000u) | ((t << 24) & 0x3F000000u);
+}
+__device__ __forceinline__ uint32_t b64_char1(uint32_t v, uint32_t d62, uint32_t d63) {
+  return b64_chars4(v, d62, d63) & 0xFFu;
+}
+
+__global__ void __launch_bounds__(kBlock) k_b64_encode(const uint8_t *in, size_t len, uint8_t *out, uint32_t url,
+                                                        uint32_t pad) {
+  const uint32_t d62 = url ? 13u : 15u, d63 = url ? 49u : 3u;
+  const size_t tid = (size_t)blockIdx.x * kBlock + threadIdx.x, nthreads = (size_t)gridDim.x * kBlock;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  const size_t ngroups = aligned ? len / 48 : 0;  // 48 bytes -> 64 characters
+  for (size_t g = tid; g < ngroups; g += nthreads) {
+    const uint4 *vi = reinterpret_cast<const uint4 *>(in) + 3 * g;
+    const uint4 a = ldg_stream_v4(vi), b = ldg_stream_v4(vi + 1), c = ldg_stream_v4(vi + 2);
+    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    uint32_t o[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // 12 bytes (3 words) -> 4 groups -> 16 characters
+      const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+      const uint32_t t0 = __byte_perm(w0, 0u, 0x4012);   // bytes 0 1 2
+      const uint32_t t1 = __byte_perm(w0, w1, 0x4345);   // bytes 3 | 0 1 of the next word (top byte: don't care)
+      const uint32_t t2 = __byte_perm(w1, w2, 0x4234);   // bytes 2 3 | 0
+      const uint32_t t3 = __byte_perm(w2, 0u, 0x4123);   // bytes 1 2 3
+      o[4 * k] = b64_chars4(b64_spread(t0), d62, d63);
+      o[4 * k + 1] = b64_chars4(b64_spread(t1), d62, d63);
+      o[4 * k + 2] = b64_chars4(b64_spread(t2), d62, d63);
+      o[4 * k + 3] = b64_chars4(b64_spread(t3), d62, d63);
+    }
+    uint4 *vo = reinterpret_cast<uint4 *>(out) + 4 * g;
+#pragma unroll
+    for (int k = 0; k < 4; k++) stg_stream_v4(vo + k, make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+  }
+  // whatever the vector path did not cover: whole groups of 3 bytes, one per thread and round
+  const size_t done = ngroups * 48, nq = (len - done) / 3;
+  for (size_t q = tid; q < nq; q += nthreads) {
+    const uint8_t *p = in + done + 3 * q;
+    const uint32_t t = ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | p[2];
+    const uint32_t ch = b64_chars4(b64_spread(t), d62, d63);
+    uint8_t *d = out + done / 3 * 4 + 4 * q;
+    d[0] = (uint8_t)ch; d[1] = (uint8_t)(ch >> 8); d[2] = (uint8_t)(ch >> 16); d[3] = (uint8_t)(ch >> 24);
+  }
+  if (tid == 0) {  // the 1 or 2 trailing bytes (reference src/scalar/base64.h:466-489)
+    const size_t full = len / 3, rem = len - 3 * full;
+    const uint8_t *p = in + 3 * full;
+    uint8_t *d = out + 4 * full;
+    if (rem == 1) {
+      const uint32_t t = (uint32_t)p[0] << 16;
+      d[0] = (uint8_t)b64_char1((t >> 18) & 63u, d62, d63);
+      d[1] = (uint8_t)b64_char1((t >> 12) & 63u, d62, d63);
+      if (pad) { d[2] = '='; d[3] = '='; }
+    } else if (rem == 2) {
+      const uint32_t t = ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8);
+      d[0] = (uint8_t)b64_char1((t >> 18) & 63u, d62, d63);
+      d[1] = (uint8_t)b64_char1((t >> 12) & 63u, d62, d63);
+      d[2] = (uint8_t)b64_char1((t >> 6) & 63u, d62, d63);
+      if (pad) d[3] = '=';
+    }
+  }
+}
+
 }  // namespace
 
 size_t base64_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, len)); }
@@ -420,6 +497,24 @@ cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t l
                                                   static_cast<FullResultPOD *>(full_res));
   }
   count_launch(2);
+  return cudaGetLastError();
+}
+
+// reference src/scalar/base64.h:515-533
+size_t base64_length_from_binary(size_t len, uint64_t options) {
+  const bool url = (options & 1u) != 0, reverse = (options & 2u) != 0;
+  const bool pad = url == reverse;  // default pads, url does not, reverse_padding flips either
+  if (!pad) return len / 3 * 4 + ((len % 3) ? (len % 3) + 1 : 0);
+  return (len + 2) / 3 * 4;
+}
+
+cudaError_t launch_binary_to_base64(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options) {
+  const bool url = (options & 1u) != 0, reverse = (options & 2u) != 0;
+  const unsigned long long want = (len / 48 + kBlock - 1) / kBlock + 1;
+  const unsigned long long cap = (unsigned long long)c.sm_count * 16;
+  k_b64_encode<<<(unsigned)(want < cap ? want : cap), kBlock, 0, c.stream>>>(
+      reinterpret_cast<const uint8_t *>(in), len, reinterpret_cast<uint8_t *>(out), url ? 1u : 0u, url == reverse ? 1u : 0u);
+  count_launch(1);
   return cudaGetLastError();
 }
 

@@ -53,6 +53,10 @@ cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *i
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
                                     uint64_t last_chunk, void *full_res);
 
+// binary_to_base64: `out` must hold base64_length_from_binary(len, options) characters.
+size_t base64_length_from_binary(size_t len, uint64_t options);
+cudaError_t launch_binary_to_base64(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options);
+
 void count_launch(int n);  // bumps the library-wide launch counter (b200_launch_count)
 
 }  // namespace b200

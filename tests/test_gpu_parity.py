@@ -476,6 +476,47 @@ def test_utf16be_twins(b, oracle):
     assert torch.equal(back, d)
 
 
+def test_binary_to_base64(b, oracle):
+    """binary_to_base64 for the four option values (default / url, with and without padding)
+    against the oracle, every length class and pointer alignment, device and host path, and a decode round trip."""
+    rng = random.Random(64)
+    for it in range(120):
+        n = rng.choice([0, 1, 2, 3, 4, 5, 47, 48, 49, 95, 96, 97, 1000, 4095, 4096, 4097, 50000, 300001])
+        raw = bytes(rng.randrange(256) for _ in range(min(n, 5000))) * (n // 5000 + 1)
+        raw = raw[:n]
+        for opt in (0, 1, 2, 3):
+            want = oracle.binary_to_base64(raw, opt)
+            assert b.base64_length_from_binary(n, opt) == len(want)
+            for mi, mo in ((0, 0), (rng.randrange(16), rng.randrange(16))):
+                d = dev(raw, misalign=mi)
+                _, o = out_buf(len(want), torch.uint8, misalign=mo)
+                assert b.binary_to_base64(d, o, opt) == len(want), (n, opt, mi, mo)
+                assert o[:len(want)].cpu().numpy().tobytes() == want, (n, opt, mi, mo)
+                check_guard(o, len(want), 0x5A)
+            if it % 10 == 0:
+                h = np.zeros(len(want) + 4, dtype=np.uint8)
+                assert b.binary_to_base64(raw, h, opt) == len(want) and h[:len(want)].tobytes() == want
+    # 64 MiB round trip through the decoder (both alphabets), and the streamed host path (> 48 MiB)
+    payload = torch.randint(0, 256, ((1 << 26) + 1,), dtype=torch.uint8, device="cuda")
+    for opt in (0, 1):
+        nchar = b.base64_length_from_binary(payload.numel(), opt)
+        text = torch.empty(nchar, dtype=torch.uint8, device="cuda")
+        assert b.binary_to_base64(payload, text, opt) == nchar
+        back = torch.empty(payload.numel() + 3, dtype=torch.uint8, device="cuda")
+        e, i, k = b.base64_to_binary_details(text, back, opt, 0)
+        assert (e, k) == (0, payload.numel()) and torch.equal(back[:k], payload)
+    hp = payload.cpu().numpy()
+    ht = np.zeros(b.base64_length_from_binary(hp.size, 0) + 4, dtype=np.uint8)
+    assert b.binary_to_base64(hp, ht, 0) == ht.size - 4
+    assert ht[:ht.size - 4].tobytes() == text_default(b, payload)
+
+
+def text_default(b, payload):
+    t = torch.empty(b.base64_length_from_binary(payload.numel(), 0), dtype=torch.uint8, device="cuda")
+    b.binary_to_base64(payload, t, 0)
+    return t.cpu().numpy().tobytes()
+
+
 def test_repeated_calls_and_epoch_wrap(b, oracle):
     """More than 4096 scan launches on one stream: the 12-bit descriptor epoch wraps and must be handled."""
     from simdutf_b200 import synth

@@ -48,6 +48,7 @@ HOT = {
     ("convert_utf16be_to_utf8", "const char16_t *"), ("convert_utf16be_to_utf8_with_errors", "const char16_t *"),
     ("convert_valid_utf16be_to_utf8", "const char16_t *"),
     ("change_endianness_utf16", "const char16_t *"),
+    ("binary_to_base64", "const char *"),
 }
 
 hdr = open(os.path.join(ref, "include/simdutf/implementation.h")).read()
