@@ -225,6 +225,15 @@ SIMDUTF_B200_API int b200_base64_to_binary(const char *d_in, size_t len, char *d
                           b200_full_result *h_res, void *stream);
 SIMDUTF_B200_API int b200_host_base64_to_binary(const char *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
                                b200_full_result *h_res);
+/* base64 decode from char16_t input — implementation::base64_to_binary[_details](const char16_t*, ...)
+ * (reference include/simdutf/implementation.h:4922-4939, 4976-5014): units above 0xFF are invalid characters
+ * (src/scalar/base64.h:24-31, :125); everything else as for `char` input.  `len` in 16-bit units. */
+SIMDUTF_B200_API int b200_base64_to_binary_utf16_async(const uint16_t *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
+                                      b200_full_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_base64_to_binary_utf16(const uint16_t *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
+                                b200_full_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_base64_to_binary_utf16(const uint16_t *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
+                                     b200_full_result *h_res);
 /* binary_to_base64 — implementation::binary_to_base64 (reference
  * include/simdutf/implementation.h:4941-4960; semantics src/scalar/base64.h:435-491).  options: base64_default (0),
  * base64_url (1), and the reverse-padding variants (2, 3).  d_out must hold base64_length_from_binary(len, options)

@@ -94,6 +94,9 @@ for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _vp, _pres, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _vp, _pres])
+SYMBOLS["b200_base64_to_binary_utf16_async"] = (_I, [_vp, _sz, _vp, _u64, _u64, _vp, _vp])
+SYMBOLS["b200_base64_to_binary_utf16"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull, _vp])
+SYMBOLS["b200_host_base64_to_binary_utf16"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull])
 SYMBOLS["b200_binary_to_base64_async"] = (_I, [_vp, _sz, _vp, _u64, _vp, _vp])
 SYMBOLS["b200_binary_to_base64"] = (_I, [_vp, _sz, _vp, _u64, _pres, _vp])
 SYMBOLS["b200_host_binary_to_base64"] = (_I, [_vp, _sz, _vp, _u64, _pres])
@@ -329,6 +332,21 @@ def base64_to_binary_details(data, out, options: int = base64_default, last_chun
         ptr, n, _keep = _host_view(data, 1)
         optr, _on, _okeep = _host_view(out, 1)
         _check(lib.b200_host_base64_to_binary(ptr, n, optr, options, last_chunk, ctypes.byref(res)), "base64_to_binary")
+    return res.astuple()
+
+
+def base64_to_binary_details_utf16(data, out, options: int = base64_default, last_chunk: int = loose):
+    """simdutf::base64_to_binary_details for char16_t input (`data`: 16-bit units) -> (error, input_count, output_count)."""
+    lib = load()
+    res = FullResult()
+    if _is_cuda_tensor(data):
+        ptr, n = _dev_view(data, 2)
+        _check(lib.b200_base64_to_binary_utf16(ptr, n, int(out.data_ptr()), options, last_chunk, ctypes.byref(res),
+                                               _stream_of(data)), "base64_to_binary_utf16")
+    else:
+        ptr, n, _keep = _host_view(data, 2)
+        optr, _on, _okeep = _host_view(out, 1)
+        _check(lib.b200_host_base64_to_binary_utf16(ptr, n, optr, options, last_chunk, ctypes.byref(res)), "base64_to_binary_utf16")
     return res.astuple()
 
 

@@ -181,6 +181,21 @@ result implementation::base64_to_binary(const char *input, size_t length, char *
   return base64_to_binary_details(input, length, output, options, last_chunk_options);
 }
 
+// ---- base64 decode, char16_t input (:4922-4939, :4976-5014) ----
+full_result implementation::base64_to_binary_details(const char16_t *input, size_t length, char *output,
+                                                     base64_options options,
+                                                     last_chunk_handling_options last_chunk_options) const noexcept {
+  b200_full_result r;
+  if (b200_host_base64_to_binary_utf16(u16(input), length, output, uint64_t(options), uint64_t(last_chunk_options), &r) != 0) {
+    return full_result(error_code::OTHER, 0, 0);
+  }
+  return full_result(error_code(r.error), size_t(r.input_count), size_t(r.output_count));
+}
+result implementation::base64_to_binary(const char16_t *input, size_t length, char *output, base64_options options,
+                                        last_chunk_handling_options last_chunk_options) const noexcept {
+  return base64_to_binary_details(input, length, output, options, last_chunk_options);
+}
+
 // ---- binary_to_base64 (:4941-4960) ----
 size_t implementation::binary_to_base64(const char *input, size_t length, char *output,
                                         base64_options options) const noexcept {

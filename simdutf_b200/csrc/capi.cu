@@ -57,6 +57,8 @@ struct StreamWs {
   size_t desc_cap = 0;
   uint32_t epoch = 0;
   void *h_slot = nullptr;  // 64 B pinned + mapped: kernels write results straight into host memory
+  void *tmp = nullptr;     // grow-only device scratch (base64 from char16_t: the narrowed characters)
+  size_t tmp_cap = 0;
 };
 
 struct DeviceCtx {
@@ -153,8 +155,20 @@ DeviceCtx *current_ctx(int *err) {
 }
 
 // Workspace of `stream`, with room for `tiles` descriptors and a fresh epoch.  Caller holds c->mu.
-int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, StreamWs **out_ws) {
+int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, StreamWs **out_ws, size_t tmp_bytes = 0) {
   StreamWs &w = c->ws[stream];
+  if (tmp_bytes > w.tmp_cap) {
+    if (w.tmp) {
+      B200_CUDA(cudaStreamSynchronize(stream));
+      B200_CUDA(cudaFree(w.tmp));
+      w.tmp = nullptr;
+      w.tmp_cap = 0;
+    }
+    const size_t want = tmp_bytes + tmp_bytes / 8 + 4096;
+    B200_CUDA(cudaMalloc(&w.tmp, want));
+    w.tmp_cap = want;
+  }
+  lc->tmp = w.tmp;
   if (!w.scratch) {
     B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&w.scratch), sizeof(Scratch)));
     B200_CUDA(launch_scratch_init(w.scratch, stream));
@@ -234,8 +248,11 @@ enum Op {
   kOpValidateUtf16BE,
   kOpUtf16BEToUtf8,
   kOpSwapUtf16,
-  kOpBase64Encode  // binary_to_base64
+  kOpBase64Encode,  // binary_to_base64
+  kOpBase64U16      // base64_to_binary for char16_t input
 };
+
+size_t tmp_needed(Op op, size_t len) { return op == kOpBase64U16 ? len + 64 : 0; }
 
 size_t tiles_needed(Op op, const void *in, size_t len) {
   switch (op) {
@@ -243,6 +260,7 @@ size_t tiles_needed(Op op, const void *in, size_t len) {
     case kOpUtf8ToUtf32: return utf8_to_utf32_tiles(in, len);
     case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return utf16_convert_tiles(in, len);
     case kOpBase64: return base64_tiles(in, len);
+    case kOpBase64U16: return base64_tiles(nullptr, len + 16);  // the narrowed copy is 16-byte aligned
     default: return 0;
   }
 }
@@ -255,7 +273,7 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
       case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE:
         B200_CUDA(launch_write_u64(static_cast<unsigned long long *>(res), 0, lc.stream));
         return 0;
-      case kOpBase64:
+      case kOpBase64: case kOpBase64U16:
         B200_CUDA(launch_write_full_result(res, B200_SUCCESS, 0, 0, lc.stream));
         return 0;
       default:
@@ -282,6 +300,9 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
       B200_CUDA(launch_change_endianness_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<uint16_t *>(out)));
       B200_CUDA(launch_write_result(res, B200_SUCCESS, len, lc.stream));
       break;
+    case kOpBase64U16:
+      B200_CUDA(launch_base64_to_binary_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), opt, lastc, res));
+      break;
     case kOpBase64Encode:
       B200_CUDA(launch_binary_to_base64(lc, static_cast<const char *>(in), len, static_cast<char *>(out), opt));
       B200_CUDA(launch_write_result(res, B200_SUCCESS, base64_length_from_binary(len, opt), lc.stream));
@@ -295,7 +316,7 @@ size_t result_bytes(Op op) {
   switch (op) {
     case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
     case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: return 8;
-    case kOpBase64: return sizeof(b200_full_result);
+    case kOpBase64: case kOpBase64U16: return sizeof(b200_full_result);
     default: return sizeof(b200_result);
   }
 }
@@ -310,7 +331,7 @@ int run_async(Op op, const void *d_in, size_t len, void *d_out, void *d_res, voi
   if (!c) return err;
   std::lock_guard<std::mutex> lock(c->mu);
   LaunchCtx lc;
-  if ((err = get_ws(c, static_cast<cudaStream_t>(stream), tiles_needed(op, d_in, len), &lc, nullptr))) return err;
+  if ((err = get_ws(c, static_cast<cudaStream_t>(stream), tiles_needed(op, d_in, len), &lc, nullptr, tmp_needed(op, len)))) return err;
   return enqueue(op, lc, d_in, len, d_out, d_res, opt, lastc);
 }
 
@@ -323,7 +344,7 @@ int run_sync(Op op, const void *d_in, size_t len, void *d_out, void *h_res, void
   std::lock_guard<std::mutex> lock(c->mu);
   LaunchCtx lc;
   StreamWs *w = nullptr;
-  if ((err = get_ws(c, static_cast<cudaStream_t>(stream), tiles_needed(op, d_in, len), &lc, &w))) return err;
+  if ((err = get_ws(c, static_cast<cudaStream_t>(stream), tiles_needed(op, d_in, len), &lc, &w, tmp_needed(op, len)))) return err;
   if ((err = enqueue(op, lc, d_in, len, d_out, w->h_slot, opt, lastc))) return err;
   B200_CUDA(cudaStreamSynchronize(lc.stream));
   std::memcpy(h_res, w->h_slot, result_bytes(op));
@@ -339,14 +360,15 @@ size_t max_out_bytes(Op op, size_t len) {
     case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return 3 * len;       // <= 3 bytes per unit
     case kOpSwapUtf16: return 2 * len;
     case kOpBase64Encode: return (len + 2) / 3 * 4;
-    case kOpBase64: return len / 4 * 3 + 3;
+    case kOpBase64: case kOpBase64U16: return len / 4 * 3 + 3;
     default: return 0;
   }
 }
 size_t in_elem_bytes(Op op) {
   switch (op) {
     case kOpCountUtf16: case kOpUtf8LenFromUtf16: case kOpValidateUtf16: case kOpUtf16ToUtf8:
-    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpSwapUtf16: return 2;
+    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpSwapUtf16:
+    case kOpBase64U16: return 2;
     default: return 1;
   }
 }
@@ -375,7 +397,7 @@ static const size_t kSegmentBytes = [] {
   return size_t(v >= 1 && v <= 1024 ? v : 32) << 20;
 }();
 
-bool op_streams(Op op) { return op != kOpBase64; }  // base64 quanta straddle any cut: single shot
+bool op_streams(Op op) { return op != kOpBase64 && op != kOpBase64U16; }  // base64 quanta straddle any cut: single shot
 
 // End (exclusive, in elements) of the segment that starts at `beg`.
 size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
@@ -494,7 +516,7 @@ int run_host_streamed(DeviceCtx *c, Op op, const void *h_in, size_t len, void *h
     B200_CUDA(cudaEventRecord(sl.h2d_done, c->s_copy));
     B200_CUDA(cudaStreamWaitEvent(c->s_main, sl.h2d_done, 0));
     LaunchCtx lc;
-    if ((err = get_ws(c, c->s_main, tiles_needed(op, sl.d_in, n), &lc, nullptr))) return err;
+    if ((err = get_ws(c, c->s_main, tiles_needed(op, sl.d_in, n), &lc, nullptr, tmp_needed(op, n)))) return err;
     if ((err = enqueue(op, lc, sl.d_in, n, sl.d_out, sl.h_res, opt, lastc))) return err;
     B200_CUDA(cudaEventRecord(sl.kernel_done, c->s_main));
     issued++;
@@ -544,14 +566,14 @@ int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint
   if (out_cap && (err = ensure(&c->d_out, &c->d_out_cap, out_cap + 16, c->s_main, c->s_copy))) return err;
   LaunchCtx lc;
   StreamWs *w = nullptr;
-  if ((err = get_ws(c, c->s_main, tiles_needed(op, c->d_in, len), &lc, &w))) return err;
+  if ((err = get_ws(c, c->s_main, tiles_needed(op, c->d_in, len), &lc, &w, tmp_needed(op, len)))) return err;
   B200_CUDA(cudaMemcpyAsync(c->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, c->s_main));
   if ((err = enqueue(op, lc, c->d_in, len, c->d_out, w->h_slot, opt, lastc))) return err;
   B200_CUDA(cudaStreamSynchronize(c->s_main));
   std::memcpy(h_res, w->h_slot, result_bytes(op));
   if (out_cap && h_out) {
     size_t produced = 0;
-    if (op == kOpBase64) {
+    if (op == kOpBase64 || op == kOpBase64U16) {
       const b200_full_result *r = static_cast<const b200_full_result *>(h_res);
       produced = (size_t)r->output_count;
       // output_count is 0 on INVALID_BASE64_CHARACTER (unpinned by the reference), so nothing is copied back then
@@ -639,6 +661,24 @@ B200_DEFINE_CONVERT_OP(convert_utf8_to_utf16be, kOpUtf8ToUtf16BE, char, uint16_t
 B200_DEFINE_CONVERT_OP(convert_utf16be_to_utf8, kOpUtf16BEToUtf8, uint16_t, char)
 B200_DEFINE_CONVERT_OP(change_endianness_utf16, kOpSwapUtf16, uint16_t, uint16_t)
 
+static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
+  return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;
+}
+int b200_base64_to_binary_utf16_async(const uint16_t *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
+                                      b200_full_result *d_res, void *stream) {
+  if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  return run_async(kOpBase64U16, d_in, len, d_out, d_res, stream, options, last_chunk);
+}
+int b200_base64_to_binary_utf16(const uint16_t *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
+                                b200_full_result *h_res, void *stream) {
+  if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  return run_sync(kOpBase64U16, d_in, len, d_out, h_res, stream, options, last_chunk);
+}
+int b200_host_base64_to_binary_utf16(const uint16_t *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
+                                     b200_full_result *h_res) {
+  if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
+  return run_host(kOpBase64U16, h_in, len, h_out, h_res, options, last_chunk);
+}
 int b200_binary_to_base64_async(const char *d_in, size_t len, char *d_out, uint64_t options, b200_result *d_res, void *stream) {
   if (options > 3) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");
   return run_async(kOpBase64Encode, d_in, len, d_out, d_res, stream, options, 0);
@@ -653,9 +693,6 @@ int b200_host_binary_to_base64(const char *h_in, size_t len, char *h_out, uint64
 }
 size_t b200_base64_length_from_binary(size_t len, uint64_t options) { return base64_length_from_binary(len, options); }
 
-static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
-  return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;
-}
 int b200_base64_to_binary_async(const char *d_in, size_t len, char *d_out, uint64_t options, uint64_t last_chunk,
                                 b200_full_result *d_res, void *stream) {
   if (!b64_options_ok(options, last_chunk)) return fail(B200_E_BAD_ARGUMENT, "bad base64 argument");

@@ -500,6 +500,28 @@ cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t l
   return cudaGetLastError();
 }
 
+// base64_to_binary for char16_t input (reference include/simdutf/implementation.h:4922-4939; the scalar decoder reads
+// `c > 255 ? invalid : table[c]`, src/scalar/base64.h:46-50): the units are narrowed one to one into the stream's
+// scratch buffer — a unit above 0xFF becomes 0xFF, which no alphabet accepts — and the byte decoder runs on the copy,
+// so positions and counts are the same.
+__global__ void __launch_bounds__(kBlock) k_b64_narrow_utf16(const uint16_t *in, size_t len, uint8_t *out) {
+  const size_t tid = (size_t)blockIdx.x * kBlock + threadIdx.x, nthreads = (size_t)gridDim.x * kBlock;
+  for (size_t i = tid; i < len; i += nthreads) {
+    const uint32_t u = in[i];
+    out[i] = (uint8_t)(u > 0xFFu ? 0xFFu : u);
+  }
+}
+
+cudaError_t launch_base64_to_binary_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, uint64_t options,
+                                          uint64_t last_chunk, void *full_res) {
+  if (!c.tmp) return cudaErrorInvalidValue;
+  const unsigned long long want = (len + kBlock - 1) / kBlock;
+  const unsigned long long cap = (unsigned long long)c.sm_count * 32;
+  k_b64_narrow_utf16<<<(unsigned)(want < cap ? (want ? want : 1) : cap), kBlock, 0, c.stream>>>(in, len, static_cast<uint8_t *>(c.tmp));
+  count_launch(1);
+  return launch_base64_to_binary(c, static_cast<const char *>(c.tmp), len, out, options, last_chunk, full_res);
+}
+
 // reference src/scalar/base64.h:515-533
 size_t base64_length_from_binary(size_t len, uint64_t options) {
   const bool url = (options & 1u) != 0, reverse = (options & 2u) != 0;

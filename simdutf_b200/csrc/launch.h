@@ -18,6 +18,7 @@ struct LaunchCtx {
   size_t desc_capacity;
   unsigned long long *cnt;  // second array of desc_capacity slots: per-tile counts (never aliases descriptors, whose
                             // epoch tags must not be imitated by stale data)
+  void *tmp;                // grow-only device scratch of the stream (sized by the caller of get_ws)
   uint32_t epoch;
   int sm_count;
   cudaStream_t stream;
@@ -53,6 +54,9 @@ cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *i
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
                                     uint64_t last_chunk, void *full_res);
 
+// base64 from char16_t input: narrows into c.tmp (len + 64 bytes), then the byte decoder
+cudaError_t launch_base64_to_binary_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, uint64_t options,
+                                          uint64_t last_chunk, void *full_res);
 // binary_to_base64: `out` must hold base64_length_from_binary(len, options) characters.
 size_t base64_length_from_binary(size_t len, uint64_t options);
 cudaError_t launch_binary_to_base64(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options);

@@ -511,6 +511,36 @@ def test_binary_to_base64(b, oracle):
     assert ht[:ht.size - 4].tobytes() == text_default(b, payload)
 
 
+def test_base64_from_utf16_input(b, oracle):
+    """base64_to_binary for char16_t input: the byte decoder on the narrowed characters, a unit above 0xFF being an
+    invalid character (reference src/scalar/base64.h:24-31, :125) — all options, device and host path."""
+    rng = random.Random(1616)
+    for it in range(80):
+        n = rng.choice([0, 1, 3, 4, 5, 63, 64, 65, 1000, 4097, 30000])
+        chars = bytearray()
+        for _ in range(n):
+            x = rng.random()
+            chars.append(rng.choice(ABC[:64]) if x < 0.9 else rng.choice(b" \t\n\r\x0c") if x < 0.98 else rng.choice(b"=*"))
+        chars += rng.choice([b"", b"=", b"==", b" = "])
+        u = np.frombuffer(bytes(chars), dtype=np.uint8).astype(np.uint16)
+        if it % 3 == 0 and u.size:
+            u[rng.randrange(u.size)] = rng.choice([0x0141, 0x2020, 0xFF41, 0x013D])  # low byte looks valid, unit is not
+        narrowed = np.where(u > 0xFF, 0xFF, u).astype(np.uint8).tobytes()
+        for opt in ((0, 1, 4, 8) if it % 2 else (0,)):
+            for lc in (0, 1, 2):
+                want, wout = oracle.base64_to_binary_details(narrowed, opt, lc)
+                cap = oracle.maximal_binary_length_from_base64(narrowed)
+                d = dev(u.view(np.uint8), dtype=torch.uint8, misalign=2 * rng.randrange(8)).view(torch.int16)
+                _, o = out_buf(cap, torch.uint8, misalign=rng.randrange(16))
+                got = b.base64_to_binary_details_utf16(d, o, opt, lc)
+                assert got[:2] == want[:2], (bytes(chars), opt, lc, got, want)
+                if want[0] not in (7, 9):
+                    assert got == want and o[:want[2]].cpu().numpy().tobytes() == wout.tobytes()
+                if it % 8 == 0:
+                    h = np.zeros(cap + 4, dtype=np.uint8)
+                    assert b.base64_to_binary_details_utf16(u, h, opt, lc)[:2] == want[:2]
+
+
 def text_default(b, payload):
     t = torch.empty(b.base64_length_from_binary(payload.numel(), 0), dtype=torch.uint8, device="cuda")
     b.binary_to_base64(payload, t, 0)

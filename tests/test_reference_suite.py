@@ -27,6 +27,8 @@ HOT = [
     "convert_utf8_to_utf16be_tests", "convert_valid_utf8_to_utf16be_tests",
     "convert_utf16be_to_utf8_tests", "convert_valid_utf16be_to_utf8_tests",
     "count_utf16be", "validate_utf16be_basic_tests", "validate_utf16be_with_errors_tests", "utf8_length_from_utf16_tests",
+    # base64 both ways, char and char16_t input, every option: the whole reference binary
+    "base64_tests",
 ]
 
 

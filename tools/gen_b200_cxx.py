@@ -49,6 +49,7 @@ HOT = {
     ("convert_valid_utf16be_to_utf8", "const char16_t *"),
     ("change_endianness_utf16", "const char16_t *"),
     ("binary_to_base64", "const char *"),
+    ("base64_to_binary", "const char16_t *"), ("base64_to_binary_details", "const char16_t *"),
 }
 
 hdr = open(os.path.join(ref, "include/simdutf/implementation.h")).read()
