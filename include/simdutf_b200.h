@@ -225,6 +225,44 @@ SIMDUTF_B200_API int b200_base64_to_binary(const char *d_in, size_t len, char *d
                           b200_full_result *h_res, void *stream);
 SIMDUTF_B200_API int b200_host_base64_to_binary(const char *h_in, size_t len, char *h_out, uint64_t options, uint64_t last_chunk,
                                b200_full_result *h_res);
+/* ------------------------------------------------------------------------- */
+/* UTF-32 family (second part).  `len` in input elements. */
+/* implementation::validate_utf32[_with_errors] (reference                      */
+/* include/simdutf/implementation.h:3533-3569; src/scalar/utf32.h:10-38),       */
+/* ::utf8_length_from_utf32 / ::utf16_length_from_utf32 (:4586-4620;            */
+/* src/scalar/utf32.h:40-66), ::convert_utf32_to_utf8[_with_errors] (:4370-4410;*/
+/* src/scalar/utf32_to_utf8/utf32_to_utf8.h:63-124),                            */
+/* ::convert_utf32_to_utf16le/be[_with_errors] (:4440-4565;                     */
+/* src/scalar/utf32_to_utf16/utf32_to_utf16.h:40-86),                           */
+/* ::convert_utf16le/be_to_utf32[_with_errors] (:4103-4259;                     */
+/* src/scalar/utf16_to_utf32/utf16_to_utf32.h:45-76).                           */
+/* result = {SUCCESS, elements written} or {SURROGATE | TOO_LARGE, input index}.*/
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_validate_utf32_with_errors_async(const uint32_t *d_in, size_t len, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_validate_utf32_with_errors(const uint32_t *d_in, size_t len, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_validate_utf32_with_errors(const uint32_t *h_in, size_t len, b200_result *h_res);
+SIMDUTF_B200_API int b200_utf8_length_from_utf32_async(const uint32_t *d_in, size_t len, uint64_t *d_res, void *stream);
+SIMDUTF_B200_API int b200_utf8_length_from_utf32(const uint32_t *d_in, size_t len, uint64_t *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_utf8_length_from_utf32(const uint32_t *h_in, size_t len, uint64_t *h_res);
+SIMDUTF_B200_API int b200_utf16_length_from_utf32_async(const uint32_t *d_in, size_t len, uint64_t *d_res, void *stream);
+SIMDUTF_B200_API int b200_utf16_length_from_utf32(const uint32_t *d_in, size_t len, uint64_t *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_utf16_length_from_utf32(const uint32_t *h_in, size_t len, uint64_t *h_res);
+SIMDUTF_B200_API int b200_convert_utf32_to_utf8_async(const uint32_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf32_to_utf8(const uint32_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf32_to_utf8(const uint32_t *h_in, size_t len, char *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf32_to_utf16le_async(const uint32_t *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf32_to_utf16le(const uint32_t *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf32_to_utf16le(const uint32_t *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf32_to_utf16be_async(const uint32_t *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf32_to_utf16be(const uint32_t *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf32_to_utf16be(const uint32_t *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf16le_to_utf32_async(const uint16_t *d_in, size_t len, uint32_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf16le_to_utf32(const uint16_t *d_in, size_t len, uint32_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf16le_to_utf32(const uint16_t *h_in, size_t len, uint32_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf16be_to_utf32_async(const uint16_t *d_in, size_t len, uint32_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf16be_to_utf32(const uint16_t *d_in, size_t len, uint32_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf16be_to_utf32(const uint16_t *h_in, size_t len, uint32_t *h_out, b200_result *h_res);
+
 /* base64 decode from char16_t input — implementation::base64_to_binary[_details](const char16_t*, ...)
  * (reference include/simdutf/implementation.h:4922-4939, 4976-5014): units above 0xFF are invalid characters
  * (src/scalar/base64.h:24-31, :125); everything else as for `char` input.  `len` in 16-bit units. */

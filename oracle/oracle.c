@@ -245,6 +245,111 @@ void oracle_change_endianness_utf16(const uint16_t *in, size_t len, uint16_t *ou
 }
 
 /* ------------------------------------------------------------------------- */
+/* UTF-32 (second part)                                 */
+/* ------------------------------------------------------------------------- */
+/* reference src/scalar/utf32.h:24-38 */
+oracle_result oracle_validate_utf32_with_errors(const uint32_t *in, size_t len) {
+  oracle_result r;
+  for (size_t pos = 0; pos < len; pos++) {
+    uint32_t w = in[pos];
+    if (w > 0x10FFFF) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+    if (w >= 0xD800 && w <= 0xDFFF) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+  }
+  r.error = ORACLE_SUCCESS; r.count = len;
+  return r;
+}
+/* reference src/scalar/utf32.h:40-53 */
+uint64_t oracle_utf8_length_from_utf32(const uint32_t *in, size_t len) {
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++) n += 1 + (in[i] > 0x7F) + (in[i] > 0x7FF) + (in[i] > 0xFFFF);
+  return n;
+}
+/* reference src/scalar/utf32.h:55-66 */
+uint64_t oracle_utf16_length_from_utf32(const uint32_t *in, size_t len) {
+  uint64_t n = 0;
+  for (size_t i = 0; i < len; i++) n += 1 + (in[i] > 0xFFFF);
+  return n;
+}
+/* reference src/scalar/utf32_to_utf8/utf32_to_utf8.h:63-124 */
+oracle_result oracle_convert_utf32_to_utf8_with_errors(const uint32_t *in, size_t len, uint8_t *out) {
+  oracle_result r;
+  uint64_t w = 0;
+  for (size_t pos = 0; pos < len; pos++) {
+    uint32_t c = in[pos];
+    if ((c & 0xFFFFFF80) == 0) {
+      out[w++] = (uint8_t)c;
+    } else if ((c & 0xFFFFF800) == 0) {
+      out[w++] = (uint8_t)((c >> 6) | 0xC0);
+      out[w++] = (uint8_t)((c & 0x3F) | 0x80);
+    } else if ((c & 0xFFFF0000) == 0) {
+      if (c >= 0xD800 && c <= 0xDFFF) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+      out[w++] = (uint8_t)((c >> 12) | 0xE0);
+      out[w++] = (uint8_t)(((c >> 6) & 0x3F) | 0x80);
+      out[w++] = (uint8_t)((c & 0x3F) | 0x80);
+    } else {
+      if (c > 0x10FFFF) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+      out[w++] = (uint8_t)((c >> 18) | 0xF0);
+      out[w++] = (uint8_t)(((c >> 12) & 0x3F) | 0x80);
+      out[w++] = (uint8_t)(((c >> 6) & 0x3F) | 0x80);
+      out[w++] = (uint8_t)((c & 0x3F) | 0x80);
+    }
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+/* reference src/scalar/utf32_to_utf16/utf32_to_utf16.h:40-86 */
+static oracle_result convert_utf32_to_utf16_impl(const uint32_t *in, size_t len, uint16_t *out, int be) {
+  oracle_result r;
+  uint64_t w = 0;
+  for (size_t pos = 0; pos < len; pos++) {
+    uint32_t c = in[pos];
+    if ((c & 0xFFFF0000) == 0) {
+      if (c >= 0xD800 && c <= 0xDFFF) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+      out[w++] = be ? swap16((uint16_t)c) : (uint16_t)c;
+    } else {
+      if (c > 0x10FFFF) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+      c -= 0x10000;
+      uint16_t hi = (uint16_t)(0xD800 + (c >> 10)), lo = (uint16_t)(0xDC00 + (c & 0x3FF));
+      out[w++] = be ? swap16(hi) : hi;
+      out[w++] = be ? swap16(lo) : lo;
+    }
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+oracle_result oracle_convert_utf32_to_utf16le_with_errors(const uint32_t *in, size_t len, uint16_t *out) {
+  return convert_utf32_to_utf16_impl(in, len, out, 0);
+}
+oracle_result oracle_convert_utf32_to_utf16be_with_errors(const uint32_t *in, size_t len, uint16_t *out) {
+  return convert_utf32_to_utf16_impl(in, len, out, 1);
+}
+/* reference src/scalar/utf16_to_utf32/utf16_to_utf32.h:45-76 */
+static oracle_result convert_utf16_to_utf32_impl(const uint16_t *in, size_t len, uint32_t *out, int be) {
+  oracle_result r;
+  size_t pos = 0; uint64_t w = 0;
+  while (pos < len) {
+    uint16_t u = ld16(in, pos, be);
+    if ((u & 0xF800) != 0xD800) {
+      out[w++] = u; pos++;
+    } else {
+      uint16_t diff = (uint16_t)(u - 0xD800);
+      if (diff > 0x3FF || pos + 1 >= len) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+      uint16_t diff2 = (uint16_t)(ld16(in, pos + 1, be) - 0xDC00);
+      if (diff2 > 0x3FF) { r.error = ORACLE_SURROGATE; r.count = pos; return r; }
+      out[w++] = ((uint32_t)diff << 10) + diff2 + 0x10000; pos += 2;
+    }
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+oracle_result oracle_convert_utf16le_to_utf32_with_errors(const uint16_t *in, size_t len, uint32_t *out) {
+  return convert_utf16_to_utf32_impl(in, len, out, 0);
+}
+oracle_result oracle_convert_utf16be_to_utf32_with_errors(const uint16_t *in, size_t len, uint32_t *out) {
+  return convert_utf16_to_utf32_impl(in, len, out, 1);
+}
+
+/* ------------------------------------------------------------------------- */
 /* Base64 (WHATWG forgiving decode)                                          */
 /* ------------------------------------------------------------------------- */
 /* Character class: 0..63 sextet, 64 = ASCII whitespace (' ' \t \n \r \f),   */

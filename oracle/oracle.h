@@ -76,6 +76,16 @@ oracle_result oracle_convert_utf16be_to_utf8_with_errors(const uint16_t *in, siz
 oracle_result oracle_convert_utf8_to_utf16be_with_errors(const uint8_t *in, size_t len, uint16_t *out);
 void oracle_change_endianness_utf16(const uint16_t *in, size_t len, uint16_t *out);
 
+/* UTF-32 family (second part) */
+oracle_result oracle_validate_utf32_with_errors(const uint32_t *in, size_t len);
+uint64_t oracle_utf8_length_from_utf32(const uint32_t *in, size_t len);
+uint64_t oracle_utf16_length_from_utf32(const uint32_t *in, size_t len);
+oracle_result oracle_convert_utf32_to_utf8_with_errors(const uint32_t *in, size_t len, uint8_t *out);
+oracle_result oracle_convert_utf32_to_utf16le_with_errors(const uint32_t *in, size_t len, uint16_t *out);
+oracle_result oracle_convert_utf32_to_utf16be_with_errors(const uint32_t *in, size_t len, uint16_t *out);
+oracle_result oracle_convert_utf16le_to_utf32_with_errors(const uint16_t *in, size_t len, uint32_t *out);
+oracle_result oracle_convert_utf16be_to_utf32_with_errors(const uint16_t *in, size_t len, uint32_t *out);
+
 uint64_t oracle_maximal_binary_length_from_base64(const uint8_t *in, size_t len);
 oracle_full_result oracle_base64_to_binary_details(const uint8_t *in, size_t len, uint8_t *out,
                                                    uint64_t options, uint64_t last_chunk);

@@ -141,6 +141,35 @@ int ref_change_endianness_utf16(const char *impl, const char16_t *in, size_t len
   auto *i = pick(impl); if (!i) return -1;
   i->change_endianness_utf16(in, len, dst); return 0;
 }
+// UTF-32 family (second part)
+int ref_validate_utf32_with_errors(const char *impl, const char32_t *in, size_t len, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->validate_utf32_with_errors(in, len);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int64_t ref_utf8_length_from_utf32(const char *impl, const char32_t *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->utf8_length_from_utf32(in, len));
+}
+int64_t ref_utf16_length_from_utf32(const char *impl, const char32_t *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->utf16_length_from_utf32(in, len));
+}
+int ref_convert_utf32_to_utf8_with_errors(const char *impl, const char32_t *in, size_t len, char *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->convert_utf32_to_utf8_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_convert_utf32_to_utf16_with_errors(const char *impl, int be, const char32_t *in, size_t len, char16_t *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = be ? i->convert_utf32_to_utf16be_with_errors(in, len, dst) : i->convert_utf32_to_utf16le_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_convert_utf16_to_utf32_with_errors(const char *impl, int be, const char16_t *in, size_t len, char32_t *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = be ? i->convert_utf16be_to_utf32_with_errors(in, len, dst) : i->convert_utf16le_to_utf32_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
 int64_t ref_maximal_binary_length_from_base64(const char *in, size_t len) {
   return int64_t(simdutf::maximal_binary_length_from_base64(in, len));
 }

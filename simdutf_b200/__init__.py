@@ -85,12 +85,14 @@ SYMBOLS = {
 for _name, _res in [("validate_utf8_with_errors", _pres), ("count_utf8", _pu64), ("utf16_length_from_utf8", _pu64),
                     ("count_utf16le", _pu64), ("utf8_length_from_utf16le", _pu64),
                     ("validate_utf16le_with_errors", _pres), ("count_utf16be", _pu64), ("utf8_length_from_utf16be", _pu64),
-                    ("validate_utf16be_with_errors", _pres)]:
+                    ("validate_utf16be_with_errors", _pres), ("validate_utf32_with_errors", _pres),
+                    ("utf8_length_from_utf32", _pu64), ("utf16_length_from_utf32", _pu64)]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _res, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _res])
 for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16le_to_utf8", "convert_utf8_to_utf16be",
-              "convert_utf16be_to_utf8", "change_endianness_utf16"]:
+              "convert_utf16be_to_utf8", "change_endianness_utf16", "convert_utf32_to_utf8", "convert_utf32_to_utf16le",
+              "convert_utf32_to_utf16be", "convert_utf16le_to_utf32", "convert_utf16be_to_utf32"]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _vp, _pres, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _vp, _pres])
@@ -298,6 +300,39 @@ def change_endianness_utf16(data, out) -> None:
     err, _n = _convert_op("change_endianness_utf16", data, 2, out)
     if err:
         raise B200Error("change_endianness_utf16 failed")
+
+
+# ---- UTF-32 family (second part) ---------------------------------------------------------------
+def validate_utf32_with_errors(data):
+    return _reduce_op("validate_utf32_with_errors", data, 4, Result()).astuple()
+
+
+def utf8_length_from_utf32(data) -> int:
+    return int(_reduce_op("utf8_length_from_utf32", data, 4, ctypes.c_uint64()).value)
+
+
+def utf16_length_from_utf32(data) -> int:
+    return int(_reduce_op("utf16_length_from_utf32", data, 4, ctypes.c_uint64()).value)
+
+
+def convert_utf32_to_utf8_with_errors(data, out):
+    return _convert_op("convert_utf32_to_utf8", data, 4, out)
+
+
+def convert_utf32_to_utf16le_with_errors(data, out):
+    return _convert_op("convert_utf32_to_utf16le", data, 4, out)
+
+
+def convert_utf32_to_utf16be_with_errors(data, out):
+    return _convert_op("convert_utf32_to_utf16be", data, 4, out)
+
+
+def convert_utf16le_to_utf32_with_errors(data, out):
+    return _convert_op("convert_utf16le_to_utf32", data, 2, out)
+
+
+def convert_utf16be_to_utf32_with_errors(data, out):
+    return _convert_op("convert_utf16be_to_utf32", data, 2, out)
 
 
 def base64_length_from_binary(length: int, options: int = 0) -> int:

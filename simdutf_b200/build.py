@@ -19,7 +19,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libsimdutf_b200.so")
-SOURCES = ["k_utf8.cu", "k_utf8_to_utf16.cu", "k_utf16.cu", "k_utf16_to_utf8.cu", "k_base64.cu", "capi.cu"]
+SOURCES = ["k_utf8.cu", "k_utf8_to_utf16.cu", "k_utf16.cu", "k_utf16_to_utf8.cu", "k_utf32.cu", "k_base64.cu", "capi.cu"]
 HEADERS = ["swar.h", "bitplane.h", "bp_device.cuh", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -96,6 +96,13 @@ REF_TESTS = [
     "convert_utf16be_to_utf8_tests", "convert_utf16be_to_utf8_with_errors_tests", "convert_valid_utf16be_to_utf8_tests",
     "count_utf16be", "validate_utf16be_basic_tests", "validate_utf16be_with_errors_tests",
     "null_safety_tests", "random_fuzzer",
+    # UTF-32 family (second part)
+    "validate_utf32_basic_tests", "validate_utf32_with_errors_tests",
+    "convert_utf32_to_utf8_tests", "convert_utf32_to_utf8_with_errors_tests", "convert_valid_utf32_to_utf8_tests",
+    "convert_utf32_to_utf16le_tests", "convert_utf32_to_utf16le_with_errors_tests", "convert_valid_utf32_to_utf16le_tests",
+    "convert_utf32_to_utf16be_tests", "convert_utf32_to_utf16be_with_errors_tests", "convert_valid_utf32_to_utf16be_tests",
+    "convert_utf16le_to_utf32_tests", "convert_utf16le_to_utf32_with_errors_tests", "convert_valid_utf16le_to_utf32_tests",
+    "convert_utf16be_to_utf32_tests", "convert_utf16be_to_utf32_with_errors_tests", "convert_valid_utf16be_to_utf32_tests",
 ]
 WITH_B200 = os.path.join(OBJ, "with_b200")
 

@@ -204,6 +204,94 @@ size_t implementation::binary_to_base64(const char *input, size_t length, char *
   return size_t(r.count);
 }
 
+// ---- UTF-32 family (second part; reference include/simdutf/implementation.h:3533-3569,
+//      4103-4259, 4370-4565, 4586-4620) ----
+static inline const uint32_t *u32(const char32_t *p) { return reinterpret_cast<const uint32_t *>(p); }
+result implementation::validate_utf32_with_errors(const char32_t *buf, size_t len) const noexcept {
+  b200_result r;
+  return to_result(b200_host_validate_utf32_with_errors(u32(buf), len, &r), r);
+}
+bool implementation::validate_utf32(const char32_t *buf, size_t len) const noexcept {
+  return validate_utf32_with_errors(buf, len).error == error_code::SUCCESS;
+}
+size_t implementation::utf8_length_from_utf32(const char32_t *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_utf8_length_from_utf32(u32(input), length, &n) == 0 ? size_t(n) : 0;
+}
+size_t implementation::utf16_length_from_utf32(const char32_t *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_utf16_length_from_utf32(u32(input), length, &n) == 0 ? size_t(n) : 0;
+}
+result implementation::convert_utf32_to_utf8_with_errors(const char32_t *input, size_t length,
+                                                         char *utf8_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf32_to_utf8(u32(input), length, utf8_buffer, &r), r);
+}
+size_t implementation::convert_utf32_to_utf8(const char32_t *input, size_t length, char *utf8_buffer) const noexcept {
+  const result r = convert_utf32_to_utf8_with_errors(input, length, utf8_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf32_to_utf8(const char32_t *input, size_t length,
+                                                   char *utf8_buffer) const noexcept {
+  return convert_utf32_to_utf8(input, length, utf8_buffer);
+}
+result implementation::convert_utf32_to_utf16le_with_errors(const char32_t *input, size_t length,
+                                                            char16_t *utf16_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf32_to_utf16le(u32(input), length, reinterpret_cast<uint16_t *>(utf16_buffer), &r), r);
+}
+size_t implementation::convert_utf32_to_utf16le(const char32_t *input, size_t length,
+                                                char16_t *utf16_buffer) const noexcept {
+  const result r = convert_utf32_to_utf16le_with_errors(input, length, utf16_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf32_to_utf16le(const char32_t *input, size_t length,
+                                                      char16_t *utf16_buffer) const noexcept {
+  return convert_utf32_to_utf16le(input, length, utf16_buffer);
+}
+result implementation::convert_utf32_to_utf16be_with_errors(const char32_t *input, size_t length,
+                                                            char16_t *utf16_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf32_to_utf16be(u32(input), length, reinterpret_cast<uint16_t *>(utf16_buffer), &r), r);
+}
+size_t implementation::convert_utf32_to_utf16be(const char32_t *input, size_t length,
+                                                char16_t *utf16_buffer) const noexcept {
+  const result r = convert_utf32_to_utf16be_with_errors(input, length, utf16_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf32_to_utf16be(const char32_t *input, size_t length,
+                                                      char16_t *utf16_buffer) const noexcept {
+  return convert_utf32_to_utf16be(input, length, utf16_buffer);
+}
+result implementation::convert_utf16le_to_utf32_with_errors(const char16_t *input, size_t length,
+                                                            char32_t *utf32_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf16le_to_utf32(u16(input), length, reinterpret_cast<uint32_t *>(utf32_buffer), &r), r);
+}
+size_t implementation::convert_utf16le_to_utf32(const char16_t *input, size_t length,
+                                                char32_t *utf32_buffer) const noexcept {
+  const result r = convert_utf16le_to_utf32_with_errors(input, length, utf32_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf16le_to_utf32(const char16_t *input, size_t length,
+                                                      char32_t *utf32_buffer) const noexcept {
+  return convert_utf16le_to_utf32(input, length, utf32_buffer);
+}
+result implementation::convert_utf16be_to_utf32_with_errors(const char16_t *input, size_t length,
+                                                            char32_t *utf32_buffer) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf16be_to_utf32(u16(input), length, reinterpret_cast<uint32_t *>(utf32_buffer), &r), r);
+}
+size_t implementation::convert_utf16be_to_utf32(const char16_t *input, size_t length,
+                                                char32_t *utf32_buffer) const noexcept {
+  const result r = convert_utf16be_to_utf32_with_errors(input, length, utf32_buffer);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf16be_to_utf32(const char16_t *input, size_t length,
+                                                      char32_t *utf32_buffer) const noexcept {
+  return convert_utf16be_to_utf32(input, length, utf32_buffer);
+}
+
 // ---- everything outside the hot path: the reference's "unsupported" answers (generated) ----
 #include "b200_stubs.inc"
 

@@ -249,7 +249,16 @@ enum Op {
   kOpUtf16BEToUtf8,
   kOpSwapUtf16,
   kOpBase64Encode,  // binary_to_base64
-  kOpBase64U16      // base64_to_binary for char16_t input
+  kOpBase64U16,     // base64_to_binary for char16_t input
+  // UTF-32 family (second part)
+  kOpValidateUtf32,
+  kOpUtf8LenFromUtf32,
+  kOpUtf16LenFromUtf32,
+  kOpUtf32ToUtf8,
+  kOpUtf32ToUtf16,
+  kOpUtf32ToUtf16BE,
+  kOpUtf16ToUtf32,
+  kOpUtf16BEToUtf32
 };
 
 size_t tmp_needed(Op op, size_t len) { return op == kOpBase64U16 ? len + 64 : 0; }
@@ -261,6 +270,8 @@ size_t tiles_needed(Op op, const void *in, size_t len) {
     case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return utf16_convert_tiles(in, len);
     case kOpBase64: return base64_tiles(in, len);
     case kOpBase64U16: return base64_tiles(nullptr, len + 16);  // the narrowed copy is 16-byte aligned
+    case kOpUtf32ToUtf8: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return utf32_family_tiles(in, 4 * len);
+    case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return utf32_family_tiles(in, 2 * len);
     default: return 0;
   }
 }
@@ -270,7 +281,7 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
   if (len == 0) {  // reference: empty input is SUCCESS / 0 everywhere on the hot path
     switch (op) {
       case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
-      case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE:
+      case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32:
         B200_CUDA(launch_write_u64(static_cast<unsigned long long *>(res), 0, lc.stream));
         return 0;
       case kOpBase64: case kOpBase64U16:
@@ -300,6 +311,14 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
       B200_CUDA(launch_change_endianness_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<uint16_t *>(out)));
       B200_CUDA(launch_write_result(res, B200_SUCCESS, len, lc.stream));
       break;
+    case kOpValidateUtf32: B200_CUDA(launch_scan_utf32(lc, static_cast<const uint32_t *>(in), len, res, 0)); break;
+    case kOpUtf8LenFromUtf32: B200_CUDA(launch_scan_utf32(lc, static_cast<const uint32_t *>(in), len, res, 1)); break;
+    case kOpUtf16LenFromUtf32: B200_CUDA(launch_scan_utf32(lc, static_cast<const uint32_t *>(in), len, res, 2)); break;
+    case kOpUtf32ToUtf8: B200_CUDA(launch_convert_utf32_to_utf8(lc, static_cast<const uint32_t *>(in), len, static_cast<char *>(out), res)); break;
+    case kOpUtf32ToUtf16: B200_CUDA(launch_convert_utf32_to_utf16(lc, static_cast<const uint32_t *>(in), len, static_cast<uint16_t *>(out), res, false)); break;
+    case kOpUtf32ToUtf16BE: B200_CUDA(launch_convert_utf32_to_utf16(lc, static_cast<const uint32_t *>(in), len, static_cast<uint16_t *>(out), res, true)); break;
+    case kOpUtf16ToUtf32: B200_CUDA(launch_convert_utf16_to_utf32(lc, static_cast<const uint16_t *>(in), len, static_cast<uint32_t *>(out), res, false)); break;
+    case kOpUtf16BEToUtf32: B200_CUDA(launch_convert_utf16_to_utf32(lc, static_cast<const uint16_t *>(in), len, static_cast<uint32_t *>(out), res, true)); break;
     case kOpBase64U16:
       B200_CUDA(launch_base64_to_binary_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), opt, lastc, res));
       break;
@@ -315,7 +334,7 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
 size_t result_bytes(Op op) {
   switch (op) {
     case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
-    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: return 8;
+    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32: return 8;
     case kOpBase64: case kOpBase64U16: return sizeof(b200_full_result);
     default: return sizeof(b200_result);
   }
@@ -360,6 +379,8 @@ size_t max_out_bytes(Op op, size_t len) {
     case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return 3 * len;       // <= 3 bytes per unit
     case kOpSwapUtf16: return 2 * len;
     case kOpBase64Encode: return (len + 2) / 3 * 4;
+    case kOpUtf32ToUtf8: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return 4 * len;  // <= 4 bytes / 2 units per code point
+    case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 4 * len;                          // <= 1 word per unit
     case kOpBase64: case kOpBase64U16: return len / 4 * 3 + 3;
     default: return 0;
   }
@@ -368,14 +389,16 @@ size_t in_elem_bytes(Op op) {
   switch (op) {
     case kOpCountUtf16: case kOpUtf8LenFromUtf16: case kOpValidateUtf16: case kOpUtf16ToUtf8:
     case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpSwapUtf16:
-    case kOpBase64U16: return 2;
+    case kOpBase64U16: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 2;
+    case kOpValidateUtf32: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32: case kOpUtf32ToUtf8: case kOpUtf32ToUtf16:
+    case kOpUtf32ToUtf16BE: return 4;
     default: return 1;
   }
 }
 size_t out_elem_bytes(Op op) {
   switch (op) {
-    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: case kOpSwapUtf16: return 2;
-    case kOpUtf8ToUtf32: return 4;
+    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: case kOpSwapUtf16: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return 2;
+    case kOpUtf8ToUtf32: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 4;
     default: return 1;
   }
 }
@@ -410,12 +433,12 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
       for (int k = 0; k < 3 && cut > beg + 1 && (p[cut] & 0xC0) == 0x80; k++) cut--;
       return cut;
     }
-    case kOpValidateUtf16: case kOpUtf16ToUtf8: {
+    case kOpValidateUtf16: case kOpUtf16ToUtf8: case kOpUtf16ToUtf32: {
       const uint16_t *p = static_cast<const uint16_t *>(h_in);
       if ((p[cut] & 0xFC00u) == 0xDC00u && (p[cut - 1] & 0xFC00u) == 0xD800u) cut--;
       return cut;
     }
-    case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: {  // the same rule on byte-swapped units
+    case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpUtf16BEToUtf32: {  // the same rule on byte-swapped units
       const uint16_t *p = static_cast<const uint16_t *>(h_in);
       if ((p[cut] & 0x00FCu) == 0x00DCu && (p[cut - 1] & 0x00FCu) == 0x00D8u) cut--;
       return cut;
@@ -642,6 +665,9 @@ B200_DEFINE_RESULT_OP(validate_utf16le_with_errors, kOpValidateUtf16, uint16_t, 
 B200_DEFINE_RESULT_OP(count_utf16be, kOpCountUtf16BE, uint16_t, uint64_t)
 B200_DEFINE_RESULT_OP(utf8_length_from_utf16be, kOpUtf8LenFromUtf16BE, uint16_t, uint64_t)
 B200_DEFINE_RESULT_OP(validate_utf16be_with_errors, kOpValidateUtf16BE, uint16_t, b200_result)
+B200_DEFINE_RESULT_OP(validate_utf32_with_errors, kOpValidateUtf32, uint32_t, b200_result)
+B200_DEFINE_RESULT_OP(utf8_length_from_utf32, kOpUtf8LenFromUtf32, uint32_t, uint64_t)
+B200_DEFINE_RESULT_OP(utf16_length_from_utf32, kOpUtf16LenFromUtf32, uint32_t, uint64_t)
 
 #define B200_DEFINE_CONVERT_OP(NAME, OP, INTYPE, OUTTYPE)                                                          \
   int b200_##NAME##_async(const INTYPE *d_in, size_t len, OUTTYPE *d_out, b200_result *d_res, void *stream) {      \
@@ -660,6 +686,11 @@ B200_DEFINE_CONVERT_OP(convert_utf16le_to_utf8, kOpUtf16ToUtf8, uint16_t, char)
 B200_DEFINE_CONVERT_OP(convert_utf8_to_utf16be, kOpUtf8ToUtf16BE, char, uint16_t)
 B200_DEFINE_CONVERT_OP(convert_utf16be_to_utf8, kOpUtf16BEToUtf8, uint16_t, char)
 B200_DEFINE_CONVERT_OP(change_endianness_utf16, kOpSwapUtf16, uint16_t, uint16_t)
+B200_DEFINE_CONVERT_OP(convert_utf32_to_utf8, kOpUtf32ToUtf8, uint32_t, char)
+B200_DEFINE_CONVERT_OP(convert_utf32_to_utf16le, kOpUtf32ToUtf16, uint32_t, uint16_t)
+B200_DEFINE_CONVERT_OP(convert_utf32_to_utf16be, kOpUtf32ToUtf16BE, uint32_t, uint16_t)
+B200_DEFINE_CONVERT_OP(convert_utf16le_to_utf32, kOpUtf16ToUtf32, uint16_t, uint32_t)
+B200_DEFINE_CONVERT_OP(convert_utf16be_to_utf32, kOpUtf16BEToUtf32, uint16_t, uint32_t)
 
 static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
   return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;

@@ -50,14 +50,18 @@ class Oracle:
                   "oracle_convert_utf8_to_utf32_with_errors", "oracle_convert_utf16le_to_utf8_with_errors",
                   "oracle_validate_utf16le_with_errors", "oracle_base64_to_binary",
                   "oracle_validate_utf16be_with_errors", "oracle_convert_utf16be_to_utf8_with_errors",
-                  "oracle_convert_utf8_to_utf16be_with_errors"):
+                  "oracle_convert_utf8_to_utf16be_with_errors", "oracle_validate_utf32_with_errors",
+                  "oracle_convert_utf32_to_utf8_with_errors", "oracle_convert_utf32_to_utf16le_with_errors",
+                  "oracle_convert_utf32_to_utf16be_with_errors", "oracle_convert_utf16le_to_utf32_with_errors",
+                  "oracle_convert_utf16be_to_utf32_with_errors"):
             getattr(L, f).restype = Res
         L.oracle_base64_to_binary_details.restype = Full
         for f in ("oracle_count_utf8", "oracle_utf16_length_from_utf8", "oracle_utf32_length_from_utf8",
                   "oracle_count_utf16le", "oracle_utf8_length_from_utf16le", "oracle_utf32_length_from_utf16le",
                   "oracle_maximal_binary_length_from_base64", "oracle_trim_partial_utf8", "oracle_trim_partial_utf16le",
                   "oracle_base64_length_from_binary", "oracle_binary_to_base64", "oracle_count_utf16be",
-                  "oracle_utf8_length_from_utf16be", "oracle_utf32_length_from_utf16be"):
+                  "oracle_utf8_length_from_utf16be", "oracle_utf32_length_from_utf16be", "oracle_utf8_length_from_utf32",
+                  "oracle_utf16_length_from_utf32"):
             getattr(L, f).restype = ctypes.c_uint64
         self.L = L
 
@@ -138,6 +142,38 @@ class Oracle:
         out = np.zeros(a.size, dtype=np.uint16)
         self.L.oracle_change_endianness_utf16(_p(a), ctypes.c_size_t(a.size), _p(out))
         return out
+
+    # --- UTF-32 family ---
+    def validate_utf32_with_errors(self, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        r = self.L.oracle_validate_utf32_with_errors(_p(a), ctypes.c_size_t(a.size))
+        return (r.error, r.count)
+
+    def utf8_length_from_utf32(self, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return int(self.L.oracle_utf8_length_from_utf32(_p(a), ctypes.c_size_t(a.size)))
+
+    def utf16_length_from_utf32(self, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return int(self.L.oracle_utf16_length_from_utf32(_p(a), ctypes.c_size_t(a.size)))
+
+    def _conv(self, fn, a, out):
+        r = getattr(self.L, fn)(_p(a), ctypes.c_size_t(a.size), _p(out))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf32_to_utf8_with_errors(self, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return self._conv("oracle_convert_utf32_to_utf8_with_errors", a, np.zeros(4 * a.size + 8, dtype=np.uint8))
+
+    def convert_utf32_to_utf16_with_errors(self, data, be=False):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return self._conv("oracle_convert_utf32_to_utf16be_with_errors" if be else "oracle_convert_utf32_to_utf16le_with_errors",
+                          a, np.zeros(2 * a.size + 8, dtype=np.uint16))
+
+    def convert_utf16_to_utf32_with_errors(self, data, be=False):
+        a = _u16(data)
+        return self._conv("oracle_convert_utf16be_to_utf32_with_errors" if be else "oracle_convert_utf16le_to_utf32_with_errors",
+                          a, np.zeros(a.size + 8, dtype=np.uint32))
 
     # --- base64 ---
     def maximal_binary_length_from_base64(self, data):
@@ -236,6 +272,40 @@ class Reference:
 
     def has_be(self):
         return hasattr(self.L, "ref_count_utf16be")
+
+    def has_utf32(self):
+        return hasattr(self.L, "ref_validate_utf32_with_errors")
+
+    def validate_utf32_with_errors(self, impl, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32); r = Res()
+        assert self.L.ref_validate_utf32_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), ctypes.byref(r)) == 0
+        return (r.error, r.count)
+
+    def utf8_length_from_utf32(self, impl, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return int(self.L.ref_utf8_length_from_utf32(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def utf16_length_from_utf32(self, impl, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return int(self.L.ref_utf16_length_from_utf32(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def convert_utf32_to_utf8_with_errors(self, impl, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32); r = Res()
+        out = np.zeros(4 * a.size + 64, dtype=np.uint8)
+        assert self.L.ref_convert_utf32_to_utf8_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf32_to_utf16_with_errors(self, impl, data, be=False):
+        a = np.ascontiguousarray(data, dtype=np.uint32); r = Res()
+        out = np.zeros(2 * a.size + 64, dtype=np.uint16)
+        assert self.L.ref_convert_utf32_to_utf16_with_errors(impl.encode(), int(be), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf16_to_utf32_with_errors(self, impl, data, be=False):
+        a = _u16(data); r = Res()
+        out = np.zeros(a.size + 64, dtype=np.uint32)
+        assert self.L.ref_convert_utf16_to_utf32_with_errors(impl.encode(), int(be), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
 
     def count_utf16be(self, impl, data):
         a = _u16(data)

@@ -476,6 +476,139 @@ def test_utf16be_twins(b, oracle):
     assert torch.equal(back, d)
 
 
+def rand_cps(rng, n, mode):
+    """UTF-32 code points: mode 0 ASCII-heavy, 1 mixed widths, 2 mixed + occasional surrogates / out-of-range."""
+    r = np.random.default_rng(rng.randrange(1 << 30))
+    if mode == 0:
+        a = r.integers(0x20, 0x7F, size=n, dtype=np.uint32)
+        k = r.random(n) < 0.02
+        a[k] = r.integers(0x80, 0x800, size=int(k.sum()), dtype=np.uint32)
+        return a
+    cls = r.integers(0, 4, size=n)
+    a = np.where(cls == 0, r.integers(0, 0x80, size=n),
+        np.where(cls == 1, r.integers(0x80, 0x800, size=n),
+        np.where(cls == 2, r.integers(0xE000, 0x10000, size=n), r.integers(0x10000, 0x110000, size=n)))).astype(np.uint32)
+    edge = r.random(n) < 0.05
+    a[edge] = r.choice(np.array([0x7F, 0x80, 0x7FF, 0x800, 0xD7FF, 0xE000, 0xFFFF, 0x10000, 0x10FFFF], dtype=np.uint32),
+                       size=int(edge.sum()))
+    if mode == 2 and n:
+        for _ in range(rng.randrange(1, 3)):
+            a[rng.randrange(n)] = rng.choice([0xD800, 0xDBFF, 0xDC00, 0xDFFF, 0x110000, 0xFFFFFFFF, 0x80000000])
+    return a
+
+
+def test_utf32_family(b, oracle):
+    """SURVEY.md §8f rank 1 (second part): validate_utf32_with_errors, utf8/utf16_length_from_utf32,
+    convert_utf32_to_utf8 / _utf16le / _utf16be, convert_utf16le/be_to_utf32 against the oracle — every width
+    mix, surrogate / too-large errors (first error wins), misaligned inputs and outputs, the host path, and a
+    256 MiB round trip."""
+    rng = random.Random(3232)
+    sizes = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 3000, 20000, 70001]
+    for it in range(90):
+        n = rng.choice(sizes)
+        a = rand_cps(rng, n, it % 3)
+        mis = rng.randrange(8)
+        dd = dev(a.view(np.uint8), misalign=4 * mis).view(torch.int32)
+        assert b.validate_utf32_with_errors(dd) == oracle.validate_utf32_with_errors(a), (a[:16], n, mis)
+        assert b.utf8_length_from_utf32(dd) == oracle.utf8_length_from_utf32(a)
+        assert b.utf16_length_from_utf32(dd) == oracle.utf16_length_from_utf32(a)
+        n8, n16 = oracle.utf8_length_from_utf32(a), oracle.utf16_length_from_utf32(a)
+        want, wout = oracle.convert_utf32_to_utf8_with_errors(a)
+        _, v8 = out_buf(n8, torch.uint8, misalign=rng.randrange(16))
+        assert b.convert_utf32_to_utf8_with_errors(dd, v8) == want, (a[:16], n, mis)
+        if want[0] == 0:
+            assert v8[:want[1]].cpu().numpy().tobytes() == wout.tobytes(), (n, mis, it)
+            check_guard(v8, want[1])
+        for be in (False, True):
+            want, wout = oracle.convert_utf32_to_utf16_with_errors(a, be)
+            _, v16 = out_buf(n16, torch.int16, misalign=rng.randrange(8))
+            fn = b.convert_utf32_to_utf16be_with_errors if be else b.convert_utf32_to_utf16le_with_errors
+            assert fn(dd, v16) == want, (a[:16], n, mis, be)
+            if want[0] == 0:
+                assert v16[:want[1]].cpu().numpy().view(np.uint16).tobytes() == wout.tobytes(), (n, mis, be, it)
+                check_guard(v16, want[1])
+        if it % 6 == 0:  # host path
+            assert b.validate_utf32_with_errors(a) == oracle.validate_utf32_with_errors(a)
+            assert b.utf8_length_from_utf32(a) == n8 and b.utf16_length_from_utf32(a) == n16
+            want, wout = oracle.convert_utf32_to_utf8_with_errors(a)
+            h8 = np.zeros(n8 + 4, dtype=np.uint8)
+            assert b.convert_utf32_to_utf8_with_errors(a, h8) == want
+            if want[0] == 0:
+                assert h8[:want[1]].tobytes() == wout.tobytes()
+            want, wout = oracle.convert_utf32_to_utf16_with_errors(a, True)
+            h16 = np.zeros(n16 + 4, dtype=np.uint16)
+            assert b.convert_utf32_to_utf16be_with_errors(a, h16) == want
+            if want[0] == 0:
+                assert h16[:want[1]].tobytes() == wout.tobytes()
+    # UTF-16 -> UTF-32, LE and BE, valid and with surrogate errors (pair split across a tile edge included)
+    for it in range(80):
+        n = rng.choice(sizes)
+        u = rand_units(rng, n, it % 3)
+        if it % 4 == 0 and n:
+            u[-1] = 0xD800 + rng.randrange(0x400)
+        if it % 5 == 0 and n > 1025:
+            u[1023], u[1024] = 0xD800 + rng.randrange(0x400), 0xDC00 + rng.randrange(0x400)
+        for be in (False, True):
+            src = u.byteswap() if be else u
+            mis = rng.randrange(8)
+            want, wout = oracle.convert_utf16_to_utf32_with_errors(src, be)
+            dd = dev(src.view(np.uint8), misalign=2 * mis).view(torch.int16)
+            n32 = oracle.count_utf16be(src) if be else oracle.count_utf16le(src)
+            _, v32 = out_buf(n32, torch.int32, misalign=rng.randrange(4))
+            fn = b.convert_utf16be_to_utf32_with_errors if be else b.convert_utf16le_to_utf32_with_errors
+            assert fn(dd, v32) == want, (u[:16], n, mis, be)
+            if want[0] == 0:
+                assert v32[:want[1]].cpu().numpy().view(np.uint32).tobytes() == wout.tobytes(), (n, mis, be, it)
+                check_guard(v32, want[1])
+            if it % 8 == 0:
+                h32 = np.zeros(n32 + 4, dtype=np.uint32)
+                assert fn(src, h32) == want
+                if want[0] == 0:
+                    assert h32[:want[1]].tobytes() == wout.tobytes()
+    # an invalid code point planted at tile edges: first error wins, earlier errors beat later ones
+    base = rand_cps(rng, 5000, 1)
+    for pos in (0, 511, 512, 513, 1023, 1024, 4999):
+        for planted in (0xD800, 0xDFFF, 0x110000, 0xFFFFFFFF):
+            a = base.copy()
+            a[pos] = planted
+            if pos < 4000:
+                a[4500] = 0xDC00  # a later error must not win
+            dd = dev(a.view(np.uint8)).view(torch.int32)
+            assert b.validate_utf32_with_errors(dd) == oracle.validate_utf32_with_errors(a)
+            _, v8 = out_buf(oracle.utf8_length_from_utf32(a), torch.uint8)
+            assert b.convert_utf32_to_utf8_with_errors(dd, v8) == oracle.convert_utf32_to_utf8_with_errors(a)[0]
+            _, v16 = out_buf(oracle.utf16_length_from_utf32(a), torch.int16)
+            assert b.convert_utf32_to_utf16le_with_errors(dd, v16) == oracle.convert_utf32_to_utf16_with_errors(a)[0]
+    # 256 MiB of UTF-8 -> UTF-32 (the UTF-8 kernel) -> UTF-8 / UTF-16 (these kernels) -> compare with the direct paths
+    from simdutf_b200 import synth
+    d = synth.mixed_utf8(1 << 28, seed=32, device="cuda")
+    cps = b.count_utf8(d)
+    u32 = torch.empty(cps, dtype=torch.int32, device="cuda")
+    assert b.convert_utf8_to_utf32_with_errors(d, u32) == (0, cps)
+    assert b.validate_utf32_with_errors(u32) == (0, cps)
+    assert b.utf8_length_from_utf32(u32) == d.numel()
+    units = b.utf16_length_from_utf8(d)
+    assert b.utf16_length_from_utf32(u32) == units
+    back8 = torch.empty(d.numel(), dtype=torch.uint8, device="cuda")
+    assert b.convert_utf32_to_utf8_with_errors(u32, back8) == (0, d.numel())
+    assert torch.equal(back8, d)
+    del back8
+    ule = torch.empty(units, dtype=torch.int16, device="cuda")
+    assert b.convert_utf8_to_utf16le_with_errors(d, ule) == (0, units)
+    got = torch.empty(units, dtype=torch.int16, device="cuda")
+    assert b.convert_utf32_to_utf16le_with_errors(u32, got) == (0, units)
+    assert torch.equal(got, ule)
+    assert b.convert_utf32_to_utf16be_with_errors(u32, got) == (0, units)
+    sw = torch.empty_like(got)
+    b.change_endianness_utf16(got, sw)
+    assert torch.equal(sw, ule)
+    back32 = torch.empty(cps, dtype=torch.int32, device="cuda")
+    assert b.convert_utf16be_to_utf32_with_errors(got, back32) == (0, cps)
+    assert torch.equal(back32, u32)
+    assert b.convert_utf16le_to_utf32_with_errors(ule, back32) == (0, cps)
+    assert torch.equal(back32, u32)
+
+
 def test_binary_to_base64(b, oracle):
     """binary_to_base64 for the four option values (default / url, with and without padding)
     against the oracle, every length class and pointer alignment, device and host path, and a decode round trip."""

@@ -148,6 +148,46 @@ def test_against_reference_library(oracle, ref):
                 r, o = ref.convert_utf16be_to_utf8_with_errors(im, be)
                 assert r == wbe[0] and o.tobytes() == wbe[1].tobytes(), (im, u)
                 assert ref.change_endianness_utf16(im, a).tobytes() == be.tobytes()
+    # UTF-32 family: code points incl. the edges, sprinkled surrogates and out-of-range values
+    for _ in range(1500):
+        n = rng.randrange(0, 70)
+        cps = []
+        for _k in range(n):
+            c = rng.randrange(8)
+            cps.append(rng.randrange(0x80) if c == 0 else rng.randrange(0x80, 0x800) if c == 1 else
+                       rng.choice([rng.randrange(0x800, 0xd800), rng.randrange(0xe000, 0x10000)]) if c == 2 else
+                       rng.randrange(0x10000, 0x110000) if c == 3 else
+                       rng.choice([0x7f, 0x80, 0x7ff, 0x800, 0xd7ff, 0xe000, 0xffff, 0x10000, 0x10ffff]) if c == 4 else
+                       rng.choice([0xd800, 0xdbff, 0xdc00, 0xdfff, 0x110000, 0xffffffff]) if c == 5 and rng.random() < 0.08 else 0x41)
+        a32 = np.array(cps, dtype=np.uint32)
+        w8 = oracle.convert_utf32_to_utf8_with_errors(a32)
+        assert oracle.validate_utf32_with_errors(a32)[0] == w8[0][0]
+        if ref.has_utf32():
+            for im in impls:
+                assert ref.validate_utf32_with_errors(im, a32) == oracle.validate_utf32_with_errors(a32), (im, cps)
+                assert ref.utf8_length_from_utf32(im, a32) == oracle.utf8_length_from_utf32(a32)
+                assert ref.utf16_length_from_utf32(im, a32) == oracle.utf16_length_from_utf32(a32)
+                r, o = ref.convert_utf32_to_utf8_with_errors(im, a32)
+                assert r == w8[0] and o.tobytes() == w8[1].tobytes(), (im, cps)
+                for be in (False, True):
+                    want = oracle.convert_utf32_to_utf16_with_errors(a32, be)
+                    r, o = ref.convert_utf32_to_utf16_with_errors(im, a32, be)
+                    assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, be, cps)
+        if w8[0][0] == 0:  # and back through UTF-16 -> UTF-32
+            for be in (False, True):
+                u16 = oracle.convert_utf32_to_utf16_with_errors(a32, be)[1]
+                back = oracle.convert_utf16_to_utf32_with_errors(u16, be)
+                assert back[0] == (0, a32.size) and back[1].tobytes() == a32.tobytes()
+    if ref.has_utf32():
+        for _ in range(1500):
+            a = np.array([rng.choice([0x41, 0x7ff, 0x4e2d, 0xd800 + rng.randrange(0x400), 0xdc00 + rng.randrange(0x400), 0xffff])
+                          for _k in range(rng.randrange(0, 40))], dtype=np.uint16)
+            for be in (False, True):
+                src = a.byteswap() if be else a
+                want = oracle.convert_utf16_to_utf32_with_errors(src, be)
+                for im in impls:
+                    r, o = ref.convert_utf16_to_utf32_with_errors(im, src, be)
+                    assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, be, a)
     abc = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/-_"
     simd = [i for i in impls if i != "fallback"] or impls
     for it in range(1500):

@@ -22,13 +22,19 @@ HOT = [
     "convert_valid_utf16le_to_utf8_tests", "count_utf8", "count_utf16le", "validate_utf16le_basic_tests",
     "validate_utf16le_with_errors_tests", "select_implementation",
     # UTF-16BE twins.  Not asserted here: convert_utf8_to_utf16be_with_errors_tests (green, but
-    # its 100 trials per case take > 10 minutes of ~60 us host-path calls) and convert_utf16be_to_utf8_with_errors_tests
-    # (its first case calls convert_utf16be_to_utf32_with_errors, still a stub; every UTF-8 case in it passes).
+    # its 100 trials per case take > 10 minutes of ~60 us host-path calls).
     "convert_utf8_to_utf16be_tests", "convert_valid_utf8_to_utf16be_tests",
-    "convert_utf16be_to_utf8_tests", "convert_valid_utf16be_to_utf8_tests",
+    "convert_utf16be_to_utf8_tests", "convert_utf16be_to_utf8_with_errors_tests", "convert_valid_utf16be_to_utf8_tests",
     "count_utf16be", "validate_utf16be_basic_tests", "validate_utf16be_with_errors_tests", "utf8_length_from_utf16_tests",
     # base64 both ways, char and char16_t input, every option: the whole reference binary
     "base64_tests",
+    # UTF-32 family (second part): every reference test binary of the family
+    "validate_utf32_basic_tests", "validate_utf32_with_errors_tests",
+    "convert_utf32_to_utf8_tests", "convert_utf32_to_utf8_with_errors_tests", "convert_valid_utf32_to_utf8_tests",
+    "convert_utf32_to_utf16le_tests", "convert_utf32_to_utf16le_with_errors_tests", "convert_valid_utf32_to_utf16le_tests",
+    "convert_utf32_to_utf16be_tests", "convert_utf32_to_utf16be_with_errors_tests", "convert_valid_utf32_to_utf16be_tests",
+    "convert_utf16le_to_utf32_tests", "convert_utf16le_to_utf32_with_errors_tests", "convert_valid_utf16le_to_utf32_tests",
+    "convert_utf16be_to_utf32_tests", "convert_utf16be_to_utf32_with_errors_tests", "convert_valid_utf16be_to_utf32_tests",
 ]
 
 

@@ -50,6 +50,19 @@ HOT = {
     ("change_endianness_utf16", "const char16_t *"),
     ("binary_to_base64", "const char *"),
     ("base64_to_binary", "const char16_t *"), ("base64_to_binary_details", "const char16_t *"),
+    # UTF-32 family (second part)
+    ("validate_utf32", "const char32_t *"), ("validate_utf32_with_errors", "const char32_t *"),
+    ("utf8_length_from_utf32", "const char32_t *"), ("utf16_length_from_utf32", "const char32_t *"),
+    ("convert_utf32_to_utf8", "const char32_t *"), ("convert_utf32_to_utf8_with_errors", "const char32_t *"),
+    ("convert_valid_utf32_to_utf8", "const char32_t *"),
+    ("convert_utf32_to_utf16le", "const char32_t *"), ("convert_utf32_to_utf16le_with_errors", "const char32_t *"),
+    ("convert_valid_utf32_to_utf16le", "const char32_t *"),
+    ("convert_utf32_to_utf16be", "const char32_t *"), ("convert_utf32_to_utf16be_with_errors", "const char32_t *"),
+    ("convert_valid_utf32_to_utf16be", "const char32_t *"),
+    ("convert_utf16le_to_utf32", "const char16_t *"), ("convert_utf16le_to_utf32_with_errors", "const char16_t *"),
+    ("convert_valid_utf16le_to_utf32", "const char16_t *"),
+    ("convert_utf16be_to_utf32", "const char16_t *"), ("convert_utf16be_to_utf32_with_errors", "const char16_t *"),
+    ("convert_valid_utf16be_to_utf32", "const char16_t *"),
 }
 
 hdr = open(os.path.join(ref, "include/simdutf/implementation.h")).read()

@@ -1,6 +1,7 @@
 """Tiny driver for ncu: runs ONE hot-path operation a few times on a device-resident synthetic buffer.
 usage: python tools/prof_one.py <op> [bytes] [reps]
-   op: convert16 | convert32 | validate_ascii | validate_mixed | length | utf16to8 | base64
+   op: convert16 | convert32 | validate_ascii | validate_mixed | length | utf16to8 | base64 |
+       utf32to8 | utf32to16 | utf32to16be | utf16to32 | validate32 | len8from32 | b64encode
 """
 import ctypes
 import os
@@ -68,5 +69,34 @@ elif op == "base64":
     n = t.numel()
     o = torch.empty(n // 4 * 3 + 3, dtype=torch.uint8, device=dev)
     run(lambda: lib.b200_base64_to_binary_async(ctypes.c_void_p(t.data_ptr()), n, ctypes.c_void_p(o.data_ptr()), 0, 0, rp, sp), n, pay.numel())
+elif op in ("utf32to8", "utf32to16", "utf32to16be", "utf16to32", "validate32", "len8from32"):
+    d = synth.mixed_utf8(nbytes, seed=2, device=dev)
+    cps = b.count_utf8(d)
+    u32 = torch.empty(cps, dtype=torch.int32, device=dev)
+    assert b.convert_utf8_to_utf32_with_errors(d, u32) == (0, cps)
+    p32 = ctypes.c_void_p(u32.data_ptr())
+    units = b.utf16_length_from_utf8(d)
+    if op == "utf32to8":
+        o = torch.empty(d.numel(), dtype=torch.uint8, device=dev)
+        run(lambda: lib.b200_convert_utf32_to_utf8_async(p32, cps, ctypes.c_void_p(o.data_ptr()), rp, sp), 4 * cps, d.numel())
+        assert torch.equal(o, d)
+    elif op in ("utf32to16", "utf32to16be"):
+        o = torch.empty(units, dtype=torch.int16, device=dev)
+        fn = lib.b200_convert_utf32_to_utf16le_async if op == "utf32to16" else lib.b200_convert_utf32_to_utf16be_async
+        run(lambda: fn(p32, cps, ctypes.c_void_p(o.data_ptr()), rp, sp), 4 * cps, 2 * units)
+    elif op == "utf16to32":
+        u16 = torch.empty(units, dtype=torch.int16, device=dev)
+        assert b.convert_utf8_to_utf16le_with_errors(d, u16) == (0, units)
+        o = torch.empty(cps, dtype=torch.int32, device=dev)
+        run(lambda: lib.b200_convert_utf16le_to_utf32_async(ctypes.c_void_p(u16.data_ptr()), units, ctypes.c_void_p(o.data_ptr()), rp, sp), 2 * units, 4 * cps)
+        assert torch.equal(o, u32)
+    elif op == "validate32":
+        run(lambda: lib.b200_validate_utf32_with_errors_async(p32, cps, rp, sp), 4 * cps, 0)
+    else:
+        run(lambda: lib.b200_utf8_length_from_utf32_async(p32, cps, rp, sp), 4 * cps, 0)
+elif op == "b64encode":
+    pay = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev)
+    o = torch.empty((nbytes + 2) // 3 * 4, dtype=torch.uint8, device=dev)
+    run(lambda: lib.b200_binary_to_base64_async(ctypes.c_void_p(pay.data_ptr()), nbytes, ctypes.c_void_p(o.data_ptr()), 0, rp, sp), nbytes, o.numel())
 else:
     raise SystemExit("unknown op " + op)
