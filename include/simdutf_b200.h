@@ -262,6 +262,55 @@ SIMDUTF_B200_API int b200_host_convert_utf16le_to_utf32(const uint16_t *h_in, si
 SIMDUTF_B200_API int b200_convert_utf16be_to_utf32_async(const uint16_t *d_in, size_t len, uint32_t *d_out, b200_result *d_res, void *stream);
 SIMDUTF_B200_API int b200_convert_utf16be_to_utf32(const uint16_t *d_in, size_t len, uint32_t *d_out, b200_result *h_res, void *stream);
 SIMDUTF_B200_API int b200_host_convert_utf16be_to_utf32(const uint16_t *h_in, size_t len, uint32_t *h_out, b200_result *h_res);
+/* ------------------------------------------------------------------------- */
+/* Latin-1 / ASCII family.  `len` in input elements.     */
+/* implementation::validate_ascii[_with_errors] (reference                      */
+/* include/simdutf/implementation.h:3409-3425; src/scalar/ascii.h:36-64),       */
+/* ::utf8_length_from_latin1 (:4622-4634; src/scalar/latin1.h:9-19),            */
+/* ::convert_latin1_to_utf8 / _utf16le / _utf16be / _utf32 (:3583-3692;         */
+/* src/scalar/latin1_to_utf8/latin1_to_utf8.h:9-46),                            */
+/* ::convert_utf8_to_latin1[_with_errors] (:3694-3760;                          */
+/* src/scalar/utf8_to_latin1/utf8_to_latin1.h:83-149),                          */
+/* ::convert_utf16le/be_to_latin1[_with_errors] (:3885-4019;                    */
+/* src/scalar/utf16_to_latin1/utf16_to_latin1.h:38-92),                         */
+/* ::convert_utf32_to_latin1[_with_errors] (:4299-4368;                         */
+/* src/scalar/utf32_to_latin1/utf32_to_latin1.h:33-62).                         */
+/* latin1_length_from_utf8 == count_utf8; the other latin1 length queries are    */
+/* the identity and have no entry point.                                         */
+/* result = {SUCCESS, elements written} or {error, input index}: TOO_LARGE for   */
+/* anything above U+00FF; UTF-8 input also TOO_SHORT / TOO_LONG / OVERLONG /     */
+/* HEADER_BITS exactly as the reference's scalar walk reports them.              */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_validate_ascii_with_errors_async(const char *d_in, size_t len, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_validate_ascii_with_errors(const char *d_in, size_t len, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_validate_ascii_with_errors(const char *h_in, size_t len, b200_result *h_res);
+SIMDUTF_B200_API int b200_utf8_length_from_latin1_async(const char *d_in, size_t len, uint64_t *d_res, void *stream);
+SIMDUTF_B200_API int b200_utf8_length_from_latin1(const char *d_in, size_t len, uint64_t *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_utf8_length_from_latin1(const char *h_in, size_t len, uint64_t *h_res);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf8_async(const char *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf8(const char *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_latin1_to_utf8(const char *h_in, size_t len, char *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf16le_async(const char *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf16le(const char *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_latin1_to_utf16le(const char *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf16be_async(const char *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf16be(const char *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_latin1_to_utf16be(const char *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf32_async(const char *d_in, size_t len, uint32_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_latin1_to_utf32(const char *d_in, size_t len, uint32_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_latin1_to_utf32(const char *h_in, size_t len, uint32_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf8_to_latin1_async(const char *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf8_to_latin1(const char *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf8_to_latin1(const char *h_in, size_t len, char *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf16le_to_latin1_async(const uint16_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf16le_to_latin1(const uint16_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf16le_to_latin1(const uint16_t *h_in, size_t len, char *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf16be_to_latin1_async(const uint16_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf16be_to_latin1(const uint16_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf16be_to_latin1(const uint16_t *h_in, size_t len, char *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_convert_utf32_to_latin1_async(const uint32_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_convert_utf32_to_latin1(const uint32_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_convert_utf32_to_latin1(const uint32_t *h_in, size_t len, char *h_out, b200_result *h_res);
 
 /* base64 decode from char16_t input — implementation::base64_to_binary[_details](const char16_t*, ...)
  * (reference include/simdutf/implementation.h:4922-4939, 4976-5014): units above 0xFF are invalid characters

@@ -350,6 +350,87 @@ oracle_result oracle_convert_utf16be_to_utf32_with_errors(const uint16_t *in, si
 }
 
 /* ------------------------------------------------------------------------- */
+/* Latin-1 / ASCII                                     */
+/* ------------------------------------------------------------------------- */
+/* reference src/scalar/ascii.h:36-64 (the 16-byte skip does not change the answer) */
+oracle_result oracle_validate_ascii_with_errors(const uint8_t *in, size_t len) {
+  oracle_result r;
+  for (size_t pos = 0; pos < len; pos++)
+    if (in[pos] >= 0x80) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+  r.error = ORACLE_SUCCESS; r.count = len;
+  return r;
+}
+/* reference src/scalar/latin1.h:9-19 */
+uint64_t oracle_utf8_length_from_latin1(const uint8_t *in, size_t len) {
+  uint64_t n = len;
+  for (size_t i = 0; i < len; i++) n += in[i] >> 7;
+  return n;
+}
+/* reference src/scalar/latin1_to_utf8/latin1_to_utf8.h:9-46 */
+uint64_t oracle_convert_latin1_to_utf8(const uint8_t *in, size_t len, uint8_t *out) {
+  uint64_t w = 0;
+  for (size_t pos = 0; pos < len; pos++) {
+    uint8_t b = in[pos];
+    if ((b & 0x80) == 0) out[w++] = b;
+    else { out[w++] = (uint8_t)((b >> 6) | 0xC0); out[w++] = (uint8_t)((b & 0x3F) | 0x80); }
+  }
+  return w;
+}
+/* reference src/scalar/latin1_to_utf16/latin1_to_utf16.h:10-24 */
+uint64_t oracle_convert_latin1_to_utf16(const uint8_t *in, size_t len, uint16_t *out, int be) {
+  for (size_t i = 0; i < len; i++) out[i] = be ? swap16((uint16_t)in[i]) : (uint16_t)in[i];
+  return len;
+}
+/* reference src/scalar/latin1_to_utf32/latin1_to_utf32.h:10-18 */
+uint64_t oracle_convert_latin1_to_utf32(const uint8_t *in, size_t len, uint32_t *out) {
+  for (size_t i = 0; i < len; i++) out[i] = in[i];
+  return len;
+}
+/* reference src/scalar/utf8_to_latin1/utf8_to_latin1.h:83-149 (the 16-byte ASCII skip does not change the answer) */
+oracle_result oracle_convert_utf8_to_latin1_with_errors(const uint8_t *in, size_t len, uint8_t *out) {
+  oracle_result r;
+  size_t pos = 0; uint64_t w = 0;
+  while (pos < len) {
+    uint8_t lead = in[pos];
+    if (lead < 0x80) { out[w++] = lead; pos++; }
+    else if ((lead & 0xE0) == 0xC0) {
+      if (pos + 1 >= len || (in[pos + 1] & 0xC0) != 0x80) { r.error = ORACLE_TOO_SHORT; r.count = pos; return r; }
+      uint32_t cp = (uint32_t)(lead & 0x1F) << 6 | (in[pos + 1] & 0x3F);
+      if (cp < 0x80) { r.error = ORACLE_OVERLONG; r.count = pos; return r; }
+      if (cp > 0xFF) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+      out[w++] = (uint8_t)cp; pos += 2;
+    } else if ((lead & 0xF0) == 0xE0 || (lead & 0xF8) == 0xF0) {
+      r.error = ORACLE_TOO_LARGE; r.count = pos; return r;
+    } else {
+      r.error = (lead & 0xC0) == 0x80 ? ORACLE_TOO_LONG : ORACLE_HEADER_BITS; r.count = pos; return r;
+    }
+  }
+  r.error = ORACLE_SUCCESS; r.count = w;
+  return r;
+}
+/* reference src/scalar/utf16_to_latin1/utf16_to_latin1.h:38-92 */
+oracle_result oracle_convert_utf16_to_latin1_with_errors(const uint16_t *in, size_t len, uint8_t *out, int be) {
+  oracle_result r;
+  for (size_t pos = 0; pos < len; pos++) {
+    uint16_t u = ld16(in, pos, be);
+    if (u & 0xFF00) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+    out[pos] = (uint8_t)u;
+  }
+  r.error = ORACLE_SUCCESS; r.count = len;
+  return r;
+}
+/* reference src/scalar/utf32_to_latin1/utf32_to_latin1.h:33-62 */
+oracle_result oracle_convert_utf32_to_latin1_with_errors(const uint32_t *in, size_t len, uint8_t *out) {
+  oracle_result r;
+  for (size_t pos = 0; pos < len; pos++) {
+    if (in[pos] & 0xFFFFFF00u) { r.error = ORACLE_TOO_LARGE; r.count = pos; return r; }
+    out[pos] = (uint8_t)in[pos];
+  }
+  r.error = ORACLE_SUCCESS; r.count = len;
+  return r;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Base64 (WHATWG forgiving decode)                                          */
 /* ------------------------------------------------------------------------- */
 /* Character class: 0..63 sextet, 64 = ASCII whitespace (' ' \t \n \r \f),   */

@@ -86,6 +86,16 @@ oracle_result oracle_convert_utf32_to_utf16be_with_errors(const uint32_t *in, si
 oracle_result oracle_convert_utf16le_to_utf32_with_errors(const uint16_t *in, size_t len, uint32_t *out);
 oracle_result oracle_convert_utf16be_to_utf32_with_errors(const uint16_t *in, size_t len, uint32_t *out);
 
+/* Latin-1 / ASCII family */
+oracle_result oracle_validate_ascii_with_errors(const uint8_t *in, size_t len);
+uint64_t oracle_utf8_length_from_latin1(const uint8_t *in, size_t len);
+uint64_t oracle_convert_latin1_to_utf8(const uint8_t *in, size_t len, uint8_t *out);
+uint64_t oracle_convert_latin1_to_utf16(const uint8_t *in, size_t len, uint16_t *out, int be);
+uint64_t oracle_convert_latin1_to_utf32(const uint8_t *in, size_t len, uint32_t *out);
+oracle_result oracle_convert_utf8_to_latin1_with_errors(const uint8_t *in, size_t len, uint8_t *out);
+oracle_result oracle_convert_utf16_to_latin1_with_errors(const uint16_t *in, size_t len, uint8_t *out, int be);
+oracle_result oracle_convert_utf32_to_latin1_with_errors(const uint32_t *in, size_t len, uint8_t *out);
+
 uint64_t oracle_maximal_binary_length_from_base64(const uint8_t *in, size_t len);
 oracle_full_result oracle_base64_to_binary_details(const uint8_t *in, size_t len, uint8_t *out,
                                                    uint64_t options, uint64_t last_chunk);

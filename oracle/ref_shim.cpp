@@ -170,6 +170,47 @@ int ref_convert_utf16_to_utf32_with_errors(const char *impl, int be, const char1
   simdutf::result r = be ? i->convert_utf16be_to_utf32_with_errors(in, len, dst) : i->convert_utf16le_to_utf32_with_errors(in, len, dst);
   out->error = int32_t(r.error); out->count = r.count; return 0;
 }
+// Latin-1 / ASCII family
+int ref_validate_ascii_with_errors(const char *impl, const char *in, size_t len, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->validate_ascii_with_errors(in, len);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int64_t ref_utf8_length_from_latin1(const char *impl, const char *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->utf8_length_from_latin1(in, len));
+}
+int64_t ref_latin1_length_from_utf8(const char *impl, const char *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->latin1_length_from_utf8(in, len));
+}
+int64_t ref_convert_latin1_to_utf8(const char *impl, const char *in, size_t len, char *dst) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->convert_latin1_to_utf8(in, len, dst));
+}
+int64_t ref_convert_latin1_to_utf16(const char *impl, int be, const char *in, size_t len, char16_t *dst) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(be ? i->convert_latin1_to_utf16be(in, len, dst) : i->convert_latin1_to_utf16le(in, len, dst));
+}
+int64_t ref_convert_latin1_to_utf32(const char *impl, const char *in, size_t len, char32_t *dst) {
+  auto *i = pick(impl); if (!i) return -1;
+  return int64_t(i->convert_latin1_to_utf32(in, len, dst));
+}
+int ref_convert_utf8_to_latin1_with_errors(const char *impl, const char *in, size_t len, char *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->convert_utf8_to_latin1_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_convert_utf16_to_latin1_with_errors(const char *impl, int be, const char16_t *in, size_t len, char *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = be ? i->convert_utf16be_to_latin1_with_errors(in, len, dst) : i->convert_utf16le_to_latin1_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
+int ref_convert_utf32_to_latin1_with_errors(const char *impl, const char32_t *in, size_t len, char *dst, ref_result *out) {
+  auto *i = pick(impl); if (!i) return -1;
+  simdutf::result r = i->convert_utf32_to_latin1_with_errors(in, len, dst);
+  out->error = int32_t(r.error); out->count = r.count; return 0;
+}
 int64_t ref_maximal_binary_length_from_base64(const char *in, size_t len) {
   return int64_t(simdutf::maximal_binary_length_from_base64(in, len));
 }

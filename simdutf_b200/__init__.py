@@ -86,13 +86,16 @@ for _name, _res in [("validate_utf8_with_errors", _pres), ("count_utf8", _pu64),
                     ("count_utf16le", _pu64), ("utf8_length_from_utf16le", _pu64),
                     ("validate_utf16le_with_errors", _pres), ("count_utf16be", _pu64), ("utf8_length_from_utf16be", _pu64),
                     ("validate_utf16be_with_errors", _pres), ("validate_utf32_with_errors", _pres),
-                    ("utf8_length_from_utf32", _pu64), ("utf16_length_from_utf32", _pu64)]:
+                    ("utf8_length_from_utf32", _pu64), ("utf16_length_from_utf32", _pu64),
+                    ("validate_ascii_with_errors", _pres), ("utf8_length_from_latin1", _pu64)]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _res, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _res])
 for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16le_to_utf8", "convert_utf8_to_utf16be",
               "convert_utf16be_to_utf8", "change_endianness_utf16", "convert_utf32_to_utf8", "convert_utf32_to_utf16le",
-              "convert_utf32_to_utf16be", "convert_utf16le_to_utf32", "convert_utf16be_to_utf32"]:
+              "convert_utf32_to_utf16be", "convert_utf16le_to_utf32", "convert_utf16be_to_utf32",
+              "convert_latin1_to_utf8", "convert_latin1_to_utf16le", "convert_latin1_to_utf16be", "convert_latin1_to_utf32",
+              "convert_utf8_to_latin1", "convert_utf16le_to_latin1", "convert_utf16be_to_latin1", "convert_utf32_to_latin1"]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _vp, _pres, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _vp, _pres])
@@ -333,6 +336,51 @@ def convert_utf16le_to_utf32_with_errors(data, out):
 
 def convert_utf16be_to_utf32_with_errors(data, out):
     return _convert_op("convert_utf16be_to_utf32", data, 2, out)
+
+
+# ---- Latin-1 / ASCII family --------------------------------------------------------------------
+def validate_ascii_with_errors(data):
+    return _reduce_op("validate_ascii_with_errors", data, 1, Result()).astuple()
+
+
+def utf8_length_from_latin1(data) -> int:
+    return int(_reduce_op("utf8_length_from_latin1", data, 1, ctypes.c_uint64()).value)
+
+
+def latin1_length_from_utf8(data) -> int:
+    return count_utf8(data)
+
+
+def convert_latin1_to_utf8(data, out):
+    return _convert_op("convert_latin1_to_utf8", data, 1, out)
+
+
+def convert_latin1_to_utf16le(data, out):
+    return _convert_op("convert_latin1_to_utf16le", data, 1, out)
+
+
+def convert_latin1_to_utf16be(data, out):
+    return _convert_op("convert_latin1_to_utf16be", data, 1, out)
+
+
+def convert_latin1_to_utf32(data, out):
+    return _convert_op("convert_latin1_to_utf32", data, 1, out)
+
+
+def convert_utf8_to_latin1_with_errors(data, out):
+    return _convert_op("convert_utf8_to_latin1", data, 1, out)
+
+
+def convert_utf16le_to_latin1_with_errors(data, out):
+    return _convert_op("convert_utf16le_to_latin1", data, 2, out)
+
+
+def convert_utf16be_to_latin1_with_errors(data, out):
+    return _convert_op("convert_utf16be_to_latin1", data, 2, out)
+
+
+def convert_utf32_to_latin1_with_errors(data, out):
+    return _convert_op("convert_utf32_to_latin1", data, 4, out)
 
 
 def base64_length_from_binary(length: int, options: int = 0) -> int:

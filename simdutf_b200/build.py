@@ -19,8 +19,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libsimdutf_b200.so")
-SOURCES = ["k_utf8.cu", "k_utf8_to_utf16.cu", "k_utf16.cu", "k_utf16_to_utf8.cu", "k_utf32.cu", "k_base64.cu", "capi.cu"]
-HEADERS = ["swar.h", "bitplane.h", "bp_device.cuh", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
+SOURCES = ["k_utf8.cu", "k_utf8_to_utf16.cu", "k_utf16.cu", "k_utf16_to_utf8.cu", "k_utf32.cu", "k_latin1.cu", "k_base64.cu", "capi.cu"]
+HEADERS = ["swar.h", "bitplane.h", "bp_device.cuh", "elem_device.cuh", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -103,6 +103,14 @@ REF_TESTS = [
     "convert_utf32_to_utf16be_tests", "convert_utf32_to_utf16be_with_errors_tests", "convert_valid_utf32_to_utf16be_tests",
     "convert_utf16le_to_utf32_tests", "convert_utf16le_to_utf32_with_errors_tests", "convert_valid_utf16le_to_utf32_tests",
     "convert_utf16be_to_utf32_tests", "convert_utf16be_to_utf32_with_errors_tests", "convert_valid_utf16be_to_utf32_tests",
+    # Latin-1 / ASCII family
+    "validate_ascii_basic_tests", "validate_ascii_with_errors_tests", "convert_latin1_to_utf8_tests",
+    "convert_latin1_to_utf16le_tests", "convert_latin1_to_utf16be_tests", "convert_latin1_to_utf32_tests",
+    "convert_utf8_to_latin1_tests", "convert_utf8_to_latin1_with_errors_tests", "convert_valid_utf8_to_latin1_tests",
+    "convert_utf16le_to_latin1_tests", "convert_utf16le_to_latin1_tests_with_errors", "convert_valid_utf16le_to_latin1_tests",
+    "convert_utf16be_to_latin1_tests", "convert_utf16be_to_latin1_tests_with_errors", "convert_valid_utf16be_to_latin1_tests",
+    "convert_utf32_to_latin1_tests", "convert_utf32_to_latin1_with_errors_tests", "convert_valid_utf32_to_latin1_tests",
+    "bele_tests",
 ]
 WITH_B200 = os.path.join(OBJ, "with_b200")
 

@@ -292,6 +292,83 @@ size_t implementation::convert_valid_utf16be_to_utf32(const char16_t *input, siz
   return convert_utf16be_to_utf32(input, length, utf32_buffer);
 }
 
+// ---- Latin-1 / ASCII family (reference include/simdutf/implementation.h:3409-3425, 3583-3692,
+//      3885-4019, 4299-4368, 4586-4649) ----
+result implementation::validate_ascii_with_errors(const char *buf, size_t len) const noexcept {
+  b200_result r;
+  return to_result(b200_host_validate_ascii_with_errors(buf, len, &r), r);
+}
+bool implementation::validate_ascii(const char *buf, size_t len) const noexcept {
+  return validate_ascii_with_errors(buf, len).error == error_code::SUCCESS;
+}
+size_t implementation::utf8_length_from_latin1(const char *input, size_t length) const noexcept {
+  uint64_t n = 0;
+  return b200_host_utf8_length_from_latin1(input, length, &n) == 0 ? size_t(n) : 0;
+}
+size_t implementation::latin1_length_from_utf8(const char *input, size_t length) const noexcept {
+  return count_utf8(input, length);
+}
+size_t implementation::convert_latin1_to_utf8(const char *input, size_t length, char *utf8_output) const noexcept {
+  b200_result r;
+  return b200_host_convert_latin1_to_utf8(input, length, utf8_output, &r) == 0 ? size_t(r.count) : 0;
+}
+size_t implementation::convert_latin1_to_utf16le(const char *input, size_t length, char16_t *utf16_output) const noexcept {
+  b200_result r;
+  return b200_host_convert_latin1_to_utf16le(input, length, reinterpret_cast<uint16_t *>(utf16_output), &r) == 0 ? size_t(r.count) : 0;
+}
+size_t implementation::convert_latin1_to_utf16be(const char *input, size_t length, char16_t *utf16_output) const noexcept {
+  b200_result r;
+  return b200_host_convert_latin1_to_utf16be(input, length, reinterpret_cast<uint16_t *>(utf16_output), &r) == 0 ? size_t(r.count) : 0;
+}
+size_t implementation::convert_latin1_to_utf32(const char *input, size_t length, char32_t *utf32_buffer) const noexcept {
+  b200_result r;
+  return b200_host_convert_latin1_to_utf32(input, length, reinterpret_cast<uint32_t *>(utf32_buffer), &r) == 0 ? size_t(r.count) : 0;
+}
+result implementation::convert_utf8_to_latin1_with_errors(const char *input, size_t length, char *output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf8_to_latin1(input, length, output, &r), r);
+}
+size_t implementation::convert_utf8_to_latin1(const char *input, size_t length, char *output) const noexcept {
+  const result r = convert_utf8_to_latin1_with_errors(input, length, output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf8_to_latin1(const char *input, size_t length, char *output) const noexcept {
+  return convert_utf8_to_latin1(input, length, output);
+}
+result implementation::convert_utf16le_to_latin1_with_errors(const char16_t *input, size_t length, char *output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf16le_to_latin1(u16(input), length, output, &r), r);
+}
+size_t implementation::convert_utf16le_to_latin1(const char16_t *input, size_t length, char *output) const noexcept {
+  const result r = convert_utf16le_to_latin1_with_errors(input, length, output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf16le_to_latin1(const char16_t *input, size_t length, char *output) const noexcept {
+  return convert_utf16le_to_latin1(input, length, output);
+}
+result implementation::convert_utf16be_to_latin1_with_errors(const char16_t *input, size_t length, char *output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf16be_to_latin1(u16(input), length, output, &r), r);
+}
+size_t implementation::convert_utf16be_to_latin1(const char16_t *input, size_t length, char *output) const noexcept {
+  const result r = convert_utf16be_to_latin1_with_errors(input, length, output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf16be_to_latin1(const char16_t *input, size_t length, char *output) const noexcept {
+  return convert_utf16be_to_latin1(input, length, output);
+}
+result implementation::convert_utf32_to_latin1_with_errors(const char32_t *input, size_t length, char *output) const noexcept {
+  b200_result r;
+  return to_result(b200_host_convert_utf32_to_latin1(u32(input), length, output, &r), r);
+}
+size_t implementation::convert_utf32_to_latin1(const char32_t *input, size_t length, char *output) const noexcept {
+  const result r = convert_utf32_to_latin1_with_errors(input, length, output);
+  return r.error ? 0 : r.count;
+}
+size_t implementation::convert_valid_utf32_to_latin1(const char32_t *input, size_t length, char *output) const noexcept {
+  return convert_utf32_to_latin1(input, length, output);
+}
+
 // ---- everything outside the hot path: the reference's "unsupported" answers (generated) ----
 #include "b200_stubs.inc"
 

@@ -258,7 +258,18 @@ enum Op {
   kOpUtf32ToUtf16,
   kOpUtf32ToUtf16BE,
   kOpUtf16ToUtf32,
-  kOpUtf16BEToUtf32
+  kOpUtf16BEToUtf32,
+  // Latin-1 / ASCII family
+  kOpValidateAscii,
+  kOpUtf8LenFromLatin1,
+  kOpLatin1ToUtf8,
+  kOpLatin1ToUtf16,
+  kOpLatin1ToUtf16BE,
+  kOpLatin1ToUtf32,
+  kOpUtf8ToLatin1,
+  kOpUtf16ToLatin1,
+  kOpUtf16BEToLatin1,
+  kOpUtf32ToLatin1
 };
 
 size_t tmp_needed(Op op, size_t len) { return op == kOpBase64U16 ? len + 64 : 0; }
@@ -272,6 +283,7 @@ size_t tiles_needed(Op op, const void *in, size_t len) {
     case kOpBase64U16: return base64_tiles(nullptr, len + 16);  // the narrowed copy is 16-byte aligned
     case kOpUtf32ToUtf8: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return utf32_family_tiles(in, 4 * len);
     case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return utf32_family_tiles(in, 2 * len);
+    case kOpLatin1ToUtf8: case kOpUtf8ToLatin1: return latin1_family_tiles(in, len);
     default: return 0;
   }
 }
@@ -282,6 +294,7 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
     switch (op) {
       case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
       case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32:
+      case kOpUtf8LenFromLatin1:
         B200_CUDA(launch_write_u64(static_cast<unsigned long long *>(res), 0, lc.stream));
         return 0;
       case kOpBase64: case kOpBase64U16:
@@ -319,6 +332,16 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
     case kOpUtf32ToUtf16BE: B200_CUDA(launch_convert_utf32_to_utf16(lc, static_cast<const uint32_t *>(in), len, static_cast<uint16_t *>(out), res, true)); break;
     case kOpUtf16ToUtf32: B200_CUDA(launch_convert_utf16_to_utf32(lc, static_cast<const uint16_t *>(in), len, static_cast<uint32_t *>(out), res, false)); break;
     case kOpUtf16BEToUtf32: B200_CUDA(launch_convert_utf16_to_utf32(lc, static_cast<const uint16_t *>(in), len, static_cast<uint32_t *>(out), res, true)); break;
+    case kOpValidateAscii: B200_CUDA(launch_scan_latin1(lc, static_cast<const char *>(in), len, res, 0)); break;
+    case kOpUtf8LenFromLatin1: B200_CUDA(launch_scan_latin1(lc, static_cast<const char *>(in), len, res, 1)); break;
+    case kOpLatin1ToUtf8: B200_CUDA(launch_convert_latin1_to_utf8(lc, static_cast<const char *>(in), len, static_cast<char *>(out), res)); break;
+    case kOpUtf8ToLatin1: B200_CUDA(launch_convert_utf8_to_latin1(lc, static_cast<const char *>(in), len, static_cast<char *>(out), res)); break;
+    case kOpLatin1ToUtf16: B200_CUDA(launch_convert_latin1_to_utf16(lc, static_cast<const char *>(in), len, static_cast<uint16_t *>(out), res, false)); break;
+    case kOpLatin1ToUtf16BE: B200_CUDA(launch_convert_latin1_to_utf16(lc, static_cast<const char *>(in), len, static_cast<uint16_t *>(out), res, true)); break;
+    case kOpLatin1ToUtf32: B200_CUDA(launch_convert_latin1_to_utf32(lc, static_cast<const char *>(in), len, static_cast<uint32_t *>(out), res)); break;
+    case kOpUtf16ToLatin1: B200_CUDA(launch_convert_utf16_to_latin1(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res, false)); break;
+    case kOpUtf16BEToLatin1: B200_CUDA(launch_convert_utf16_to_latin1(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res, true)); break;
+    case kOpUtf32ToLatin1: B200_CUDA(launch_convert_utf32_to_latin1(lc, static_cast<const uint32_t *>(in), len, static_cast<char *>(out), res)); break;
     case kOpBase64U16:
       B200_CUDA(launch_base64_to_binary_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), opt, lastc, res));
       break;
@@ -334,7 +357,8 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
 size_t result_bytes(Op op) {
   switch (op) {
     case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
-    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32: return 8;
+    case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32:
+    case kOpUtf8LenFromLatin1: return 8;
     case kOpBase64: case kOpBase64U16: return sizeof(b200_full_result);
     default: return sizeof(b200_result);
   }
@@ -382,6 +406,9 @@ size_t max_out_bytes(Op op, size_t len) {
     case kOpUtf32ToUtf8: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return 4 * len;  // <= 4 bytes / 2 units per code point
     case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 4 * len;                          // <= 1 word per unit
     case kOpBase64: case kOpBase64U16: return len / 4 * 3 + 3;
+    case kOpLatin1ToUtf8: case kOpLatin1ToUtf16: case kOpLatin1ToUtf16BE: return 2 * len;  // <= 2 bytes / 1 unit per byte
+    case kOpLatin1ToUtf32: return 4 * len;
+    case kOpUtf8ToLatin1: case kOpUtf16ToLatin1: case kOpUtf16BEToLatin1: case kOpUtf32ToLatin1: return len;
     default: return 0;
   }
 }
@@ -389,16 +416,17 @@ size_t in_elem_bytes(Op op) {
   switch (op) {
     case kOpCountUtf16: case kOpUtf8LenFromUtf16: case kOpValidateUtf16: case kOpUtf16ToUtf8:
     case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpSwapUtf16:
-    case kOpBase64U16: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 2;
+    case kOpBase64U16: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: case kOpUtf16ToLatin1: case kOpUtf16BEToLatin1: return 2;
     case kOpValidateUtf32: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32: case kOpUtf32ToUtf8: case kOpUtf32ToUtf16:
-    case kOpUtf32ToUtf16BE: return 4;
+    case kOpUtf32ToUtf16BE: case kOpUtf32ToLatin1: return 4;
     default: return 1;
   }
 }
 size_t out_elem_bytes(Op op) {
   switch (op) {
-    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: case kOpSwapUtf16: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return 2;
-    case kOpUtf8ToUtf32: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 4;
+    case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: case kOpSwapUtf16: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE:
+    case kOpLatin1ToUtf16: case kOpLatin1ToUtf16BE: return 2;
+    case kOpUtf8ToUtf32: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: case kOpLatin1ToUtf32: return 4;
     default: return 1;
   }
 }
@@ -428,7 +456,7 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
   size_t cut = beg + per;
   if (cut >= len) return len;
   switch (op) {
-    case kOpValidateUtf8: case kOpUtf8ToUtf16: case kOpUtf8ToUtf32: case kOpUtf8ToUtf16BE: {
+    case kOpValidateUtf8: case kOpUtf8ToUtf16: case kOpUtf8ToUtf32: case kOpUtf8ToUtf16BE: case kOpUtf8ToLatin1: {
       const unsigned char *p = static_cast<const unsigned char *>(h_in);
       for (int k = 0; k < 3 && cut > beg + 1 && (p[cut] & 0xC0) == 0x80; k++) cut--;
       return cut;
@@ -668,6 +696,8 @@ B200_DEFINE_RESULT_OP(validate_utf16be_with_errors, kOpValidateUtf16BE, uint16_t
 B200_DEFINE_RESULT_OP(validate_utf32_with_errors, kOpValidateUtf32, uint32_t, b200_result)
 B200_DEFINE_RESULT_OP(utf8_length_from_utf32, kOpUtf8LenFromUtf32, uint32_t, uint64_t)
 B200_DEFINE_RESULT_OP(utf16_length_from_utf32, kOpUtf16LenFromUtf32, uint32_t, uint64_t)
+B200_DEFINE_RESULT_OP(validate_ascii_with_errors, kOpValidateAscii, char, b200_result)
+B200_DEFINE_RESULT_OP(utf8_length_from_latin1, kOpUtf8LenFromLatin1, char, uint64_t)
 
 #define B200_DEFINE_CONVERT_OP(NAME, OP, INTYPE, OUTTYPE)                                                          \
   int b200_##NAME##_async(const INTYPE *d_in, size_t len, OUTTYPE *d_out, b200_result *d_res, void *stream) {      \
@@ -691,6 +721,14 @@ B200_DEFINE_CONVERT_OP(convert_utf32_to_utf16le, kOpUtf32ToUtf16, uint32_t, uint
 B200_DEFINE_CONVERT_OP(convert_utf32_to_utf16be, kOpUtf32ToUtf16BE, uint32_t, uint16_t)
 B200_DEFINE_CONVERT_OP(convert_utf16le_to_utf32, kOpUtf16ToUtf32, uint16_t, uint32_t)
 B200_DEFINE_CONVERT_OP(convert_utf16be_to_utf32, kOpUtf16BEToUtf32, uint16_t, uint32_t)
+B200_DEFINE_CONVERT_OP(convert_latin1_to_utf8, kOpLatin1ToUtf8, char, char)
+B200_DEFINE_CONVERT_OP(convert_latin1_to_utf16le, kOpLatin1ToUtf16, char, uint16_t)
+B200_DEFINE_CONVERT_OP(convert_latin1_to_utf16be, kOpLatin1ToUtf16BE, char, uint16_t)
+B200_DEFINE_CONVERT_OP(convert_latin1_to_utf32, kOpLatin1ToUtf32, char, uint32_t)
+B200_DEFINE_CONVERT_OP(convert_utf8_to_latin1, kOpUtf8ToLatin1, char, char)
+B200_DEFINE_CONVERT_OP(convert_utf16le_to_latin1, kOpUtf16ToLatin1, uint16_t, char)
+B200_DEFINE_CONVERT_OP(convert_utf16be_to_latin1, kOpUtf16BEToLatin1, uint16_t, char)
+B200_DEFINE_CONVERT_OP(convert_utf32_to_latin1, kOpUtf32ToLatin1, uint32_t, char)
 
 static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
   return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;

@@ -12,32 +12,13 @@
 // destination's 16-byte vectors) and streams its own vectors out.
 // Every element is judged on its own (UTF-16 input: together with its two neighbours), so the first error is the
 // atomicMin of (index << 8 | code).
-#include <cstdlib>
-#include <type_traits>
-
-#include "bp_device.cuh"
-#include "device_common.cuh"
-#include "launch.h"
+#include "elem_device.cuh"
 
 namespace b200 {
 
 namespace {
 
-using bpd::kChunkTiles;
-using bpd::kThreads;
-using bpd::kWarpsPerCta;
-
-constexpr uint32_t kTileBytes = 2048u;  // 64 input bytes per lane
-
-__device__ __forceinline__ InView make_view_elems(const void *p, size_t bytes) {
-  InView v;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
-  v.vbeg = a & 15u;
-  v.vend = v.vbeg + bytes;
-  return v;
-}
-__device__ __forceinline__ uint32_t bswap16(uint32_t u) { return ((u >> 8) | (u << 8)) & 0xFFFFu; }
+using namespace elem;
 
 // ---- per-element rules -----------------------------------------------------------------------------------
 // count(v, nv): output elements of input element v; emit(): the same count, the elements packed little-endian
@@ -98,210 +79,6 @@ struct U16ToU32 {
   }
 };
 
-template <class T>
-struct Shape {
-  using In = typename T::In;
-  using Out = typename T::Out;
-  static constexpr uint32_t kInPerLane = 64u / sizeof(In);            // 16 code points or 32 units
-  static constexpr uint32_t kVec = 16u / sizeof(Out);                 // output elements per 16-byte vector
-  static constexpr uint32_t kMaxOut = kInPerLane * T::kMax;           // per lane
-  static constexpr uint32_t kStrideWords = (((kMaxOut + kVec) * sizeof(Out) + 3u) / 4u) | 1u;
-  static constexpr uint32_t kSmemBytes = kWarpsPerCta * 32u * kStrideWords * 4u;
-  static constexpr uint32_t kMaxVec = (kMaxOut + kVec - 1u) / kVec;
-};
-
-// Element i (virtual index from the aligned base) of the input; zero outside the buffer.
-template <class In>
-__device__ __forceinline__ uint32_t elem_guarded(const InView &in, long long i) {
-  const long long pos = i * (long long)sizeof(In);
-  if (pos < (long long)in.vbeg || pos >= (long long)in.vend) return 0u;
-  return (uint32_t)__ldg(reinterpret_cast<const In *>(in.base) + i);
-}
-
-// This lane's 64 input bytes as elements (zero filler outside the buffer).
-template <class In>
-__device__ __forceinline__ void load_lane(const InView &in, unsigned long long r0, bool interior, uint32_t (&w)[16]) {
-  if (interior) {
-    const uint4 *gp = in.base + (r0 >> 4);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint4 v = __ldg(gp + j);
-      w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      bool ins;
-      load_granule(in, (r0 >> 4) + (unsigned long long)j, &w[4 * j], ins);
-    }
-  }
-}
-template <class In>
-__device__ __forceinline__ uint32_t lane_elem(const uint32_t (&w)[16], int i) {
-  return sizeof(In) == 4 ? w[i] : (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-}
-
-// ---- counts pass -----------------------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(kThreads) k_elem_tile_counts(const void *ptr, size_t bytes, uint16_t *tile_cnt,
-                                                                unsigned long long *chunk_off, uint32_t num_tiles,
-                                                                uint32_t num_chunks, Scratch *scr) {
-  using S = Shape<T>;
-  using In = typename T::In;
-  const InView in = make_view_elems(ptr, bytes);
-  const unsigned lane = threadIdx.x & 31u;
-  bpd::counts_pass(
-      [&](uint32_t t) -> uint32_t {
-        const unsigned long long t0 = (unsigned long long)t * kTileBytes, r0 = t0 + lane * 64ull;
-        const bool interior = t0 >= in.vbeg && t0 + kTileBytes <= in.vend;
-        uint32_t w[16];
-        load_lane<In>(in, r0, interior, w);
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int i = 0; i < (int)S::kInPerLane; i++) {
-          const unsigned long long pos = r0 + (unsigned long long)i * sizeof(In);
-          const uint32_t c = T::count(lane_elem<In>(w, i), 0u, 0u);
-          cnt += (interior || (pos >= in.vbeg && pos < in.vend)) ? c : 0u;
-        }
-        return bpd::warp_sum_u32(cnt);
-      },
-      tile_cnt, chunk_off, num_tiles, num_chunks, scr);
-}
-
-// ---- emit pass -------------------------------------------------------------------------------------------
-template <class Out>
-__device__ __forceinline__ void sts_elem(uint32_t addr, uint32_t v) {
-  if (sizeof(Out) == 1) bpd::sts_u8(addr, v);
-  else if (sizeof(Out) == 2) bpd::sts_u16(addr, v);
-  else bpd::sts_u32(addr, v);
-}
-
-template <class T, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-k_elem_transcode(const void *ptr, size_t bytes, typename T::Out *out, const uint16_t *tile_cnt,
-                 const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
-                 ResultPOD *res) {
-  using S = Shape<T>;
-  using In = typename T::In;
-  using Out = typename T::Out;
-  extern __shared__ __align__(16) uint32_t smem[];
-  const InView in = make_view_elems(ptr, bytes);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
-  uint32_t *region_w = smem + (warp * 32u + lane) * S::kStrideWords;
-  Out *region = reinterpret_cast<Out *>(region_w);
-  const unsigned long long out_elems = (unsigned long long)(reinterpret_cast<uintptr_t>(out) / sizeof(Out));
-  const long long first_elem = (long long)(in.vbeg / sizeof(In)), end_elem = (long long)(in.vend / sizeof(In));
-
-  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
-    const unsigned long long t0 = (unsigned long long)tile * kTileBytes, r0 = t0 + lane * 64ull;
-    const bool interior = t0 >= in.vbeg + 16ull && t0 + kTileBytes + 16ull <= in.vend;
-    const uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
-    const unsigned long long coff = chunk_off[tile / kChunkTiles];
-    uint32_t w[16];
-    load_lane<In>(in, r0, interior, w);
-    const long long e0 = (long long)(r0 / sizeof(In));  // virtual index of this lane's first element
-    uint32_t pv = 0, nv = 0;
-    if (T::kNeedsNeighbours) {
-      pv = elem_guarded<In>(in, e0 - 1);
-      nv = elem_guarded<In>(in, e0 + (long long)S::kInPerLane);
-    }
-    const unsigned long long goff = coff + bpd::warp_sum_u32(before);
-
-    // per-element outputs, kept packed; count first (the lane's offset decides where its region starts)
-    uint32_t P[S::kInPerLane];
-    uint32_t n[S::kInPerLane];
-    uint32_t cnt = 0;
-    long long bad_at = -1;
-    int bad_code = 0;
-#pragma unroll
-    for (int i = 0; i < (int)S::kInPerLane; i++) {
-      const long long idx = e0 + i;
-      const bool inside = interior || (idx >= first_elem && idx < end_elem);
-      const uint32_t v = lane_elem<In>(w, i);
-      const uint32_t p = i ? lane_elem<In>(w, i - 1) : pv;
-      const uint32_t nx = i + 1 < (int)S::kInPerLane ? lane_elem<In>(w, i + 1 < (int)S::kInPerLane ? i + 1 : i) : nv;
-      int err;
-      uint32_t c = T::emit(v, p, nx, idx > first_elem, idx + 1 < end_elem, P[i], err);
-      if (!inside) { c = 0; err = 0; }
-      if (err && bad_at < 0) { bad_at = idx; bad_code = err; }
-      n[i] = c;
-      cnt += c;
-    }
-    if (bad_at >= 0) {
-      const unsigned long long key = err_key((unsigned long long)(bad_at - first_elem), bad_code);
-      if (key < ld_relaxed_u64(&scr->err_key)) report_error(scr, key);
-    }
-    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
-    const unsigned long long G = goff + (incl - cnt);
-    const uint32_t a = (uint32_t)((out_elems + G) & (S::kVec - 1u));
-
-    // compaction into the private region
-    {
-      uint32_t sp = (uint32_t)__cvta_generic_to_shared(region + a);
-#pragma unroll
-      for (int i = 0; i < (int)S::kInPerLane; i++) {
-#pragma unroll
-        for (uint32_t k = 0; k < T::kMax; k++) {
-          if (k < n[i]) sts_elem<Out>(sp + k * (uint32_t)sizeof(Out), sizeof(Out) == 4 ? P[i] : P[i] >> (8u * (uint32_t)sizeof(Out) * k));
-        }
-        sp += n[i] * (uint32_t)sizeof(Out);
-      }
-    }
-    __syncwarp();
-
-    // staging -> global: a lane owns the 16-byte vectors that hold its elements except its last partial one, which
-    // the lane to its right completes (it copies the elements in front of its own first one from this lane's tail)
-    {
-      Out *gbase = out + G - a;
-      const uint32_t end = a + cnt;
-      if (__all_sync(kFull, cnt >= S::kVec)) {
-        const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
-        if (lane > 0) {
-          const Out *src = region - S::kStrideWords * (4u / (uint32_t)sizeof(Out)) + (prev_end - a);
-#pragma unroll
-          for (uint32_t u = 0; u + 1 < S::kVec; u++)
-            if (u < a) region[u] = src[u];
-        }
-        const uint32_t vfull = end / S::kVec;
-        uint32_t v0 = 0;
-        if (lane == 0 && a > 0) {
-#pragma unroll
-          for (uint32_t u = 1; u < S::kVec; u++)
-            if (u >= a) gbase[u] = region[u];
-          v0 = 1;
-        }
-        if (lane == 31) {
-#pragma unroll
-          for (uint32_t u = 0; u + 1 < S::kVec; u++) {
-            const uint32_t i = vfull * S::kVec + u;
-            if (i < end) gbase[i] = region[i];
-          }
-        }
-#pragma unroll
-        for (uint32_t v = 0; v < S::kMaxVec; v++) {
-          if (v >= v0 && v < vfull) {
-            uint4 x;
-            x.x = region_w[4u * v];
-            x.y = region_w[4u * v + 1u];
-            x.z = region_w[4u * v + 2u];
-            x.w = region_w[4u * v + 3u];
-            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, x);
-          }
-        }
-      } else {
-        for (uint32_t i = a; i < end; i++) gbase[i] = region[i];
-      }
-    }
-    __syncwarp();
-  }
-
-  if (grid_last_thread(scr)) {
-    bpd::write_result_from_key(res, ld_relaxed_u64(&scr->err_key), chunk_off[num_chunks]);
-    scratch_reset(scr);
-  }
-}
-
 // ---- reductions: validate_utf32, utf8/utf16 length from utf32 ---------------------------------------------
 // MODE 0: validate (first error), 1: utf8_length_from_utf32, 2: utf16_length_from_utf32
 template <int MODE>
@@ -356,51 +133,6 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf32(const uint32_t *in, size_
     else *static_cast<unsigned long long *>(out) = ld_relaxed_u64(&scr->acc0);
     scratch_reset(scr);
   }
-}
-
-inline size_t tiles_for(const void *in, size_t bytes) {
-  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + bytes;
-  return (span + kTileBytes - 1) / kTileBytes;
-}
-inline size_t workspace_slots(size_t tiles) {
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
-}
-
-template <class T>
-cudaError_t launch_elem(const LaunchCtx &c, const void *in, size_t len, void *out, void *res) {
-  using S = Shape<T>;
-  constexpr int MINB = 2;
-  const size_t bytes = len * sizeof(typename T::In);
-  const size_t tiles = tiles_for(in, bytes);
-  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_elem_transcode<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_elem_transcode<T, MINB>, kThreads, S::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    per_sm = n < 1 ? 1 : n;
-  }
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  unsigned long long *chunk_off = c.desc;
-  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
-  {
-    const size_t cap = (size_t)c.sm_count * 8;
-    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_elem_tile_counts<T><<<grid, kThreads, 0, c.stream>>>(in, bytes, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch);
-  }
-  {
-    const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t cap = (size_t)c.sm_count * per_sm;
-    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_elem_transcode<T, MINB><<<grid, kThreads, S::kSmemBytes, c.stream>>>(
-        in, bytes, static_cast<typename T::Out *>(out), tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch,
-        static_cast<ResultPOD *>(res));
-  }
-  count_launch(2);
-  return cudaGetLastError();
 }
 
 }  // namespace

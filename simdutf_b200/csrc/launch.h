@@ -54,6 +54,16 @@ cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *i
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
                                     uint64_t last_chunk, void *full_res);
 
+// Latin-1 / ASCII family (k_latin1.cu): scan mode 0 validate_ascii_with_errors (res = b200_result),
+// 1 utf8_length_from_latin1 (res = uint64)
+size_t latin1_family_tiles(const void *in, size_t bytes);
+cudaError_t launch_scan_latin1(const LaunchCtx &c, const char *in, size_t len, void *res, int mode);
+cudaError_t launch_convert_latin1_to_utf8(const LaunchCtx &c, const char *in, size_t len, char *out, void *res);
+cudaError_t launch_convert_utf8_to_latin1(const LaunchCtx &c, const char *in, size_t len, char *out, void *res);
+cudaError_t launch_convert_latin1_to_utf16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res, bool big_endian);
+cudaError_t launch_convert_latin1_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res);
+cudaError_t launch_convert_utf16_to_latin1(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res, bool big_endian);
+cudaError_t launch_convert_utf32_to_latin1(const LaunchCtx &c, const uint32_t *in, size_t len, char *out, void *res);
 // UTF-32 family (k_utf32.cu): scan mode 0 validate_utf32_with_errors (res = b200_result), 1 utf8_length_from_utf32,
 // 2 utf16_length_from_utf32 (res = uint64)
 size_t utf32_family_tiles(const void *in, size_t bytes);

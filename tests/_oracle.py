@@ -53,7 +53,9 @@ class Oracle:
                   "oracle_convert_utf8_to_utf16be_with_errors", "oracle_validate_utf32_with_errors",
                   "oracle_convert_utf32_to_utf8_with_errors", "oracle_convert_utf32_to_utf16le_with_errors",
                   "oracle_convert_utf32_to_utf16be_with_errors", "oracle_convert_utf16le_to_utf32_with_errors",
-                  "oracle_convert_utf16be_to_utf32_with_errors"):
+                  "oracle_convert_utf16be_to_utf32_with_errors", "oracle_validate_ascii_with_errors",
+                  "oracle_convert_utf8_to_latin1_with_errors", "oracle_convert_utf16_to_latin1_with_errors",
+                  "oracle_convert_utf32_to_latin1_with_errors"):
             getattr(L, f).restype = Res
         L.oracle_base64_to_binary_details.restype = Full
         for f in ("oracle_count_utf8", "oracle_utf16_length_from_utf8", "oracle_utf32_length_from_utf8",
@@ -61,7 +63,8 @@ class Oracle:
                   "oracle_maximal_binary_length_from_base64", "oracle_trim_partial_utf8", "oracle_trim_partial_utf16le",
                   "oracle_base64_length_from_binary", "oracle_binary_to_base64", "oracle_count_utf16be",
                   "oracle_utf8_length_from_utf16be", "oracle_utf32_length_from_utf16be", "oracle_utf8_length_from_utf32",
-                  "oracle_utf16_length_from_utf32"):
+                  "oracle_utf16_length_from_utf32", "oracle_utf8_length_from_latin1", "oracle_convert_latin1_to_utf8",
+                  "oracle_convert_latin1_to_utf16", "oracle_convert_latin1_to_utf32"):
             getattr(L, f).restype = ctypes.c_uint64
         self.L = L
 
@@ -175,6 +178,44 @@ class Oracle:
         return self._conv("oracle_convert_utf16be_to_utf32_with_errors" if be else "oracle_convert_utf16le_to_utf32_with_errors",
                           a, np.zeros(a.size + 8, dtype=np.uint32))
 
+    # --- Latin-1 / ASCII family ---
+    def validate_ascii_with_errors(self, data):
+        a = _u8(data)
+        r = self.L.oracle_validate_ascii_with_errors(_p(a), ctypes.c_size_t(a.size))
+        return (r.error, r.count)
+
+    def utf8_length_from_latin1(self, data):
+        a = _u8(data)
+        return int(self.L.oracle_utf8_length_from_latin1(_p(a), ctypes.c_size_t(a.size)))
+
+    def convert_latin1_to_utf8(self, data):
+        a = _u8(data); out = np.zeros(2 * a.size + 8, dtype=np.uint8)
+        n = int(self.L.oracle_convert_latin1_to_utf8(_p(a), ctypes.c_size_t(a.size), _p(out)))
+        return out[:n]
+
+    def convert_latin1_to_utf16(self, data, be=False):
+        a = _u8(data); out = np.zeros(a.size + 8, dtype=np.uint16)
+        n = int(self.L.oracle_convert_latin1_to_utf16(_p(a), ctypes.c_size_t(a.size), _p(out), int(be)))
+        return out[:n]
+
+    def convert_latin1_to_utf32(self, data):
+        a = _u8(data); out = np.zeros(a.size + 8, dtype=np.uint32)
+        n = int(self.L.oracle_convert_latin1_to_utf32(_p(a), ctypes.c_size_t(a.size), _p(out)))
+        return out[:n]
+
+    def convert_utf8_to_latin1_with_errors(self, data):
+        a = _u8(data)
+        return self._conv("oracle_convert_utf8_to_latin1_with_errors", a, np.zeros(a.size + 8, dtype=np.uint8))
+
+    def convert_utf16_to_latin1_with_errors(self, data, be=False):
+        a = _u16(data); out = np.zeros(a.size + 8, dtype=np.uint8)
+        r = self.L.oracle_convert_utf16_to_latin1_with_errors(_p(a), ctypes.c_size_t(a.size), _p(out), int(be))
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf32_to_latin1_with_errors(self, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32)
+        return self._conv("oracle_convert_utf32_to_latin1_with_errors", a, np.zeros(a.size + 8, dtype=np.uint8))
+
     # --- base64 ---
     def maximal_binary_length_from_base64(self, data):
         a = _u8(data)
@@ -275,6 +316,52 @@ class Reference:
 
     def has_utf32(self):
         return hasattr(self.L, "ref_validate_utf32_with_errors")
+
+    def has_latin1(self):
+        return hasattr(self.L, "ref_validate_ascii_with_errors")
+
+    def validate_ascii_with_errors(self, impl, data):
+        a = _u8(data); r = Res()
+        assert self.L.ref_validate_ascii_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), ctypes.byref(r)) == 0
+        return (r.error, r.count)
+
+    def utf8_length_from_latin1(self, impl, data):
+        a = _u8(data)
+        return int(self.L.ref_utf8_length_from_latin1(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def latin1_length_from_utf8(self, impl, data):
+        a = _u8(data)
+        return int(self.L.ref_latin1_length_from_utf8(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    def convert_latin1_to_utf8(self, impl, data):
+        a = _u8(data); out = np.zeros(2 * a.size + 64, dtype=np.uint8)
+        n = int(self.L.ref_convert_latin1_to_utf8(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out)))
+        return out[:n]
+
+    def convert_latin1_to_utf16(self, impl, data, be=False):
+        a = _u8(data); out = np.zeros(a.size + 64, dtype=np.uint16)
+        n = int(self.L.ref_convert_latin1_to_utf16(impl.encode(), int(be), _p(a), ctypes.c_size_t(a.size), _p(out)))
+        return out[:n]
+
+    def convert_latin1_to_utf32(self, impl, data):
+        a = _u8(data); out = np.zeros(a.size + 64, dtype=np.uint32)
+        n = int(self.L.ref_convert_latin1_to_utf32(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out)))
+        return out[:n]
+
+    def convert_utf8_to_latin1_with_errors(self, impl, data):
+        a = _u8(data); r = Res(); out = np.zeros(a.size + 64, dtype=np.uint8)
+        assert self.L.ref_convert_utf8_to_latin1_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf16_to_latin1_with_errors(self, impl, data, be=False):
+        a = _u16(data); r = Res(); out = np.zeros(a.size + 64, dtype=np.uint8)
+        assert self.L.ref_convert_utf16_to_latin1_with_errors(impl.encode(), int(be), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
+
+    def convert_utf32_to_latin1_with_errors(self, impl, data):
+        a = np.ascontiguousarray(data, dtype=np.uint32); r = Res(); out = np.zeros(a.size + 64, dtype=np.uint8)
+        assert self.L.ref_convert_utf32_to_latin1_with_errors(impl.encode(), _p(a), ctypes.c_size_t(a.size), _p(out), ctypes.byref(r)) == 0
+        return (r.error, r.count), (out[: r.count] if r.error == 0 else out[:0])
 
     def validate_utf32_with_errors(self, impl, data):
         a = np.ascontiguousarray(data, dtype=np.uint32); r = Res()

@@ -609,6 +609,152 @@ def test_utf32_family(b, oracle):
     assert torch.equal(back32, u32)
 
 
+def test_latin1_family(b, oracle):
+    """validate_ascii_with_errors, utf8_length_from_latin1, latin1_length_from_utf8,
+    convert_latin1_to_utf8 / _utf16le / _utf16be / _utf32, convert_utf8 / utf16le / utf16be / utf32_to_latin1
+    against the oracle — all byte values, every error class of the UTF-8 walk, misaligned inputs and outputs,
+    the host path, and a 256 MiB round trip."""
+    rng = random.Random(8859)
+    sizes = [0, 1, 2, 3, 4, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 2047, 2048, 2049, 4096, 10000, 70001, 300000]
+    u8pool = [0x00, 0x41, 0x7f, 0x80, 0xbf, 0xc0, 0xc1, 0xc2, 0xc3, 0xc4, 0xdf, 0xe0, 0xef, 0xf0, 0xf7, 0xf8, 0xff]
+    for it in range(90):
+        n = rng.choice(sizes)
+        r = np.random.default_rng(rng.randrange(1 << 30))
+        a = r.integers(0, 0x80, size=n, dtype=np.uint8)
+        if it % 3:
+            k = r.random(n) < (0.02 if it % 3 == 1 else 0.4)
+            a[k] = r.integers(0x80, 0x100, size=int(k.sum()), dtype=np.uint8)
+        d = a.tobytes()
+        mis = rng.randrange(16)
+        dd = dev(d, misalign=mis)
+        assert b.validate_ascii_with_errors(dd) == oracle.validate_ascii_with_errors(d), (n, mis, it)
+        assert b.utf8_length_from_latin1(dd) == oracle.utf8_length_from_latin1(d)
+        want = oracle.convert_latin1_to_utf8(d)
+        _, v8 = out_buf(len(want), torch.uint8, misalign=rng.randrange(16))
+        assert b.convert_latin1_to_utf8(dd, v8) == (0, len(want)), (n, mis, it)
+        assert v8[:len(want)].cpu().numpy().tobytes() == want.tobytes(), (n, mis, it)
+        check_guard(v8, len(want))
+        for be in (False, True):
+            w16 = oracle.convert_latin1_to_utf16(d, be)
+            _, v16 = out_buf(n, torch.int16, misalign=rng.randrange(8))
+            fn = b.convert_latin1_to_utf16be if be else b.convert_latin1_to_utf16le
+            assert fn(dd, v16) == (0, n)
+            assert v16[:n].cpu().numpy().view(np.uint16).tobytes() == w16.tobytes(), (n, mis, be, it)
+            check_guard(v16, n)
+        w32 = oracle.convert_latin1_to_utf32(d)
+        _, v32 = out_buf(n, torch.int32, misalign=rng.randrange(4))
+        assert b.convert_latin1_to_utf32(dd, v32) == (0, n)
+        assert v32[:n].cpu().numpy().view(np.uint32).tobytes() == w32.tobytes(), (n, mis, it)
+        check_guard(v32, n)
+        # and back: the UTF-8 we just made is valid Latin-1-range UTF-8
+        u8 = want.tobytes()
+        d8 = dev(u8, misalign=rng.randrange(16))
+        assert b.latin1_length_from_utf8(d8) == n
+        _, vl = out_buf(n, torch.uint8, misalign=rng.randrange(16))
+        assert b.convert_utf8_to_latin1_with_errors(d8, vl) == (0, n), (n, it)
+        assert vl[:n].cpu().numpy().tobytes() == d
+        check_guard(vl, n)
+        if it % 6 == 0:  # host path
+            assert b.validate_ascii_with_errors(d) == oracle.validate_ascii_with_errors(d)
+            assert b.utf8_length_from_latin1(d) == len(want)
+            h8 = np.zeros(len(want) + 4, dtype=np.uint8)
+            assert b.convert_latin1_to_utf8(d, h8) == (0, len(want)) and h8[:len(want)].tobytes() == want.tobytes()
+            h16 = np.zeros(n + 4, dtype=np.uint16)
+            assert b.convert_latin1_to_utf16be(d, h16) == (0, n) and h16[:n].tobytes() == oracle.convert_latin1_to_utf16(d, True).tobytes()
+            hl = np.zeros(n + 4, dtype=np.uint8)
+            assert b.convert_utf8_to_latin1_with_errors(u8, hl) == (0, n) and hl[:n].tobytes() == d
+    # UTF-8 -> Latin-1 error classes: damaged Latin-1-range UTF-8 and byte soup from the class edges
+    for it in range(120):
+        n = rng.choice(sizes[:20])
+        if it % 2:
+            t = bytearray("".join(chr(rng.randrange(0x100) if rng.random() < 0.4 else rng.randrange(0x80)) for _ in range(n)).encode())
+            for _ in range(rng.randrange(1, 3)):
+                if t:
+                    t[rng.randrange(len(t))] = rng.choice(u8pool)
+        else:
+            t = bytearray(rng.choice(u8pool) if rng.random() < 0.05 else 0x41 for _ in range(n))
+            if n > 2049 and it % 4 == 0:
+                t[2047:2049] = b"\xc3\xa9"  # a 2-byte character across the tile edge
+        t = bytes(t)
+        mis = rng.randrange(16)
+        want, wout = oracle.convert_utf8_to_latin1_with_errors(t)
+        dd = dev(t, misalign=mis)
+        _, vl = out_buf(oracle.count_utf8(t), torch.uint8, misalign=rng.randrange(16))
+        assert b.convert_utf8_to_latin1_with_errors(dd, vl) == want, (t[:64].hex(), len(t), mis, it)
+        if want[0] == 0:
+            assert vl[:want[1]].cpu().numpy().tobytes() == wout.tobytes()
+            check_guard(vl, want[1])
+        if it % 10 == 0:
+            hl = np.zeros(len(t) + 4, dtype=np.uint8)
+            assert b.convert_utf8_to_latin1_with_errors(t, hl) == want
+    # UTF-16 / UTF-32 -> Latin-1 with a too-large element planted (first one wins)
+    for it in range(60):
+        n = rng.choice(sizes)
+        r = np.random.default_rng(rng.randrange(1 << 30))
+        a16 = r.integers(0, 0x100, size=n, dtype=np.uint16)
+        a32 = a16.astype(np.uint32)
+        if it % 2 and n:
+            for _ in range(rng.randrange(1, 3)):
+                k = rng.randrange(n)
+                a16[k] = rng.choice([0x100, 0x7ff, 0xd800, 0xff00, 0xffff])
+                a32[k] = rng.choice([0x100, 0xffff, 0x10ffff, 0xffffff41, 0x80000000])
+        for be in (False, True):
+            src = a16.byteswap() if be else a16
+            mis = rng.randrange(8)
+            want, wout = oracle.convert_utf16_to_latin1_with_errors(src, be)
+            dd = dev(src.view(np.uint8), misalign=2 * mis).view(torch.int16)
+            _, vl = out_buf(n, torch.uint8, misalign=rng.randrange(16))
+            fn = b.convert_utf16be_to_latin1_with_errors if be else b.convert_utf16le_to_latin1_with_errors
+            assert fn(dd, vl) == want, (n, mis, be, it)
+            if want[0] == 0:
+                assert vl[:n].cpu().numpy().tobytes() == wout.tobytes()
+                check_guard(vl, n)
+            if it % 10 == 0:
+                hl = np.zeros(n + 4, dtype=np.uint8)
+                assert fn(src, hl) == want
+        want, wout = oracle.convert_utf32_to_latin1_with_errors(a32)
+        dd = dev(a32.view(np.uint8), misalign=4 * rng.randrange(4)).view(torch.int32)
+        _, vl = out_buf(n, torch.uint8, misalign=rng.randrange(16))
+        assert b.convert_utf32_to_latin1_with_errors(dd, vl) == want, (n, it)
+        if want[0] == 0:
+            assert vl[:n].cpu().numpy().tobytes() == wout.tobytes()
+            check_guard(vl, n)
+    # 256 MiB of Latin-1 (30 % high bytes): -> UTF-8 -> validate as UTF-8 -> back; -> UTF-16LE -> back; -> UTF-32 -> back
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(59)
+    lat = torch.randint(0, 0x80, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    hi = torch.rand(n, device="cuda", generator=g) < 0.3
+    lat = torch.where(hi, lat | 0x80, lat)
+    del hi
+    n8 = b.utf8_length_from_latin1(lat)
+    assert n8 == n + int((lat >= 0x80).sum())
+    assert b.validate_ascii_with_errors(lat) == (5, int(torch.nonzero(lat >= 0x80)[0]))
+    u8 = torch.empty(n8, dtype=torch.uint8, device="cuda")
+    assert b.convert_latin1_to_utf8(lat, u8) == (0, n8)
+    assert b.validate_utf8_with_errors(u8) == (0, n8)
+    assert b.latin1_length_from_utf8(u8) == n
+    back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert b.convert_utf8_to_latin1_with_errors(u8, back) == (0, n)
+    assert torch.equal(back, lat)
+    del u8
+    u16 = torch.empty(n, dtype=torch.int16, device="cuda")
+    assert b.convert_latin1_to_utf16le(lat, u16) == (0, n)
+    assert torch.equal(u16, lat.to(torch.int16))
+    back.zero_()
+    assert b.convert_utf16le_to_latin1_with_errors(u16, back) == (0, n)
+    assert torch.equal(back, lat)
+    assert b.convert_latin1_to_utf16be(lat, u16) == (0, n)
+    back.zero_()
+    assert b.convert_utf16be_to_latin1_with_errors(u16, back) == (0, n)
+    assert torch.equal(back, lat)
+    del u16
+    u32 = torch.empty(n, dtype=torch.int32, device="cuda")
+    assert b.convert_latin1_to_utf32(lat, u32) == (0, n)
+    back.zero_()
+    assert b.convert_utf32_to_latin1_with_errors(u32, back) == (0, n)
+    assert torch.equal(back, lat)
+
+
 def test_binary_to_base64(b, oracle):
     """binary_to_base64 for the four option values (default / url, with and without padding)
     against the oracle, every length class and pointer alignment, device and host path, and a decode round trip."""

@@ -188,6 +188,51 @@ def test_against_reference_library(oracle, ref):
                 for im in impls:
                     r, o = ref.convert_utf16_to_utf32_with_errors(im, src, be)
                     assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, be, a)
+    # Latin-1 / ASCII family
+    u8pool = [0x00, 0x41, 0x7f, 0x80, 0xbf, 0xc0, 0xc1, 0xc2, 0xc3, 0xc4, 0xdf, 0xe0, 0xef, 0xf0, 0xf7, 0xf8, 0xff]
+    for it in range(3000):
+        n = rng.randrange(0, 80)
+        mode = it % 4
+        if mode == 0:    # Latin-1 bytes
+            d = bytes(rng.randrange(256) if rng.random() < 0.3 else rng.randrange(0x80) for _ in range(n))
+        elif mode == 1:  # valid Latin-1-range UTF-8
+            d = "".join(chr(rng.randrange(0x100) if rng.random() < 0.4 else rng.randrange(0x80)) for _ in range(n)).encode()
+        elif mode == 2:  # the same with one byte damaged
+            d = bytearray("".join(chr(rng.randrange(0x100) if rng.random() < 0.4 else rng.randrange(0x80)) for _ in range(n)).encode())
+            if d:
+                d[rng.randrange(len(d))] = rng.choice(u8pool)
+            d = bytes(d)
+        else:            # byte soup from the class edges
+            d = bytes(rng.choice(u8pool) if rng.random() < 0.5 else 0x41 for _ in range(n))
+        w1 = oracle.convert_utf8_to_latin1_with_errors(d)
+        if ref.has_latin1():
+            for im in impls:
+                assert ref.validate_ascii_with_errors(im, d) == oracle.validate_ascii_with_errors(d), (im, d)
+                assert ref.utf8_length_from_latin1(im, d) == oracle.utf8_length_from_latin1(d)
+                assert ref.latin1_length_from_utf8(im, d) == oracle.count_utf8(d)
+                assert ref.convert_latin1_to_utf8(im, d).tobytes() == oracle.convert_latin1_to_utf8(d).tobytes()
+                assert ref.convert_latin1_to_utf32(im, d).tobytes() == oracle.convert_latin1_to_utf32(d).tobytes()
+                for be in (False, True):
+                    assert ref.convert_latin1_to_utf16(im, d, be).tobytes() == oracle.convert_latin1_to_utf16(d, be).tobytes()
+                r, o = ref.convert_utf8_to_latin1_with_errors(im, d)
+                assert r == w1[0] and o.tobytes() == w1[1].tobytes(), (im, d, r, w1[0])
+        if w1[0][0] == 0:
+            assert oracle.convert_latin1_to_utf8(w1[1]).tobytes() == d
+            assert w1[0][1] == oracle.count_utf8(d)
+    for it in range(1500):
+        n = rng.randrange(0, 50)
+        a16 = np.array([rng.randrange(0x100) if rng.random() < 0.97 else rng.choice([0x100, 0x7ff, 0xd800, 0xffff]) for _ in range(n)], dtype=np.uint16)
+        a32 = np.array([rng.randrange(0x100) if rng.random() < 0.97 else rng.choice([0x100, 0xffff, 0x10ffff, 0xffffff41]) for _ in range(n)], dtype=np.uint32)
+        if ref.has_latin1():
+            for im in impls:
+                for be in (False, True):
+                    src = a16.byteswap() if be else a16
+                    want = oracle.convert_utf16_to_latin1_with_errors(src, be)
+                    r, o = ref.convert_utf16_to_latin1_with_errors(im, src, be)
+                    assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, be, a16)
+                want = oracle.convert_utf32_to_latin1_with_errors(a32)
+                r, o = ref.convert_utf32_to_latin1_with_errors(im, a32)
+                assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, a32)
     abc = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/-_"
     simd = [i for i in impls if i != "fallback"] or impls
     for it in range(1500):

@@ -35,6 +35,16 @@ HOT = [
     "convert_utf32_to_utf16be_tests", "convert_utf32_to_utf16be_with_errors_tests", "convert_valid_utf32_to_utf16be_tests",
     "convert_utf16le_to_utf32_tests", "convert_utf16le_to_utf32_with_errors_tests", "convert_valid_utf16le_to_utf32_tests",
     "convert_utf16be_to_utf32_tests", "convert_utf16be_to_utf32_with_errors_tests", "convert_valid_utf16be_to_utf32_tests",
+    # Latin-1 / ASCII family: every reference test binary of the family except
+    # convert_utf32_to_latin1_with_errors_tests, whose second case makes 64 million calls (1000 trials x 1000 values x
+    # 64 positions; ~30 us per host-path call = half an hour) — its first case and the other 17 binaries are asserted
+    "validate_ascii_basic_tests", "validate_ascii_with_errors_tests", "convert_latin1_to_utf8_tests",
+    "convert_latin1_to_utf16le_tests", "convert_latin1_to_utf16be_tests", "convert_latin1_to_utf32_tests",
+    "convert_utf8_to_latin1_tests", "convert_utf8_to_latin1_with_errors_tests", "convert_valid_utf8_to_latin1_tests",
+    "convert_utf16le_to_latin1_tests", "convert_utf16le_to_latin1_tests_with_errors", "convert_valid_utf16le_to_latin1_tests",
+    "convert_utf16be_to_latin1_tests", "convert_utf16be_to_latin1_tests_with_errors", "convert_valid_utf16be_to_latin1_tests",
+    "convert_utf32_to_latin1_tests", "convert_valid_utf32_to_latin1_tests",
+    "bele_tests",
 ]
 
 

@@ -63,6 +63,19 @@ HOT = {
     ("convert_valid_utf16le_to_utf32", "const char16_t *"),
     ("convert_utf16be_to_utf32", "const char16_t *"), ("convert_utf16be_to_utf32_with_errors", "const char16_t *"),
     ("convert_valid_utf16be_to_utf32", "const char16_t *"),
+    # Latin-1 / ASCII family
+    ("validate_ascii", "const char *"), ("validate_ascii_with_errors", "const char *"),
+    ("utf8_length_from_latin1", "const char *"), ("latin1_length_from_utf8", "const char *"),
+    ("convert_latin1_to_utf8", "const char *"), ("convert_latin1_to_utf16le", "const char *"),
+    ("convert_latin1_to_utf16be", "const char *"), ("convert_latin1_to_utf32", "const char *"),
+    ("convert_utf8_to_latin1", "const char *"), ("convert_utf8_to_latin1_with_errors", "const char *"),
+    ("convert_valid_utf8_to_latin1", "const char *"),
+    ("convert_utf16le_to_latin1", "const char16_t *"), ("convert_utf16le_to_latin1_with_errors", "const char16_t *"),
+    ("convert_valid_utf16le_to_latin1", "const char16_t *"),
+    ("convert_utf16be_to_latin1", "const char16_t *"), ("convert_utf16be_to_latin1_with_errors", "const char16_t *"),
+    ("convert_valid_utf16be_to_latin1", "const char16_t *"),
+    ("convert_utf32_to_latin1", "const char32_t *"), ("convert_utf32_to_latin1_with_errors", "const char32_t *"),
+    ("convert_valid_utf32_to_latin1", "const char32_t *"),
 }
 
 hdr = open(os.path.join(ref, "include/simdutf/implementation.h")).read()

@@ -1,7 +1,8 @@
 """Tiny driver for ncu: runs ONE hot-path operation a few times on a device-resident synthetic buffer.
 usage: python tools/prof_one.py <op> [bytes] [reps]
    op: convert16 | convert32 | validate_ascii | validate_mixed | length | utf16to8 | base64 |
-       utf32to8 | utf32to16 | utf32to16be | utf16to32 | validate32 | len8from32 | b64encode
+       utf32to8 | utf32to16 | utf32to16be | utf16to32 | validate32 | len8from32 | b64encode |
+       l1to8 | l1to16 | l1to32 | u8tol1 | u16tol1 | u32tol1 | validate_ascii_op | len8froml1
 """
 import ctypes
 import os
@@ -94,6 +95,41 @@ elif op in ("utf32to8", "utf32to16", "utf32to16be", "utf16to32", "validate32", "
         run(lambda: lib.b200_validate_utf32_with_errors_async(p32, cps, rp, sp), 4 * cps, 0)
     else:
         run(lambda: lib.b200_utf8_length_from_utf32_async(p32, cps, rp, sp), 4 * cps, 0)
+elif op in ("l1to8", "l1to16", "l1to32", "u8tol1", "u16tol1", "u32tol1", "validate_ascii_op", "len8froml1"):
+    g = torch.Generator(device=dev).manual_seed(59)
+    lat = torch.randint(0, 0x80, (nbytes,), dtype=torch.uint8, device=dev, generator=g)
+    if op != "validate_ascii_op":
+        lat = torch.where(torch.rand(nbytes, device=dev, generator=g) < 0.3, lat | 0x80, lat)
+    n = nbytes
+    pl = ctypes.c_void_p(lat.data_ptr())
+    n8 = b.utf8_length_from_latin1(lat)
+    if op == "validate_ascii_op":
+        run(lambda: lib.b200_validate_ascii_with_errors_async(pl, n, rp, sp), n, 0)
+    elif op == "len8froml1":
+        run(lambda: lib.b200_utf8_length_from_latin1_async(pl, n, rp, sp), n, 0)
+    elif op == "l1to8":
+        o = torch.empty(n8, dtype=torch.uint8, device=dev)
+        run(lambda: lib.b200_convert_latin1_to_utf8_async(pl, n, ctypes.c_void_p(o.data_ptr()), rp, sp), n, n8)
+    elif op == "l1to16":
+        o = torch.empty(n, dtype=torch.int16, device=dev)
+        run(lambda: lib.b200_convert_latin1_to_utf16le_async(pl, n, ctypes.c_void_p(o.data_ptr()), rp, sp), n, 2 * n)
+    elif op == "l1to32":
+        o = torch.empty(n, dtype=torch.int32, device=dev)
+        run(lambda: lib.b200_convert_latin1_to_utf32_async(pl, n, ctypes.c_void_p(o.data_ptr()), rp, sp), n, 4 * n)
+    elif op == "u8tol1":
+        u8 = torch.empty(n8, dtype=torch.uint8, device=dev)
+        assert b.convert_latin1_to_utf8(lat, u8) == (0, n8)
+        o = torch.empty(n, dtype=torch.uint8, device=dev)
+        run(lambda: lib.b200_convert_utf8_to_latin1_async(ctypes.c_void_p(u8.data_ptr()), n8, ctypes.c_void_p(o.data_ptr()), rp, sp), n8, n)
+        assert torch.equal(o, lat)
+    elif op == "u16tol1":
+        u16 = lat.to(torch.int16)
+        o = torch.empty(n, dtype=torch.uint8, device=dev)
+        run(lambda: lib.b200_convert_utf16le_to_latin1_async(ctypes.c_void_p(u16.data_ptr()), n, ctypes.c_void_p(o.data_ptr()), rp, sp), 2 * n, n)
+    else:
+        u32 = lat.to(torch.int32)
+        o = torch.empty(n, dtype=torch.uint8, device=dev)
+        run(lambda: lib.b200_convert_utf32_to_latin1_async(ctypes.c_void_p(u32.data_ptr()), n, ctypes.c_void_p(o.data_ptr()), rp, sp), 4 * n, n)
 elif op == "b64encode":
     pay = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev)
     o = torch.empty((nbytes + 2) // 3 * 4, dtype=torch.uint8, device=dev)
