@@ -311,6 +311,27 @@ SIMDUTF_B200_API int b200_host_convert_utf16be_to_latin1(const uint16_t *h_in, s
 SIMDUTF_B200_API int b200_convert_utf32_to_latin1_async(const uint32_t *d_in, size_t len, char *d_out, b200_result *d_res, void *stream);
 SIMDUTF_B200_API int b200_convert_utf32_to_latin1(const uint32_t *d_in, size_t len, char *d_out, b200_result *h_res, void *stream);
 SIMDUTF_B200_API int b200_host_convert_utf32_to_latin1(const uint32_t *h_in, size_t len, char *h_out, b200_result *h_res);
+/* ------------------------------------------------------------------------- */
+/* SURVEY.md §8f rank 4.                                                        */
+/* implementation::to_well_formed_utf16le/be (reference                          */
+/* include/simdutf/implementation.h:3498-3531; src/scalar/utf16.h:141-166):      */
+/* out[i] = U+FFFD where in[i] is a lone surrogate, else in[i]; d_in == d_out is */
+/* allowed; result = {SUCCESS, len}.                                             */
+/* implementation::detect_encodings (:3344-3354;                                 */
+/* src/fallback/implementation.cpp:8-32, src/encoding_types.cpp:32-49): the      */
+/* encoding_type of a BOM if there is one, else the OR of UTF8 (1), UTF16_LE (2) */
+/* and UTF32_LE (8) for every encoding the buffer validates as.  The device      */
+/* flavours need a 4-byte aligned d_in.                                          */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_to_well_formed_utf16le_async(const uint16_t *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_to_well_formed_utf16le(const uint16_t *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_to_well_formed_utf16le(const uint16_t *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_to_well_formed_utf16be_async(const uint16_t *d_in, size_t len, uint16_t *d_out, b200_result *d_res, void *stream);
+SIMDUTF_B200_API int b200_to_well_formed_utf16be(const uint16_t *d_in, size_t len, uint16_t *d_out, b200_result *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_to_well_formed_utf16be(const uint16_t *h_in, size_t len, uint16_t *h_out, b200_result *h_res);
+SIMDUTF_B200_API int b200_detect_encodings_async(const char *d_in, size_t len, uint64_t *d_res, void *stream);
+SIMDUTF_B200_API int b200_detect_encodings(const char *d_in, size_t len, uint64_t *h_res, void *stream);
+SIMDUTF_B200_API int b200_host_detect_encodings(const char *h_in, size_t len, uint64_t *h_res);
 
 /* base64 decode from char16_t input — implementation::base64_to_binary[_details](const char16_t*, ...)
  * (reference include/simdutf/implementation.h:4922-4939, 4976-5014): units above 0xFF are invalid characters

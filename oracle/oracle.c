@@ -431,6 +431,36 @@ oracle_result oracle_convert_utf32_to_latin1_with_errors(const uint32_t *in, siz
 }
 
 /* ------------------------------------------------------------------------- */
+/* to_well_formed_utf16 and detect_encodings           */
+/* ------------------------------------------------------------------------- */
+/* reference src/scalar/utf16.h:141-166 */
+void oracle_to_well_formed_utf16(const uint16_t *in, size_t len, uint16_t *out, int be) {
+  const uint16_t repl = be ? 0xFDFF : 0xFFFD;
+  int high_prev = 0;
+  size_t i = 0;
+  for (; i < len; i++) {
+    uint16_t u = ld16(in, i, be);
+    int high = (u & 0xFC00) == 0xD800, low = (u & 0xFC00) == 0xDC00;
+    if (high_prev && !low) out[i - 1] = repl;
+    out[i] = (!high_prev && low) ? repl : in[i];
+    high_prev = high;
+  }
+  if (high_prev) out[i - 1] = repl;
+}
+/* reference src/encoding_types.cpp:32-49 (BOM::check_bom) and src/fallback/implementation.cpp:8-32 */
+int oracle_detect_encodings(const uint8_t *in, size_t len) {
+  if (len >= 2 && in[0] == 0xFF && in[1] == 0xFE) return (len >= 4 && in[2] == 0 && in[3] == 0) ? 8 : 2;
+  if (len >= 2 && in[0] == 0xFE && in[1] == 0xFF) return 4;
+  if (len >= 4 && in[0] == 0 && in[1] == 0 && in[2] == 0xFE && in[3] == 0xFF) return 16;
+  if (len >= 4 && in[0] == 0xEF && in[1] == 0xBB && in[2] == 0xBF) return 1;
+  int out = 0;
+  if (oracle_validate_utf8_with_errors(in, len).error == ORACLE_SUCCESS) out |= 1;
+  if (len % 2 == 0 && oracle_validate_utf16le_with_errors((const uint16_t *)in, len / 2).error == ORACLE_SUCCESS) out |= 2;
+  if (len % 4 == 0 && oracle_validate_utf32_with_errors((const uint32_t *)in, len / 4).error == ORACLE_SUCCESS) out |= 8;
+  return out;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Base64 (WHATWG forgiving decode)                                          */
 /* ------------------------------------------------------------------------- */
 /* Character class: 0..63 sextet, 64 = ASCII whitespace (' ' \t \n \r \f),   */

@@ -96,6 +96,10 @@ oracle_result oracle_convert_utf8_to_latin1_with_errors(const uint8_t *in, size_
 oracle_result oracle_convert_utf16_to_latin1_with_errors(const uint16_t *in, size_t len, uint8_t *out, int be);
 oracle_result oracle_convert_utf32_to_latin1_with_errors(const uint32_t *in, size_t len, uint8_t *out);
 
+/* SURVEY.md §8f rank 4 */
+void oracle_to_well_formed_utf16(const uint16_t *in, size_t len, uint16_t *out, int be);
+int oracle_detect_encodings(const uint8_t *in, size_t len);
+
 uint64_t oracle_maximal_binary_length_from_base64(const uint8_t *in, size_t len);
 oracle_full_result oracle_base64_to_binary_details(const uint8_t *in, size_t len, uint8_t *out,
                                                    uint64_t options, uint64_t last_chunk);

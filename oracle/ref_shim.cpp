@@ -211,6 +211,16 @@ int ref_convert_utf32_to_latin1_with_errors(const char *impl, const char32_t *in
   simdutf::result r = i->convert_utf32_to_latin1_with_errors(in, len, dst);
   out->error = int32_t(r.error); out->count = r.count; return 0;
 }
+// SURVEY.md §8f rank 4
+int ref_to_well_formed_utf16(const char *impl, int be, const char16_t *in, size_t len, char16_t *dst) {
+  auto *i = pick(impl); if (!i) return -1;
+  if (be) i->to_well_formed_utf16be(in, len, dst); else i->to_well_formed_utf16le(in, len, dst);
+  return 0;
+}
+int ref_detect_encodings(const char *impl, const char *in, size_t len) {
+  auto *i = pick(impl); if (!i) return -1;
+  return i->detect_encodings(in, len);
+}
 int64_t ref_maximal_binary_length_from_base64(const char *in, size_t len) {
   return int64_t(simdutf::maximal_binary_length_from_base64(in, len));
 }

@@ -87,7 +87,8 @@ for _name, _res in [("validate_utf8_with_errors", _pres), ("count_utf8", _pu64),
                     ("validate_utf16le_with_errors", _pres), ("count_utf16be", _pu64), ("utf8_length_from_utf16be", _pu64),
                     ("validate_utf16be_with_errors", _pres), ("validate_utf32_with_errors", _pres),
                     ("utf8_length_from_utf32", _pu64), ("utf16_length_from_utf32", _pu64),
-                    ("validate_ascii_with_errors", _pres), ("utf8_length_from_latin1", _pu64)]:
+                    ("validate_ascii_with_errors", _pres), ("utf8_length_from_latin1", _pu64),
+                    ("detect_encodings", _pu64)]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _res, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _res])
@@ -95,7 +96,8 @@ for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf32", "convert_utf16
               "convert_utf16be_to_utf8", "change_endianness_utf16", "convert_utf32_to_utf8", "convert_utf32_to_utf16le",
               "convert_utf32_to_utf16be", "convert_utf16le_to_utf32", "convert_utf16be_to_utf32",
               "convert_latin1_to_utf8", "convert_latin1_to_utf16le", "convert_latin1_to_utf16be", "convert_latin1_to_utf32",
-              "convert_utf8_to_latin1", "convert_utf16le_to_latin1", "convert_utf16be_to_latin1", "convert_utf32_to_latin1"]:
+              "convert_utf8_to_latin1", "convert_utf16le_to_latin1", "convert_utf16be_to_latin1", "convert_utf32_to_latin1",
+              "to_well_formed_utf16le", "to_well_formed_utf16be"]:
     SYMBOLS[f"b200_{_name}_async"] = (_I, [_vp, _sz, _vp, _vp, _vp])
     SYMBOLS[f"b200_{_name}"] = (_I, [_vp, _sz, _vp, _pres, _vp])
     SYMBOLS[f"b200_host_{_name}"] = (_I, [_vp, _sz, _vp, _pres])
@@ -381,6 +383,20 @@ def convert_utf16be_to_latin1_with_errors(data, out):
 
 def convert_utf32_to_latin1_with_errors(data, out):
     return _convert_op("convert_utf32_to_latin1", data, 4, out)
+
+
+# ---- SURVEY.md §8f rank 4 ---------------------------------------------------------------------------------------------
+def to_well_formed_utf16le(data, out) -> None:
+    _convert_op("to_well_formed_utf16le", data, 2, out)
+
+
+def to_well_formed_utf16be(data, out) -> None:
+    _convert_op("to_well_formed_utf16be", data, 2, out)
+
+
+def detect_encodings(data) -> int:
+    """OR of encoding_type values: UTF8 = 1, UTF16_LE = 2, UTF16_BE = 4, UTF32_LE = 8, UTF32_BE = 16."""
+    return int(_reduce_op("detect_encodings", data, 1, ctypes.c_uint64()).value)
 
 
 def base64_length_from_binary(length: int, options: int = 0) -> int:

@@ -111,6 +111,8 @@ REF_TESTS = [
     "convert_utf16be_to_latin1_tests", "convert_utf16be_to_latin1_tests_with_errors", "convert_valid_utf16be_to_latin1_tests",
     "convert_utf32_to_latin1_tests", "convert_utf32_to_latin1_with_errors_tests", "convert_valid_utf32_to_latin1_tests",
     "bele_tests",
+    # SURVEY.md §8f rank 4
+    "to_well_formed_utf16_tests", "detect_encodings_tests",
 ]
 WITH_B200 = os.path.join(OBJ, "with_b200")
 

@@ -369,7 +369,21 @@ size_t implementation::convert_valid_utf32_to_latin1(const char32_t *input, size
   return convert_utf32_to_latin1(input, length, output);
 }
 
-// ---- everything outside the hot path: the reference's "unsupported" answers (generated) ----
+// ---- SURVEY.md §8f rank 4 (reference include/simdutf/implementation.h:3344-3354, 3498-3531) ----
+void implementation::to_well_formed_utf16le(const char16_t *input, size_t len, char16_t *output) const noexcept {
+  b200_result r;
+  (void)b200_host_to_well_formed_utf16le(u16(input), len, reinterpret_cast<uint16_t *>(output), &r);
+}
+void implementation::to_well_formed_utf16be(const char16_t *input, size_t len, char16_t *output) const noexcept {
+  b200_result r;
+  (void)b200_host_to_well_formed_utf16be(u16(input), len, reinterpret_cast<uint16_t *>(output), &r);
+}
+int implementation::detect_encodings(const char *input, size_t length) const noexcept {
+  uint64_t bits = 0;
+  return b200_host_detect_encodings(input, length, &bits) == 0 ? int(bits) : 0;
+}
+
+// ---- anything the reference adds later: its "unsupported" answers (generated; empty against this reference) ----
 #include "b200_stubs.inc"
 
 } // namespace b200

@@ -269,10 +269,14 @@ enum Op {
   kOpUtf8ToLatin1,
   kOpUtf16ToLatin1,
   kOpUtf16BEToLatin1,
-  kOpUtf32ToLatin1
+  kOpUtf32ToLatin1,
+  // SURVEY.md §8f rank 4
+  kOpWellFormedUtf16,
+  kOpWellFormedUtf16BE,
+  kOpDetect
 };
 
-size_t tmp_needed(Op op, size_t len) { return op == kOpBase64U16 ? len + 64 : 0; }
+size_t tmp_needed(Op op, size_t len) { return op == kOpBase64U16 ? len + 64 : op == kOpDetect ? 64 : 0; }
 
 size_t tiles_needed(Op op, const void *in, size_t len) {
   switch (op) {
@@ -296,6 +300,9 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
       case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32:
       case kOpUtf8LenFromLatin1:
         B200_CUDA(launch_write_u64(static_cast<unsigned long long *>(res), 0, lc.stream));
+        return 0;
+      case kOpDetect:  // the empty buffer validates as UTF-8, UTF-16LE and UTF-32LE (reference src/fallback/implementation.cpp:15-31)
+        B200_CUDA(launch_write_u64(static_cast<unsigned long long *>(res), 1 | 2 | 8, lc.stream));
         return 0;
       case kOpBase64: case kOpBase64U16:
         B200_CUDA(launch_write_full_result(res, B200_SUCCESS, 0, 0, lc.stream));
@@ -342,6 +349,19 @@ int enqueue(Op op, const LaunchCtx &lc, const void *in, size_t len, void *out, v
     case kOpUtf16ToLatin1: B200_CUDA(launch_convert_utf16_to_latin1(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res, false)); break;
     case kOpUtf16BEToLatin1: B200_CUDA(launch_convert_utf16_to_latin1(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), res, true)); break;
     case kOpUtf32ToLatin1: B200_CUDA(launch_convert_utf32_to_latin1(lc, static_cast<const uint32_t *>(in), len, static_cast<char *>(out), res)); break;
+    case kOpWellFormedUtf16: case kOpWellFormedUtf16BE:
+      B200_CUDA(launch_to_well_formed_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<uint16_t *>(out), op == kOpWellFormedUtf16BE));
+      B200_CUDA(launch_write_result(res, B200_SUCCESS, len, lc.stream));
+      break;
+    case kOpDetect: {  // three validations of the same resident buffer, then the combining step
+      if (reinterpret_cast<uintptr_t>(in) & 3u) return fail(B200_E_BAD_ARGUMENT, "detect_encodings: device buffer must be 4-byte aligned");
+      char *slots = static_cast<char *>(lc.tmp);
+      B200_CUDA(launch_validate_utf8(lc, static_cast<const char *>(in), len, slots));
+      if (len % 2 == 0) B200_CUDA(launch_validate_utf16(lc, static_cast<const uint16_t *>(in), len / 2, slots + 16, false));
+      if (len % 4 == 0) B200_CUDA(launch_scan_utf32(lc, static_cast<const uint32_t *>(in), len / 4, slots + 32, 0));
+      B200_CUDA(launch_detect_finish(lc, static_cast<const char *>(in), len, slots, slots + 16, slots + 32, static_cast<unsigned long long *>(res)));
+      break;
+    }
     case kOpBase64U16:
       B200_CUDA(launch_base64_to_binary_utf16(lc, static_cast<const uint16_t *>(in), len, static_cast<char *>(out), opt, lastc, res));
       break;
@@ -358,7 +378,7 @@ size_t result_bytes(Op op) {
   switch (op) {
     case kOpCountUtf8: case kOpUtf16LenFromUtf8: case kOpCountUtf16: case kOpUtf8LenFromUtf16:
     case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32:
-    case kOpUtf8LenFromLatin1: return 8;
+    case kOpUtf8LenFromLatin1: case kOpDetect: return 8;
     case kOpBase64: case kOpBase64U16: return sizeof(b200_full_result);
     default: return sizeof(b200_result);
   }
@@ -401,7 +421,7 @@ size_t max_out_bytes(Op op, size_t len) {
     case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: return 2 * len;       // <= 1 unit per input byte
     case kOpUtf8ToUtf32: return 4 * len;
     case kOpUtf16ToUtf8: case kOpUtf16BEToUtf8: return 3 * len;       // <= 3 bytes per unit
-    case kOpSwapUtf16: return 2 * len;
+    case kOpSwapUtf16: case kOpWellFormedUtf16: case kOpWellFormedUtf16BE: return 2 * len;
     case kOpBase64Encode: return (len + 2) / 3 * 4;
     case kOpUtf32ToUtf8: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE: return 4 * len;  // <= 4 bytes / 2 units per code point
     case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: return 4 * len;                          // <= 1 word per unit
@@ -416,7 +436,8 @@ size_t in_elem_bytes(Op op) {
   switch (op) {
     case kOpCountUtf16: case kOpUtf8LenFromUtf16: case kOpValidateUtf16: case kOpUtf16ToUtf8:
     case kOpCountUtf16BE: case kOpUtf8LenFromUtf16BE: case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpSwapUtf16:
-    case kOpBase64U16: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: case kOpUtf16ToLatin1: case kOpUtf16BEToLatin1: return 2;
+    case kOpBase64U16: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: case kOpUtf16ToLatin1: case kOpUtf16BEToLatin1:
+    case kOpWellFormedUtf16: case kOpWellFormedUtf16BE: return 2;
     case kOpValidateUtf32: case kOpUtf8LenFromUtf32: case kOpUtf16LenFromUtf32: case kOpUtf32ToUtf8: case kOpUtf32ToUtf16:
     case kOpUtf32ToUtf16BE: case kOpUtf32ToLatin1: return 4;
     default: return 1;
@@ -425,7 +446,7 @@ size_t in_elem_bytes(Op op) {
 size_t out_elem_bytes(Op op) {
   switch (op) {
     case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: case kOpSwapUtf16: case kOpUtf32ToUtf16: case kOpUtf32ToUtf16BE:
-    case kOpLatin1ToUtf16: case kOpLatin1ToUtf16BE: return 2;
+    case kOpLatin1ToUtf16: case kOpLatin1ToUtf16BE: case kOpWellFormedUtf16: case kOpWellFormedUtf16BE: return 2;
     case kOpUtf8ToUtf32: case kOpUtf16ToUtf32: case kOpUtf16BEToUtf32: case kOpLatin1ToUtf32: return 4;
     default: return 1;
   }
@@ -448,7 +469,8 @@ static const size_t kSegmentBytes = [] {
   return size_t(v >= 1 && v <= 1024 ? v : 32) << 20;
 }();
 
-bool op_streams(Op op) { return op != kOpBase64 && op != kOpBase64U16; }  // base64 quanta straddle any cut: single shot
+// base64 quanta straddle any cut, detect_encodings is three verdicts about the whole buffer: single shot
+bool op_streams(Op op) { return op != kOpBase64 && op != kOpBase64U16 && op != kOpDetect; }
 
 // End (exclusive, in elements) of the segment that starts at `beg`.
 size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
@@ -461,12 +483,12 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
       for (int k = 0; k < 3 && cut > beg + 1 && (p[cut] & 0xC0) == 0x80; k++) cut--;
       return cut;
     }
-    case kOpValidateUtf16: case kOpUtf16ToUtf8: case kOpUtf16ToUtf32: {
+    case kOpValidateUtf16: case kOpUtf16ToUtf8: case kOpUtf16ToUtf32: case kOpWellFormedUtf16: {
       const uint16_t *p = static_cast<const uint16_t *>(h_in);
       if ((p[cut] & 0xFC00u) == 0xDC00u && (p[cut - 1] & 0xFC00u) == 0xD800u) cut--;
       return cut;
     }
-    case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpUtf16BEToUtf32: {  // the same rule on byte-swapped units
+    case kOpValidateUtf16BE: case kOpUtf16BEToUtf8: case kOpUtf16BEToUtf32: case kOpWellFormedUtf16BE: {  // the same rule on byte-swapped units
       const uint16_t *p = static_cast<const uint16_t *>(h_in);
       if ((p[cut] & 0x00FCu) == 0x00DCu && (p[cut - 1] & 0x00FCu) == 0x00D8u) cut--;
       return cut;
@@ -603,6 +625,7 @@ int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint
   if (bad_args(h_in, len, h_res)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
   if (len == 0) {  // never touches CUDA (reference tests/null_safety_tests.cpp:7-95)
     std::memset(h_res, 0, result_bytes(op));
+    if (op == kOpDetect) *static_cast<uint64_t *>(h_res) = 1 | 2 | 8;  // "" is valid UTF-8, UTF-16LE and UTF-32LE
     return 0;
   }
   int err;
@@ -698,6 +721,7 @@ B200_DEFINE_RESULT_OP(utf8_length_from_utf32, kOpUtf8LenFromUtf32, uint32_t, uin
 B200_DEFINE_RESULT_OP(utf16_length_from_utf32, kOpUtf16LenFromUtf32, uint32_t, uint64_t)
 B200_DEFINE_RESULT_OP(validate_ascii_with_errors, kOpValidateAscii, char, b200_result)
 B200_DEFINE_RESULT_OP(utf8_length_from_latin1, kOpUtf8LenFromLatin1, char, uint64_t)
+B200_DEFINE_RESULT_OP(detect_encodings, kOpDetect, char, uint64_t)
 
 #define B200_DEFINE_CONVERT_OP(NAME, OP, INTYPE, OUTTYPE)                                                          \
   int b200_##NAME##_async(const INTYPE *d_in, size_t len, OUTTYPE *d_out, b200_result *d_res, void *stream) {      \
@@ -729,6 +753,8 @@ B200_DEFINE_CONVERT_OP(convert_utf8_to_latin1, kOpUtf8ToLatin1, char, char)
 B200_DEFINE_CONVERT_OP(convert_utf16le_to_latin1, kOpUtf16ToLatin1, uint16_t, char)
 B200_DEFINE_CONVERT_OP(convert_utf16be_to_latin1, kOpUtf16BEToLatin1, uint16_t, char)
 B200_DEFINE_CONVERT_OP(convert_utf32_to_latin1, kOpUtf32ToLatin1, uint32_t, char)
+B200_DEFINE_CONVERT_OP(to_well_formed_utf16le, kOpWellFormedUtf16, uint16_t, uint16_t)
+B200_DEFINE_CONVERT_OP(to_well_formed_utf16be, kOpWellFormedUtf16BE, uint16_t, uint16_t)
 
 static bool b64_options_ok(uint64_t options, uint64_t last_chunk) {
   return (options <= 5 || options == 8 || options == 12) && last_chunk <= 2;

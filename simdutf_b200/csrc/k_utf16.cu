@@ -236,6 +236,70 @@ __global__ void __launch_bounds__(kBlock) k_swap_utf16(const uint16_t *in, size_
   }
 }
 
+// to_well_formed_utf16le/be (reference src/scalar/utf16.h:141-166; include/simdutf/implementation.h:3498-3531):
+// out[i] = U+FFFD (in the buffer's byte order) where in[i] is a lone surrogate — a low one not behind a high one, a
+// high one not in front of a low one or at the end — else in[i].  The rule is u16_bad() per unit with its two
+// neighbours.  in == out is allowed: a neighbour that another thread has already replaced was a LONE surrogate, so it
+// did not pair with this unit and U+FFFD in its place (not a surrogate) leads to the same decision.
+template <bool BE>
+__device__ __forceinline__ uint32_t well_formed_unit(uint32_t u, uint32_t pu, bool has_prev, uint32_t nu, bool has_next) {
+  const uint32_t a = BE ? swap16x2(u) & 0xFFFFu : u, pa = BE ? swap16x2(pu) & 0xFFFFu : pu, na = BE ? swap16x2(nu) & 0xFFFFu : nu;
+  return u16_bad(a, pa, has_prev, na, has_next) ? (BE ? 0xFDFFu : 0xFFFDu) : u;
+}
+template <bool BE>
+__global__ void __launch_bounds__(kBlock) k_well_formed_utf16(const uint16_t *in, size_t len, uint16_t *out) {
+  const size_t tid = (size_t)blockIdx.x * kBlock + threadIdx.x, nthreads = (size_t)gridDim.x * kBlock;
+  const uintptr_t ai = reinterpret_cast<uintptr_t>(in), ao = reinterpret_cast<uintptr_t>(out);
+  auto element = [&](size_t i) {
+    const uint32_t pu = i ? in[i - 1] : 0u, nu = i + 1 < len ? in[i + 1] : 0u;
+    out[i] = (uint16_t)well_formed_unit<BE>(in[i], pu, i > 0, nu, i + 1 < len);
+  };
+  if (((ai ^ ao) & 15u) == 0) {  // same misalignment: a common 16-byte grid exists
+    size_t head = ((16u - (ai & 15u)) & 15u) >> 1;
+    if (head > len) head = len;
+    const size_t nvec = (len - head) >> 3;
+    const uint4 *vi = reinterpret_cast<const uint4 *>(in + head);
+    uint4 *vo = reinterpret_cast<uint4 *>(out + head);
+    for (size_t v = tid; v < nvec; v += nthreads) {
+      const size_t i0 = head + 8 * v;
+      const uint4 x = ldg_stream_v4(vi + v);
+      const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+      uint32_t u[10];
+      u[0] = i0 ? in[i0 - 1] : 0u;
+      u[9] = i0 + 8 < len ? in[i0 + 8] : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) u[k + 1] = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+      uint32_t o[4];
+      if (((x.x | x.y | x.z | x.w) & (BE ? 0x00800080u : 0x80008000u)) == 0) {  // no unit >= 0x8000: nothing to replace
+        o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          const uint32_t lo = well_formed_unit<BE>(u[k + 1], u[k], i0 + k > 0, u[k + 2], i0 + k + 1 < len);
+          const uint32_t hi = well_formed_unit<BE>(u[k + 2], u[k + 1], true, u[k + 3], i0 + k + 2 < len);
+          o[k >> 1] = lo | (hi << 16);
+        }
+      }
+      stg_stream_v4(vo + v, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+    const size_t done = head + nvec * 8;
+    for (size_t i = tid; i < head; i += nthreads) element(i);
+    for (size_t i = done + tid; i < len; i += nthreads) element(i);
+  } else {
+    for (size_t i = tid; i < len; i += nthreads) element(i);
+  }
+}
+
+cudaError_t launch_to_well_formed_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, uint16_t *out, bool big_endian) {
+  const unsigned long long want = (len / 8 + kBlock - 1) / kBlock + 1;
+  const unsigned long long cap = (unsigned long long)c.sm_count * 16;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (big_endian) k_well_formed_utf16<true><<<grid, kBlock, 0, c.stream>>>(in, len, out);
+  else k_well_formed_utf16<false><<<grid, kBlock, 0, c.stream>>>(in, len, out);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, uint16_t *out) {
   const unsigned long long want = (len / 8 + kBlock - 1) / kBlock + 1;
   const unsigned long long cap = (unsigned long long)c.sm_count * 16;

@@ -135,6 +135,26 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf32(const uint32_t *in, size_
   }
 }
 
+// detect_encodings (reference src/fallback/implementation.cpp:8-32, src/encoding_types.cpp:32-49): a BOM is trusted;
+// otherwise the answer is the set of encodings the buffer validates as.  The three validators have already run on
+// this stream into r8 / r16 / r32 (the latter two only when the length allows); this combines them.
+__global__ void k_detect_finish(const uint8_t *in, size_t len, const ResultPOD *r8, const ResultPOD *r16, const ResultPOD *r32,
+                                unsigned long long *out) {
+  const uint32_t b0 = len > 0 ? in[0] : 0x100u, b1 = len > 1 ? in[1] : 0x100u, b2 = len > 2 ? in[2] : 0x100u,
+                 b3 = len > 3 ? in[3] : 0x100u;
+  unsigned long long ans = 0;
+  if (b0 == 0xFFu && b1 == 0xFEu) ans = (b2 == 0u && b3 == 0u) ? 8u : 2u;                         // UTF32_LE : UTF16_LE
+  else if (b0 == 0xFEu && b1 == 0xFFu) ans = 4u;                                                   // UTF16_BE
+  else if (b0 == 0u && b1 == 0u && b2 == 0xFEu && b3 == 0xFFu) ans = 16u;                          // UTF32_BE
+  else if (len >= 4 && b0 == 0xEFu && b1 == 0xBBu && b2 == 0xBFu) ans = 1u;                        // UTF8
+  else {
+    if (r8->error == kSuccess) ans |= 1u;
+    if ((len & 1u) == 0 && r16->error == kSuccess) ans |= 2u;
+    if ((len & 3u) == 0 && r32->error == kSuccess) ans |= 8u;
+  }
+  *out = ans;
+}
+
 }  // namespace
 
 size_t utf32_family_tiles(const void *in, size_t bytes) { return workspace_slots(tiles_for(in, bytes)); }
@@ -157,6 +177,14 @@ cudaError_t launch_scan_utf32(const LaunchCtx &c, const uint32_t *in, size_t len
   if (mode == 0) k_scan_utf32<0><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, out);
   else if (mode == 1) k_scan_utf32<1><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, out);
   else k_scan_utf32<2><<<grid, kBlock, 0, c.stream>>>(in, len, c.scratch, out);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_detect_finish(const LaunchCtx &c, const char *in, size_t len, const void *r8, const void *r16, const void *r32,
+                                 unsigned long long *out) {
+  k_detect_finish<<<1, 1, 0, c.stream>>>(reinterpret_cast<const uint8_t *>(in), len, static_cast<const ResultPOD *>(r8),
+                                         static_cast<const ResultPOD *>(r16), static_cast<const ResultPOD *>(r32), out);
   count_launch(1);
   return cudaGetLastError();
 }

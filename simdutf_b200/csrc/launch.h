@@ -54,6 +54,10 @@ cudaError_t launch_change_endianness_utf16(const LaunchCtx &c, const uint16_t *i
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
                                     uint64_t last_chunk, void *full_res);
 
+// to_well_formed_utf16le/be (k_utf16.cu) and the combining step of detect_encodings (k_utf32.cu) — SURVEY.md §8f rank 4
+cudaError_t launch_to_well_formed_utf16(const LaunchCtx &c, const uint16_t *in, size_t len, uint16_t *out, bool big_endian);
+cudaError_t launch_detect_finish(const LaunchCtx &c, const char *in, size_t len, const void *r8, const void *r16, const void *r32,
+                                 unsigned long long *out);
 // Latin-1 / ASCII family (k_latin1.cu): scan mode 0 validate_ascii_with_errors (res = b200_result),
 // 1 utf8_length_from_latin1 (res = uint64)
 size_t latin1_family_tiles(const void *in, size_t bytes);

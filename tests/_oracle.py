@@ -216,6 +216,17 @@ class Oracle:
         a = np.ascontiguousarray(data, dtype=np.uint32)
         return self._conv("oracle_convert_utf32_to_latin1_with_errors", a, np.zeros(a.size + 8, dtype=np.uint8))
 
+    # --- SURVEY.md §8f rank 4 ---
+    def to_well_formed_utf16(self, data, be=False):
+        a = _u16(data); out = np.zeros(a.size, dtype=np.uint16)
+        self.L.oracle_to_well_formed_utf16(_p(a), ctypes.c_size_t(a.size), _p(out), int(be))
+        return out
+
+    def detect_encodings(self, data):
+        a = np.zeros(len(bytes(data)) + 4, dtype=np.uint32).view(np.uint8)[: len(bytes(data))]  # 4-byte aligned copy
+        a[:] = np.frombuffer(bytes(data), dtype=np.uint8)
+        return int(self.L.oracle_detect_encodings(_p(a), ctypes.c_size_t(a.size)))
+
     # --- base64 ---
     def maximal_binary_length_from_base64(self, data):
         a = _u8(data)
@@ -319,6 +330,19 @@ class Reference:
 
     def has_latin1(self):
         return hasattr(self.L, "ref_validate_ascii_with_errors")
+
+    def has_rank4(self):
+        return hasattr(self.L, "ref_detect_encodings")
+
+    def to_well_formed_utf16(self, impl, data, be=False):
+        a = _u16(data); out = np.zeros(a.size, dtype=np.uint16)
+        assert self.L.ref_to_well_formed_utf16(impl.encode(), int(be), _p(a), ctypes.c_size_t(a.size), _p(out)) == 0
+        return out
+
+    def detect_encodings(self, impl, data):
+        a = np.zeros(len(bytes(data)) + 4, dtype=np.uint32).view(np.uint8)[: len(bytes(data))]
+        a[:] = np.frombuffer(bytes(data), dtype=np.uint8)
+        return int(self.L.ref_detect_encodings(impl.encode(), _p(a), ctypes.c_size_t(a.size)))
 
     def validate_ascii_with_errors(self, impl, data):
         a = _u8(data); r = Res()

@@ -755,6 +755,59 @@ def test_latin1_family(b, oracle):
     assert torch.equal(back, lat)
 
 
+def test_well_formed_and_detect(b, oracle):
+    """to_well_formed_utf16le/be (also in place) and detect_encodings against the oracle."""
+    rng = random.Random(44)
+    sizes = [0, 1, 2, 7, 8, 9, 15, 16, 17, 1023, 1024, 1025, 5000, 70001]
+    for it in range(80):
+        n = rng.choice(sizes)
+        u = rand_units(rng, n, it % 3)
+        if it % 4 == 0 and n:
+            u[-1] = 0xD800 + rng.randrange(0x400)
+        if it % 5 == 0 and n > 10:
+            u[7], u[8] = 0xD800 + rng.randrange(0x400), 0xDC00 + rng.randrange(0x400)  # a pair across a vector edge
+        n = len(u)
+        for be in (False, True):
+            src = u.byteswap() if be else u
+            want = oracle.to_well_formed_utf16(src, be)
+            mis = rng.randrange(8)
+            dd = dev(src.view(np.uint8), misalign=2 * mis).view(torch.int16)
+            fn = b.to_well_formed_utf16be if be else b.to_well_formed_utf16le
+            for omis in (mis, (mis + 3) % 8):
+                _, vo = out_buf(n, torch.int16, misalign=omis)
+                fn(dd, vo)
+                assert vo[:n].cpu().numpy().view(np.uint16).tobytes() == want.tobytes(), (u[:16], n, mis, omis, be)
+                check_guard(vo, n)
+            val = b.validate_utf16be_with_errors if be else b.validate_utf16le_with_errors
+            assert val(vo[:n]) == (0, n)
+            fn(dd, dd)  # in place
+            assert dd.cpu().numpy().view(np.uint16).tobytes() == want.tobytes()
+            if it % 8 == 0:
+                h = np.zeros(n + 1, dtype=np.uint16)
+                fn(src, h)
+                assert h[:n].tobytes() == want.tobytes()
+    boms = [b"\xff\xfe", b"\xff\xfe\x00\x00", b"\xfe\xff", b"\x00\x00\xfe\xff", b"\xef\xbb\xbf", b"\xef\xbb", b""]
+    for it in range(150):
+        n = rng.choice([0, 1, 2, 3, 4, 5, 8, 31, 64, 1000, 4099, 70000])
+        text = "".join(rng.choice("aé中😀 ") for _ in range(n))
+        d = rng.choice(boms[-2:] if it % 3 else boms) + text.encode(rng.choice(["utf-8", "utf-16-le", "utf-32-le"]))
+        if it % 4 == 0:
+            d = bytes(rng.randrange(256) for _ in range(n))
+        if it % 7 == 0 and d:
+            k = rng.randrange(len(d))
+            d = d[:k] + bytes([rng.randrange(256)]) + d[k + 1:]
+        want = oracle.detect_encodings(d)
+        assert b.detect_encodings(dev(d)) == want, (d[:32].hex(), len(d))
+        if it % 5 == 0:
+            assert b.detect_encodings(d) == want
+    from simdutf_b200 import synth
+    d = synth.mixed_utf8(1 << 28, seed=4, device="cuda")
+    assert b.detect_encodings(d) & 1
+    u = synth.mixed_utf16le(1 << 27, seed=5, device="cuda")
+    got = b.detect_encodings(u.view(torch.uint8))
+    assert got & 2 and not got & 1
+
+
 def test_binary_to_base64(b, oracle):
     """binary_to_base64 for the four option values (default / url, with and without padding)
     against the oracle, every length class and pointer alignment, device and host path, and a decode round trip."""

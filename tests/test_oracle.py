@@ -233,6 +233,36 @@ def test_against_reference_library(oracle, ref):
                 want = oracle.convert_utf32_to_latin1_with_errors(a32)
                 r, o = ref.convert_utf32_to_latin1_with_errors(im, a32)
                 assert r == want[0] and o.tobytes() == want[1].tobytes(), (im, a32)
+    # to_well_formed_utf16 and detect_encodings
+    if ref.has_rank4():
+        for it in range(2000):
+            a = np.array([rng.choice([0x41, 0x4e2d, 0xd800 + rng.randrange(0x400), 0xdc00 + rng.randrange(0x400), 0xfffd])
+                          for _k in range(rng.randrange(0, 40))], dtype=np.uint16)
+            for be in (False, True):
+                src = a.byteswap() if be else a
+                want = oracle.to_well_formed_utf16(src, be)
+                for im in impls:
+                    assert ref.to_well_formed_utf16(im, src, be).tobytes() == want.tobytes(), (im, be, a)
+        boms = [b"\xff\xfe", b"\xff\xfe\x00\x00", b"\xfe\xff", b"\x00\x00\xfe\xff", b"\xef\xbb\xbf", b"\xef\xbb"]
+        for it in range(3000):
+            n = rng.randrange(0, 64)
+            mode = it % 5
+            if mode == 0:
+                d = "".join(rng.choice("aé中😀 ") for _ in range(n)).encode("utf-8")
+            elif mode == 1:
+                d = "".join(rng.choice("aé中😀 ") for _ in range(n)).encode("utf-16-le")
+            elif mode == 2:
+                d = "".join(rng.choice("aé中😀 ") for _ in range(n)).encode("utf-32-le")
+            elif mode == 3:
+                d = bytes(rng.randrange(256) for _ in range(n))
+            else:
+                d = rng.choice(boms) + "".join(rng.choice("aé中") for _ in range(n)).encode(rng.choice(["utf-8", "utf-16-le", "utf-32-le"]))
+            if rng.random() < 0.2 and d:
+                k = rng.randrange(len(d))
+                d = d[:k] + bytes([rng.randrange(256)]) + d[k + 1:]
+            want = oracle.detect_encodings(d)
+            for im in impls:
+                assert ref.detect_encodings(im, d) == want, (im, d, want)
     abc = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/-_"
     simd = [i for i in impls if i != "fallback"] or impls
     for it in range(1500):

@@ -45,6 +45,8 @@ HOT = [
     "convert_utf16be_to_latin1_tests", "convert_utf16be_to_latin1_tests_with_errors", "convert_valid_utf16be_to_latin1_tests",
     "convert_utf32_to_latin1_tests", "convert_valid_utf32_to_latin1_tests",
     "bele_tests",
+    # SURVEY.md §8f rank 4
+    "to_well_formed_utf16_tests", "detect_encodings_tests",
 ]
 
 

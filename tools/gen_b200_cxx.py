@@ -76,6 +76,9 @@ HOT = {
     ("convert_valid_utf16be_to_latin1", "const char16_t *"),
     ("convert_utf32_to_latin1", "const char32_t *"), ("convert_utf32_to_latin1_with_errors", "const char32_t *"),
     ("convert_valid_utf32_to_latin1", "const char32_t *"),
+    # SURVEY.md §8f rank 4
+    ("to_well_formed_utf16le", "const char16_t *"), ("to_well_formed_utf16be", "const char16_t *"),
+    ("detect_encodings", "const char *"),
 }
 
 hdr = open(os.path.join(ref, "include/simdutf/implementation.h")).read()

@@ -1,4 +1,4 @@
-timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "latin1_family or utf32_family" 2>&1 | tail -25
-for op in l1to8 l1to16 l1to32 u8tol1 u16tol1 u32tol1 validate_ascii_op len8froml1; do timeout 300 python tools/prof_one.py $op $((1<<29)) 5 2>&1 | tail -2; done
-timeout 1500 python -m pytest tests/test_reference_suite.py -m gpu -q -k "latin1 or ascii or bele" 2>&1 | tail -15
-timeout 600 simdutf_b200/build/with_b200/random_fuzzer -a b200 > gpurun_out/ref_random_fuzzer.log 2>&1; echo "random_fuzzer rc=$?"; tail -5 gpurun_out/ref_random_fuzzer.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "well_formed" 2>&1 | tail -25
+for t in convert_valid_utf32_to_latin1_tests bele_tests to_well_formed_utf16_tests detect_encodings_tests; do
+  s=$(date +%s); timeout 400 simdutf_b200/build/with_b200/$t -a b200 > gpurun_out/ref_$t.log 2>&1; echo "$t rc=$? OK=$(grep -c ' OK' gpurun_out/ref_$t.log) secs=$(( $(date +%s) - s ))"; grep -v " OK" gpurun_out/ref_$t.log | head -6
+done
