@@ -493,6 +493,71 @@ def side_measurements(b, lib, synth, torch, device, stream, sp, peak, K):
     assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[2].item()) == int(payload.numel())
     out["config4_base64_to_binary_2GiB"] = {"input_gbs": nt / ms / 1e6, "ms": ms,
                                             "frac_of_peak": (nt + int(payload.numel())) / ms / 1e6 / peak}
+    # §8f rank 2: binary_to_base64 of the decoded payload
+    npay = int(payload.numel())
+    enc = torch.empty((npay + 2) // 3 * 4, dtype=torch.uint8, device=device)
+    ms = timeit(lambda: lib.b200_binary_to_base64_async(ctypes.c_void_p(payload.data_ptr()), npay, ctypes.c_void_p(enc.data_ptr()), 0, res_p, sp), K)
+    out["next_binary_to_base64_1.5GiB"] = {"input_gbs": npay / ms / 1e6, "ms": ms, "frac_of_peak": (npay + int(enc.numel())) / ms / 1e6 / peak}
+    del text, payload, ob, enc
+
+    def rec(key, ms, nin, nout):
+        out[key] = {"input_gbs": nin / ms / 1e6, "ms": ms, "frac_of_peak": (nin + nout) / ms / 1e6 / peak}
+
+    def p_(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    # §8f rank 1 (second part): the UTF-32 family on the code points of 1 GiB of mixed UTF-8
+    m = synth.mixed_utf8(GIB, seed=2, device=device)
+    n8 = int(m.numel())
+    cps = b.count_utf8(m)
+    units = b.utf16_length_from_utf8(m)
+    u32 = torch.empty(cps, dtype=torch.int32, device=device)
+    assert b.convert_utf8_to_utf32_with_errors(m, u32) == (0, cps)
+    u16 = torch.empty(units, dtype=torch.int16, device=device)
+    assert b.convert_utf8_to_utf16le_with_errors(m, u16) == (0, units)
+    del m
+    half = max(3, K // 2)
+    rec("next_validate_utf32", timeit(lambda: lib.b200_validate_utf32_with_errors_async(p_(u32), cps, res_p, sp), K), 4 * cps, 0)
+    rec("next_utf8_length_from_utf32", timeit(lambda: lib.b200_utf8_length_from_utf32_async(p_(u32), cps, res_p, sp), K), 4 * cps, 0)
+    o8 = torch.empty(n8, dtype=torch.uint8, device=device)
+    rec("next_convert_utf32_to_utf8", timeit(lambda: lib.b200_convert_utf32_to_utf8_async(p_(u32), cps, p_(o8), res_p, sp), half), 4 * cps, n8)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == n8
+    del o8
+    o16 = torch.empty(units, dtype=torch.int16, device=device)
+    rec("next_convert_utf32_to_utf16le", timeit(lambda: lib.b200_convert_utf32_to_utf16le_async(p_(u32), cps, p_(o16), res_p, sp), half), 4 * cps, 2 * units)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == units
+    o32 = torch.empty(cps, dtype=torch.int32, device=device)
+    rec("next_convert_utf16le_to_utf32", timeit(lambda: lib.b200_convert_utf16le_to_utf32_async(p_(u16), units, p_(o32), res_p, sp), half), 2 * units, 4 * cps)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == cps
+    # §8f rank 4: to_well_formed_utf16le (a map) and detect_encodings (three validations of one buffer)
+    rec("next_to_well_formed_utf16le", timeit(lambda: lib.b200_to_well_formed_utf16le_async(p_(u16), units, p_(o16), res_p, sp), K), 2 * units, 2 * units)
+    nb16 = 2 * units // 4 * 4
+    rec("next_detect_encodings_utf16_text", timeit(lambda: lib.b200_detect_encodings_async(p_(u16), nb16, res_p, sp), half), nb16, 0)
+    del u32, u16, o16, o32
+    # §8f rank 3: the Latin-1 / ASCII family on 1 GiB of Latin-1 with 30 % bytes >= 0x80
+    g = torch.Generator(device=device).manual_seed(59)
+    lat = torch.randint(0, 0x80, (GIB,), dtype=torch.uint8, device=device, generator=g)
+    lat = torch.where(torch.rand(GIB, device=device, generator=g) < 0.3, lat | 0x80, lat)
+    nl = GIB
+    rec("next_validate_ascii", timeit(lambda: lib.b200_validate_ascii_with_errors_async(p_(lat), nl, res_p, sp), K), nl, 0)
+    rec("next_utf8_length_from_latin1", timeit(lambda: lib.b200_utf8_length_from_latin1_async(p_(lat), nl, res_p, sp), K), nl, 0)
+    n8 = b.utf8_length_from_latin1(lat)
+    o8 = torch.empty(n8, dtype=torch.uint8, device=device)
+    rec("next_convert_latin1_to_utf8", timeit(lambda: lib.b200_convert_latin1_to_utf8_async(p_(lat), nl, p_(o8), res_p, sp), half), nl, n8)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == n8
+    ol = torch.empty(nl, dtype=torch.uint8, device=device)
+    rec("next_convert_utf8_to_latin1", timeit(lambda: lib.b200_convert_utf8_to_latin1_async(p_(o8), n8, p_(ol), res_p, sp), half), n8, nl)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == nl
+    del o8
+    o16 = torch.empty(nl, dtype=torch.int16, device=device)
+    rec("next_convert_latin1_to_utf16le", timeit(lambda: lib.b200_convert_latin1_to_utf16le_async(p_(lat), nl, p_(o16), res_p, sp), K), nl, 2 * nl)
+    rec("next_convert_utf16le_to_latin1", timeit(lambda: lib.b200_convert_utf16le_to_latin1_async(p_(o16), nl, p_(ol), res_p, sp), K), 2 * nl, nl)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == nl
+    del o16
+    o32 = torch.empty(nl, dtype=torch.int32, device=device)
+    rec("next_convert_latin1_to_utf32", timeit(lambda: lib.b200_convert_latin1_to_utf32_async(p_(lat), nl, p_(o32), res_p, sp), K), nl, 4 * nl)
+    rec("next_convert_utf32_to_latin1", timeit(lambda: lib.b200_convert_utf32_to_latin1_async(p_(o32), nl, p_(ol), res_p, sp), K), 4 * nl, nl)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == nl
     return out
 
 
