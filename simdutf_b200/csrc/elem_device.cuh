@@ -9,6 +9,9 @@
 //   count(v)            output elements of input element v (what the length query of the conversion returns)
 //   emit(v, prev, next, has_prev, has_next, P, err)  the same count, the elements packed little-endian into P
 //                       (first element lowest, Out-sized fields) and the element's own error code
+//   kFast               byte input only: the trait also has fast_pass1(w, prev, next, bad) — the lane's output count
+//                       from SWAR arithmetic on its 16 input words, plus "some element of this lane may be in error"
+//                       (conservative) — used for tiles that lie wholly inside the buffer
 // Every element is judged on its own (or with its two neighbours), so the first error is the atomicMin of
 // (index << 8 | code).
 #pragma once
@@ -99,6 +102,12 @@ __global__ void __launch_bounds__(kThreads) k_elem_tile_counts(const void *ptr, 
         uint32_t w[16];
         load_lane<In>(in, r0, interior, w);
         uint32_t cnt = 0;
+        if constexpr (T::kFast) {
+          if (interior) {
+            bool bad;
+            return bpd::warp_sum_u32(T::fast_pass1(w, 0u, 0u, bad));
+          }
+        }
 #pragma unroll
         for (int i = 0; i < (int)S::kInPerLane; i++) {
           const unsigned long long pos = r0 + (unsigned long long)i * sizeof(In);
@@ -177,14 +186,22 @@ k_elem_transcode(const void *ptr, size_t bytes, typename T::Out *out, const uint
     uint32_t cnt = 0;
     long long bad_at = -1;
     int bad_code = 0;
+    bool fast = false, suspect = true;
+    if constexpr (T::kFast) {
+      fast = interior;
+      if (fast) cnt = T::fast_pass1(w, pv, nv, suspect);
+    }
+    if (!fast || suspect) {  // element by element: the count (the same number) and the first error
+      cnt = 0;
 #pragma unroll
-    for (int i = 0; i < (int)S::kInPerLane; i++) {
-      int err;
-      uint32_t Pi;
-      const uint32_t c = eval(i, Pi, err);
-      if (err && bad_at < 0) { bad_at = e0 + i; bad_code = err; }
-      if (kKeep) { P[i] = Pi; n[i] = c; }
-      cnt += c;
+      for (int i = 0; i < (int)S::kInPerLane; i++) {
+        int err;
+        uint32_t Pi;
+        const uint32_t c = eval(i, Pi, err);
+        if (err && bad_at < 0) { bad_at = e0 + i; bad_code = err; }
+        if (kKeep) { P[i] = Pi; n[i] = c; }
+        cnt += c;
+      }
     }
     if (bad_at >= 0) {
       const unsigned long long key = err_key((unsigned long long)(bad_at - first_elem), bad_code);
@@ -199,6 +216,12 @@ k_elem_transcode(const void *ptr, size_t bytes, typename T::Out *out, const uint
       for (int i = 0; i < (int)S::kInPerLane; i++) {
         if (kKeep) {
           store(sp, P[i], n[i]);
+        } else if (fast) {  // inside the buffer: no bounds, no error bookkeeping
+          int err;
+          uint32_t Pi;
+          const uint32_t nx = i + 1 < (int)S::kInPerLane ? lane_elem<In>(w, i + 1 < (int)S::kInPerLane ? i + 1 : i) : nv;
+          const uint32_t c = T::emit(lane_elem<In>(w, i), 0u, nx, true, true, Pi, err);
+          store(sp, Pi, c);
         } else {
           int err;
           uint32_t Pi;

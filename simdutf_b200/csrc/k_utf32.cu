@@ -28,6 +28,7 @@ struct U32ToU8 {
   using Out = uint8_t;
   static constexpr uint32_t kMax = 4;
   static constexpr bool kNeedsNeighbours = false;
+  static constexpr bool kFast = false;
   __device__ static uint32_t count(uint32_t w, uint32_t, uint32_t) { return 1u + (w > 0x7Fu) + (w > 0x7FFu) + (w > 0xFFFFu); }
   __device__ static uint32_t emit(uint32_t w, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = w > 0x10FFFFu ? kTooLarge : ((w & 0xFFFFF800u) == 0xD800u ? kSurrogate : kSuccess);
@@ -45,6 +46,7 @@ struct U32ToU16 {
   using Out = uint16_t;
   static constexpr uint32_t kMax = 2;
   static constexpr bool kNeedsNeighbours = false;
+  static constexpr bool kFast = false;
   __device__ static uint32_t count(uint32_t w, uint32_t, uint32_t) { return 1u + (w > 0xFFFFu); }
   __device__ static uint32_t emit(uint32_t w, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = w > 0x10FFFFu ? kTooLarge : ((w & 0xFFFFF800u) == 0xD800u ? kSurrogate : kSuccess);
@@ -64,6 +66,7 @@ struct U16ToU32 {
   using Out = uint32_t;
   static constexpr uint32_t kMax = 1;
   static constexpr bool kNeedsNeighbours = true;
+  static constexpr bool kFast = false;
   // one code point per unit that is not a low surrogate (== count_utf16 / utf32_length_from_utf16, so a buffer
   // sized by that query is never overrun); a high surrogate emits the pair's code point, looking one unit ahead
   __device__ static uint32_t count(uint32_t u, uint32_t, uint32_t) {

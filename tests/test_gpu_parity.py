@@ -664,13 +664,16 @@ def test_latin1_family(b, oracle):
             hl = np.zeros(n + 4, dtype=np.uint8)
             assert b.convert_utf8_to_latin1_with_errors(u8, hl) == (0, n) and hl[:n].tobytes() == d
     # UTF-8 -> Latin-1 error classes: damaged Latin-1-range UTF-8 and byte soup from the class edges
-    for it in range(120):
-        n = rng.choice(sizes[:20])
+    for it in range(160):
+        n = rng.choice(sizes[:20] if it < 120 else [6000, 10000, 70001])  # the larger ones have interior tiles (SWAR screen)
         if it % 2:
             t = bytearray("".join(chr(rng.randrange(0x100) if rng.random() < 0.4 else rng.randrange(0x80)) for _ in range(n)).encode())
             for _ in range(rng.randrange(1, 3)):
                 if t:
                     t[rng.randrange(len(t))] = rng.choice(u8pool)
+            if it >= 120 and it % 4 == 1:  # exactly one damaged byte, deep inside
+                t = bytearray("".join(chr(rng.randrange(0x100) if rng.random() < 0.4 else rng.randrange(0x80)) for _ in range(n)).encode())
+                t[rng.randrange(2100, len(t) - 2100)] = rng.choice(u8pool[3:])
         else:
             t = bytearray(rng.choice(u8pool) if rng.random() < 0.05 else 0x41 for _ in range(n))
             if n > 2049 and it % 4 == 0:
