@@ -118,7 +118,14 @@ __global__ void __launch_bounds__(kBlock) k_validate_utf8(const char *ptr, size_
         if (b0 < in.vend && in.vend <= b0 + 32ull && tail_truncated(in)) badblocks |= 1u << j;
       }
     }
-    if (badblocks) {
+    if (__any_sync(kFull, badblocks != 0u)) {
+      // An error that is already on record in front of this chunk makes the chunk — and every later chunk of this
+      // warp — irrelevant (the first error wins, the key only ever decreases): stop reading.  Keeps validation of
+      // text in the wrong encoding (detect_encodings) from locating an error in every block.
+      unsigned long long cur = ld_relaxed_u64(&scr->err_key);
+      cur = __shfl_sync(kFull, cur, 0);
+      const long long first = (long long)(g0 * 16ull) - 3 - (long long)in.vbeg;
+      if (cur != kNoError && (long long)(cur >> 8) < first) break;
 #pragma unroll
       for (int j = 0; j < ITEMS / 2; j++) {
         const long long b0 = (long long)(r0 + 32ull * j);
