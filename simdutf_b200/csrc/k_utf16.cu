@@ -45,6 +45,25 @@ __device__ __forceinline__ void check_surrogates(const InView &in, Scratch *scr,
     any |= ~((x | ((x & 0x7FFF7FFFu) + 0x7FFF7FFFu)) | 0x7FFF7FFFu);  // 0x8000 per zero half
   }
   if (!any) return;
+  // Surrogates present (common in real text: every supplementary character is a pair).  Exact screen on both halves
+  // of each word at once: the low surrogates must be exactly the units behind the high surrogates — the unit before
+  // the granule (upper half of pw) and the one after it (lower half of nw) included.  Only a granule that fails it
+  // is searched unit by unit.
+  {
+    auto is16 = [](uint32_t x, uint32_t tag) -> uint32_t {  // 0x8000 per half with (half & 0xFC00) == tag
+      const uint32_t z = (x & 0xFC00FC00u) ^ tag;
+      return ~(((z & 0x7FFF7FFFu) + 0x7FFF7FFFu) | z) & 0x80008000u;
+    };
+    uint32_t wrong = 0, hprev = is16(pw, 0xD800D800u);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t H = is16(w[k], 0xD800D800u), L = is16(w[k], 0xDC00DC00u);
+      wrong |= __funnelshift_l(hprev, H, 16) ^ L;
+      hprev = H;
+    }
+    wrong |= (hprev >> 16) ^ (is16(nw, 0xDC00DC00u) & 0x8000u);
+    if (!wrong) return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     if (!((valid >> i) & 1u)) continue;
