@@ -289,7 +289,22 @@ __global__ void __launch_bounds__(kBlock) k_well_formed_utf16(const uint16_t *in
 #pragma unroll
       for (int k = 0; k < 8; k++) u[k + 1] = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
       uint32_t o[4];
-      if (((x.x | x.y | x.z | x.w) & (BE ? 0x00800080u : 0x80008000u)) == 0) {  // no unit >= 0x8000: nothing to replace
+      // Exact screen (the one of check_surrogates): the low surrogates of this vector must be exactly the units
+      // behind the high surrogates, the unit before and the unit after the vector included.  Well-formed vectors
+      // — all of them in valid text — are copied through.
+      auto is16 = [](uint32_t v, uint32_t tag) -> uint32_t {  // 0x8000 per half with (half & 0xFC00) == tag
+        const uint32_t z = ((BE ? swap16x2(v) : v) & 0xFC00FC00u) ^ tag;
+        return ~(((z & 0x7FFF7FFFu) + 0x7FFF7FFFu) | z) & 0x80008000u;
+      };
+      uint32_t wrong = 0, hprev = is16(u[0] << 16, 0xD800D800u);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t H = is16(w[k], 0xD800D800u), L = is16(w[k], 0xDC00DC00u);
+        wrong |= __funnelshift_l(hprev, H, 16) ^ L;
+        hprev = H;
+      }
+      wrong |= (hprev >> 16) ^ (is16(u[9], 0xDC00DC00u) & 0x8000u);
+      if (!wrong) {
         o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
       } else {
 #pragma unroll
