@@ -30,11 +30,8 @@ struct L1ToU8 {
   __device__ static uint32_t count(uint32_t b, uint32_t, uint32_t) { return 1u + (b >> 7); }
   // 64 + the number of bytes >= 0x80: the high bits summed as packed byte counters (<= 16 each)
   __device__ static uint32_t fast_pass1(const uint32_t (&w)[16], uint32_t, uint32_t, bool &bad) {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) acc += (w[j] >> 7) & 0x01010101u;
     bad = false;
-    return 64u + ((acc * 0x01010101u) >> 24);
+    return 64u + l1_high_count64(w);  // swar.h (host-tested)
   }
   __device__ static uint32_t emit(uint32_t b, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = kSuccess;
@@ -60,22 +57,7 @@ struct U8ToL1 {
   // 64 - the number of continuation bytes; `bad` (conservative) unless every byte >= 0xC0 is C2 / C3 and the
   // continuation bytes are exactly the bytes behind those leads (the lane's neighbours pb / nb included)
   __device__ static uint32_t fast_pass1(const uint32_t (&w)[16], uint32_t pb, uint32_t nb, bool &bad) {
-    uint32_t acc = 0, wrong = 0;
-    uint32_t lead_prev = pb >= 0xC0u ? 0x80000000u : 0u;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const uint32_t hi = w[j] & 0x80808080u, b6 = (w[j] << 1) & 0x80808080u;
-      const uint32_t cont = hi & ~b6, lead = hi & b6;
-      const uint32_t x = (w[j] & 0xFEFEFEFEu) ^ 0xC2C2C2C2u;                // zero bytes <=> C2 / C3
-      const uint32_t nz = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;             // bit 7 set <=> byte of x non-zero
-      wrong |= lead & nz;
-      wrong |= __funnelshift_l(lead_prev, lead, 8) ^ cont;                   // lead flags moved to the byte behind them
-      lead_prev = lead;
-      acc += cont >> 7;
-    }
-    wrong |= (lead_prev >> 24) ^ ((nb & 0xC0u) == 0x80u ? 0x80u : 0u);       // the lane's last lead needs nb to continue it
-    bad = wrong != 0u;
-    return 64u - ((acc * 0x01010101u) >> 24);
+    return 64u - u8l1_screen64(w, pb, nb, &bad);  // swar.h (host-tested)
   }
   // branch-free; when the caller ignores err (tiles screened by fast_pass1) only the two selects for P and the count remain
   __device__ static uint32_t emit(uint32_t b, uint32_t pb, uint32_t nb, bool has_prev, bool has_next, uint32_t &P, int &err) {

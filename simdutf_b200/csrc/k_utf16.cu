@@ -49,21 +49,7 @@ __device__ __forceinline__ void check_surrogates(const InView &in, Scratch *scr,
   // of each word at once: the low surrogates must be exactly the units behind the high surrogates — the unit before
   // the granule (upper half of pw) and the one after it (lower half of nw) included.  Only a granule that fails it
   // is searched unit by unit.
-  {
-    auto is16 = [](uint32_t x, uint32_t tag) -> uint32_t {  // 0x8000 per half with (half & 0xFC00) == tag
-      const uint32_t z = (x & 0xFC00FC00u) ^ tag;
-      return ~(((z & 0x7FFF7FFFu) + 0x7FFF7FFFu) | z) & 0x80008000u;
-    };
-    uint32_t wrong = 0, hprev = is16(pw, 0xD800D800u);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t H = is16(w[k], 0xD800D800u), L = is16(w[k], 0xDC00DC00u);
-      wrong |= __funnelshift_l(hprev, H, 16) ^ L;
-      hprev = H;
-    }
-    wrong |= (hprev >> 16) ^ (is16(nw, 0xDC00DC00u) & 0x8000u);
-    if (!wrong) return;
-  }
+  if (!u16_pairing_screen(w, pw, nw)) return;  // swar.h (host-tested)
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     if (!((valid >> i) & 1u)) continue;
@@ -292,18 +278,10 @@ __global__ void __launch_bounds__(kBlock) k_well_formed_utf16(const uint16_t *in
       // Exact screen (the one of check_surrogates): the low surrogates of this vector must be exactly the units
       // behind the high surrogates, the unit before and the unit after the vector included.  Well-formed vectors
       // — all of them in valid text — are copied through.
-      auto is16 = [](uint32_t v, uint32_t tag) -> uint32_t {  // 0x8000 per half with (half & 0xFC00) == tag
-        const uint32_t z = ((BE ? swap16x2(v) : v) & 0xFC00FC00u) ^ tag;
-        return ~(((z & 0x7FFF7FFFu) + 0x7FFF7FFFu) | z) & 0x80008000u;
-      };
-      uint32_t wrong = 0, hprev = is16(u[0] << 16, 0xD800D800u);
+      uint32_t ws[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t H = is16(w[k], 0xD800D800u), L = is16(w[k], 0xDC00DC00u);
-        wrong |= __funnelshift_l(hprev, H, 16) ^ L;
-        hprev = H;
-      }
-      wrong |= (hprev >> 16) ^ (is16(u[9], 0xDC00DC00u) & 0x8000u);
+      for (int k = 0; k < 4; k++) ws[k] = BE ? swap16x2(w[k]) : w[k];
+      const uint32_t wrong = u16_pairing_screen(ws, BE ? swap16x2(u[0] << 16) : u[0] << 16, BE ? swap16x2(u[9]) : u[9]);
       if (!wrong) {
         o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
       } else {

@@ -145,6 +145,57 @@ B200_HD bool u16_bad(uint32_t u, uint32_t pu, bool has_prev, uint32_t nu, bool h
   return false;
 }
 // ---------------------------------------------------------------------------------------------
+// Exact pairing screen for 8 UTF-16 units (4 little-endian words; BE callers swap first): zero iff the low
+// surrogates are exactly the units behind the high surrogates, the unit before the group (upper half of pw) and
+// the unit after it (lower half of nw) included.  Zero implies u16_bad() is false for all 8 units; non-zero means
+// one of them is bad OR the unit before is a lone high / the unit after a lone low surrogate (reported by their
+// own groups): callers treat non-zero as "search this group unit by unit".
+// ---------------------------------------------------------------------------------------------
+B200_HD uint32_t u16_is_tag(uint32_t x, uint32_t tag) {  // 0x8000 per 16-bit half with (half & 0xFC00) == tag's half
+  const uint32_t z = (x & 0xFC00FC00u) ^ tag;
+  return ~(((z & 0x7FFF7FFFu) + 0x7FFF7FFFu) | z) & 0x80008000u;
+}
+B200_HD uint32_t u16_pairing_screen(const uint32_t w[4], uint32_t pw, uint32_t nw) {
+  uint32_t wrong = 0, hprev = u16_is_tag(pw, 0xD800D800u);
+  for (int k = 0; k < 4; k++) {
+    const uint32_t H = u16_is_tag(w[k], 0xD800D800u), L = u16_is_tag(w[k], 0xDC00DC00u);
+    wrong |= ((H << 16) | (hprev >> 16)) ^ L;  // the high-surrogate flags moved to the unit behind them
+    hprev = H;
+  }
+  return wrong | ((hprev >> 16) ^ (u16_is_tag(nw, 0xDC00DC00u) & 0x8000u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// UTF-8 -> Latin-1 (reference src/scalar/utf8_to_latin1/utf8_to_latin1.h:83-149) on 64 bytes = 16 words at once:
+// returns the number of continuation bytes (64 minus it is the output length) and sets *suspect unless every byte
+// >= 0xC0 is C2 / C3 and the continuation bytes are exactly the bytes behind those leads (pb / nb: the byte before
+// and after the 64).  *suspect == false  =>  the reference's walk finds no error in these 64 bytes.
+// ---------------------------------------------------------------------------------------------
+B200_HD uint32_t u8l1_screen64(const uint32_t w[16], uint32_t pb, uint32_t nb, bool *suspect) {
+  uint32_t acc = 0, wrong = 0;
+  uint32_t lead_prev = pb >= 0xC0u ? 0x80000000u : 0u;
+  for (int j = 0; j < 16; j++) {
+    const uint32_t hi = w[j] & 0x80808080u, b6 = (w[j] << 1) & 0x80808080u;
+    const uint32_t cont = hi & ~b6, lead = hi & b6;
+    const uint32_t x = (w[j] & 0xFEFEFEFEu) ^ 0xC2C2C2C2u;     // zero bytes <=> C2 / C3
+    const uint32_t nz = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 set <=> byte of x non-zero
+    wrong |= lead & nz;
+    wrong |= ((lead << 8) | (lead_prev >> 24)) ^ cont;          // the lead flags moved to the byte behind them
+    lead_prev = lead;
+    acc += cont >> 7;                                           // packed byte counters, <= 16 each
+  }
+  wrong |= (lead_prev >> 24) ^ ((nb & 0xC0u) == 0x80u ? 0x80u : 0u);  // the last lead needs nb to continue it
+  *suspect = wrong != 0u;
+  return (acc * 0x01010101u) >> 24;
+}
+// Latin-1 -> UTF-8: bytes >= 0x80 among 64 (each becomes two bytes)
+B200_HD uint32_t l1_high_count64(const uint32_t w[16]) {
+  uint32_t acc = 0;
+  for (int j = 0; j < 16; j++) acc += (w[j] >> 7) & 0x01010101u;
+  return (acc * 0x01010101u) >> 24;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Base64 character classes: 0..63 sextet, 64 ASCII whitespace (' ' \t \n \r \f), 255 anything else.
 // Equals the three 256-entry tables at reference src/tables/base64_tables.h:791-849
 // (to_base64_value / to_base64_url_value / to_base64_default_or_url_value).

@@ -395,6 +395,65 @@ static std::vector<uint8_t> gen_b64(size_t n) {
   return o;
 }
 
+// ---- SWAR screens of the widened rows (swar.h: u16_pairing_screen, u8l1_screen64, l1_high_count64) ---------------
+// u16_pairing_screen over 8 units with both neighbours must be zero exactly when none of the 8 units is a bad
+// surrogate (u16_bad); a lone low surrogate right behind or a lone high surrogate right in front of the group may
+// also raise it (conservative: those are reported by their own groups).
+static void test_u16_screen() {
+  static const uint16_t pool[] = {0x0041, 0x4E2D, 0xD7FF, 0xD800, 0xDBFF, 0xDC00, 0xDFFF, 0xE000, 0xFFFD};
+  uint16_t u[10];
+  for (auto &x : u) x = rnd(3) ? pool[rnd(9)] : (uint16_t)(0xD800 + rnd(0x800));
+  if (rnd(4) == 0) for (int i = 1; i + 1 < 10; i += 2) { u[i] = (uint16_t)(0xD800 + rnd(0x400)); u[i + 1] = (uint16_t)(0xDC00 + rnd(0x400)); }
+  uint32_t w[4];
+  for (int k = 0; k < 4; k++) w[k] = (uint32_t)u[1 + 2 * k] | ((uint32_t)u[2 + 2 * k] << 16);
+  const uint32_t pw = ((uint32_t)u[0] << 16) | rnd(0x10000), nw = (uint32_t)u[9] | (rnd(0x10000) << 16);
+  bool any_bad = false;
+  for (int i = 1; i <= 8; i++) any_bad = any_bad || b200::u16_bad(u[i], u[i - 1], true, u[i + 1], true);
+  const bool next_lone_low = ((u[9] & 0xFC00) == 0xDC00 && (u[8] & 0xFC00) != 0xD800) ||
+                             ((u[0] & 0xFC00) == 0xD800 && (u[1] & 0xFC00) != 0xDC00);  // or: the unit before is a lone high
+  const uint32_t wrong = b200::u16_pairing_screen(w, pw, nw);
+  CHECK(!(any_bad && wrong == 0), "u16 screen missed a bad surrogate");
+  CHECK(!(wrong != 0 && !any_bad && !next_lone_low), "u16 screen raised without cause %08x: %04x | %04x %04x %04x %04x %04x %04x %04x %04x | %04x", wrong,
+        u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7], u[8], u[9]);
+}
+// u8l1_screen64: the continuation count is exact; suspect == false implies the oracle's walk over the 64 bytes
+// (with the byte before and after) reports nothing inside them.
+static void test_u8l1_screen() {
+  static const uint8_t pool[] = {0x00, 0x41, 0x7F, 0x80, 0xA9, 0xBF, 0xC0, 0xC1, 0xC2, 0xC3, 0xC4, 0xDF, 0xE0, 0xEF, 0xF0, 0xF7, 0xF8, 0xFF};
+  uint8_t b[66];
+  const int mode = rnd(4);
+  for (int i = 0; i < 66;) {
+    if (mode == 0) { b[i++] = pool[rnd(18)]; continue; }
+    if (rnd(3) == 0 && i + 1 < 66) { b[i++] = (uint8_t)(0xC2 + rnd(2)); b[i++] = (uint8_t)(0x80 + rnd(64)); }
+    else b[i++] = (uint8_t)rnd(0x80);
+  }
+  if (mode == 1) b[rnd(66)] = pool[rnd(18)];
+  if (mode == 2) { const int k = rnd(66); b[k] = (uint8_t)rnd(256); }
+  uint32_t w[16];
+  for (int j = 0; j < 16; j++) w[j] = (uint32_t)b[1 + 4 * j] | ((uint32_t)b[2 + 4 * j] << 8) | ((uint32_t)b[3 + 4 * j] << 16) | ((uint32_t)b[4 + 4 * j] << 24);
+  bool suspect = false;
+  const uint32_t conts = b200::u8l1_screen64(w, b[0], b[65], &suspect);
+  uint32_t want_conts = 0, want_high = 0;
+  for (int i = 1; i <= 64; i++) { want_conts += (b[i] & 0xC0) == 0x80; want_high += b[i] >> 7; }
+  CHECK(conts == want_conts, "u8l1 continuation count %u vs %u", conts, want_conts);
+  CHECK(b200::l1_high_count64(w) == want_high, "l1 high count");
+  // the reference's walk over all 66 bytes: the first error, if any, must not lie in [1, 64] unless suspect
+  std::vector<uint8_t> out(80);
+  // start the walk on a character boundary: if b[0] is a lead, include it; if it is a lone continuation the walk errs at 0
+  const oracle_result r = oracle_convert_utf8_to_latin1_with_errors(b, 66, out.data());
+  // (a byte >= 0xE0 in front is an error of the lane before, which sorts first: nothing to prove about this lane then)
+  if (!suspect && b[0] < 0xE0) {
+    // walk again from byte 1 when byte 0 itself is the problem (it belongs to the previous lane)
+    oracle_result r1 = r;
+    if (r.error != ORACLE_SUCCESS && r.count == 0) {
+      const int skip = ((b[0] & 0xE0) == 0xC0 && (b[1] & 0xC0) == 0x80) ? 2 : 1;
+      r1 = oracle_convert_utf8_to_latin1_with_errors(b + skip, 66 - skip, out.data());
+      if (r1.error != ORACLE_SUCCESS) r1.count += skip;
+    }
+    CHECK(r1.error == ORACLE_SUCCESS || r1.count > 64, "u8l1 screen missed error %d at %llu", (int)r1.error, (unsigned long long)r1.count);
+  }
+}
+
 int main(int argc, char **argv) {
   const long iters = argc > 1 ? atol(argv[1]) : 20000;
   rng.seed(argc > 2 ? atoll(argv[2]) : 12345);
@@ -411,6 +470,7 @@ int main(int argc, char **argv) {
     test_b64(b, opts[rnd(8)], rnd(3));
     test_b64_bitplane(b, opts[rnd(8)]);
     if (it < 256) { std::vector<uint8_t> all(256); for (int i = 0; i < 256; i++) all[i] = (uint8_t)(i + it); test_b64_bitplane(all, opts[it & 7]); }
+    for (int k = 0; k < 8; k++) { test_u16_screen(); test_u8l1_screen(); }
     if (failures > 50) break;
   }
   // known-answer edge cases
