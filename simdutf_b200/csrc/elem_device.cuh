@@ -11,7 +11,8 @@
 //                       (first element lowest, Out-sized fields) and the element's own error code
 //   kFast               byte input only: the trait also has fast_pass1(w, prev, next, bad) — the lane's output count
 //                       from SWAR arithmetic on its 16 input words, plus "some element of this lane may be in error"
-//                       (conservative) — used for tiles that lie wholly inside the buffer
+//                       (conservative) — and emit_word(w, next_word, sp), which stages the output of four input
+//                       bytes of a lane that passed the screen; both are used for tiles wholly inside the buffer
 // Every element is judged on its own (or with its two neighbours), so the first error is the atomicMin of
 // (index << 8 | code).
 #pragma once
@@ -210,7 +211,16 @@ k_elem_transcode(const void *ptr, size_t bytes, typename T::Out *out, const uint
     const uint32_t incl = bpd::warp_inclusive_u32(cnt);
     const unsigned long long G = goff + (incl - cnt);
     const uint32_t a = (uint32_t)((out_elems + G) & (S::kVec - 1u));
-    {
+    bool word_emit = false;
+    if constexpr (T::kFast) {
+      word_emit = fast && !suspect;  // a screened lane of a tile inside the buffer: four input bytes per step
+      if (word_emit) {
+        uint32_t sp = (uint32_t)__cvta_generic_to_shared(region + a);
+#pragma unroll
+        for (int j = 0; j < 16; j++) T::emit_word(w[j], j < 15 ? w[j < 15 ? j + 1 : j] : nv, sp);
+      }
+    }
+    if (!word_emit) {
       uint32_t sp = (uint32_t)__cvta_generic_to_shared(region + a);
 #pragma unroll
       for (int i = 0; i < (int)S::kInPerLane; i++) {

@@ -33,6 +33,18 @@ struct L1ToU8 {
     bad = false;
     return 64u + l1_high_count64(w);  // swar.h (host-tested)
   }
+  // four input bytes -> 4..8 staged bytes (tiles inside the buffer)
+  __device__ static void emit_word(uint32_t w, uint32_t, uint32_t &sp) {
+    uint32_t f, c;
+    const uint32_t hi = l1u8_word(w, &f, &c);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t h = (hi >> (8 * k)) & 1u;
+      bpd::sts_u8(sp, f >> (8 * k));
+      if (h) bpd::sts_u8(sp + 1u, c >> (8 * k));
+      sp += 1u + h;
+    }
+  }
   __device__ static uint32_t emit(uint32_t b, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = kSuccess;
     const uint32_t hi = b >> 7;
@@ -58,6 +70,17 @@ struct U8ToL1 {
   // continuation bytes are exactly the bytes behind those leads (the lane's neighbours pb / nb included)
   __device__ static uint32_t fast_pass1(const uint32_t (&w)[16], uint32_t pb, uint32_t nb, bool &bad) {
     return 64u - u8l1_screen64(w, pb, nb, &bad);  // swar.h (host-tested)
+  }
+  // four input bytes of a screened lane -> 0..4 staged bytes; wn: the word behind them (its low byte is all that is used)
+  __device__ static void emit_word(uint32_t w, uint32_t wn, uint32_t &sp) {
+    uint32_t keep7;
+    const uint32_t o = u8l1_word(w, wn, &keep7);
+    const uint32_t k0 = (keep7 >> 7) & 1u, k1 = (keep7 >> 15) & 1u, k2 = (keep7 >> 23) & 1u, k3 = keep7 >> 31;
+    if (k0) bpd::sts_u8(sp, o);
+    if (k1) bpd::sts_u8(sp + k0, o >> 8);
+    if (k2) bpd::sts_u8(sp + k0 + k1, o >> 16);
+    if (k3) bpd::sts_u8(sp + k0 + k1 + k2, o >> 24);
+    sp += k0 + k1 + k2 + k3;
   }
   // branch-free; when the caller ignores err (tiles screened by fast_pass1) only the two selects for P and the count remain
   __device__ static uint32_t emit(uint32_t b, uint32_t pb, uint32_t nb, bool has_prev, bool has_next, uint32_t &P, int &err) {

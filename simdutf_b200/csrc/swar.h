@@ -195,6 +195,27 @@ B200_HD uint32_t l1_high_count64(const uint32_t w[16]) {
   return (acc * 0x01010101u) >> 24;
 }
 
+// Four bytes of VALID Latin-1-range UTF-8 at once (the lane passed u8l1_screen64): byte k of the result is the Latin-1
+// byte of the character that STARTS at input byte k (itself if ASCII, else two bits of the C2/C3 lead and six of the
+// byte behind it — wn supplies the byte behind byte 3); *keep7 has bit 7 of byte k set unless input byte k is a
+// continuation byte (those produce nothing).
+B200_HD uint32_t u8l1_word(uint32_t w, uint32_t wn, uint32_t *keep7) {
+  const uint32_t nxt = (w >> 8) | (wn << 24);
+  const uint32_t b6 = (w << 1) & 0x80808080u;
+  const uint32_t m = ((w & b6) >> 7) * 0xFFu;  // 0xFF per byte >= 0xC0
+  const uint32_t val = ((w & 0x03030303u) << 6) | (nxt & 0x3F3F3F3Fu);
+  *keep7 = ((w & ~b6) & 0x80808080u) ^ 0x80808080u;
+  return (w & ~m) | (val & m);
+}
+// Four Latin-1 bytes at once: *first = the first UTF-8 byte of each (itself, or C2/C3), *second = the continuation
+// byte of each (meaningful where the byte is >= 0x80); returns 1 per byte >= 0x80 at bits 0, 8, 16, 24.
+B200_HD uint32_t l1u8_word(uint32_t w, uint32_t *first, uint32_t *second) {
+  const uint32_t hi = (w >> 7) & 0x01010101u, m = hi * 0xFFu;
+  *first = (w & ~m) | ((((w >> 6) & 0x03030303u) | 0xC0C0C0C0u) & m);
+  *second = (w & 0x3F3F3F3Fu) | 0x80808080u;
+  return hi;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Base64 character classes: 0..63 sextet, 64 ASCII whitespace (' ' \t \n \r \f), 255 anything else.
 // Equals the three 256-entry tables at reference src/tables/base64_tables.h:791-849

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../oracle/oracle.h"
@@ -437,6 +438,37 @@ static void test_u8l1_screen() {
   for (int i = 1; i <= 64; i++) { want_conts += (b[i] & 0xC0) == 0x80; want_high += b[i] >> 7; }
   CHECK(conts == want_conts, "u8l1 continuation count %u vs %u", conts, want_conts);
   CHECK(b200::l1_high_count64(w) == want_high, "l1 high count");
+  // the word-at-a-time emitters against the byte rules
+  {
+    std::vector<uint8_t> l8;
+    for (int j = 0; j < 16; j++) {
+      uint32_t f, c;
+      const uint32_t hi = b200::l1u8_word(w[j], &f, &c);
+      for (int k = 0; k < 4; k++) {
+        l8.push_back((uint8_t)(f >> (8 * k)));
+        if ((hi >> (8 * k)) & 1u) l8.push_back((uint8_t)(c >> (8 * k)));
+      }
+    }
+    std::vector<uint8_t> want8(140);
+    const uint64_t n8 = oracle_convert_latin1_to_utf8(b + 1, 64, want8.data());
+    CHECK(l8.size() == n8 && std::equal(l8.begin(), l8.end(), want8.begin()), "l1u8_word");
+  }
+  if (!suspect && b[0] < 0xE0) {
+    std::vector<uint8_t> got;
+    for (int j = 0; j < 16; j++) {
+      uint32_t keep7;
+      const uint32_t o = b200::u8l1_word(w[j], j < 15 ? w[j + 1] : (uint32_t)b[65], &keep7);
+      for (int k = 0; k < 4; k++) if ((keep7 >> (8 * k + 7)) & 1u) got.push_back((uint8_t)(o >> (8 * k)));
+    }
+    // the oracle on the characters that START inside the 64 bytes (a leading continuation byte belongs to the lane before;
+    // a trailing C2/C3 lead takes its second byte from b[65])
+    const int from = ((b[1] & 0xC0) == 0x80) ? 2 : 1;
+    const int to = ((b[64] & 0xE0) == 0xC0) ? 66 : 65;
+    std::vector<uint8_t> want(80);
+    const oracle_result rr = oracle_convert_utf8_to_latin1_with_errors(b + from, to - from, want.data());
+    CHECK(rr.error == ORACLE_SUCCESS && rr.count == got.size() && std::equal(got.begin(), got.end(), want.begin()),
+          "u8l1_word: %d, %llu vs %zu", (int)rr.error, (unsigned long long)rr.count, got.size());
+  }
   // the reference's walk over all 66 bytes: the first error, if any, must not lie in [1, 64] unless suspect
   std::vector<uint8_t> out(80);
   // start the walk on a character boundary: if b[0] is a lead, include it; if it is a lone continuation the walk errs at 0
