@@ -306,7 +306,7 @@ inline size_t workspace_slots(size_t tiles) {
 template <class T>
 cudaError_t launch_elem(const LaunchCtx &c, const void *in, size_t len, void *out, void *res) {
   using S = Shape<T>;
-  constexpr int MINB = 2;
+  constexpr int MINB = sizeof(typename T::In) == 4 ? 3 : 2;  // 16 elements per lane leave room for a third CTA per SM
   const size_t bytes = len * sizeof(typename T::In);
   const size_t tiles = tiles_for(in, bytes);
   if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
