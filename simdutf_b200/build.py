@@ -137,6 +137,10 @@ def build_reference_integration(ref: str = "/root/reference", tests: bool = True
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", lib] + inc +
              [os.path.join(WITH_B200, "simdutf_b200_unity.cpp"), os.path.join(CSRC, "b200_implementation.cpp"),
               "-L" + PKG, "-lsimdutf_b200", "-Wl,-rpath,$ORIGIN/../.."])
+        # the two patched translation units are derived from reference sources: they exist only for this compile
+        for tmp in ("simdutf_b200_unity.cpp", "implementation_b200.cpp"):
+            if os.path.exists(os.path.join(WITH_B200, tmp)):
+                os.remove(os.path.join(WITH_B200, tmp))
     if tests:
         tinc = ["-I" + os.path.join(ref, "include"), "-I" + ref, "-I" + os.path.join(ref, "tests")]
         helpers = sorted(os.path.join(ref, "tests", d, f) for d in ("helpers", "reference")

@@ -2,9 +2,9 @@
 //
 // Modelled on the reference's per-kernel headers (e.g. src/simdutf/haswell/implementation.h:13-19): a final
 // subclass of simdutf::implementation (reference include/simdutf/implementation.h:3302-5066) named "b200".
-// Every virtual of the hot path forwards to one b200_host_* entry point of the C ABI
-// (include/simdutf_b200.h); the rest return the reference's "unsupported" values (generated stubs, see
-// tools/gen_b200_cxx.py).  C++11-clean: it is #included by the reference's unity translation unit.
+// Every pure virtual of this reference forwards to one b200_host_* entry point of the C ABI
+// (include/simdutf_b200.h); a virtual a later reference adds would get the reference's "unsupported" value
+// (generated, tools/gen_b200_cxx.py; empty today).  C++11-clean: it is #included by the reference's unity translation unit.
 #ifndef SIMDUTF_B200_IMPLEMENTATION_H
 #define SIMDUTF_B200_IMPLEMENTATION_H
 

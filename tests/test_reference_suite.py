@@ -3,8 +3,8 @@ simdutf::b200::implementation (simdutf_b200/build/with_b200, built by build.buil
 build container — they travel to the GPU box as prebuilt files), run with `-a b200`: every TEST in them then
 exercises the CUDA kernels through the C++ virtuals (reference tests/helpers/test.cpp:143-207).
 
-Only binaries whose tests stay inside the hot path are required to pass; the others call
-virtuals that are still "unsupported" stubs (§8f) and are reported, not asserted."""
+Every pure virtual of simdutf::implementation is served by a kernel (SURVEY.md §8a + §8f ranks 1-4), so every
+binary listed here must pass; SLOW holds the ones that are green but consist of 10^6..10^8 tiny calls."""
 import os
 import subprocess
 
