@@ -1,6 +1,7 @@
 """CPU tests (-m "not gpu"): pin the oracle (oracle/oracle.c) against
   1. the golden vectors (tests/golden/golden.json): known-answer tests transcribed from the reference's own
      tests, and outputs recorded from the reference library by tests/golden/make_golden.py;
+     (tests/golden/golden_next.json / make_golden_next.py: the same for the SURVEY.md §8f families);
   2. the unmodified reference library (oracle/_ref, icelake + haswell + fallback kernels) on seeded random
      inputs, when it is present (build container; it also travels to the GPU box as a prebuilt .so).
 """
@@ -86,6 +87,59 @@ def _rand_utf8(rng, n):
     if mode == 3 and b:
         b[rng.randrange(len(b))] = rng.choice(SPECIAL)
     return bytes(b)
+
+
+def test_recorded_next(oracle):
+    """the oracle against outputs recorded from the reference library
+    (tests/golden/golden_next.json, made by tests/golden/make_golden_next.py) — pins these restatements where
+    /root/reference is absent."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_next.json")) as f:
+        g = json.load(f)
+
+    def u16(d):
+        return np.frombuffer(d, dtype=np.uint16)
+
+    def u32(d):
+        return np.frombuffer(d, dtype=np.uint32)
+
+    def res(r):
+        (e, c), o = r
+        return [e, c, o.tobytes().hex()]
+
+    table = {
+        "count_utf16be": lambda d: oracle.count_utf16be(u16(d)),
+        "utf8_length_from_utf16be": lambda d: oracle.utf8_length_from_utf16be(u16(d)),
+        "validate_utf16be_with_errors": lambda d: list(oracle.validate_utf16be_with_errors(u16(d))),
+        "convert_utf16be_to_utf8_with_errors": lambda d: res(oracle.convert_utf16be_to_utf8_with_errors(u16(d))),
+        "convert_utf16le_to_utf32_with_errors": lambda d: res(oracle.convert_utf16_to_utf32_with_errors(u16(d), False)),
+        "convert_utf16be_to_utf32_with_errors": lambda d: res(oracle.convert_utf16_to_utf32_with_errors(u16(d), True)),
+        "to_well_formed_utf16le": lambda d: oracle.to_well_formed_utf16(u16(d), False).tobytes().hex(),
+        "to_well_formed_utf16be": lambda d: oracle.to_well_formed_utf16(u16(d), True).tobytes().hex(),
+        "validate_utf32_with_errors": lambda d: list(oracle.validate_utf32_with_errors(u32(d))),
+        "utf8_length_from_utf32": lambda d: oracle.utf8_length_from_utf32(u32(d)),
+        "utf16_length_from_utf32": lambda d: oracle.utf16_length_from_utf32(u32(d)),
+        "convert_utf32_to_utf8_with_errors": lambda d: res(oracle.convert_utf32_to_utf8_with_errors(u32(d))),
+        "convert_utf32_to_utf16le_with_errors": lambda d: res(oracle.convert_utf32_to_utf16_with_errors(u32(d), False)),
+        "convert_utf32_to_utf16be_with_errors": lambda d: res(oracle.convert_utf32_to_utf16_with_errors(u32(d), True)),
+        "convert_utf32_to_latin1_with_errors": lambda d: res(oracle.convert_utf32_to_latin1_with_errors(u32(d))),
+        "convert_utf16le_to_latin1_with_errors": lambda d: res(oracle.convert_utf16_to_latin1_with_errors(u16(d), False)),
+        "convert_utf16be_to_latin1_with_errors": lambda d: res(oracle.convert_utf16_to_latin1_with_errors(u16(d), True)),
+        "validate_ascii_with_errors": lambda d: list(oracle.validate_ascii_with_errors(d)),
+        "utf8_length_from_latin1": lambda d: oracle.utf8_length_from_latin1(d),
+        "latin1_length_from_utf8": lambda d: oracle.count_utf8(d),
+        "convert_latin1_to_utf8": lambda d: oracle.convert_latin1_to_utf8(d).tobytes().hex(),
+        "convert_latin1_to_utf16le": lambda d: oracle.convert_latin1_to_utf16(d, False).tobytes().hex(),
+        "convert_latin1_to_utf16be": lambda d: oracle.convert_latin1_to_utf16(d, True).tobytes().hex(),
+        "convert_latin1_to_utf32": lambda d: oracle.convert_latin1_to_utf32(d).tobytes().hex(),
+        "convert_utf8_to_latin1_with_errors": lambda d: res(oracle.convert_utf8_to_latin1_with_errors(d)),
+        "detect_encodings": lambda d: oracle.detect_encodings(d),
+    }
+    seen = set()
+    for v in g["recorded"]:
+        d = bytes.fromhex(v["input"])
+        assert table[v["func"]](d) == v["out"], v
+        seen.add(v["func"])
+    assert seen == set(table), set(table) - seen
 
 
 def test_against_reference_library(oracle, ref):
