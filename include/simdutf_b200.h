@@ -24,8 +24,13 @@
  * or throws (reference CMakeLists.txt:173-214), and it has NO CPU fallback: with
  * no sm_100 device present every compute entry point returns B200_E_NO_DEVICE.
  *
- * Lengths are in CODE UNITS of the input encoding (bytes for UTF-8 / base64,
- * 16-bit units for UTF-16), as in the reference.
+ * Lengths are in CODE UNITS of the input encoding (bytes for UTF-8 / Latin-1 /
+ * base64, 16-bit units for UTF-16, 32-bit units for UTF-32), as in the reference.
+ *
+ * Coverage: the hot path of SURVEY.md §8a and all of §8f (UTF-16BE twins, UTF-32
+ * family, Latin-1 / ASCII, base64 encode and char16_t decode, to_well_formed_utf16,
+ * detect_encodings, change_endianness_utf16): every pure virtual of
+ * simdutf::implementation has an entry point here.
  */
 #ifndef SIMDUTF_B200_H
 #define SIMDUTF_B200_H
