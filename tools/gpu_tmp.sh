@@ -1,1 +1,2 @@
-timeout 120 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 2 gpurun_out/bench.err
+# scratch script for one-off gpurun calls (overwritten freely); the maintained entry point is tools/gpu_full.sh
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
