@@ -99,6 +99,29 @@ def test_no_device_means_loud_failure(lib):
         b.validate_utf8_with_errors(data)
     with pytest.raises(b.B200Error):
         b.count_utf8(data)
+    # every host-pointer compute entry point, the widened families included: no silent CPU answer
+    out = np.zeros(64, dtype=np.uint8)
+    u16 = np.array([0x41, 0xD83D, 0xDE00], dtype=np.uint16)
+    u32 = np.array([0x41, 0x1F600], dtype=np.uint32)
+    calls = [
+        lambda: b.utf16_length_from_utf8(data), lambda: b.convert_utf8_to_utf16le_with_errors(data, out.view(np.uint16)),
+        lambda: b.convert_utf8_to_utf32_with_errors(data, out.view(np.uint32)), lambda: b.count_utf16le(u16),
+        lambda: b.validate_utf16le_with_errors(u16), lambda: b.convert_utf16le_to_utf8_with_errors(u16, out),
+        lambda: b.count_utf16be(u16), lambda: b.convert_utf16be_to_utf8_with_errors(u16, out),
+        lambda: b.validate_utf32_with_errors(u32), lambda: b.utf8_length_from_utf32(u32),
+        lambda: b.convert_utf32_to_utf8_with_errors(u32, out), lambda: b.convert_utf32_to_utf16le_with_errors(u32, out.view(np.uint16)),
+        lambda: b.convert_utf16le_to_utf32_with_errors(u16, out.view(np.uint32)),
+        lambda: b.validate_ascii_with_errors(data), lambda: b.utf8_length_from_latin1(data),
+        lambda: b.convert_latin1_to_utf8(data, out), lambda: b.convert_latin1_to_utf16le(data, out.view(np.uint16)),
+        lambda: b.convert_latin1_to_utf32(data, out.view(np.uint32)), lambda: b.convert_utf8_to_latin1_with_errors(data, out),
+        lambda: b.convert_utf16le_to_latin1_with_errors(u16, out), lambda: b.convert_utf32_to_latin1_with_errors(u32, out),
+        lambda: b.to_well_formed_utf16le(u16, out.view(np.uint16)[:3]), lambda: b.detect_encodings(data),
+        lambda: b.base64_to_binary_details(b"QUJD", out, 0, 0), lambda: b.binary_to_base64(data, out, 0),
+    ]
+    for i, call in enumerate(calls):
+        with pytest.raises(b.B200Error):
+            call()
+            raise AssertionError(f"call {i} answered without a device")
 
 
 def test_swar_logic_against_oracle_on_cpu():
