@@ -1,9 +1,16 @@
 /* oracle/oracle.c — TEST INFRASTRUCTURE ONLY (see oracle.h for the rules).
  *
- * CPU restatement of the reference's scalar semantics for the hot path.  It is
- * written from the behaviour described in SURVEY.md Appendix A and the cited
+ * CPU restatement of the reference's scalar semantics for the hot path
+ *  and the families around it (§8f ranks 1-4: UTF-16BE, UTF-32,
+ * Latin-1 / ASCII, base64 encode, to_well_formed_utf16, detect_encodings).  It
+ * is written from the behaviour described in SURVEY.md Appendix A and the cited
  * reference lines, as one decode-one-character routine per encoding rather
  * than a transcription of the reference's loops.
+ *
+ * PARITY PINNED: every function here is checked against the reference's golden
+ * vectors / recorded outputs (tests/golden/golden.json, golden_next.json) and,
+ * where oracle/_ref exists, differentially against the unmodified reference
+ * library's icelake / haswell / fallback kernels (tests/test_oracle.py).
  */
 #include "oracle.h"
 #include <string.h>
