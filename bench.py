@@ -87,7 +87,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own kernels (oracle/_ref) on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(sample_bytes: int, threads: int, steps: int, warmup: int, seed: int = 2):
+def cpu_reference_run(sample_bytes: int, threads: int, steps: int, warmup: int, seed: int = 2, stream: bool = False):
     """Times utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors of the UNMODIFIED reference library
     (best kernel of this host: icelake or haswell) on a `sample_bytes` sample of the config-2 distribution,
     split over `threads` host threads with the recipe of the reference's benchmarks/threaded.cpp:69-88.
@@ -95,7 +95,15 @@ def cpu_reference_run(sample_bytes: int, threads: int, steps: int, warmup: int, 
     import numpy as np
     from simdutf_b200 import synth
     from tests._oracle import Oracle, Reference
-    data = synth.mixed_utf8(sample_bytes, seed=seed).numpy()
+    import torch
+    # generation is plumbing: done on the GPU when there is one (seconds instead of minutes for 1 GiB; the same generator
+    # and seed as this repo's arm, so the two arms time the very same bytes), then moved to the host
+    gdev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    if stream:
+        total = synth.stream_total_len(seed, sample_bytes, gdev)
+        data = synth.stream_range(seed, 0, total, gdev).cpu().numpy()
+    else:
+        data = synth.mixed_utf8(sample_bytes, seed=seed, device=gdev).cpu().numpy()
     n = int(data.size)
     ref = Reference.load_or_none()
     out = np.empty(n + 64, dtype=np.uint16)
@@ -172,20 +180,51 @@ def threaded_cpp_run(sample_bytes: int, seed: int = 2):
             "sample": f"{n} bytes of the config-2 mixed UTF-8 distribution (seed {seed}) from a file"}
 
 
+def workload_config(world: int, shard_bytes: int, total_bytes: int | None):
+    """The `config` object, identical for this repo's arm and the reference arm (the driver compares them)."""
+    if world == 1 and total_bytes is None:
+        return {
+            "workload": "configs[1]: utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors on 1 GiB of synthetic mixed "
+                        "1-4-byte UTF-8 (seed 2), bit-exact output",
+            "nominal_bytes_per_gpu": shard_bytes, "total_nominal_bytes": shard_bytes, "seed": 2,
+            "char_mix": "25% each 1/2/3/4-byte code points (ASCII / Latin / CJK / emoji), i.i.d.",
+            "l2_policy": "inputs and outputs (>= 1 GiB each) far exceed the 126 MB L2; no flush needed",
+            "parallelism": "single GPU",
+        }
+    total = total_bytes if total_bytes is not None else world * shard_bytes
+    return {
+        "workload": f"configs[4]: ONE global buffer of {total / GIB:g} GiB of synthetic mixed 1-4-byte UTF-8 (counter-based block "
+                    f"stream, seed 5; 16 GiB at 8 GPUs) cut into {world} shards at k*N/G backed up to a code-point boundary "
+                    "(simdutf_b200.sharded.utf8_shard_bounds); per shard utf16_length_from_utf8 + "
+                    "convert_utf8_to_utf16le_with_errors; one NCCL all_gather of (length, error, count) per step; global "
+                    "first error and output offsets derived on the device from the gathered triplets",
+        "nominal_bytes_per_gpu": total // world, "total_nominal_bytes": total, "seed": 5,
+        "char_mix": "25% each 1/2/3/4-byte code points (ASCII / Latin / CJK / emoji), i.i.d.",
+        "l2_policy": "inputs and outputs (>= 1 GiB each) far exceed the 126 MB L2; no flush needed",
+        "parallelism": f"shards x{world}",
+    }
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = max(1, args.gpus)
     threads = os.cpu_count() or 1
-    r = cpu_reference_run(args.cpu_sample_bytes, threads, args.steps, args.warmup)
+    shard = args.shard_bytes if args.shard_bytes else (GIB if world == 1 else 2 * GIB)
+    cfg = workload_config(world, shard, args.total_bytes)
+    # N = 1: the whole 1 GiB buffer of configs[1] (same bytes as this repo's arm when a GPU is there to generate it);
+    # N > 1: a bounded 1 GiB sample of the config-5 stream
+    sample = args.cpu_sample_bytes if args.cpu_sample_bytes else min(GIB, cfg["total_nominal_bytes"])
+    r = cpu_reference_run(sample, threads, args.steps, args.warmup, seed=2 if world == 1 and args.total_bytes is None else 5,
+                          stream=not (world == 1 and args.total_bytes is None))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1] (bounded sample): utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors, "
-                               "mixed 1-4-byte UTF-8", "bytes_per_step": r["bytes"], "threads": threads,
-                   "kernel": r["impl"], "l2_policy": "n/a (CPU)"},
-        "cpu_baseline": {"value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "config": cfg,
+        "cpu_baseline": {"value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "kernel": r["impl"], "bytes_per_step": r["bytes"]},
         "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,6 +252,29 @@ def _emit(line: dict) -> None:
 
 
 _REAL_STDOUT = None
+EXTRA_WARMUP_STEPS = 512  # fixed count (never a rank-local clock: every rank must issue the same collectives)
+
+
+def make_shard(world, rank, shard_bytes, total_bytes, device, synth, sharded):
+    """This rank's input.  N = 1: configs[1] (1 GiB, seed 2).  N > 1 (or --total-bytes): this rank's slice of the ONE
+    global config-5 stream, cut at k*N/G backed up to a code-point boundary.  Returns (tensor, cuts or None)."""
+    if world == 1 and total_bytes is None:
+        return synth.mixed_utf8(shard_bytes, seed=2, device=device), None
+    seed = 5
+    nominal = total_bytes if total_bytes is not None else world * shard_bytes
+    total = synth.stream_total_len(seed, nominal, device)
+    cache = {}
+
+    def peek(i):
+        if i not in cache:
+            lo = max(0, i - 4)
+            vals = synth.stream_range(seed, lo, min(total, i + 4), device).cpu().tolist()
+            for j, v in enumerate(vals):
+                cache[lo + j] = v
+        return cache[i]
+
+    cuts = sharded.utf8_shard_bounds(peek, total, world)
+    return synth.stream_range(seed, cuts[rank], cuts[rank + 1], device), cuts
 
 
 def main():
@@ -222,10 +284,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--shard-bytes", type=int, default=GIB, help="input bytes per GPU")
-    ap.add_argument("--cpu-sample-bytes", type=int, default=256 << 20)
+    ap.add_argument("--shard-bytes", type=int, default=0, help="input bytes per GPU (default: 1 GiB at N=1, 2 GiB at N>1)")
+    ap.add_argument("--total-bytes", type=int, default=None, help="size of the ONE global config-5 buffer (default N x shard)")
+    ap.add_argument("--cpu-sample-bytes", type=int, default=0, help="reference arm / cpu_baseline sample (default: 1 GiB)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-extras", action="store_true", help="skip the config-1/3/4 side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3/4 and §8f side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -249,25 +312,23 @@ def main():
     b.set_device(local_rank)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
+    shard_bytes = args.shard_bytes if args.shard_bytes else (GIB if world == 1 else 2 * GIB)
+    cfg = workload_config(world, shard_bytes, args.total_bytes)
 
     # ---- inputs resident in HBM ------------------------------------------------------------------------------
-    d_in = synth.mixed_utf8(args.shard_bytes, seed=2 + rank, device=device)  # whole characters: an independent shard
+    d_in, cuts = make_shard(world, rank, shard_bytes, args.total_bytes, device, synth, sharded)
     n = int(d_in.numel())
     units = b.utf16_length_from_utf8(d_in)
     d_out = torch.empty(units, dtype=torch.int16, device=device)
     d_cnt = torch.zeros(1, dtype=torch.int64, device=device)
-    # [n, b200_result {int32 error; pad; uint64 count}]: the kernels write the result straight into the buffer that is
-    # all-gathered, so the multi-GPU step adds no copy and no host->device traffic
-    gather_in = torch.zeros(3, dtype=torch.int64, device=device)
-    gather_in[0] = n
-    d_res = gather_in[1:3]
+    # the convert kernel writes its b200_result straight into the triplet that is all-gathered: the multi-GPU step
+    # adds one collective and one launch of the library's combine kernel, no copy, no host synchronisation
+    comb = sharded.DeviceCombiner(lib, device, n)
     stream = torch.cuda.current_stream(device)
     sp = ctypes.c_void_p(stream.cuda_stream)
     in_p, out_p = ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr())
-    cnt_p, res_p = ctypes.c_void_p(d_cnt.data_ptr()), ctypes.c_void_p(d_res.data_ptr())
-    gather_out = torch.zeros(3 * world, dtype=torch.int64, device=device)
-    no_key = torch.full((1,), sharded.NO_ERROR_KEY, dtype=torch.int64, device=device)
-    key = torch.zeros(1, dtype=torch.int64, device=device)
+    cnt_p, res_p = ctypes.c_void_p(d_cnt.data_ptr()), comb.result_ptr
+    sharded_run = cuts is not None
 
     def step(ev=None):
         if ev:
@@ -280,26 +341,19 @@ def main():
             ev[2].record(stream)
         if st:
             raise RuntimeError("b200 launch failed: " + lib.b200_last_error().decode())
-        if world > 1:  # the sharded path's two collectives, fed from the device-side results (no host sync)
-            dist.all_gather_into_tensor(gather_out, gather_in)
-            err = d_res[0:1] & 0xFF
-            torch.where(err != 0, (d_res[1:2] << 8) | err, no_key, out=key)
-            dist.all_reduce(key, op=dist.ReduceOp.MIN)
+        if sharded_run:
+            comb.step(sp)
 
-    # nvidia-smi samples every 200 ms and a step takes ~2 ms: start sampling before the warm-up and keep the GPU
-    # under the same load (untimed extra warm-up steps) long enough for the sampler to see it
+    # nvidia-smi samples every 200 ms and a step takes ~1-3 ms: start sampling before the warm-up and keep the GPU
+    # under the same load for a FIXED number of untimed steps, so that the sampler sees the clocks under load
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_load = time.perf_counter()
-    for _ in range(W):
+    for _ in range(W + EXTRA_WARMUP_STEPS):
         step()
     torch.cuda.synchronize(device)
-    while time.perf_counter() - t_load < 1.0:
-        for _ in range(16):
-            step()
-        torch.cuda.synchronize(device)
-    assert int(d_cnt.item()) == units and int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == units
+    local = comb.triplet.cpu().tolist()
+    assert int(d_cnt.item()) == units and local[1] & 0xFFFFFFFF == 0 and local[2] == units
 
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -318,12 +372,12 @@ def main():
     launches = b.launch_count() - launches0
     ms_total = t_beg.elapsed_time(t_end)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    nbytes = torch.tensor([n], dtype=torch.int64, device=device)
+    tot = torch.tensor([n, units], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_total = float(t.item())
-    total_bytes = int(nbytes.item())
+    total_bytes, total_units = (int(x) for x in tot.tolist())
     ms_per_step = ms_total / K
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
     conv_ms = [e[1].elapsed_time(e[2]) for e in evs]
@@ -332,13 +386,32 @@ def main():
     peak, peak_src = measured_peak()
     algo_bytes = n + 2 * units  # input read once + output written once
     achieved = algo_bytes / (conv_avg * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("convert_utf8_to_utf16le", {}).get("dram_bytes_per_launch")
+            tj = json.load(f).get("convert_utf8_to_utf16le", {})
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     except Exception:
         pass
-    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == units
+    shard_check = None
+    if sharded_run:  # the combined result every rank holds: global SUCCESS, global count, this rank's offsets
+        g = comb.read()
+        assert (g.error, g.count) == (0, total_units), (g, total_units)
+        assert g.in_offset == cuts[rank] and cuts[-1] == total_bytes
+        offs = torch.tensor([g.out_offset], dtype=torch.int64, device=device)
+        alloffs = torch.empty(world, dtype=torch.int64, device=device)
+        allunits = torch.empty(world, dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_gather_into_tensor(alloffs, offs)
+            dist.all_gather_into_tensor(allunits, torch.tensor([units], dtype=torch.int64, device=device))
+        else:
+            alloffs, allunits = offs, torch.tensor([units], dtype=torch.int64, device=device)
+        ex = (torch.cumsum(allunits, 0) - allunits).tolist()
+        assert alloffs.tolist() == ex, (alloffs.tolist(), ex)
+        shard_check = {"cuts": cuts, "cut_backups": [int(cuts[-1] * k // world - cuts[k]) for k in range(1, world)],
+                       "global_result": [g.error, g.count], "out_offsets": ex}
+    else:
+        assert local[1] & 0xFFFFFFFF == 0 and local[2] == units
 
     # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region ---------------------------
     h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -369,44 +442,51 @@ def main():
     assert same, "host path and device path disagree"
     del h_in, h_out
 
+    # ---- the other half of BASELINE.json's metric: validate_utf8_with_errors (config 1 ASCII, and the mixed buffer) ----
+    val = {}
+    if rank == 0 and world == 1:
+        del d_out
+        val = validate_measurements(lib, synth, torch, device, stream, sp, peak, K, d_in)
     extras = {}
     if not args.no_extras and rank == 0 and world == 1:
+        del d_in
         extras = side_measurements(b, lib, synth, torch, device, stream, sp, peak, K)
 
     cpu = cpu1 = cpu_thr = None
     if rank == 0 and world == 1:  # the CPU baseline is reported at N = 1 only
-        cpu = cpu_reference_run(args.cpu_sample_bytes, os.cpu_count() or 1, 3, 1)
-        cpu1 = cpu_reference_run(min(args.cpu_sample_bytes, 128 << 20), 1, 2, 1)
-        cpu_thr = threaded_cpp_run(min(args.cpu_sample_bytes, 64 << 20))
+        sample = args.cpu_sample_bytes if args.cpu_sample_bytes else GIB
+        cpu = cpu_reference_run(sample, os.cpu_count() or 1, 3, 1)
+        cpu1 = cpu_reference_run(min(sample, 128 << 20), 1, 2, 1)
+        cpu_thr = threaded_cpp_run(min(sample, 64 << 20))
     if rank == 0:
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": CONVERT_KERNEL_NAME,
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg,
+                "best_launch_ms": min(conv_ms), "median_launch_ms": statistics.median(conv_ms),
+                "peak_source": peak_src,
+                "length_kernel_ms": sum(len_ms) / len(len_ms),
+                "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9,
+                "length_kernel_frac": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9 / peak}
+        roof.update(val)
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {
-                "workload": ("configs[1]: utf16_length_from_utf8 + convert_utf8_to_utf16le_with_errors, 1 GiB mixed 1-4-byte UTF-8"
-                             if world == 1 else
-                             "configs[4] weak: one mixed-UTF-8 shard per GPU (code-point-boundary cuts), length + convert per shard, "
-                             "all_gather(lengths) + all_reduce-min(first error) per step"),
-                "bytes_per_gpu": n, "utf16_units_per_gpu": units, "seed": "2+rank", "char_mix": "25% each 1/2/3/4-byte, i.i.d.",
-                "l2_policy": "inputs (1 GiB) and outputs (1 GiB) far exceed the 126 MB L2; no flush needed",
-                "parallelism": f"shards x{world}",
-            },
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_utf16_tile_counts + k_utf8_transcode_bp (convert_utf8_to_utf16le_with_errors = two launches; bit-plane transcoder)",
-                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": conv_avg,
-                         "best_launch_ms": min(conv_ms), "median_launch_ms": statistics.median(conv_ms),
-                         "peak_source": peak_src,
-                         "length_kernel_ms": sum(len_ms) / len(len_ms),
-                         "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9},
+            "config": cfg,
+            "bytes_per_step": total_bytes, "utf16_units_per_step": total_units,
+            "roofline": roof,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cpu_baseline_1thread": ({k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu1 else None),
             "cpu_baseline_threaded_cpp": cpu_thr,
-            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 2 * units + 24,
-                    "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers)",
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * total_bytes,
+                    "d2h_bytes_per_step": 2 * total_units + 24 * world,
+                    "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers), one "
+                           "process per GPU on its own shard",
                     "ms_per_step": float(te.item()) * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "sharded": shard_check,
             "extra": extras,
         }
         _emit(line)
@@ -414,6 +494,48 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+CONVERT_KERNEL_NAME = ("k_utf16_tile_counts + k_utf8_transcode_bp (convert_utf8_to_utf16le_with_errors = two launches; "
+                       "bit-plane transcoder)")
+
+
+def _timeit(torch, device, stream, fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) / reps
+
+
+def validate_measurements(lib, synth, torch, device, stream, sp, peak, K, mixed):
+    """validate_utf8_with_errors, the first half of BASELINE.json's metric: config 1 (1 GiB ASCII) and the mixed buffer of
+    config 2.  Device-resident, CUDA events; algorithmic bytes = the input, read once.  Goes into the `roofline` object."""
+    d_res = torch.zeros(4, dtype=torch.int64, device=device)
+    res_p = ctypes.c_void_p(d_res.data_ptr())
+    out = {}
+    a = synth.ascii_text(GIB, seed=1, device=device)
+    n = int(a.numel())
+    ap_ = ctypes.c_void_p(a.data_ptr())
+    ms = _timeit(torch, device, stream, lambda: lib.b200_validate_utf8_with_errors_async(ap_, n, res_p, sp), K)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == n
+    out["validate_utf8_ascii_gbs"] = n / ms / 1e6
+    out["validate_utf8_ascii_frac"] = n / ms / 1e6 / peak
+    out["validate_utf8_ascii_ms"] = ms
+    del a
+    n = int(mixed.numel())
+    mp = ctypes.c_void_p(mixed.data_ptr())
+    ms = _timeit(torch, device, stream, lambda: lib.b200_validate_utf8_with_errors_async(mp, n, res_p, sp), K)
+    assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == n
+    out["validate_utf8_mixed_gbs"] = n / ms / 1e6
+    out["validate_utf8_mixed_frac"] = n / ms / 1e6 / peak
+    out["validate_utf8_mixed_ms"] = ms
+    return out
 
 
 def side_measurements(b, lib, synth, torch, device, stream, sp, peak, K):

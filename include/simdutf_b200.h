@@ -371,6 +371,29 @@ SIMDUTF_B200_API size_t b200_host_trim_partial_utf16le(const uint16_t *h_in, siz
 /* Same, on device data (synchronous, copies <= 4 bytes back). */
 SIMDUTF_B200_API int b200_trim_partial_utf8(const char *d_in, size_t len, size_t *h_trimmed, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Sharded (multi-GPU) path, SURVEY.md §8e: a buffer cut with the helpers above */
+/* is processed shard by shard by the single-GPU entry points; every shard      */
+/* leaves a triplet {input length, b200_result} (3 x uint64, the result written */
+/* in place by the *_async call).  After the triplets of all shards have been   */
+/* gathered in shard order (one NCCL all_gather across processes),              */
+/* b200_sharded_combine_async turns them into the global result — the first     */
+/* error in buffer order, i.e. the minimum of (position << 8 | code), the value */
+/* an NCCL min-allreduce of that key yields, or {SUCCESS, total} — and this     */
+/* shard's global input / output offsets, on the device, in one launch.         */
+/* count_is_length != 0: the operation's success count is the validated input   */
+/* length (validate_*) rather than an output size.                              */
+/* ------------------------------------------------------------------------- */
+typedef struct b200_sharded_result {
+  int32_t error;        /* global simdutf::error_code */
+  uint32_t reserved_;
+  uint64_t count;       /* total output elements on success, global input position on error */
+  uint64_t in_offset;   /* this shard's first input element in the whole buffer */
+  uint64_t out_offset;  /* this shard's first output element in the whole output */
+} b200_sharded_result;
+SIMDUTF_B200_API int b200_sharded_combine_async(const uint64_t *d_gathered, int world, int rank, int count_is_length,
+                                                b200_sharded_result *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

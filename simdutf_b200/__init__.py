@@ -111,6 +111,7 @@ SYMBOLS["b200_base64_length_from_binary"] = (_sz, [_sz, _u64])
 SYMBOLS["b200_base64_to_binary_async"] = (_I, [_vp, _sz, _vp, _u64, _u64, _vp, _vp])
 SYMBOLS["b200_base64_to_binary"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull, _vp])
 SYMBOLS["b200_host_base64_to_binary"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull])
+SYMBOLS["b200_sharded_combine_async"] = (_I, [_vp, _I, _I, _I, _vp, _vp])
 
 _lib = None
 

@@ -204,6 +204,7 @@ int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, Strea
   lc->desc_capacity = w.desc_cap;
   lc->epoch = w.epoch;
   lc->sm_count = c->sm_count;
+  lc->device = c->device;
   lc->stream = stream;
   if (out_ws) *out_ws = &w;
   return 0;
@@ -841,6 +842,16 @@ int b200_trim_partial_utf8(const char *d_in, size_t len, size_t *h_trimmed, void
   }
   // tail holds the last n bytes right-aligned; run the host rule on them
   *h_trimmed = len - n + b200_host_trim_partial_utf8(tail + (3 - n), n);
+  return 0;
+}
+
+int b200_sharded_combine_async(const uint64_t *d_gathered, int world, int rank, int count_is_length,
+                               b200_sharded_result *d_out, void *stream) {
+  if (!d_gathered || !d_out || world < 1 || world > 4096 || rank < 0 || rank >= world) return fail(B200_E_BAD_ARGUMENT, "bad sharded_combine argument");
+  int err;
+  if (!current_ctx(&err)) return err;
+  B200_CUDA(launch_sharded_combine(reinterpret_cast<const unsigned long long *>(d_gathered), world, rank, count_is_length,
+                                   reinterpret_cast<unsigned long long *>(d_out), static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -310,14 +310,11 @@ cudaError_t launch_elem(const LaunchCtx &c, const void *in, size_t len, void *ou
   const size_t bytes = len * sizeof(typename T::In);
   const size_t tiles = tiles_for(in, bytes);
   if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_elem_transcode<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kSmemBytes);
+  static KernelCache kc;
+  int per_sm = 1;
+  {
+    cudaError_t e = kernel_per_sm(kc, c.device, k_elem_transcode<T, MINB>, kThreads, S::kSmemBytes, &per_sm);
     if (e != cudaSuccess) return e;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_elem_transcode<T, MINB>, kThreads, S::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    per_sm = n < 1 ? 1 : n;
   }
   const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
   unsigned long long *chunk_off = c.desc;

@@ -465,12 +465,11 @@ cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t l
                                     uint64_t last_chunk, void *full_res) {
   const size_t tiles = tiles_for(in, len);
   if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_b64_decode_bp, kBlock, 0);
+  static KernelCache kc;
+  int per_sm = 1;
+  {
+    cudaError_t e = kernel_per_sm(kc, c.device, k_b64_decode_bp, kBlock, 0, &per_sm);
     if (e != cudaSuccess) return e;
-    per_sm = n < 1 ? 1 : n;
   }
   // reference include/simdutf/implementation.h:2782-2800 and src/scalar/base64.h:66-69
   const uint32_t url = (options & 1u) ? 1u : 0u;

@@ -365,14 +365,11 @@ inline size_t workspace_slots(size_t tiles) {
 
 template <int MINB, bool BE>
 cudaError_t launch_u16to8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res, size_t tiles) {
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_utf16_to_utf8_bp<MINB, BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  static KernelCache kc;
+  int per_sm = 1;
+  {
+    cudaError_t e = kernel_per_sm(kc, c.device, k_utf16_to_utf8_bp<MINB, BE>, kThreads, kSmemBytes, &per_sm);
     if (e != cudaSuccess) return e;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_utf16_to_utf8_bp<MINB, BE>, kThreads, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    per_sm = n < 1 ? 1 : n;
   }
   const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
   unsigned long long *chunk_off = c.desc;

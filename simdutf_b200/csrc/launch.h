@@ -21,8 +21,33 @@ struct LaunchCtx {
   void *tmp;                // grow-only device scratch of the stream (sized by the caller of get_ws)
   uint32_t epoch;
   int sm_count;
+  int device;               // index of the device the stream belongs to (per-device kernel attribute caches)
   cudaStream_t stream;
 };
+
+// Per-kernel, per-device cache of "dynamic shared memory attribute set + resident CTAs per SM".  The attribute and the
+// occupancy answer belong to a DEVICE, not to the process: one process may drive several devices (b200_set_device,
+// the multi-device host path).  Callers hold the device's context mutex, so slot `device` has one writer.
+constexpr int kMaxDevices = 16;
+struct KernelCache {
+  int per_sm[kMaxDevices] = {};
+};
+template <class Kernel>
+inline cudaError_t kernel_per_sm(KernelCache &kc, int device, Kernel kernel, int threads, size_t smem_bytes, int *per_sm) {
+  if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (kc.per_sm[device] == 0) {
+    if (smem_bytes > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+      if (e != cudaSuccess) return e;
+    }
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem_bytes);
+    if (e != cudaSuccess) return e;
+    kc.per_sm[device] = n < 1 ? 1 : n;
+  }
+  *per_sm = kc.per_sm[device];
+  return cudaSuccess;
+}
 
 // Tiles (descriptors) the look-back kernels need for an input of `len` elements.
 size_t utf8_to_utf16_tiles(const void *in, size_t len);
@@ -84,6 +109,11 @@ cudaError_t launch_base64_to_binary_utf16(const LaunchCtx &c, const uint16_t *in
 // binary_to_base64: `out` must hold base64_length_from_binary(len, options) characters.
 size_t base64_length_from_binary(size_t len, uint64_t options);
 cudaError_t launch_binary_to_base64(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options);
+
+// combining step of the sharded path (k_sharded.cu): `gathered` = world triplets {input length, result.error, result.count};
+// out = b200_sharded_result
+cudaError_t launch_sharded_combine(const unsigned long long *gathered, int world, int rank, int count_is_length,
+                                   unsigned long long *out, cudaStream_t stream);
 
 void count_launch(int n);  // bumps the library-wide launch counter (b200_launch_count)
 

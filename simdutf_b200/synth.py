@@ -88,6 +88,52 @@ def mixed_utf8(nbytes: int, seed: int = 2, device="cpu", classes=UTF8_MIX) -> to
     return torch.cat(pieces) if len(pieces) != 1 else pieces[0]
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Config 5: ONE global buffer of any size, addressable by byte range, so that every rank of a sharded run can
+# materialise exactly its own slice [c_k, c_k+1) of it (plus a few bytes around the nominal cut points) without any
+# rank ever holding the whole 16 GiB.  The stream is a sequence of independent fixed-size blocks, block k generated
+# by a counter-based seed (seed, k); a block is whole characters of the config-2 distribution padded with <= 3
+# ASCII '.' to exactly STREAM_BLOCK bytes.  STREAM_BLOCK is odd, so the nominal cuts k*N/G of a power-of-two total
+# never coincide with block boundaries: they land mid-distribution, inside a character 60 % of the time.
+# ------------------------------------------------------------------------------------------------------------
+STREAM_BLOCK = (1 << 26) + 1
+
+
+def stream_block(seed: int, k: int, device="cpu", block: int = STREAM_BLOCK) -> torch.Tensor:
+    b = mixed_utf8(block, seed=(seed * 1000003 + k * 7919 + 12345) & 0x7FFFFFFF, device=device)
+    pad = block - int(b.numel())
+    if pad:
+        b = torch.cat([b, torch.full((pad,), 0x2E, dtype=torch.uint8, device=device)])
+    return b
+
+
+def stream_range(seed: int, lo: int, hi: int, device="cpu", block: int = STREAM_BLOCK) -> torch.Tensor:
+    """Bytes [lo, hi) of the global stream."""
+    out = torch.empty(max(0, hi - lo), dtype=torch.uint8, device=device)
+    k = lo // block
+    pos = lo
+    while pos < hi:
+        b = stream_block(seed, k, device, block)
+        a = pos - k * block
+        take = min(block - a, hi - pos)
+        out[pos - lo: pos - lo + take] = b[a: a + take]
+        pos += take
+        k += 1
+    return out
+
+
+def stream_total_len(seed: int, nominal: int, device="cpu", block: int = STREAM_BLOCK) -> int:
+    """Length of the longest whole-character prefix of the stream that fits in `nominal` bytes."""
+    lo = max(0, nominal - 4)
+    tail = stream_range(seed, lo, nominal + 1, device, block).cpu().tolist()
+    cut = nominal
+    for _ in range(3):
+        if cut <= 0 or (tail[cut - lo] & 0xC0) != 0x80:
+            break
+        cut -= 1
+    return cut
+
+
 UTF16_MIX = [(0x20, 0x7F), (0xA0, 0x800), (0x800, 0xD800), (0x10000, 0x110000)]
 
 

@@ -191,3 +191,42 @@ def test_sharded_combine_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o[-3000:]
+
+
+def test_config5_stream_is_addressable_by_range(oracle):
+    """The config-5 global buffer (synth.stream_*): any byte range can be materialised on its own, ranges concatenate to
+    the whole, the whole is valid UTF-8 of the right length, and nominal midpoints do not sit on block boundaries."""
+    from simdutf_b200 import sharded, synth
+    block = (1 << 16) + 1
+    nominal = 5 * (1 << 16) + 1234
+    total = synth.stream_total_len(7, nominal, "cpu", block)
+    assert nominal - 3 <= total <= nominal
+    whole = synth.stream_range(7, 0, total, "cpu", block).numpy()
+    assert oracle.validate_utf8_with_errors(whole) == (0, total)
+    for lo, hi in ((0, 10), (block - 3, block + 5), (12345, 3 * block + 17), (total - 9, total)):
+        assert np.array_equal(synth.stream_range(7, lo, hi, "cpu", block).numpy(), whole[lo:hi])
+    cuts = sharded.utf8_shard_bounds(lambda i: int(whole[i]), total, 4)
+    assert all(c % block != 0 for c in cuts[1:-1])
+    for a, b_ in zip(cuts, cuts[1:]):
+        assert oracle.validate_utf8_with_errors(whole[a:b_]) == (0, b_ - a)
+
+
+def test_fold_triplets_matches_whole_buffer(oracle):
+    """The combining arithmetic shared by sharded.combine and the device kernel k_sharded_combine."""
+    from simdutf_b200 import sharded, synth
+    data = synth.mixed_utf8(40000, seed=13).numpy().copy()
+    for bad in ((), (30001,), (123, 30001), (9000,)):
+        d = data.copy()
+        for i in bad:
+            d[i] = 0xFF
+        cuts = sharded.utf8_shard_bounds(lambda i: int(data[i]), d.size, 4)
+        trip = []
+        for a, b_ in zip(cuts, cuts[1:]):
+            (e, c), _ = oracle.convert_utf8_to_utf16le_with_errors(d[a:b_])
+            trip.append((b_ - a, e, c))
+        (we, wc), _ = oracle.convert_utf8_to_utf16le_with_errors(d)
+        for r in range(4):
+            e, c, in_off, out_off = sharded.fold_triplets(trip, r)
+            assert (e, c) == (we, wc) and in_off == cuts[r]
+        vt = [(b_ - a,) + oracle.validate_utf8_with_errors(d[a:b_]) for a, b_ in zip(cuts, cuts[1:])]
+        assert sharded.fold_triplets(vt, 0, count_is_length=True)[:2] == oracle.validate_utf8_with_errors(d)

@@ -12,7 +12,10 @@ for vals in rows[2:]:
         except Exception: return None
     s = {
         "kernel": d.get("Kernel Name"), "grid": d.get("launch__grid_size"), "regs": f("launch__registers_per_thread"),
-        "duration_ms": f("gpu__time_duration.sum"),
+        # ncu reports gpu__time_duration.sum in the unit of the CSV's second header row (us for these kernels); keep
+        # the number with its unit instead of guessing (round-1 summaries labelled microseconds as "duration_ms")
+        "duration": f("gpu__time_duration.sum"),
+        "duration_unit": units[hdr.index("gpu__time_duration.sum")] if "gpu__time_duration.sum" in hdr else None,
         "dram_read_MB": f("dram__bytes_read.sum"), "dram_write_MB": f("dram__bytes_write.sum"),
         "dram_pct_peak": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "sm_throughput_pct": f("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
