@@ -310,6 +310,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     lib = b.load()
     b.set_device(local_rank)
+    for kv in filter(None, os.environ.get("B200_BENCH_TUNE", "").split(",")):  # experiments only: "conv_minb=4,segment_mb=64"
+        k, v = kv.split("=")
+        b.set_tuning(k, int(v))
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     shard_bytes = args.shard_bytes if args.shard_bytes else (GIB if world == 1 else 2 * GIB)
@@ -496,8 +499,8 @@ def main():
     return 0
 
 
-CONVERT_KERNEL_NAME = ("k_utf16_tile_counts + k_utf8_transcode_bp (convert_utf8_to_utf16le_with_errors = two launches; "
-                       "bit-plane transcoder)")
+CONVERT_KERNEL_NAME = ("k_utf8_transcode_sp (convert_utf8_to_utf16le_with_errors = ONE launch: bit-plane transcoder with the "
+                       "output offsets from a decoupled look-back; the input crosses HBM once)")
 
 
 def _timeit(torch, device, stream, fn, reps):

@@ -14,8 +14,11 @@
  *   b200_<op>(d_in, ..., h_result, stream)
  *       DEVICE data pointers, result returned to the HOST (synchronises stream).
  *   b200_host_<op>(h_in, ..., h_result)
- *       HOST pointers (pinned or pageable): staged through the context's device
- *       buffers in pipelined chunks.  This is what the C++ virtuals call.
+ *       HOST pointers (pinned or pageable): staged through the calling thread's
+ *       device buffers in pipelined segments, over one or several devices
+ *       (b200_host_set_devices); inputs of a few KiB take a zero-copy path.
+ *       DEVICE pointers are recognised (cudaPointerGetAttributes) and processed
+ *       in place on their device.  This is what the C++ virtuals call.
  *
  * Return value of every function: 0 on success, otherwise a CUDA error code
  * (cudaError_t, > 0) or a negative B200_E_* code.  simdutf-level outcomes
@@ -393,6 +396,39 @@ typedef struct b200_sharded_result {
 } b200_sharded_result;
 SIMDUTF_B200_API int b200_sharded_combine_async(const uint64_t *d_gathered, int world, int rank, int count_is_length,
                                                 b200_sharded_result *d_out, void *stream);
+
+/* One process, several devices (SURVEY.md §8b "_mgpu variants taking per-device shard descriptors", §7 step 5).  */
+/* Shard i is device-resident on shards[i].device: d_in / len (code units) / d_out as for the single-GPU entry     */
+/* point of the same name (d_out unused by validate / length).  Every shard runs on its own device and stream; the */
+/* triplets are exchanged with one ncclAllGather over NVLink (communicators created once per device list with      */
+/* ncclCommInitAll; NCCL is resolved with dlopen("libnccl.so.2"), and 24-byte peer copies carry the triplets when  */
+/* it is absent or when two shards share a device); the combine kernel runs on every device.  h_results[i] is the  */
+/* global result as device i sees it (all equal) plus shard i's offsets.  The call returns when all devices are    */
+/* done.  For b200_mgpu_utf16_length_from_utf8 the global count is the sum of the shard lengths in UTF-16 units.   */
+/* b200_mgpu_last_gather(): 1 if the last call exchanged over NCCL, 2 if it used peer copies.                      */
+typedef struct b200_shard {
+  int32_t device;
+  uint32_t reserved_;
+  const void *d_in;
+  uint64_t len;
+  void *d_out;
+} b200_shard;
+SIMDUTF_B200_API int b200_mgpu_validate_utf8_with_errors(const b200_shard *shards, int n, b200_sharded_result *h_results);
+SIMDUTF_B200_API int b200_mgpu_utf16_length_from_utf8(const b200_shard *shards, int n, b200_sharded_result *h_results);
+SIMDUTF_B200_API int b200_mgpu_convert_utf8_to_utf16le(const b200_shard *shards, int n, b200_sharded_result *h_results);
+SIMDUTF_B200_API int b200_mgpu_convert_utf8_to_utf32(const b200_shard *shards, int n, b200_sharded_result *h_results);
+SIMDUTF_B200_API int b200_mgpu_convert_utf16le_to_utf8(const b200_shard *shards, int n, b200_sharded_result *h_results);
+SIMDUTF_B200_API int b200_mgpu_last_gather(void);
+
+/* Host-pointer calls over several devices: after b200_host_set_devices(n) the b200_host_* calls of the calling      */
+/* thread — hence the C++ virtuals of simdutf::b200::implementation — cut large buffers into segments and deal them  */
+/* round-robin to n devices (b200_get_device(), +1, ...), each with its own staging ring, streams and PCIe link; the */
+/* results are folded exactly like shards.  Default 1.  Small inputs always use one device.                          */
+SIMDUTF_B200_API int b200_host_set_devices(int n);
+SIMDUTF_B200_API int b200_host_get_devices(void);
+/* Experiment knobs for tools/ and profiles/ ("conv_minb", "segment_mb", "no_nccl"; 0 = default).  The library never */
+/* reads the environment.                                                                                            */
+SIMDUTF_B200_API int b200_set_tuning(const char *name, int value);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,21 @@ class FullResult(ctypes.Structure):
         return (int(self.error), int(self.input_count))
 
 
+class Shard(ctypes.Structure):
+    """b200_shard (include/simdutf_b200.h): one device-resident shard of a sharded multi-device call."""
+    _fields_ = [("device", ctypes.c_int32), ("reserved_", ctypes.c_uint32), ("d_in", ctypes.c_void_p),
+                ("len", ctypes.c_uint64), ("d_out", ctypes.c_void_p)]
+
+
+class ShardedResultC(ctypes.Structure):
+    """b200_sharded_result (include/simdutf_b200.h)."""
+    _fields_ = [("error", ctypes.c_int32), ("reserved_", ctypes.c_uint32), ("count", ctypes.c_uint64),
+                ("in_offset", ctypes.c_uint64), ("out_offset", ctypes.c_uint64)]
+
+    def astuple(self):
+        return (int(self.error), int(self.count), int(self.in_offset), int(self.out_offset))
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -112,6 +127,13 @@ SYMBOLS["b200_base64_to_binary_async"] = (_I, [_vp, _sz, _vp, _u64, _u64, _vp, _
 SYMBOLS["b200_base64_to_binary"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull, _vp])
 SYMBOLS["b200_host_base64_to_binary"] = (_I, [_vp, _sz, _vp, _u64, _u64, _pfull])
 SYMBOLS["b200_sharded_combine_async"] = (_I, [_vp, _I, _I, _I, _vp, _vp])
+for _name in ["validate_utf8_with_errors", "utf16_length_from_utf8", "convert_utf8_to_utf16le", "convert_utf8_to_utf32",
+              "convert_utf16le_to_utf8"]:
+    SYMBOLS[f"b200_mgpu_{_name}"] = (_I, [_vp, _I, _vp])
+SYMBOLS["b200_mgpu_last_gather"] = (_I, [])
+SYMBOLS["b200_host_set_devices"] = (_I, [_I])
+SYMBOLS["b200_host_get_devices"] = (_I, [])
+SYMBOLS["b200_set_tuning"] = (_I, [ctypes.c_char_p, _I])
 
 _lib = None
 
@@ -143,6 +165,32 @@ def device_count() -> int:
 
 def set_device(index: int) -> None:
     _check(load().b200_set_device(index), "b200_set_device")
+
+
+def host_set_devices(n: int) -> None:
+    """The calling thread's b200_host_* calls spread large buffers over `n` devices."""
+    _check(load().b200_host_set_devices(n), "b200_host_set_devices")
+
+
+def set_tuning(name: str, value: int) -> None:
+    _check(load().b200_set_tuning(name.encode(), value), "b200_set_tuning")
+
+
+def mgpu(name: str, shards):
+    """Sharded multi-device call b200_mgpu_<name>: `shards` = [(device index, input CUDA tensor, output CUDA tensor or
+    None), ...] in buffer order.  Returns one (error, count, in_offset, out_offset) per shard."""
+    lib = load()
+    n = len(shards)
+    arr = (Shard * n)()
+    unit = 2 if name.startswith("convert_utf16") else 1
+    for i, (dev, t_in, t_out) in enumerate(shards):
+        arr[i].device = dev
+        arr[i].d_in = t_in.data_ptr() if t_in.numel() else None
+        arr[i].len = (t_in.numel() * t_in.element_size()) // unit
+        arr[i].d_out = t_out.data_ptr() if t_out is not None else None
+    res = (ShardedResultC * n)()
+    _check(getattr(lib, f"b200_mgpu_{name}")(arr, n, res), f"b200_mgpu_{name}")
+    return [r.astuple() for r in res]
 
 
 def launch_count() -> int:

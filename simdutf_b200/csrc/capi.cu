@@ -1,10 +1,21 @@
-// capi.cu — the C ABI declared in include/simdutf_b200.h: per-device context, per-stream workspace,
-// the three call flavours (async / sync device pointers, host pointers), error mapping.
+// capi.cu — the C ABI declared in include/simdutf_b200.h: device contexts, per-stream workspaces, the call flavours
+// (async / sync device pointers, host pointers over one or several devices, the sharded multi-device entry points),
+// error mapping.
 //
 // No CPU fallback lives here: every compute entry point ends in a kernel launch from k_*.cu or fails
 // with B200_E_NO_DEVICE / a CUDA error code.  The library never prints, throws or aborts
-// (reference CMakeLists.txt:173-214 forbids it for anything linked into libsimdutf).
+// (reference CMakeLists.txt:173-214 forbids it for anything linked into libsimdutf) and never reads the environment.
+//
+// State and threading (reference: the library is re-entrant and stateless, include/simdutf/implementation.h:5123-5161;
+// benchmarks/threaded.cpp calls it from two threads at once):
+//   * DeviceCtx (one per device, process-wide): SM count and the per-STREAM workspaces of caller-provided streams.  Its
+//     mutex is held only while a call looks up / grows a workspace and enqueues its launches — never across a
+//     synchronisation — so two caller threads overlap their copies and kernels.
+//   * HostPath (one per device PER CALLING THREAD): the streams, staging buffers, segment ring and pinned result slots
+//     of the host-pointer path.  Nothing in it is shared, so host calls of different threads never wait on each other.
+//   * A call never leaves the calling thread's current CUDA device changed (DeviceGuard).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -20,10 +31,13 @@ namespace b200 {
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+static std::atomic<int> g_tuning[kTuneKeyCount];
+int tuning(int key) { return key >= 0 && key < kTuneKeyCount ? g_tuning[key].load(std::memory_order_relaxed) : 0; }
 
 namespace {
 
 thread_local int tl_device = 0;
+thread_local int tl_host_devices = 1;  // devices the host-pointer path of this thread spreads its segments over
 thread_local char tl_error[256] = {0};
 
 int fail(int code, const char *what) {
@@ -47,8 +61,31 @@ int fail(int code, const char *what) {
     if (e_ != cudaSuccess) return fail((int)e_, #expr);   \
   } while (0)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t enter(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    if (prev != device) {
+      const cudaError_t e = cudaSetDevice(device);
+      if (e != cudaSuccess) return e;
+      changed = prev >= 0;
+    }
+    return cudaSuccess;
+  }
+  void leave() {
+    if (changed) cudaSetDevice(prev);
+    changed = false;
+  }
+  ~DeviceGuard() { leave(); }
+};
+
 // ---------------------------------------------------------------------------------------------
-// Per-stream workspace: one Scratch line, the look-back descriptors, a pinned result slot.
+// Per-stream workspace: one Scratch line, the look-back descriptors.
 // ---------------------------------------------------------------------------------------------
 struct StreamWs {
   Scratch *scratch = nullptr;
@@ -56,7 +93,6 @@ struct StreamWs {
   unsigned long long *cnt = nullptr;
   size_t desc_cap = 0;
   uint32_t epoch = 0;
-  void *h_slot = nullptr;  // 64 B pinned + mapped: kernels write results straight into host memory
   void *tmp = nullptr;     // grow-only device scratch (base64 from char16_t: the narrowed characters)
   size_t tmp_cap = 0;
 };
@@ -64,31 +100,10 @@ struct StreamWs {
 struct DeviceCtx {
   int device = -1;
   int sm_count = 0;
-  bool ok = false;
   std::mutex mu;
   std::unordered_map<cudaStream_t, StreamWs> ws;
-  // host-pointer path
-  cudaStream_t s_main = nullptr, s_copy = nullptr, s_back = nullptr;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  void *d_in = nullptr;
-  size_t d_in_cap = 0;
-  void *d_out = nullptr;
-  size_t d_out_cap = 0;
-  // streaming host path: a ring of segment slots (device staging in/out, events, a pinned result slot each)
-  static constexpr int kRing = 3;
-  struct Slot {
-    void *d_in = nullptr;
-    size_t d_in_cap = 0;
-    void *d_out = nullptr;
-    size_t d_out_cap = 0;
-    cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
-    void *h_res = nullptr;  // 64 B pinned + mapped
-    bool d2h_pending = false;
-  } ring[kRing];
-  bool ring_ok = false;
 };
 
-constexpr int kMaxDevices = 16;
 DeviceCtx g_ctx[kMaxDevices];
 std::once_flag g_count_once;
 int g_device_count = 0;
@@ -121,41 +136,36 @@ int device_count() {
   return g_device_count;
 }
 
-// Returns the context of the calling thread's device, made current; nullptr if unusable.
-DeviceCtx *current_ctx(int *err) {
+// The context of `device`, made current through `guard`; nullptr (and *err set) if unusable.
+DeviceCtx *enter_device(int device, DeviceGuard &guard, int *err) {
   const int n = device_count();
-  if (n <= 0 || tl_device < 0 || tl_device >= n) {
+  if (n <= 0 || device < 0 || device >= n) {
     *err = fail(B200_E_NO_DEVICE, "no usable sm_100 device");
     return nullptr;
   }
-  int cur = -1;
-  if (cudaGetDevice(&cur) != cudaSuccess || cur != tl_device) {
-    cudaError_t e = cudaSetDevice(tl_device);
-    if (e != cudaSuccess) {
-      *err = fail((int)e, "cudaSetDevice");
-      return nullptr;
-    }
-  }
-  DeviceCtx *c = &g_ctx[tl_device];
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (!c->ok) {
-    cudaError_t e = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-      *err = fail((int)e, "context init");
-      return nullptr;
-    }
-    c->ok = true;
+  const cudaError_t e = guard.enter(device);
+  if (e != cudaSuccess) {
+    *err = fail((int)e, "cudaSetDevice");
+    return nullptr;
   }
   *err = 0;
-  return c;
+  return &g_ctx[device];
 }
 
-// Workspace of `stream`, with room for `tiles` descriptors and a fresh epoch.  Caller holds c->mu.
-int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, StreamWs **out_ws, size_t tmp_bytes = 0) {
+// Where does `p` live?  >= 0: device memory (or managed memory) of that device; -1: host memory / unknown to CUDA.
+int device_of_pointer(const void *p) {
+  if (!p) return -1;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return a.device;
+  return -1;
+}
+
+// Workspace of `stream`, with room for `tiles` descriptors and a fresh epoch.  Caller holds c->mu and has c->device current.
+int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, size_t tmp_bytes = 0) {
   StreamWs &w = c->ws[stream];
   if (tmp_bytes > w.tmp_cap) {
     if (w.tmp) {
@@ -169,10 +179,15 @@ int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, Strea
     w.tmp_cap = want;
   }
   lc->tmp = w.tmp;
-  if (!w.scratch) {
-    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&w.scratch), sizeof(Scratch)));
-    B200_CUDA(launch_scratch_init(w.scratch, stream));
-    B200_CUDA(cudaHostAlloc(&w.h_slot, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  if (!w.scratch) {  // published only once it is allocated AND initialised
+    Scratch *s = nullptr;
+    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&s), sizeof(Scratch)));
+    const cudaError_t e = launch_scratch_init(s, stream);
+    if (e != cudaSuccess) {
+      cudaFree(s);
+      return fail((int)e, "scratch init");
+    }
+    w.scratch = s;
   }
   if (tiles > w.desc_cap) {
     size_t cap = w.desc_cap ? w.desc_cap : 4096;
@@ -185,9 +200,17 @@ int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, Strea
       w.cnt = nullptr;
       w.desc_cap = 0;
     }
-    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&w.desc), cap * sizeof(unsigned long long)));
-    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&w.cnt), cap * sizeof(unsigned long long)));
-    B200_CUDA(cudaMemsetAsync(w.desc, 0, cap * sizeof(unsigned long long), stream));
+    unsigned long long *d = nullptr, *k = nullptr;
+    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), cap * sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&k), cap * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d, 0, cap * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) {
+      cudaFree(d);
+      if (k) cudaFree(k);
+      return fail((int)e, "descriptor allocation");
+    }
+    w.desc = d;
+    w.cnt = k;
     w.desc_cap = cap;
     w.epoch = 0;
   }
@@ -206,15 +229,122 @@ int get_ws(DeviceCtx *c, cudaStream_t stream, size_t tiles, LaunchCtx *lc, Strea
   lc->sm_count = c->sm_count;
   lc->device = c->device;
   lc->stream = stream;
-  if (out_ws) *out_ws = &w;
   return 0;
 }
 
-int ensure(void **buf, size_t *cap, size_t need, cudaStream_t s_main, cudaStream_t s_copy) {
+// ---------------------------------------------------------------------------------------------
+// HostPath: everything the host-pointer flavour needs on one device, private to the calling thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRing = 3;
+constexpr size_t kSmallIn = 32 * 1024;    // inputs up to this many bytes take the zero-copy path
+constexpr size_t kSmallOut = 128 * 1024;  // (their output bound is <= 4x the input)
+
+struct HostPath {
+  int device = -1;
+  bool ok = false;
+  cudaStream_t s_main = nullptr, s_copy = nullptr, s_back = nullptr;
+  void *h_slot = nullptr;  // 64 B pinned + mapped: kernels write results straight into host memory
+  void *d_in = nullptr;    // single-shot staging
+  size_t d_in_cap = 0;
+  void *d_out = nullptr;
+  size_t d_out_cap = 0;
+  void *m_in = nullptr;    // zero-copy path: pinned + mapped input / output windows the kernels use directly
+  void *m_out = nullptr;
+  unsigned long long *d_trip = nullptr;  // sharded entry points: [3] triplet, [3 * kMaxShards] gathered, [4] combined (device)
+  void *h_comb = nullptr;                // pinned copy of the combined result
+  struct Slot {
+    void *d_in = nullptr;
+    size_t d_in_cap = 0;
+    void *d_out = nullptr;
+    size_t d_out_cap = 0;
+    cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
+    void *h_res = nullptr;  // 64 B pinned + mapped
+    bool d2h_pending = false;
+  } ring[kRing];
+  bool ring_ok = false;
+
+  void release() {
+    if (device < 0) return;
+    DeviceGuard g;
+    if (g.enter(device) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    if (s_main) cudaStreamSynchronize(s_main);
+    if (s_copy) cudaStreamSynchronize(s_copy);
+    if (s_back) cudaStreamSynchronize(s_back);
+    {  // the streams' workspaces
+      DeviceCtx &c = g_ctx[device];
+      std::lock_guard<std::mutex> lock(c.mu);
+      for (cudaStream_t s : {s_main, s_copy, s_back}) {
+        auto it = c.ws.find(s);
+        if (s && it != c.ws.end()) {
+          cudaFree(it->second.scratch);
+          cudaFree(it->second.desc);
+          cudaFree(it->second.cnt);
+          cudaFree(it->second.tmp);
+          c.ws.erase(it);
+        }
+      }
+    }
+    for (auto &sl : ring) {
+      cudaFree(sl.d_in);
+      cudaFree(sl.d_out);
+      if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+      if (sl.kernel_done) cudaEventDestroy(sl.kernel_done);
+      if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+      if (sl.h_res) cudaFreeHost(sl.h_res);
+      sl = Slot();
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_trip);
+    if (h_slot) cudaFreeHost(h_slot);
+    if (h_comb) cudaFreeHost(h_comb);
+    if (m_in) cudaFreeHost(m_in);
+    if (m_out) cudaFreeHost(m_out);
+    if (s_main) cudaStreamDestroy(s_main);
+    if (s_copy) cudaStreamDestroy(s_copy);
+    if (s_back) cudaStreamDestroy(s_back);
+    cudaGetLastError();
+    *this = HostPath();
+  }
+};
+struct HostPaths {
+  HostPath p[kMaxDevices];
+  ~HostPaths() {  // thread exit: give the device memory and the streams back
+    for (auto &h : p) h.release();
+  }
+};
+thread_local HostPaths tl_paths;
+
+constexpr int kMaxShards = 64;
+
+// This thread's HostPath on the CURRENT device `device` (created on first use).
+int host_path(int device, HostPath **out) {
+  HostPath &h = tl_paths.p[device];
+  if (!h.ok) {
+    h.device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h.s_main, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h.s_copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h.s_back, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h.h_slot, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h.h_comb, 64 * kMaxShards, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h.d_trip), (3 + 3 * kMaxShards + 4) * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+      h.release();
+      return fail((int)e, "host path init");
+    }
+    h.ok = true;
+  }
+  *out = &h;
+  return 0;
+}
+
+int ensure(void **buf, size_t *cap, size_t need, cudaStream_t s_main) {
   if (need <= *cap) return 0;
   if (*buf) {
     B200_CUDA(cudaStreamSynchronize(s_main));
-    B200_CUDA(cudaStreamSynchronize(s_copy));
     B200_CUDA(cudaFree(*buf));
     *buf = nullptr;
     *cap = 0;
@@ -385,38 +515,7 @@ size_t result_bytes(Op op) {
   }
 }
 
-bool bad_args(const void *in, size_t len, const void *res) { return res == nullptr || (in == nullptr && len != 0); }
 
-// async flavour: device pointers, device result slot
-int run_async(Op op, const void *d_in, size_t len, void *d_out, void *d_res, void *stream, uint64_t opt = 0, uint64_t lastc = 0) {
-  if (bad_args(d_in, len, d_res)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
-  int err;
-  DeviceCtx *c = current_ctx(&err);
-  if (!c) return err;
-  std::lock_guard<std::mutex> lock(c->mu);
-  LaunchCtx lc;
-  if ((err = get_ws(c, static_cast<cudaStream_t>(stream), tiles_needed(op, d_in, len), &lc, nullptr, tmp_needed(op, len)))) return err;
-  return enqueue(op, lc, d_in, len, d_out, d_res, opt, lastc);
-}
-
-// sync flavour: device data pointers, result delivered to the host
-int run_sync(Op op, const void *d_in, size_t len, void *d_out, void *h_res, void *stream, uint64_t opt = 0, uint64_t lastc = 0) {
-  if (bad_args(d_in, len, h_res)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
-  int err;
-  DeviceCtx *c = current_ctx(&err);
-  if (!c) return err;
-  std::lock_guard<std::mutex> lock(c->mu);
-  LaunchCtx lc;
-  StreamWs *w = nullptr;
-  if ((err = get_ws(c, static_cast<cudaStream_t>(stream), tiles_needed(op, d_in, len), &lc, &w, tmp_needed(op, len)))) return err;
-  if ((err = enqueue(op, lc, d_in, len, d_out, w->h_slot, opt, lastc))) return err;
-  B200_CUDA(cudaStreamSynchronize(lc.stream));
-  std::memcpy(h_res, w->h_slot, result_bytes(op));
-  return 0;
-}
-
-// Output elements an operation can produce at most for `len` input elements (sizes the device staging
-// buffer of the host path; the caller's own buffer is only ever written up to the returned count).
 size_t max_out_bytes(Op op, size_t len) {
   switch (op) {
     case kOpUtf8ToUtf16: case kOpUtf8ToUtf16BE: return 2 * len;       // <= 1 unit per input byte
@@ -453,29 +552,82 @@ size_t out_elem_bytes(Op op) {
   }
 }
 
+bool bad_args(const void *in, size_t len, const void *res) { return res == nullptr || (in == nullptr && len != 0); }
+
+// Workspace lookup + launches of one operation, atomically with respect to other threads using the same device
+// (a two-launch operation must not interleave with another call on the same stream's workspace).
+int locked_enqueue(DeviceCtx *c, cudaStream_t stream, Op op, const void *in, size_t len, void *out, void *res, uint64_t opt,
+                   uint64_t lastc) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  LaunchCtx lc;
+  int err;
+  if ((err = get_ws(c, stream, tiles_needed(op, in, len), &lc, tmp_needed(op, len)))) return err;
+  return enqueue(op, lc, in, len, out, res, opt, lastc);
+}
+
+// Device of a device-pointer call: where the data lives (a tensor on cuda:1 runs on GPU 1 whatever b200_set_device
+// said), else the calling thread's selected device.
+int call_device(const void *d_in, const void *d_out, const void *d_res) {
+  int d = device_of_pointer(d_in);
+  if (d < 0) d = device_of_pointer(d_out);
+  if (d < 0) d = device_of_pointer(d_res);
+  return d >= 0 ? d : tl_device;
+}
+
+// async flavour: device pointers, device result slot
+int run_async(Op op, const void *d_in, size_t len, void *d_out, void *d_res, void *stream, uint64_t opt = 0, uint64_t lastc = 0) {
+  if (bad_args(d_in, len, d_res)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
+  int err;
+  DeviceGuard guard;
+  DeviceCtx *c = enter_device(call_device(d_in, d_out, d_res), guard, &err);
+  if (!c) return err;
+  return locked_enqueue(c, static_cast<cudaStream_t>(stream), op, d_in, len, d_out, d_res, opt, lastc);
+}
+
+// sync flavour: device data pointers, result delivered to the host through this thread's pinned slot
+int run_sync_on(int device, cudaStream_t stream, bool own_stream, Op op, const void *d_in, size_t len, void *d_out, void *h_res,
+                uint64_t opt, uint64_t lastc) {
+  int err;
+  DeviceGuard guard;
+  DeviceCtx *c = enter_device(device, guard, &err);
+  if (!c) return err;
+  HostPath *h = nullptr;
+  if ((err = host_path(device, &h))) return err;
+  if (own_stream) stream = h->s_main;
+  if ((err = locked_enqueue(c, stream, op, d_in, len, d_out, h->h_slot, opt, lastc))) return err;
+  B200_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(h_res, h->h_slot, result_bytes(op));
+  return 0;
+}
+int run_sync(Op op, const void *d_in, size_t len, void *d_out, void *h_res, void *stream, uint64_t opt = 0, uint64_t lastc = 0) {
+  if (bad_args(d_in, len, h_res)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
+  return run_sync_on(call_device(d_in, d_out, nullptr), static_cast<cudaStream_t>(stream), false, op, d_in, len, d_out, h_res, opt, lastc);
+}
+
 // ---------------------------------------------------------------------------------------------
-// Streaming host path.  Large host buffers are cut into segments (on a character boundary where the operation
-// validates: the rule of simdutf::trim_partial_utf8 / _utf16le, reference src/scalar/utf8.h:257-288,
-// src/scalar/utf16.h:114-124, as benchmarks/threaded.cpp:69-74 uses it) and pipelined through a ring of device
-// staging slots: H2D of segment c+1 (copy stream) overlaps the kernels of segment c (main stream) and the D2H of
-// segment c-1 (back stream), so a call costs about max(H2D, D2H) instead of H2D + kernel + D2H, and device
-// memory stays bounded by the ring whatever the input size.  Segments are independent calls of the very same
-// kernels; their results are combined exactly like the shards of the multi-GPU path (first error in buffer
-// order wins, counts add up).
+// Streaming host path, over ONE OR SEVERAL devices.  Large host buffers are cut into segments (on a character boundary
+// where the operation validates: the rule of simdutf::trim_partial_utf8 / _utf16le, reference src/scalar/utf8.h:257-288,
+// src/scalar/utf16.h:114-124, as benchmarks/threaded.cpp:69-74 uses it) and pipelined through a ring of device staging
+// slots: H2D of a later segment (copy stream) overlaps the kernels of the current one (main stream) and the D2H of an
+// earlier one (back stream), so a call costs about max(H2D, D2H) instead of H2D + kernel + D2H, and device memory stays
+// bounded by the ring whatever the input size.  With n devices (b200_host_set_devices) segment s goes to device s mod n:
+// every device has its own ring, streams and PCIe link, so the host-to-host throughput is n links wide; this one
+// thread only enqueues asynchronous work and folds results.  Segments are independent calls of the very same kernels;
+// their results are combined exactly like the shards of the multi-GPU path (first error in buffer order wins, counts
+// add up, a segment's output lands at the sum of the counts before it).
 // ---------------------------------------------------------------------------------------------
-// B200_TUNE_SEG_MB overrides the segment size for experiments (tools/).
-static const size_t kSegmentBytes = [] {
-  const char *e = getenv("B200_TUNE_SEG_MB");
-  const long v = (e && *e) ? atol(e) : 0;
-  return size_t(v >= 1 && v <= 1024 ? v : 32) << 20;
-}();
+constexpr size_t kDefaultSegmentMB = 32;
+size_t segment_bytes() {
+  const int v = tuning(kTuneSegMB);
+  return size_t(v >= 1 && v <= 1024 ? v : (int)kDefaultSegmentMB) << 20;
+}
 
 // base64 quanta straddle any cut, detect_encodings is three verdicts about the whole buffer: single shot
 bool op_streams(Op op) { return op != kOpBase64 && op != kOpBase64U16 && op != kOpDetect; }
 
 // End (exclusive, in elements) of the segment that starts at `beg`.
-size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
-  const size_t per = kSegmentBytes / in_elem_bytes(op);
+size_t segment_end(Op op, const void *h_in, size_t len, size_t beg, size_t seg_bytes) {
+  const size_t per = seg_bytes / in_elem_bytes(op);
   size_t cut = beg + per;
   if (cut >= len) return len;
   switch (op) {
@@ -499,15 +651,15 @@ size_t segment_end(Op op, const void *h_in, size_t len, size_t beg) {
   }
 }
 
-int ring_init(DeviceCtx *c) {
-  if (c->ring_ok) return 0;
-  for (auto &sl : c->ring) {
+int ring_init(HostPath *h) {
+  if (h->ring_ok) return 0;
+  for (auto &sl : h->ring) {
     B200_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
     B200_CUDA(cudaHostAlloc(&sl.h_res, 64, cudaHostAllocMapped | cudaHostAllocPortable));
   }
-  c->ring_ok = true;
+  h->ring_ok = true;
   return 0;
 }
 
@@ -523,93 +675,116 @@ int slot_ensure(void **buf, size_t *cap, size_t need) {
   return 0;
 }
 
-int run_host_streamed(DeviceCtx *c, Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint64_t opt,
+struct DevSet {
+  int n = 0;
+  int dev[kMaxDevices];
+  HostPath *hp[kMaxDevices];
+};
+
+int run_host_streamed(const DevSet &ds, Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint64_t opt,
                       uint64_t lastc) {
   int err;
-  if ((err = ring_init(c))) return err;
+  const size_t seg_bytes = segment_bytes();
   const size_t ieb = in_elem_bytes(op), oeb = out_elem_bytes(op);
   const bool converts = max_out_bytes(op, 1) != 0;
   const bool is_count = result_bytes(op) == 8;
   const unsigned char *in_bytes = static_cast<const unsigned char *>(h_in);
   unsigned char *out_bytes = static_cast<unsigned char *>(h_out);
+  const size_t n = (size_t)ds.n, capacity = n * kRing, window = 2 * n;
 
   struct Seg { size_t beg, end; };
-  Seg segs[DeviceCtx::kRing];
+  Seg segs[kMaxDevices * kRing] = {};
   size_t issued = 0, retired = 0;      // segment counters
   size_t next_beg = 0, out_elems = 0;  // input cursor (elements), output cursor (elements)
   unsigned long long count_sum = 0;
   b200_result final_res = {B200_SUCCESS, 0, 0};
   bool failed = false;
+  auto slot_of = [&](size_t s) -> HostPath::Slot & { return ds.hp[s % n]->ring[(s / n) % kRing]; };
 
-  auto retire = [&](size_t s) -> int {  // wait for segment s, fold its result, start its copy back
-    DeviceCtx::Slot &sl = c->ring[s % DeviceCtx::kRing];
-    B200_CUDA(cudaEventSynchronize(sl.kernel_done));
-    if (is_count) {
-      count_sum += *static_cast<const uint64_t *>(sl.h_res);
-      return 0;
-    }
-    const b200_result r = *static_cast<const b200_result *>(sl.h_res);
-    if (r.error != B200_SUCCESS) {
-      if (!failed) {
-        failed = true;
-        final_res.error = r.error;
-        final_res.count = segs[s % DeviceCtx::kRing].beg + r.count;  // position in the whole buffer
+  // Everything below runs as a lambda so that ANY failure leaves no copy or kernel in flight on the caller's buffers and
+  // no stale `d2h_pending` flag behind (the drain after it).
+  auto body = [&]() -> int {
+    auto retire = [&](size_t s) -> int {  // wait for segment s, fold its result, start its copy back
+      HostPath *h = ds.hp[s % n];
+      HostPath::Slot &sl = slot_of(s);
+      DeviceGuard g;
+      B200_CUDA(g.enter(h->device));
+      B200_CUDA(cudaEventSynchronize(sl.kernel_done));
+      if (is_count) {
+        count_sum += *static_cast<const uint64_t *>(sl.h_res);
+        return 0;
+      }
+      const b200_result r = *static_cast<const b200_result *>(sl.h_res);
+      if (r.error != B200_SUCCESS) {
+        if (!failed) {
+          failed = true;
+          final_res.error = r.error;
+          final_res.count = segs[s % capacity].beg + r.count;  // position in the whole buffer
+        }
+        return 0;
+      }
+      if (failed) return 0;
+      if (converts) {
+        if (r.count && out_bytes) {
+          B200_CUDA(cudaMemcpyAsync(out_bytes + out_elems * oeb, sl.d_out, (size_t)r.count * oeb, cudaMemcpyDeviceToHost, h->s_back));
+          B200_CUDA(cudaEventRecord(sl.d2h_done, h->s_back));
+          sl.d2h_pending = true;
+        }
+        out_elems += (size_t)r.count;
       }
       return 0;
-    }
-    if (failed) return 0;
-    if (converts) {
-      if (r.count && out_bytes) {
-        B200_CUDA(cudaMemcpyAsync(out_bytes + out_elems * oeb, sl.d_out, (size_t)r.count * oeb, cudaMemcpyDeviceToHost, c->s_back));
-        B200_CUDA(cudaEventRecord(sl.d2h_done, c->s_back));
-        sl.d2h_pending = true;
-      }
-      out_elems += (size_t)r.count;
-    }
-    return 0;
-  };
+    };
 
-  while (next_beg < len && !failed) {
-    DeviceCtx::Slot &sl = c->ring[issued % DeviceCtx::kRing];
-    if (issued >= (size_t)DeviceCtx::kRing) {  // the slot's previous tenant must be completely done
-      if (retired + DeviceCtx::kRing <= issued) {
+    while (next_beg < len && !failed) {
+      // the slot's previous tenant (segment issued - capacity) must be completely done
+      while (retired + window <= issued && !failed) {
         if ((err = retire(retired))) return err;
         retired++;
-        if (failed) break;
       }
+      if (failed) break;
+      HostPath *h = ds.hp[issued % n];
+      HostPath::Slot &sl = slot_of(issued);
+      DeviceGuard g;
+      B200_CUDA(g.enter(h->device));
       if (sl.d2h_pending) {
         B200_CUDA(cudaEventSynchronize(sl.d2h_done));
         sl.d2h_pending = false;
       }
+      const size_t beg = next_beg, end = segment_end(op, h_in, len, beg, seg_bytes), cnt = end - beg;
+      segs[issued % capacity] = {beg, end};
+      if ((err = slot_ensure(&sl.d_in, &sl.d_in_cap, seg_bytes + 64))) return err;
+      if (converts && (err = slot_ensure(&sl.d_out, &sl.d_out_cap, max_out_bytes(op, seg_bytes / ieb) + 64))) return err;
+      B200_CUDA(cudaMemcpyAsync(sl.d_in, in_bytes + beg * ieb, cnt * ieb, cudaMemcpyHostToDevice, h->s_copy));
+      B200_CUDA(cudaEventRecord(sl.h2d_done, h->s_copy));
+      B200_CUDA(cudaStreamWaitEvent(h->s_main, sl.h2d_done, 0));
+      if ((err = locked_enqueue(&g_ctx[h->device], h->s_main, op, sl.d_in, cnt, sl.d_out, sl.h_res, opt, lastc))) return err;
+      B200_CUDA(cudaEventRecord(sl.kernel_done, h->s_main));
+      issued++;
+      next_beg = end;
     }
-    const size_t beg = next_beg, end = segment_end(op, h_in, len, beg), n = end - beg;
-    segs[issued % DeviceCtx::kRing] = {beg, end};
-    if ((err = slot_ensure(&sl.d_in, &sl.d_in_cap, kSegmentBytes + 64))) return err;
-    if (converts && (err = slot_ensure(&sl.d_out, &sl.d_out_cap, max_out_bytes(op, kSegmentBytes / ieb) + 64))) return err;
-    B200_CUDA(cudaMemcpyAsync(sl.d_in, in_bytes + beg * ieb, n * ieb, cudaMemcpyHostToDevice, c->s_copy));
-    B200_CUDA(cudaEventRecord(sl.h2d_done, c->s_copy));
-    B200_CUDA(cudaStreamWaitEvent(c->s_main, sl.h2d_done, 0));
-    LaunchCtx lc;
-    if ((err = get_ws(c, c->s_main, tiles_needed(op, sl.d_in, n), &lc, nullptr, tmp_needed(op, n)))) return err;
-    if ((err = enqueue(op, lc, sl.d_in, n, sl.d_out, sl.h_res, opt, lastc))) return err;
-    B200_CUDA(cudaEventRecord(sl.kernel_done, c->s_main));
-    issued++;
-    next_beg = end;
-    // keep one segment in flight behind the one just issued: retire everything older
-    while (retired + 1 < issued && !failed) {
+    while (retired < issued) {
       if ((err = retire(retired))) return err;
       retired++;
     }
-  }
-  while (retired < issued) {
-    if ((err = retire(retired))) return err;
-    retired++;
-  }
-  for (auto &sl : c->ring) {
-    if (sl.d2h_pending) {
-      B200_CUDA(cudaEventSynchronize(sl.d2h_done));
-      sl.d2h_pending = false;
+    return 0;
+  };
+  err = body();
+  // drain: whatever happened, nothing of this call stays in flight
+  for (int i = 0; i < ds.n; i++) {
+    HostPath *h = ds.hp[i];
+    DeviceGuard g;
+    if (g.enter(h->device) != cudaSuccess) continue;
+    if (err) {
+      cudaStreamSynchronize(h->s_copy);
+      cudaStreamSynchronize(h->s_main);
     }
+    cudaError_t e = cudaStreamSynchronize(h->s_back);
+    for (auto &sl : h->ring) sl.d2h_pending = false;
+    if (e != cudaSuccess && !err) err = fail((int)e, "cudaStreamSynchronize(copy back)");
+  }
+  if (err) {
+    cudaGetLastError();
+    return err;
   }
   if (is_count) {
     *static_cast<uint64_t *>(h_res) = count_sum;
@@ -620,8 +795,48 @@ int run_host_streamed(DeviceCtx *c, Op op, const void *h_in, size_t len, void *h
   return 0;
 }
 
-// host flavour: host pointers in and out.  H2D on the context's stream, the kernel, then a D2H of exactly
-// the elements the result says were produced.
+size_t produced_elems(Op op, const void *h_res, size_t out_cap) {
+  size_t produced = 0;
+  if (op == kOpBase64 || op == kOpBase64U16) {
+    // output_count is 0 on INVALID_BASE64_CHARACTER (unpinned by the reference), so nothing is copied back then
+    produced = (size_t)static_cast<const b200_full_result *>(h_res)->output_count;
+  } else {
+    const b200_result *r = static_cast<const b200_result *>(h_res);
+    produced = r->error == B200_SUCCESS ? (size_t)r->count : 0;
+  }
+  const size_t cap = out_cap / out_elem_bytes(op);
+  return produced > cap ? cap : produced;
+}
+
+// Small inputs (the reference's test binaries make 10^5..10^8 calls on <= 256-byte strings): no
+// staging copies at all.  The text is memcpy'd into a pinned, device-mapped window, the kernels read it and write
+// their output and result straight through PCIe into mapped host memory, and one stream synchronisation ends the
+// call: launch + sync instead of H2D + launch + sync + D2H + sync.
+int run_host_small(HostPath *h, DeviceCtx *c, Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint64_t opt,
+                   uint64_t lastc) {
+  int err;
+  if (!h->m_in) {
+    B200_CUDA(cudaHostAlloc(&h->m_in, kSmallIn + 256, cudaHostAllocMapped | cudaHostAllocPortable));
+    B200_CUDA(cudaHostAlloc(&h->m_out, kSmallOut + 256, cudaHostAllocMapped | cudaHostAllocPortable));
+  }
+  const size_t in_bytes = len * in_elem_bytes(op);
+  const size_t out_cap = max_out_bytes(op, len);
+  // keep the caller's alignment modulo 16: the kernels' paths depend on it and the parity tests sweep it
+  char *win = static_cast<char *>(h->m_in) + (reinterpret_cast<uintptr_t>(h_in) & 15u);
+  char *wout = static_cast<char *>(h->m_out) + (reinterpret_cast<uintptr_t>(h_out) & 15u);
+  std::memcpy(win, h_in, in_bytes);
+  if ((err = locked_enqueue(c, h->s_main, op, win, len, wout, h->h_slot, opt, lastc))) return err;
+  B200_CUDA(cudaStreamSynchronize(h->s_main));
+  std::memcpy(h_res, h->h_slot, result_bytes(op));
+  if (out_cap && h_out) {
+    const size_t produced = produced_elems(op, h_res, out_cap);
+    if (produced) std::memcpy(h_out, wout, produced * out_elem_bytes(op));
+  }
+  return 0;
+}
+
+// host flavour: host pointers in and out (device pointers are recognised and processed in place: the C++ virtuals of
+// simdutf::b200::implementation cannot know what their caller holds).
 int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint64_t opt = 0, uint64_t lastc = 0) {
   if (bad_args(h_in, len, h_res)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
   if (len == 0) {  // never touches CUDA (reference tests/null_safety_tests.cpp:7-95)
@@ -629,40 +844,204 @@ int run_host(Op op, const void *h_in, size_t len, void *h_out, void *h_res, uint
     if (op == kOpDetect) *static_cast<uint64_t *>(h_res) = 1 | 2 | 8;  // "" is valid UTF-8, UTF-16LE and UTF-32LE
     return 0;
   }
+  if (device_count() <= 0) return fail(B200_E_NO_DEVICE, "no usable sm_100 device");
+  const int pdev = device_of_pointer(h_in);
+  if (pdev >= 0) {  // device-resident data: the output pointer must be device memory too
+    if (max_out_bytes(op, 1) != 0 && h_out && device_of_pointer(h_out) < 0) return fail(B200_E_BAD_ARGUMENT, "device input with host output");
+    return run_sync_on(pdev, nullptr, true, op, h_in, len, h_out, h_res, opt, lastc);
+  }
   int err;
-  DeviceCtx *c = current_ctx(&err);
-  if (!c) return err;
-  std::lock_guard<std::mutex> lock(c->mu);
-  if (op_streams(op) && len * in_elem_bytes(op) > kSegmentBytes + kSegmentBytes / 2)
-    return run_host_streamed(c, op, h_in, len, h_out, h_res, opt, lastc);
   const size_t in_bytes = len * in_elem_bytes(op);
   const size_t out_cap = max_out_bytes(op, len);
-  if ((err = ensure(&c->d_in, &c->d_in_cap, in_bytes + 16, c->s_main, c->s_copy))) return err;
-  if (out_cap && (err = ensure(&c->d_out, &c->d_out_cap, out_cap + 16, c->s_main, c->s_copy))) return err;
-  LaunchCtx lc;
-  StreamWs *w = nullptr;
-  if ((err = get_ws(c, c->s_main, tiles_needed(op, c->d_in, len), &lc, &w, tmp_needed(op, len)))) return err;
-  B200_CUDA(cudaMemcpyAsync(c->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, c->s_main));
-  if ((err = enqueue(op, lc, c->d_in, len, c->d_out, w->h_slot, opt, lastc))) return err;
-  B200_CUDA(cudaStreamSynchronize(c->s_main));
-  std::memcpy(h_res, w->h_slot, result_bytes(op));
-  if (out_cap && h_out) {
-    size_t produced = 0;
-    if (op == kOpBase64 || op == kOpBase64U16) {
-      const b200_full_result *r = static_cast<const b200_full_result *>(h_res);
-      produced = (size_t)r->output_count;
-      // output_count is 0 on INVALID_BASE64_CHARACTER (unpinned by the reference), so nothing is copied back then
-    } else {
-      const b200_result *r = static_cast<const b200_result *>(h_res);
-      produced = r->error == B200_SUCCESS ? (size_t)r->count : 0;
+  const size_t seg = segment_bytes();
+  if (op_streams(op) && in_bytes > seg + seg / 2) {
+    DevSet ds;
+    const int avail = device_count();
+    const int want = tl_host_devices < 1 ? 1 : (tl_host_devices > avail ? avail : tl_host_devices);
+    // no point in waking a device for less than two segments of its own
+    const size_t nseg = (in_bytes + seg - 1) / seg;
+    ds.n = (size_t)want > nseg / 2 ? (int)(nseg / 2 ? nseg / 2 : 1) : want;
+    for (int i = 0; i < ds.n; i++) {
+      ds.dev[i] = (tl_device + i) % avail;
+      DeviceGuard g;
+      if (!enter_device(ds.dev[i], g, &err)) return err;
+      if ((err = host_path(ds.dev[i], &ds.hp[i]))) return err;
+      if ((err = ring_init(ds.hp[i]))) return err;
     }
-    if (produced > out_cap / out_elem_bytes(op)) produced = out_cap / out_elem_bytes(op);
+    return run_host_streamed(ds, op, h_in, len, h_out, h_res, opt, lastc);
+  }
+  DeviceGuard guard;
+  DeviceCtx *c = enter_device(tl_device, guard, &err);
+  if (!c) return err;
+  HostPath *h = nullptr;
+  if ((err = host_path(tl_device, &h))) return err;
+  if (in_bytes <= kSmallIn && out_cap <= kSmallOut && tmp_needed(op, len) == 0)
+    return run_host_small(h, c, op, h_in, len, h_out, h_res, opt, lastc);
+  if ((err = ensure(&h->d_in, &h->d_in_cap, in_bytes + 16, h->s_main))) return err;
+  if (out_cap && (err = ensure(&h->d_out, &h->d_out_cap, out_cap + 16, h->s_main))) return err;
+  B200_CUDA(cudaMemcpyAsync(h->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, h->s_main));
+  if ((err = locked_enqueue(c, h->s_main, op, h->d_in, len, h->d_out, h->h_slot, opt, lastc))) {
+    cudaStreamSynchronize(h->s_main);  // the copy reads the caller's buffer: do not return while it is in flight
+    return err;
+  }
+  B200_CUDA(cudaStreamSynchronize(h->s_main));
+  std::memcpy(h_res, h->h_slot, result_bytes(op));
+  if (out_cap && h_out) {
+    const size_t produced = produced_elems(op, h_res, out_cap);
     if (produced) {
-      B200_CUDA(cudaMemcpyAsync(h_out, c->d_out, produced * out_elem_bytes(op), cudaMemcpyDeviceToHost, c->s_main));
-      B200_CUDA(cudaStreamSynchronize(c->s_main));
+      B200_CUDA(cudaMemcpyAsync(h_out, h->d_out, produced * out_elem_bytes(op), cudaMemcpyDeviceToHost, h->s_main));
+      B200_CUDA(cudaStreamSynchronize(h->s_main));
     }
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded multi-device entry points (SURVEY.md §8b "_mgpu variants taking per-device shard descriptors", §7 step 5):
+// ONE process drives several devices.  Every shard is an independent launch of the single-GPU kernels on its own
+// device and stream, leaving the triplet {length, result} in that device's memory; the triplets are exchanged with one
+// ncclAllGather over NVLink (communicators from ncclCommInitAll, one rank per device; NCCL is resolved at run time
+// with dlopen so that the library has no link-time dependency on it) and k_sharded_combine turns them into the global
+// result and the shard's offsets on every device.  Without NCCL, or with several shards on one device, the same
+// triplets travel as 24-byte peer copies instead.  Nothing but the final 32-byte results crosses to the host.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  bool tried = false, ok = false;
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+struct CommSet {
+  int n = 0;
+  int dev[kMaxDevices];
+  void *comm[kMaxDevices];
+};
+CommSet g_comms[8];
+int g_comm_sets = 0;
+
+// Communicators for exactly this ordered device list, or nullptr (NCCL absent / init failed).  Caller holds g_nccl_mu.
+CommSet *nccl_comms(const int *dev, int n) {
+  if (!g_nccl.tried) {
+    g_nccl.tried = true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) {
+      g_nccl.CommInitAll = reinterpret_cast<int (*)(void **, int, const int *)>(dlsym(lib, "ncclCommInitAll"));
+      g_nccl.AllGather = reinterpret_cast<int (*)(const void *, void *, size_t, int, void *, cudaStream_t)>(dlsym(lib, "ncclAllGather"));
+      g_nccl.GroupStart = reinterpret_cast<int (*)()>(dlsym(lib, "ncclGroupStart"));
+      g_nccl.GroupEnd = reinterpret_cast<int (*)()>(dlsym(lib, "ncclGroupEnd"));
+      g_nccl.ok = g_nccl.CommInitAll && g_nccl.AllGather && g_nccl.GroupStart && g_nccl.GroupEnd;
+    }
+  }
+  if (!g_nccl.ok || tuning(kTuneNoNccl)) return nullptr;
+  for (int s = 0; s < g_comm_sets; s++) {
+    if (g_comms[s].n == n && std::memcmp(g_comms[s].dev, dev, n * sizeof(int)) == 0) return &g_comms[s];
+  }
+  if (g_comm_sets >= 8) return nullptr;
+  CommSet &cs = g_comms[g_comm_sets];
+  cs.n = n;
+  std::memcpy(cs.dev, dev, n * sizeof(int));
+  if (g_nccl.CommInitAll(cs.comm, n, dev) != 0) return nullptr;
+  g_comm_sets++;
+  return &cs;
+}
+
+std::atomic<int> g_last_gather{0};  // 1 = NCCL all_gather, 2 = peer copies (b200_mgpu_last_gather, for tests / logs)
+
+constexpr int kNcclUint64 = 5;  // ncclDataType_t, nccl.h
+
+int run_mgpu(Op op, const b200_shard *shards, int n, b200_sharded_result *h_results, int count_is_length) {
+  if (!shards || !h_results || n < 1 || n > kMaxShards) return fail(B200_E_BAD_ARGUMENT, "bad shard list");
+  int err;
+  const bool is_count = result_bytes(op) == 8;
+  HostPath *hp[kMaxShards] = {};
+  cudaEvent_t ev[kMaxShards] = {};
+  bool distinct = n <= kMaxDevices;
+  for (int i = 0; i < n; i++) {
+    if (bad_args(shards[i].d_in, shards[i].len, &err)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
+    for (int j = 0; j < i; j++) distinct = distinct && shards[i].device != shards[j].device;
+  }
+  auto cleanup = [&]() {
+    for (int i = 0; i < n; i++) {
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+  };
+  auto trip_of = [&](int i) { return hp[i]->d_trip + 3 * i; };
+  auto gathered_of = [&](int i) { return hp[i]->d_trip + 3 * kMaxShards; };
+  auto comb_of = [&](int i) { return hp[i]->d_trip + 6 * kMaxShards + 4 * i; };
+  auto body = [&]() -> int {
+    // 1. every shard: its triplet header, then the kernels, on its own device and stream
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g;
+      DeviceCtx *c = enter_device(shards[i].device, g, &err);
+      if (!c) return err;
+      if ((err = host_path(shards[i].device, &hp[i]))) return err;
+      HostPath *h = hp[i];
+      B200_CUDA(launch_write_u64(trip_of(i), (unsigned long long)shards[i].len, h->s_main));
+      if (is_count) B200_CUDA(launch_write_u64(trip_of(i) + 1, 0ull, h->s_main));
+      void *res = is_count ? static_cast<void *>(trip_of(i) + 2) : static_cast<void *>(trip_of(i) + 1);
+      if ((err = locked_enqueue(c, h->s_main, op, shards[i].d_in, (size_t)shards[i].len, shards[i].d_out, res, 0, 0))) return err;
+      B200_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+      B200_CUDA(cudaEventRecord(ev[i], h->s_main));
+    }
+    // 2. exchange the triplets
+    CommSet *cs = nullptr;
+    if (distinct) {
+      int devs[kMaxDevices];
+      for (int i = 0; i < n; i++) devs[i] = shards[i].device;
+      std::lock_guard<std::mutex> lock(g_nccl_mu);
+      cs = nccl_comms(devs, n);
+      if (cs) {
+        if (g_nccl.GroupStart() != 0) return fail(B200_E_NO_DEVICE, "ncclGroupStart");
+        for (int i = 0; i < n; i++) {
+          if (g_nccl.AllGather(trip_of(i), gathered_of(i), 3, kNcclUint64, cs->comm[i], hp[i]->s_main) != 0) {
+            g_nccl.GroupEnd();
+            return fail(B200_E_NO_DEVICE, "ncclAllGather");
+          }
+        }
+        if (g_nccl.GroupEnd() != 0) return fail(B200_E_NO_DEVICE, "ncclGroupEnd");
+      }
+    }
+    g_last_gather.store(cs ? 1 : 2, std::memory_order_relaxed);
+    if (!cs) {
+      for (int i = 0; i < n; i++) {
+        DeviceGuard g;
+        B200_CUDA(g.enter(shards[i].device));
+        for (int j = 0; j < n; j++) {
+          if (j != i) B200_CUDA(cudaStreamWaitEvent(hp[i]->s_main, ev[j], 0));
+          B200_CUDA(cudaMemcpyPeerAsync(gathered_of(i) + 3 * j, shards[i].device, hp[j]->d_trip + 3 * j, shards[j].device, 24, hp[i]->s_main));
+        }
+      }
+    }
+    // 3. combine on every device, results to pinned host memory
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g;
+      B200_CUDA(g.enter(shards[i].device));
+      B200_CUDA(launch_sharded_combine(gathered_of(i), n, i, count_is_length, comb_of(i), hp[i]->s_main));
+      B200_CUDA(cudaMemcpyAsync(static_cast<char *>(hp[i]->h_comb) + 32 * i, comb_of(i), 32, cudaMemcpyDeviceToHost, hp[i]->s_main));
+    }
+    for (int i = 0; i < n; i++) {
+      DeviceGuard g;
+      B200_CUDA(g.enter(shards[i].device));
+      B200_CUDA(cudaStreamSynchronize(hp[i]->s_main));
+      std::memcpy(&h_results[i], static_cast<char *>(hp[i]->h_comb) + 32 * i, sizeof(b200_sharded_result));
+    }
+    return 0;
+  };
+  err = body();
+  if (err) {
+    for (int i = 0; i < n; i++) {
+      if (shards[i].device >= 0 && shards[i].device < device_count() && tl_paths.p[shards[i].device].ok) {
+        DeviceGuard g;
+        if (g.enter(shards[i].device) == cudaSuccess) cudaStreamSynchronize(tl_paths.p[shards[i].device].s_main);
+      }
+    }
+    cudaGetLastError();
+  }
+  cleanup();
+  return err;
 }
 
 }  // namespace
@@ -687,7 +1066,8 @@ const char *b200_last_error(void) { return tl_error; }
 int b200_host_alloc(void **ptr, size_t bytes) {
   if (!ptr) return fail(B200_E_BAD_ARGUMENT, "null pointer");
   int err;
-  if (!current_ctx(&err)) return err;
+  DeviceGuard guard;
+  if (!enter_device(tl_device, guard, &err)) return err;
   B200_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
   return 0;
 }
@@ -833,7 +1213,8 @@ size_t b200_host_trim_partial_utf16le(const uint16_t *h_in, size_t len) {
 int b200_trim_partial_utf8(const char *d_in, size_t len, size_t *h_trimmed, void *stream) {
   if (!h_trimmed || (!d_in && len)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
   int err;
-  if (!current_ctx(&err)) return err;
+  DeviceGuard guard;
+  if (!enter_device(call_device(d_in, nullptr, nullptr), guard, &err)) return err;
   char tail[3] = {0, 0, 0};
   const size_t n = len < 3 ? len : 3;
   if (n) {
@@ -849,10 +1230,48 @@ int b200_sharded_combine_async(const uint64_t *d_gathered, int world, int rank, 
                                b200_sharded_result *d_out, void *stream) {
   if (!d_gathered || !d_out || world < 1 || world > 4096 || rank < 0 || rank >= world) return fail(B200_E_BAD_ARGUMENT, "bad sharded_combine argument");
   int err;
-  if (!current_ctx(&err)) return err;
+  DeviceGuard guard;
+  if (!enter_device(call_device(d_gathered, d_out, nullptr), guard, &err)) return err;
   B200_CUDA(launch_sharded_combine(reinterpret_cast<const unsigned long long *>(d_gathered), world, rank, count_is_length,
                                    reinterpret_cast<unsigned long long *>(d_out), static_cast<cudaStream_t>(stream)));
   return 0;
 }
+
+
+// ---- host-pointer path over several devices, experiment knobs ----
+int b200_host_set_devices(int n) {
+  if (n < 1 || n > device_count()) return fail(B200_E_NO_DEVICE, "b200_host_set_devices: not that many sm_100 devices");
+  tl_host_devices = n;
+  return 0;
+}
+int b200_host_get_devices(void) { return tl_host_devices; }
+int b200_set_tuning(const char *name, int value) {
+  static const char *const names[] = {"conv_minb", "segment_mb", "no_nccl"};
+  for (int k = 0; k < 3; k++) {
+    if (name && std::strcmp(name, names[k]) == 0) {
+      g_tuning[k].store(value, std::memory_order_relaxed);
+      return 0;
+    }
+  }
+  return fail(B200_E_BAD_ARGUMENT, "unknown tuning knob");
+}
+
+// ---- sharded multi-device entry points ----
+int b200_mgpu_validate_utf8_with_errors(const b200_shard *shards, int n, b200_sharded_result *h_results) {
+  return run_mgpu(kOpValidateUtf8, shards, n, h_results, 1);
+}
+int b200_mgpu_utf16_length_from_utf8(const b200_shard *shards, int n, b200_sharded_result *h_results) {
+  return run_mgpu(kOpUtf16LenFromUtf8, shards, n, h_results, 0);
+}
+int b200_mgpu_convert_utf8_to_utf16le(const b200_shard *shards, int n, b200_sharded_result *h_results) {
+  return run_mgpu(kOpUtf8ToUtf16, shards, n, h_results, 0);
+}
+int b200_mgpu_convert_utf8_to_utf32(const b200_shard *shards, int n, b200_sharded_result *h_results) {
+  return run_mgpu(kOpUtf8ToUtf32, shards, n, h_results, 0);
+}
+int b200_mgpu_convert_utf16le_to_utf8(const b200_shard *shards, int n, b200_sharded_result *h_results) {
+  return run_mgpu(kOpUtf16ToUtf8, shards, n, h_results, 0);
+}
+int b200_mgpu_last_gather(void) { return g_last_gather.load(std::memory_order_relaxed); }
 
 }  // extern "C"

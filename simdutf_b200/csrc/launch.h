@@ -117,4 +117,9 @@ cudaError_t launch_sharded_combine(const unsigned long long *gathered, int world
 
 void count_launch(int n);  // bumps the library-wide launch counter (b200_launch_count)
 
+// Experiment knobs (b200_set_tuning in the C ABI; tools/ and profiles/ use them to compare kernel variants inside
+// one build).  The library never reads the environment.
+enum TuneKey { kTuneConvMinB = 0, kTuneSegMB = 1, kTuneNoNccl = 2, kTuneKeyCount = 8 };
+int tuning(int key);  // 0 = default  // bumps the library-wide launch counter (b200_launch_count)
+
 }  // namespace b200

@@ -115,3 +115,134 @@ def test_two_rank_cut_buffer_vs_reference(tmp_path):
             raise
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o[-4000:]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# One process, several devices: the native b200_mgpu_* entry points and the multi-device host-pointer path.
+# ------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def b():
+    import simdutf_b200
+    simdutf_b200.load()
+    assert simdutf_b200.device_count() >= 1
+    simdutf_b200.set_device(0)
+    return simdutf_b200
+
+
+def _whole(ref, oracle, data):
+    if ref is not None:
+        return ref.convert_utf8_to_utf16le_with_errors(ref.best, data)
+    return oracle.convert_utf8_to_utf16le_with_errors(data)
+
+
+@pytest.mark.parametrize("layout", ["distinct_devices", "three_shards_device0", "distinct_devices_no_nccl"])
+def test_mgpu_entry_points_vs_reference(b, oracle, ref, layout):
+    """b200_mgpu_convert_utf8_to_utf16le / _validate / _utf16_length on a cut buffer, shards on different devices
+    (triplets over ncclAllGather) or several on one device (peer copies), against one whole-buffer reference call."""
+    import numpy as np
+    import torch
+    from simdutf_b200 import sharded, synth
+    ndev = b.device_count()
+    if layout.startswith("distinct"):
+        devs = list(range(min(ndev, 4)))
+    else:
+        devs = [0, 0, 0]
+    b.set_tuning("no_nccl", 1 if layout.endswith("no_nccl") else 0)
+    try:
+        data = synth.mixed_utf8(6 << 20, seed=21).numpy().copy()
+        for case in ("valid", "error_in_last_shard", "error_in_first_and_last"):
+            d = data.copy()
+            cuts = sharded.utf8_shard_bounds(lambda i: int(data[i]), d.size, len(devs))
+            if case != "valid":
+                d[cuts[-2] + 4321] = 0xF8
+            if case == "error_in_first_and_last":
+                d[99] = 0x80
+            shards, outs = [], []
+            for k, dev in enumerate(devs):
+                t_in = torch.from_numpy(d[cuts[k]:cuts[k + 1]].copy()).to(f"cuda:{dev}")
+                units = oracle.utf16_length_from_utf8(d[cuts[k]:cuts[k + 1]])
+                t_out = torch.full((units + 64,), 0x5A5A, dtype=torch.int16, device=f"cuda:{dev}")
+                shards.append((dev, t_in, t_out))
+                outs.append((t_out, units))
+            (werr, wcnt), wout = _whole(ref, oracle, d)
+            res = b.mgpu("convert_utf8_to_utf16le", shards)
+            want_gather = 1 if (layout == "distinct_devices") else 2
+            assert b.load().b200_mgpu_last_gather() == want_gather
+            for k, (e, c, in_off, out_off) in enumerate(res):
+                assert (e, c) == (werr, wcnt), (layout, case, k, res)
+                assert in_off == cuts[k]
+                t_out, units = outs[k]
+                assert bool((t_out[units:] == 0x5A5A).all()), "output overrun"
+                if werr == 0:
+                    got = t_out[:units].cpu().numpy().view(np.uint16)
+                    assert np.array_equal(wout[out_off:out_off + units], got), (layout, case, k)
+            vres = b.mgpu("validate_utf8_with_errors", [(dv, ti, None) for dv, ti, _ in shards])
+            assert all((e, c) == oracle.validate_utf8_with_errors(d) for e, c, _, _ in vres), vres
+            lres = b.mgpu("utf16_length_from_utf8", [(dv, ti, None) for dv, ti, _ in shards])
+            assert all((e, c) == (0, oracle.utf16_length_from_utf8(d)) for e, c, _, _ in lres), lres
+    finally:
+        b.set_tuning("no_nccl", 0)
+
+
+def test_host_path_over_all_devices_and_threads(b, oracle, ref):
+    """b200_host_set_devices(n): a host buffer cut into segments dealt round-robin to every visible device gives the
+    same (error, count) and the same output bytes as the reference; two threads calling at once do not disturb each
+    other (per-thread host paths)."""
+    import threading
+    import numpy as np
+    from simdutf_b200 import synth
+    ndev = b.device_count()
+    b.set_tuning("segment_mb", 2)
+    try:
+        data = synth.mixed_utf8(40 << 20, seed=22).numpy().copy()
+        bad = data.copy()
+        bad[31 << 20] = 0xFF
+        (werr, wcnt), wout = _whole(ref, oracle, data)
+        want_bad = oracle.validate_utf8_with_errors(bad)
+        results = {}
+
+        def work(tag, devices):
+            b.set_device(0)
+            b.host_set_devices(devices)
+            out = np.zeros(wcnt + 64, dtype=np.uint16)
+            r = b.convert_utf8_to_utf16le_with_errors(data, out)
+            rb = b.convert_utf8_to_utf16le_with_errors(bad, np.zeros(wcnt + 64, dtype=np.uint16))
+            n16 = b.utf16_length_from_utf8(data)
+            results[tag] = (r, rb, n16, bool(np.array_equal(out[:wcnt], wout)), bool((out[wcnt:] == 0).all()))
+
+        ts = [threading.Thread(target=work, args=(f"t{i}", ndev if i == 0 else 1)) for i in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for tag, (r, rb, n16, same, clean) in results.items():
+            assert r == (werr, wcnt) and rb == want_bad and n16 == wcnt and same and clean, (tag, r, rb, n16, same, clean)
+        assert len(results) == 2
+    finally:
+        b.set_tuning("segment_mb", 0)
+        b.host_set_devices(1)
+
+
+def test_device_pointers_through_the_host_flavour(b, oracle):
+    """The C++ virtuals only have b200_host_*: device-resident data handed to them is recognised and processed in place
+    (cudaPointerGetAttributes), and a call never leaves the caller's current CUDA device changed."""
+    import ctypes
+    import numpy as np
+    import torch
+    from simdutf_b200 import synth
+    lib = b.load()
+    data = synth.mixed_utf8(300_000, seed=23)
+    dev = b.device_count() - 1
+    d = data.to(f"cuda:{dev}")
+    units = oracle.utf16_length_from_utf8(data.numpy())
+    out = torch.zeros(units, dtype=torch.int16, device=f"cuda:{dev}")
+    torch.cuda.set_device(0)
+    res = b.Result()
+    st = lib.b200_host_convert_utf8_to_utf16le(ctypes.c_void_p(d.data_ptr()), d.numel(), ctypes.c_void_p(out.data_ptr()), ctypes.byref(res))
+    assert st == 0 and res.astuple() == (0, units)
+    (_, _), wout = oracle.convert_utf8_to_utf16le_with_errors(data.numpy())
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), wout)
+    assert torch.cuda.current_device() == 0
+    # a tensor on the LAST device through the device-pointer flavour, without b200_set_device
+    assert b.validate_utf8_with_errors(d) == (0, d.numel())
+    assert torch.cuda.current_device() == 0
