@@ -306,8 +306,10 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        cpu_group = dist.new_group(backend="gloo")  # host-side barrier for the phases in which rank 0 drives every GPU itself
     lib = b.load()
     b.set_device(local_rank)
     for kv in filter(None, os.environ.get("B200_BENCH_TUNE", "").split(",")):  # experiments only: "conv_minb=4,segment_mb=64"
@@ -445,10 +447,22 @@ def main():
     assert same, "host path and device path disagree"
     del h_in, h_out
 
+    # ---- e2e at N > 1, the drop-in way: ONE process (rank 0) hands the WHOLE global buffer, in host memory, to the host-
+    # pointer C ABI, which deals its segments to all N devices (b200_host_set_devices).  The other ranks wait on a
+    # host-side (gloo) barrier so that no NCCL kernel of theirs spins on the GPUs meanwhile.
+    e2e_one = None
+    if sharded_run and world > 1:
+        del d_out
+        torch.cuda.empty_cache()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            e2e_one = one_process_e2e(b, lib, synth, torch, device, world, total_bytes, total_units, args.e2e_steps)
+        dist.barrier(group=cpu_group)
+
     # ---- the other half of BASELINE.json's metric: validate_utf8_with_errors (config 1 ASCII, and the mixed buffer) ----
     val = {}
     if rank == 0 and world == 1:
-        del d_out
+        d_out = None
         val = validate_measurements(lib, synth, torch, device, stream, sp, peak, K, d_in)
     extras = {}
     if not args.no_extras and rank == 0 and world == 1:
@@ -482,11 +496,12 @@ def main():
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cpu_baseline_1thread": ({k: cpu1[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu1 else None),
             "cpu_baseline_threaded_cpp": cpu_thr,
-            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * total_bytes,
-                    "d2h_bytes_per_step": 2 * total_units + 24 * world,
-                    "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers), one "
-                           "process per GPU on its own shard",
-                    "ms_per_step": float(te.item()) * 1e3},
+            "e2e": ({"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 2 * total_bytes,
+                     "d2h_bytes_per_step": 2 * total_units + 24 * world,
+                     "api": "b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le (pinned host buffers)",
+                     "ms_per_step": float(te.item()) * 1e3} if e2e_one is None else
+                    dict(e2e_one, per_rank_processes={"value": e2e_value, "ms_per_step": float(te.item()) * 1e3,
+                                                      "what": "the same two calls issued by N processes, each on its own shard and GPU"})),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "sharded": shard_check,
@@ -497,6 +512,42 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def one_process_e2e(b, lib, synth, torch, device, world, total_bytes, total_units, steps):
+    """utf16_length_from_utf8 + convert_utf8_to_utf16le on the whole global buffer through b200_host_* from ONE process
+    over `world` devices.  Host buffers are pinned; every byte crosses PCIe inside the timed region."""
+    seed = 5
+    h_in = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
+    for lo in range(0, total_bytes, GIB):
+        hi = min(total_bytes, lo + GIB)
+        h_in[lo:hi].copy_(synth.stream_range(seed, lo, hi, device))
+    h_out = torch.empty(total_units, dtype=torch.int16, pin_memory=True)
+    torch.cuda.empty_cache()
+    hres, hcnt = b.Result(), ctypes.c_uint64()
+    hin_p, hout_p = ctypes.c_void_p(h_in.data_ptr()), ctypes.c_void_p(h_out.data_ptr())
+    b.host_set_devices(world)
+
+    def step():
+        st = lib.b200_host_utf16_length_from_utf8(hin_p, total_bytes, ctypes.byref(hcnt))
+        st |= lib.b200_host_convert_utf8_to_utf16le(hin_p, total_bytes, hout_p, ctypes.byref(hres))
+        if st:
+            raise RuntimeError("b200 host call failed: " + lib.b200_last_error().decode())
+
+    try:
+        step()
+        assert hcnt.value == total_units and hres.astuple() == (0, total_units), (hcnt.value, hres.astuple(), total_units)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        sec = (time.perf_counter() - t0) / steps
+    finally:
+        b.host_set_devices(1)
+    return {"value": total_bytes / sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 2 * total_bytes,
+            "d2h_bytes_per_step": 2 * total_units + 24,
+            "api": f"b200_host_utf16_length_from_utf8 + b200_host_convert_utf8_to_utf16le on the whole buffer from ONE process, "
+                   f"segments dealt to {world} devices (b200_host_set_devices), pinned host buffers",
+            "ms_per_step": sec * 1e3}
 
 
 CONVERT_KERNEL_NAME = ("k_utf8_transcode_sp (convert_utf8_to_utf16le_with_errors = ONE launch: bit-plane transcoder with the "

@@ -10,6 +10,12 @@
 
 #include "simdutf_b200.h"
 
+#ifdef SIMDUTF_INTERNAL_TESTS
+  #include <cstdio>
+  #include <cstdlib>
+  #include <vector>
+#endif
+
 namespace simdutf {
 namespace b200 {
 
@@ -382,6 +388,61 @@ int implementation::detect_encodings(const char *input, size_t length) const noe
   uint64_t bits = 0;
   return b200_host_detect_encodings(input, length, &bits) == 0 ? int(bits) : 0;
 }
+
+#ifdef SIMDUTF_INTERNAL_TESTS
+// ---- internal_tests() (reference include/simdutf/implementation.h:5036; src/ppc64/implementation.cpp:898-913 is the
+// reference's own example: procedures abort() on failure).  Test-only code behind the reference's developer flag. ----
+namespace {
+void check(bool ok, const char *what) {
+  if (!ok) {
+    fprintf(stderr, "b200 internal test failed: %s (%s)\n", what, b200_last_error());
+    abort();
+  }
+}
+std::vector<char> mixed_text(size_t n) {  // valid UTF-8, 1-4-byte characters in rotation
+  static const char *const chars[4] = {"a", "\xC3\xA9", "\xE4\xB8\xAD", "\xF0\x9F\x98\x80"};
+  std::vector<char> v;
+  v.reserve(n + 4);
+  for (size_t i = 0; v.size() + 4 <= n; i++) {
+    const char *c = chars[(i * 7 + i / 5) & 3];
+    while (*c) v.push_back(*c++);
+  }
+  return v;
+}
+void host_path_over_all_devices(const simdutf::implementation &impl) {
+  const int ndev = b200_device_count();
+  const std::vector<char> text = mixed_text(size_t(96) << 20);
+  const size_t units = impl.utf16_length_from_utf8(text.data(), text.size());
+  std::vector<char16_t> one(units + 8, 0x5A5A), all(units + 8, 0x5A5A);
+  check(b200_host_set_devices(1) == 0, "set_devices(1)");
+  const result r1 = impl.convert_utf8_to_utf16le_with_errors(text.data(), text.size(), one.data());
+  check(b200_host_set_devices(ndev) == 0, "set_devices(all)");
+  const result rn = impl.convert_utf8_to_utf16le_with_errors(text.data(), text.size(), all.data());
+  check(impl.utf16_length_from_utf8(text.data(), text.size()) == units, "length over all devices");
+  b200_host_set_devices(1);
+  check(r1.error == SUCCESS && r1.count == units && rn.error == SUCCESS && rn.count == units, "result over all devices");
+  check(one == all && all[units] == 0x5A5A, "output over all devices equals output of one device");
+}
+void shard_helpers_and_combine(const simdutf::implementation &impl) {
+  std::vector<char> text = mixed_text(size_t(3) << 20);
+  text[(2u << 20) + 12345] = char(0xFF);
+  const result whole = impl.validate_utf8_with_errors(text.data(), text.size());
+  // cut in three at k*N/3 backed up with the trim helper, validate shard by shard, fold: first error in buffer order
+  size_t cuts[4] = {0, 0, 0, text.size()};
+  for (int k = 1; k < 3; k++) cuts[k] = b200_host_trim_partial_utf8(text.data(), text.size() * k / 3);
+  result folded(SUCCESS, text.size());
+  for (int k = 2; k >= 0; k--) {
+    const result r = impl.validate_utf8_with_errors(text.data() + cuts[k], cuts[k + 1] - cuts[k]);
+    if (r.error) folded = result(r.error, cuts[k] + r.count);
+  }
+  check(folded.error == whole.error && folded.count == whole.count && whole.error == HEADER_BITS, "sharded validate equals whole-buffer validate");
+}
+} // namespace
+std::vector<simdutf::implementation::TestProcedure> implementation::internal_tests() const {
+  return {TestProcedure{"b200_host_path_over_all_devices", host_path_over_all_devices},
+          TestProcedure{"b200_shard_helpers_and_combine", shard_helpers_and_combine}};
+}
+#endif // SIMDUTF_INTERNAL_TESTS
 
 // ---- anything the reference adds later: its "unsupported" answers (generated; empty against this reference) ----
 #include "b200_stubs.inc"

@@ -28,6 +28,12 @@ public:
   uint32_t required_instruction_sets() const override;
 
 #include "b200_decls.inc"
+
+#ifdef SIMDUTF_INTERNAL_TESTS
+  // Developer hook of the reference (include/simdutf/implementation.h:5016-5037, tests/internal_tests.cpp): what the
+  // public API cannot reach — the host path spread over every device, the per-thread host paths, the shard helpers.
+  std::vector<TestProcedure> internal_tests() const override;
+#endif
 };
 
 } // namespace b200

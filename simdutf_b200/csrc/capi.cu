@@ -330,7 +330,7 @@ int host_path(int device, HostPath **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h.s_back, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaHostAlloc(&h.h_slot, 64, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess) e = cudaHostAlloc(&h.h_comb, 64 * kMaxShards, cudaHostAllocPortable);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h.d_trip), (3 + 3 * kMaxShards + 4) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h.d_trip), 10 * kMaxShards * sizeof(unsigned long long));
     if (e != cudaSuccess) {
       h.release();
       return fail((int)e, "host path init");
@@ -1011,7 +1011,10 @@ int run_mgpu(Op op, const b200_shard *shards, int n, b200_sharded_result *h_resu
         B200_CUDA(g.enter(shards[i].device));
         for (int j = 0; j < n; j++) {
           if (j != i) B200_CUDA(cudaStreamWaitEvent(hp[i]->s_main, ev[j], 0));
-          B200_CUDA(cudaMemcpyPeerAsync(gathered_of(i) + 3 * j, shards[i].device, hp[j]->d_trip + 3 * j, shards[j].device, 24, hp[i]->s_main));
+          if (shards[i].device == shards[j].device)
+            B200_CUDA(cudaMemcpyAsync(gathered_of(i) + 3 * j, hp[j]->d_trip + 3 * j, 24, cudaMemcpyDeviceToDevice, hp[i]->s_main));
+          else
+            B200_CUDA(cudaMemcpyPeerAsync(gathered_of(i) + 3 * j, shards[i].device, hp[j]->d_trip + 3 * j, shards[j].device, 24, hp[i]->s_main));
         }
       }
     }

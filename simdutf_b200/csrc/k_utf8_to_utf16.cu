@@ -46,12 +46,12 @@ template <int K, bool W32>
 struct Geom {
   static constexpr uint32_t kRegionBytes = 32u * K;              // contiguous input bytes per lane
   static constexpr uint32_t kTileBytes = 32u * kRegionBytes;     // per warp
-  static constexpr uint32_t kCtaTileBytes = kWarpsPerCta * kTileBytes;
+  static constexpr uint32_t kCtaTileBytes = 7u * kTileBytes;           // kWorkers warp-tiles
   static constexpr uint32_t kVec = W32 ? 4u : 8u;                // output elements per 16-byte vector
   static constexpr uint32_t kUnitBytes = W32 ? 4u : 2u;
   // a warp emits at most one element per input byte, in front of which sit up to kVec-1 elements of alignment pad
   static constexpr uint32_t kStageBytes = ((kTileBytes + kVec) * kUnitBytes + 15u) & ~15u;
-  static constexpr uint32_t kSmemBytes = kWarpsPerCta * kStageBytes;
+  static constexpr uint32_t kSmemBytes = 7u * (kStageBytes + kTileBytes);  // per worker warp: staging + plane stash
 };
 
 __device__ __forceinline__ InView make_view16(const void *p, size_t len_bytes) {
@@ -165,7 +165,41 @@ __device__ __forceinline__ unsigned long long cta_lookback128(unsigned long long
 // K3: the single-pass bit-plane transcoder.
 // BE (UTF-16 only): big-endian units — the low and high byte planes of the unit trade places before the
 // transposition back (free), the ASCII paths put the byte into the upper half.
+//
+// Warp roles.  kWorkers = 7 worker warps transcode; warp 7 is the SCAN warp: it takes the tickets, publishes the CTA
+// aggregates, runs the look-backs and hands the tile offsets to the workers.  The workers are software-pipelined by one
+// tile: in iteration i they run pass 1 of tile i (planes, masks, counts), park the planes in a lane-private shared-
+// memory stash, and then run pass 2 of tile i-1, whose offset the scan warp resolved while they were busy.  Nobody
+// waits for a look-back: a chained scan makes tile t wait for the SLOWEST of its in-flight predecessors to publish,
+// and with ~590 CTAs in flight that straggler costs several microseconds per tile (measured: 1.2-1.5 ms per GiB with
+// the look-back on the workers' critical path, against ~0.9 for the transcoding itself); one tile of slack absorbs it.
+// Producer/consumer hand-offs use mbarriers in shared memory, never a CTA-wide barrier.
 // ---------------------------------------------------------------------------------------------
+constexpr int kWorkers = 7;
+constexpr int kScanWarp = kWorkers;
+// Hand-offs go through mbarrier objects in shared memory (one arrival releases any number of waiters, and waiters do not
+// wait for EACH OTHER the way the threads of a bar.sync do): a worker that is ahead never waits for a slower worker,
+// only for the scan warp's data.
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {  // release: this thread's earlier shared-memory writes are visible to waiters
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {  // acquire
+  uint32_t done;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <int K, int MINB, bool W32, bool BE>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_utf8_transcode_sp(const char *ptr, size_t len, typename std::conditional<W32, uint32_t, uint16_t>::type *out,
@@ -174,280 +208,351 @@ k_utf8_transcode_sp(const char *ptr, size_t len, typename std::conditional<W32, 
   using Gm = Geom<K, W32>;
   using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
   constexpr uint32_t kUB = Gm::kUnitBytes;
-  extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ uint32_t s_tot[2][kWarpsPerCta];
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_next;
+  extern __shared__ __align__(16) uint32_t smem[];  // [kWorkers staging buffers][kWorkers plane stashes]
+  __shared__ uint32_t s_tot[2][8];               // workers -> scan warp: the warp totals of tile i (slot i & 1)
+  __shared__ unsigned long long s_goff[2][8];    // scan warp -> workers: every worker's global output offset for tile i
+  __shared__ uint32_t s_ticket[2];               // scan warp -> workers: the CTA-tile of iteration i
+  __shared__ __align__(8) unsigned long long s_mbar[6];  // [0,1] ticket posted, [2,3] offsets posted, [4,5] totals in
   const InView in = make_view16(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(smem) + warp * Gm::kStageBytes;  // this warp's staging buffer
-  const bool poison = starts_with_continuation(in);
-  const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) / sizeof(OutT));
-  const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (see bpd::bump)
-
-  if (threadIdx.x == 0) s_next = atomicAdd(&scr->ticket, 1u);
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s_mbar);
+  if (threadIdx.x == 0) {
+    mbar_init(mb + 0, 1); mbar_init(mb + 8, 1);
+    mbar_init(mb + 16, 1); mbar_init(mb + 24, 1);
+    mbar_init(mb + 32, kWorkers); mbar_init(mb + 40, kWorkers);
+  }
   __syncthreads();
-  uint32_t ct = s_next;
 
-  for (uint32_t iter = 0; ct < num_cta_tiles; iter++) {
-    const uint32_t par = iter & 1u;
-    // the ticket of the NEXT tile: requested now, consumed after the scan, so its round trip hides behind pass 1
-    uint32_t next_ticket = 0;
-    if (threadIdx.x == 32) next_ticket = atomicAdd(&scr->ticket, 1u);
-
-    const uint32_t tile = ct * kWarpsPerCta + warp;
-    const bool active = tile < num_tiles;                                     // warp-uniform
-    const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;  // virtual byte offsets from in.base
-    const unsigned long long r0 = t0 + (unsigned long long)lane * Gm::kRegionBytes;
-    const bool interior = active && t0 >= in.vbeg + 16ull && t0 + Gm::kTileBytes + 16ull <= in.vend;
-    // ---- this lane's 32K contiguous bytes, the word before them and the byte after them ----
-    uint32_t B[K][8];
-    uint32_t pw = 0, nbyte = 0;
-    if (interior) {
-      const uint4 *gp = in.base + (r0 >> 4);
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        const uint4 v0 = __ldg(gp + 2 * j), v1 = __ldg(gp + 2 * j + 1);
-        B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
-        B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
-      }
-      pw = __ldg(reinterpret_cast<const uint32_t *>(in.base) + (r0 >> 2) - 1);
-      nbyte = __ldg(reinterpret_cast<const uint8_t *>(in.base) + r0 + Gm::kRegionBytes);
-    } else if (active) {
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        bool ins;
-        load_granule(in, (r0 >> 4) + 2ull * j, &B[j][0], ins);
-        load_granule(in, (r0 >> 4) + 2ull * j + 1ull, &B[j][4], ins);
-      }
-      pw = load_word_guarded(in, (long long)(r0 >> 2) - 1);
-      const unsigned long long np = r0 + Gm::kRegionBytes;
-      nbyte = (np >= in.vbeg && np < in.vend) ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(in.base) + np) : 0u;
-    } else {
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) B[j][i] = 0u;
-      }
+  if (warp == kScanWarp) {
+    // ================================ scan warp ================================
+    // Slot / phase discipline: the barrier of slot p = i & 1 completes its (i >> 1)-th phase for iteration i.  Nobody
+    // can be two phases behind: the scan warp posts ticket i+2 only after every worker has delivered the totals of
+    // tile i+1, i.e. has long consumed ticket i and offsets i-1.
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&scr->ticket, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if (lane == 0) {
+      s_ticket[0] = t;
+      mbar_arrive(mb + 0);
     }
-
-    // ---- pass 1: planes, emit masks, counts ----
-    uint32_t hi = pw;
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) hi |= B[j][i];
-    }
-    const bool ascii_tile = !__any_sync(kFull, (hi & kH) != 0u);
-    uint32_t em[K];
-    uint32_t cnt = 0;
-    if (!ascii_tile) {
-      uint32_t prev_l4;
-      {
-        uint32_t v[8];
-        bp::planes_of_tail_word(pw, v);
-        prev_l4 = v[7] & v[6] & v[5] & v[4];
+    for (uint32_t iter = 0; t < num_cta_tiles; iter++) {
+      const uint32_t par = iter & 1u, ph = (iter >> 1) & 1u;
+      mbar_wait(mb + 32 + 8 * par, ph);  // the workers' totals of tile t
+      // reserve the next tile NOW: the workers pick it up a whole pass 2 later, so the ticket's round trip and the L2
+      // prefetch of exactly that tile are off their critical path
+      uint32_t tn = 0;
+      if (lane == 0) tn = atomicAdd(&scr->ticket, 1u);
+      tn = __shfl_sync(kFull, tn, 0);
+      if (lane == 0) {
+        s_ticket[par ^ 1u] = tn;
+        mbar_arrive(mb + 8 * (par ^ 1u));
       }
+      if (tn < num_cta_tiles) {
+        const char *nx = reinterpret_cast<const char *>(in.base) + (unsigned long long)tn * Gm::kCtaTileBytes;
 #pragma unroll
-      for (int j = 0; j < K; j++) {
-        const uint32_t nb = (j + 1 < K) ? B[(j + 1 < K) ? j + 1 : j][0] : nbyte;  // read BEFORE block j+1 is transposed
-        const uint32_t next_nc = ((nb & 0xC0u) != 0x80u) ? 1u : 0u;
-        bp::transpose_in(B[j]);
-        uint32_t m = W32 ? bp::emit32_mask(B[j], next_nc) : bp::emit16_mask(B[j], prev_l4, next_nc);
-        prev_l4 = B[j][7] & B[j][6] & B[j][5] & B[j][4];
-        if (!interior) m &= range_mask32(in, r0 + 32ull * j);
-        if (poison) m = 0;
-        em[j] = m;
-        cnt += (uint32_t)__popc(m);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        uint32_t m = active ? 0xFFFFFFFFu : 0u;
-        if (!interior && active) m &= range_mask32(in, r0 + 32ull * j);
-        if (poison) m = 0;
-        em[j] = m;
-        cnt += (uint32_t)__popc(m);
-      }
-    }
-    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
-    const uint32_t wtot = __shfl_sync(kFull, incl, 31);
-    if (lane == 0) s_tot[par][warp] = wtot;
-    if (threadIdx.x == 32) s_next = next_ticket;
-    __syncthreads();  // (A) warp totals and the next ticket are in shared memory
-
-    // ---- scan: the tile's global output offset ----
-    if (warp == 0) {
-      const uint32_t agg = __reduce_add_sync(kFull, lane < (unsigned)kWarpsPerCta ? s_tot[par][lane] : 0u);
-      const unsigned long long excl = cta_lookback128(desc, epoch, ct, agg, scr);
-      if (lane == 0) s_base = excl;
-    }
-    __syncthreads();  // (B)
-    const uint32_t next_ct = s_next;
-    unsigned long long goff = s_base;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerCta; w++)
-      if ((unsigned)w < warp) goff += s_tot[par][w];
-    if (next_ct < num_cta_tiles) {  // pull the next tile into L2 while this one is transcoded
-      const char *nx = reinterpret_cast<const char *>(in.base) + (unsigned long long)next_ct * Gm::kCtaTileBytes +
-                       (unsigned long long)threadIdx.x * Gm::kRegionBytes;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-    }
-    ct = next_ct;
-    if (!active || wtot == 0u) continue;  // warp-uniform: nothing to emit (no errors either: an empty tile has no bytes,
-                                          // and a tile that emits nothing is poisoned or all-out-of-range)
-
-    const uint32_t a_w = (uint32_t)((out_units + goff) & (Gm::kVec - 1u));  // offset of the tile inside a 16-byte output vector
-    const uint32_t excl_lane = incl - cnt;
-    uint32_t badblocks = 0;
-
-    // ---- pass 2: units, compaction into the warp's staging buffer ----
-    // The running store address lives in a 32-bit shared-space register; it advances through the multiplier
-    // (`one` * 2 + address) and the upper unit of a word is extracted with IMAD.HI, so that the compaction costs
-    // the ALU pipe nothing but the predicate extraction.
-    if (!ascii_tile) {
-      bp::Carry carry = bp::carry_from_word(pw);
-      uint32_t spa = stage_addr + kUB * (a_w + excl_lane);
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        // four independent store chains (positions 0-7, 8-15, 16-23, 24-31): a chain's address register can
-        // only advance once the store before it has read it, so one chain alone would serialise the block
-        const uint32_t m = em[j];
-        uint32_t s0 = spa;
-        uint32_t s1 = spa + kUB * (uint32_t)__popc(m & 0xFFu);
-        uint32_t s2 = spa + kUB * (uint32_t)__popc(m & 0xFFFFu);
-        uint32_t s3 = spa + kUB * (uint32_t)__popc(m & 0xFFFFFFu);
-        spa += kUB * (uint32_t)__popc(m);
-        if (W32) {
-          uint32_t C[32];
-          const uint32_t err = bp::utf8_to_utf32_block<true>(B[j], carry, C);
-          if (err) badblocks |= 1u << j;
-          bp::transpose_out21(C);
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            if (m & (1u << i)) {
-              sts_u32(s0, C[i]);
-              s0 = bpd::bump<4>(s0, one);
-            }
-            if (m & (1u << (8 + i))) {
-              sts_u32(s1, C[8 + i]);
-              s1 = bpd::bump<4>(s1, one);
-            }
-            if (m & (1u << (16 + i))) {
-              sts_u32(s2, C[16 + i]);
-              s2 = bpd::bump<4>(s2, one);
-            }
-            if (m & (1u << (24 + i))) {
-              sts_u32(s3, C[24 + i]);
-              s3 = bpd::bump<4>(s3, one);
-            }
-          }
-        } else {
-          uint32_t U[16];
-          const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
-          if (err) badblocks |= 1u << j;
-          if (BE) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const uint32_t t = U[k];
-              U[k] = U[k + 8];
-              U[k + 8] = t;
-            }
-          }
-          bp::transpose_out16(U);
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            if (m & (1u << i)) {
-              sts_u16(s0, U[i]);
-              s0 = bpd::bump<2>(s0, one);
-            }
-            if (m & (1u << (8 + i))) {
-              sts_u16(s1, U[8 + i]);
-              s1 = bpd::bump<2>(s1, one);
-            }
-            if (m & (1u << (16 + i))) {
-              sts_u16(s2, __umulhi(U[i], 65536u));
-              s2 = bpd::bump<2>(s2, one);
-            }
-            if (m & (1u << (24 + i))) {
-              sts_u16(s3, __umulhi(U[8 + i], 65536u));
-              s3 = bpd::bump<2>(s3, one);
-            }
-          }
+        for (uint32_t k = 0; k < (Gm::kCtaTileBytes + 4095u) / 4096u; k++) {
+          const uint32_t off = k * 4096u + lane * 128u;
+          if (off < Gm::kCtaTileBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
         }
       }
-    } else {
-      if (interior && !poison && a_w == 0u) {
-        // every lane emits exactly 32K elements and the tile's output is vector-aligned: widen in registers and store
-        // straight to global memory (nothing staged, no errors possible in an all-ASCII interior tile)
-        uint4 *gv = reinterpret_cast<uint4 *>(out + goff + excl_lane);
+      const uint32_t mine = lane < (unsigned)kWorkers ? s_tot[par][lane] : 0u;
+      const uint32_t incl = bpd::warp_inclusive_u32(mine);
+      const uint32_t agg = __shfl_sync(kFull, incl, 31);
+      const unsigned long long excl = cta_lookback128(desc, epoch, t, agg, scr);
+      if (lane < (unsigned)kWorkers) s_goff[par][lane] = excl + (incl - mine);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mb + 16 + 8 * par);
+      t = tn;
+    }
+  } else {
+    // ================================ workers ================================
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(smem) + warp * Gm::kStageBytes;
+    const OutT *stage = reinterpret_cast<const OutT *>(smem) + (size_t)warp * (Gm::kStageBytes / kUB);
+    const uint32_t stash_addr = (uint32_t)__cvta_generic_to_shared(smem) + kWorkers * Gm::kStageBytes + warp * Gm::kTileBytes + lane * 16u;
+    const bool poison = starts_with_continuation(in);
+    const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) / sizeof(OutT));
+    const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (see bpd::bump)
+
+    // the tile whose pass 2 is pending (per-lane: masks, lane offset, word before the region; warp-uniform: the rest)
+    bool have_prev = false;
+    uint32_t p_em[K], p_excl = 0, p_pw = 0, p_tile = 0, p_wtot = 0, p_par = 0, p_ph = 0;
+    bool p_ascii = false, p_interior = false, p_active = false;
+#pragma unroll
+    for (int j = 0; j < K; j++) p_em[j] = 0;
+
+    for (uint32_t iter = 0;; iter++) {
+      const uint32_t par = iter & 1u, ph = (iter >> 1) & 1u;
+      mbar_wait(mb + 8 * par, ph);
+      const uint32_t ct = s_ticket[par];
+      const bool more = ct < num_cta_tiles;  // CTA-uniform
+      uint32_t B[K][8];
+      uint32_t c_em[K], c_excl = 0, c_pw = 0, c_wtot = 0;
+      bool c_ascii = false, c_interior = false, c_active = false;
+      const uint32_t tile = ct * kWorkers + warp;
+      if (more) {
+        c_active = tile < num_tiles;                                               // warp-uniform
+        const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;   // virtual byte offsets from in.base
+        const unsigned long long r0 = t0 + (unsigned long long)lane * Gm::kRegionBytes;
+        c_interior = c_active && t0 >= in.vbeg + 16ull && t0 + Gm::kTileBytes + 16ull <= in.vend;
+        // ---- this lane's 32K contiguous bytes, the word before them and the byte after them ----
+        uint32_t nbyte = 0;
+        if (c_interior) {
+          const uint4 *gp = in.base + (r0 >> 4);
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            const uint4 v0 = __ldg(gp + 2 * j), v1 = __ldg(gp + 2 * j + 1);
+            B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
+            B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
+          }
+          c_pw = __ldg(reinterpret_cast<const uint32_t *>(in.base) + (r0 >> 2) - 1);
+          nbyte = __ldg(reinterpret_cast<const uint8_t *>(in.base) + r0 + Gm::kRegionBytes);
+        } else if (c_active) {
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            bool ins;
+            load_granule(in, (r0 >> 4) + 2ull * j, &B[j][0], ins);
+            load_granule(in, (r0 >> 4) + 2ull * j + 1ull, &B[j][4], ins);
+          }
+          c_pw = load_word_guarded(in, (long long)(r0 >> 2) - 1);
+          const unsigned long long np = r0 + Gm::kRegionBytes;
+          nbyte = (np >= in.vbeg && np < in.vend) ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(in.base) + np) : 0u;
+        } else {
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) B[j][i] = 0u;
+          }
+        }
+        // ---- pass 1: planes, emit masks, counts ----
+        uint32_t hi = c_pw;
 #pragma unroll
         for (int j = 0; j < K; j++) {
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const uint32_t w = B[j][k];
-            if (W32) {
-              stg_stream_v4(gv + 8 * j + k, make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24));
-            } else if ((k & 1) == 0) {
-              const uint32_t w1 = B[j][k + 1];
-              constexpr uint32_t s01 = BE ? 0x1404u : 0x4140u, s23 = BE ? 0x3424u : 0x4342u;
-              stg_stream_v4(gv + 4 * j + (k >> 1), make_uint4(__byte_perm(w, 0u, s01), __byte_perm(w, 0u, s23),
-                                                               __byte_perm(w1, 0u, s01), __byte_perm(w1, 0u, s23)));
-            }
+          for (int i = 0; i < 8; i++) hi |= B[j][i];
+        }
+        c_ascii = !__any_sync(kFull, (hi & kH) != 0u);
+        uint32_t cnt = 0;
+        if (!c_ascii) {
+          uint32_t prev_l4;
+          {
+            uint32_t v[8];
+            bp::planes_of_tail_word(c_pw, v);
+            prev_l4 = v[7] & v[6] & v[5] & v[4];
+          }
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            const uint32_t nb = (j + 1 < K) ? B[(j + 1 < K) ? j + 1 : j][0] : nbyte;  // read BEFORE block j+1 is transposed
+            const uint32_t next_nc = ((nb & 0xC0u) != 0x80u) ? 1u : 0u;
+            bp::transpose_in(B[j]);
+            uint32_t m = W32 ? bp::emit32_mask(B[j], next_nc) : bp::emit16_mask(B[j], prev_l4, next_nc);
+            prev_l4 = B[j][7] & B[j][6] & B[j][5] & B[j][4];
+            if (!c_interior) m &= range_mask32(in, r0 + 32ull * j);
+            if (poison) m = 0;
+            c_em[j] = m;
+            cnt += (uint32_t)__popc(m);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            uint32_t m = c_active ? 0xFFFFFFFFu : 0u;
+            if (!c_interior && c_active) m &= range_mask32(in, r0 + 32ull * j);
+            if (poison) m = 0;
+            c_em[j] = m;
+            cnt += (uint32_t)__popc(m);
           }
         }
-        continue;  // warp-uniform
-      }
-      uint32_t spa = stage_addr + kUB * (a_w + excl_lane);
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        const uint32_t m = em[j];
-#pragma unroll
-        for (int p = 0; p < 32; p++) {
-          if (m & (1u << p)) {
-            const uint32_t byte = (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu;
-            if (W32) {
-              sts_u32(spa, byte);
-              spa = bpd::bump<4>(spa, one);
-            } else {
-              sts_u16(spa, BE ? byte << 8 : byte);
-              spa = bpd::bump<2>(spa, one);
-            }
-          }
+        const uint32_t incl = bpd::warp_inclusive_u32(cnt);
+        c_wtot = __shfl_sync(kFull, incl, 31);
+        c_excl = incl - cnt;
+        if (lane == 0) {
+          s_tot[par][warp] = c_wtot;
+          mbar_arrive(mb + 32 + 8 * par);
         }
-      }
-    }
-    // ---- exact error location (rare): the detector only says "in this block or the 3 bytes before it" ----
-    if (!interior) {
+      } else {
 #pragma unroll
-      for (int j = 0; j < K; j++) {
-        const unsigned long long b0 = r0 + 32ull * j;
-        if (b0 < in.vend && in.vend <= b0 + 32ull && tail_truncated16(in)) badblocks |= 1u << j;
+        for (int j = 0; j < K; j++) c_em[j] = 0;
       }
-    }
-    if (badblocks) {
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        const long long b0 = (long long)(r0 + 32ull * j);
-        if (badblocks & (1u << j)) u8_locate_error(in, scr, b0 - 3, b0 + 32);
-      }
-    }
-    __syncwarp();
 
-    // ---- staging -> global: the warp's elements [a_w, a_w + wtot) of the staging buffer go to out[goff ...] ----
-    {
-      OutT *gbase = out + goff - a_w;  // 16-byte aligned
-      const uint32_t end = a_w + wtot;
-      const uint32_t v0 = a_w ? 1u : 0u, v1 = end / Gm::kVec;
-      const uint32_t head_end = a_w ? (end < Gm::kVec ? end : Gm::kVec) : 0u;
-      for (uint32_t v = v0 + lane; v < v1; v += 32u)
-        stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, lds_v4(stage_addr + 16u * v));
-      const OutT *stage = reinterpret_cast<const OutT *>(smem) + (size_t)warp * (Gm::kStageBytes / kUB);
-      if (lane >= a_w && lane < head_end) gbase[lane] = stage[lane];  // first partial vector (shared with the previous tile)
-      const uint32_t ti = v1 * Gm::kVec + lane;                        // last partial vector (shared with the next tile)
-      if (lane < Gm::kVec && ti >= head_end && ti < end) gbase[ti] = stage[ti];
+      // ---- the planes of tile i go to the stash, those of tile i-1 come back ----
+      if (more || have_prev) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+          if (have_prev) {
+            v0 = lds_v4(stash_addr + (2u * j) * 512u);
+            v1 = lds_v4(stash_addr + (2u * j + 1u) * 512u);
+          }
+          if (more) {
+            sts_v4(stash_addr + (2u * j) * 512u, B[j][0], B[j][1], B[j][2], B[j][3]);
+            sts_v4(stash_addr + (2u * j + 1u) * 512u, B[j][4], B[j][5], B[j][6], B[j][7]);
+          }
+          B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
+          B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
+        }
+      }
+
+      if (have_prev) {
+        // ---- pass 2 of the pending tile ----
+        mbar_wait(mb + 16 + 8 * p_par, p_ph);
+        const unsigned long long goff = s_goff[p_par][warp];
+        const unsigned long long r0 = (unsigned long long)p_tile * Gm::kTileBytes + (unsigned long long)lane * Gm::kRegionBytes;
+        const uint32_t a_w = (uint32_t)((out_units + goff) & (Gm::kVec - 1u));  // offset of the tile inside a 16-byte output vector
+        uint32_t badblocks = 0;
+        bool staged = false;
+        if (p_active) {
+          // The running store address lives in a 32-bit shared-space register; it advances through the multiplier
+          // (`one` * 2 + address) and the upper unit of a word is extracted with IMAD.HI, so that the compaction
+          // costs the ALU pipe nothing but the predicate extraction.
+          if (!p_ascii) {
+            staged = true;
+            bp::Carry carry = bp::carry_from_word(p_pw);
+            uint32_t spa = stage_addr + kUB * (a_w + p_excl);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              // four independent store chains (positions 0-7, 8-15, 16-23, 24-31): a chain's address register can
+              // only advance once the store before it has read it, so one chain alone would serialise the block
+              const uint32_t m = p_em[j];
+              uint32_t s0 = spa;
+              uint32_t s1 = spa + kUB * (uint32_t)__popc(m & 0xFFu);
+              uint32_t s2 = spa + kUB * (uint32_t)__popc(m & 0xFFFFu);
+              uint32_t s3 = spa + kUB * (uint32_t)__popc(m & 0xFFFFFFu);
+              spa += kUB * (uint32_t)__popc(m);
+              if (W32) {
+                uint32_t C[32];
+                const uint32_t err = bp::utf8_to_utf32_block<true>(B[j], carry, C);
+                if (err) badblocks |= 1u << j;
+                bp::transpose_out21(C);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                  if (m & (1u << i)) {
+                    sts_u32(s0, C[i]);
+                    s0 = bpd::bump<4>(s0, one);
+                  }
+                  if (m & (1u << (8 + i))) {
+                    sts_u32(s1, C[8 + i]);
+                    s1 = bpd::bump<4>(s1, one);
+                  }
+                  if (m & (1u << (16 + i))) {
+                    sts_u32(s2, C[16 + i]);
+                    s2 = bpd::bump<4>(s2, one);
+                  }
+                  if (m & (1u << (24 + i))) {
+                    sts_u32(s3, C[24 + i]);
+                    s3 = bpd::bump<4>(s3, one);
+                  }
+                }
+              } else {
+                uint32_t U[16];
+                const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
+                if (err) badblocks |= 1u << j;
+                if (BE) {
+#pragma unroll
+                  for (int k = 0; k < 8; k++) {
+                    const uint32_t t = U[k];
+                    U[k] = U[k + 8];
+                    U[k + 8] = t;
+                  }
+                }
+                bp::transpose_out16(U);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                  if (m & (1u << i)) {
+                    sts_u16(s0, U[i]);
+                    s0 = bpd::bump<2>(s0, one);
+                  }
+                  if (m & (1u << (8 + i))) {
+                    sts_u16(s1, U[8 + i]);
+                    s1 = bpd::bump<2>(s1, one);
+                  }
+                  if (m & (1u << (16 + i))) {
+                    sts_u16(s2, __umulhi(U[i], 65536u));
+                    s2 = bpd::bump<2>(s2, one);
+                  }
+                  if (m & (1u << (24 + i))) {
+                    sts_u16(s3, __umulhi(U[8 + i], 65536u));
+                    s3 = bpd::bump<2>(s3, one);
+                  }
+                }
+              }
+            }
+          } else if (p_interior && !poison && a_w == 0u) {
+            // every lane emits exactly 32K elements and the tile's output is vector-aligned: widen in registers and
+            // store straight to global memory (nothing staged, no errors possible in an all-ASCII interior tile)
+            uint4 *gv = reinterpret_cast<uint4 *>(out + goff + p_excl);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                const uint32_t w = B[j][k];
+                if (W32) {
+                  stg_stream_v4(gv + 8 * j + k, make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24));
+                } else if ((k & 1) == 0) {
+                  const uint32_t w1 = B[j][k + 1];
+                  constexpr uint32_t s01 = BE ? 0x1404u : 0x4140u, s23 = BE ? 0x3424u : 0x4342u;
+                  stg_stream_v4(gv + 4 * j + (k >> 1), make_uint4(__byte_perm(w, 0u, s01), __byte_perm(w, 0u, s23),
+                                                                   __byte_perm(w1, 0u, s01), __byte_perm(w1, 0u, s23)));
+                }
+              }
+            }
+          } else {
+            staged = true;
+            uint32_t spa = stage_addr + kUB * (a_w + p_excl);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const uint32_t m = p_em[j];
+#pragma unroll
+              for (int p = 0; p < 32; p++) {
+                if (m & (1u << p)) {
+                  const uint32_t byte = (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu;
+                  if (W32) {
+                    sts_u32(spa, byte);
+                    spa = bpd::bump<4>(spa, one);
+                  } else {
+                    sts_u16(spa, BE ? byte << 8 : byte);
+                    spa = bpd::bump<2>(spa, one);
+                  }
+                }
+              }
+            }
+          }
+          // ---- exact error location (rare): the detector only says "in this block or the 3 bytes before it" ----
+          if (!p_interior) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const unsigned long long b0 = r0 + 32ull * j;
+              if (b0 < in.vend && in.vend <= b0 + 32ull && tail_truncated16(in)) badblocks |= 1u << j;
+            }
+          }
+          if (badblocks) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const long long b0 = (long long)(r0 + 32ull * j);
+              if (badblocks & (1u << j)) u8_locate_error(in, scr, b0 - 3, b0 + 32);
+            }
+          }
+        }
+        __syncwarp();
+        // ---- staging -> global: the warp's elements [a_w, a_w + wtot) of the staging buffer go to out[goff ...] ----
+        if (staged && p_wtot) {
+          OutT *gbase = out + goff - a_w;  // 16-byte aligned
+          const uint32_t end = a_w + p_wtot;
+          const uint32_t v0 = a_w ? 1u : 0u, v1 = end / Gm::kVec;
+          const uint32_t head_end = a_w ? (end < Gm::kVec ? end : Gm::kVec) : 0u;
+          for (uint32_t v = v0 + lane; v < v1; v += 32u)
+            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, lds_v4(stage_addr + 16u * v));
+          if (lane >= a_w && lane < head_end) gbase[lane] = stage[lane];  // first partial vector (shared with the previous tile)
+          const uint32_t ti = v1 * Gm::kVec + lane;                        // last partial vector (shared with the next tile)
+          if (lane < Gm::kVec && ti >= head_end && ti < end) gbase[ti] = stage[ti];
+        }
+        __syncwarp();  // the staging buffer is rewritten by the next tile
+      }
+      if (!more) break;
+      have_prev = true;
+#pragma unroll
+      for (int j = 0; j < K; j++) p_em[j] = c_em[j];
+      p_excl = c_excl; p_pw = c_pw; p_tile = tile; p_wtot = c_wtot; p_par = par; p_ph = ph;
+      p_ascii = c_ascii; p_interior = c_interior; p_active = c_active;
     }
-    __syncwarp();  // the staging buffer is rewritten by the next tile
   }
 
   if (grid_last_thread(scr)) {
@@ -462,7 +567,7 @@ inline size_t tiles_for(const void *in, size_t len_bytes, int k) {
   const size_t per_tile = (size_t)1024 * k;
   return (span + per_tile - 1) / per_tile;
 }
-inline size_t cta_tiles_for(size_t tiles) { return (tiles + kWarpsPerCta - 1) / kWarpsPerCta; }
+inline size_t cta_tiles_for(size_t tiles) { return (tiles + kWorkers - 1) / kWorkers; }
 
 template <int K, int MINB, bool W32, bool BE>
 cudaError_t launch_sp(const LaunchCtx &c, const char *in, size_t len, void *out, void *res) {

@@ -45,7 +45,15 @@ HOT = [
     "bele_tests",
     # SURVEY.md §8f rank 4
     "to_well_formed_utf16_tests", "detect_encodings_tests",
+    # whole-API binaries: null / empty arguments, the differential fuzzers (random_fuzzer walks EVERY supported
+    # implementation, b200 included, and compares them), round trips over every family, the README's examples, the
+    # std::span and atomic-ref front ends (free functions: routed to b200 with SIMDUTF_FORCE_IMPLEMENTATION, reference
+    # src/implementation.cpp:1294-1305), and the internal_tests() hook (simdutf::b200::implementation provides two)
+    "null_safety_tests", "random_fuzzer", "basic_fuzzer", "special_tests", "readme_tests", "span_tests",
+    "atomic_base64_tests", "internal_tests",
 ]
+# what a passing run must print besides exiting 0 (default: the harness's "OK")
+MARKER = {"select_implementation": None, "random_fuzzer": "testing: b200", "internal_tests": "b200_host_path_over_all_devices"}
 
 # Green as well, but made of 10^6..10^8 calls on <= 256-byte inputs (a CPU does those in nanoseconds, a host-path call
 # costs ~30-60 us): minutes to half an hour each on the GPU box.  Run with B200_SLOW_TESTS=1.  Measured on a B200:
@@ -64,9 +72,11 @@ def test_reference_binary_with_b200(name):
     exe = os.path.join(D, name)
     if not os.path.exists(exe):
         pytest.skip("reference test binaries were not built (no /root/reference at build time)")
-    p = subprocess.run([exe, "-a", "b200"], capture_output=True, text=True, timeout=3000 if name in SLOW else 600)
+    env = dict(os.environ, SIMDUTF_FORCE_IMPLEMENTATION="b200")  # free functions (simdutf::validate_utf8, ...) use b200 too
+    p = subprocess.run([exe, "-a", "b200"], capture_output=True, text=True, timeout=3000 if name in SLOW else 600, env=env)
     out = p.stdout + p.stderr
     assert "unsupported by the current processor" not in out, "b200 reported itself unsupported on a GPU box"
     assert p.returncode == 0, out[-3000:]
-    if name != "select_implementation":
-        assert "OK" in out
+    marker = MARKER.get(name, "OK")
+    if marker is not None:
+        assert marker in out, out[-3000:]

@@ -11,10 +11,11 @@ Writes into <out_dir>:
                        "unsupported" values as the reference's unsupported_implementation
                        (src/implementation.cpp:792-1253): 0 / false / result(OTHER, 0).  (No CPU fallback is
                        allowed inside the b200 implementation, so forwarding to another kernel is not an option.)
-  implementation_b200.cpp   the reference's src/implementation.cpp with three insertions: the b200 header, a
-                       get_b200_singleton(), and one list entry AFTER the fallback singleton (so automatic
+  implementation_b200.cpp   the reference's src/implementation.cpp with four insertions: the b200 header, a
+                       get_b200_singleton(), one list entry AFTER the fallback singleton (so automatic
                        detection never picks it; it is selected by name, by assigning
-                       get_active_implementation(), or with SIMDUTF_FORCE_IMPLEMENTATION=b200).
+                       get_active_implementation(), or with SIMDUTF_FORCE_IMPLEMENTATION=b200), and the
+                       SIMDUTF_IMPLEMENTATION_B200 term in the SIMDUTF_SINGLE_IMPLEMENTATION sum.
   simdutf_b200_unity.cpp    the reference's unity TU src/simdutf.cpp with its `#include "implementation.cpp"`
                        redirected to the file above.
 """
@@ -135,6 +136,12 @@ impl = impl.replace(anchor1, '''static const b200::implementation *get_b200_sing
 }
 ''' + anchor1)
 impl = impl.replace(anchor2, anchor2 + "          get_b200_singleton(),\n")
+# SIMDUTF_SINGLE_IMPLEMENTATION (reference src/implementation.cpp:107-112, SURVEY gotcha G3): with exactly one CPU kernel
+# compiled in, the free functions bypass the active-implementation pointer and b200 could never be selected; count it.
+anchor3 = "SIMDUTF_IMPLEMENTATION_LASX + SIMDUTF_IMPLEMENTATION_FALLBACK =="
+assert impl.count(anchor3) == 1, "reference SIMDUTF_SINGLE_IMPLEMENTATION layout changed"
+impl = impl.replace(anchor3, "SIMDUTF_IMPLEMENTATION_LASX + SIMDUTF_IMPLEMENTATION_FALLBACK + SIMDUTF_IMPLEMENTATION_B200 ==")
+impl = "#ifndef SIMDUTF_IMPLEMENTATION_B200\n#define SIMDUTF_IMPLEMENTATION_B200 1\n#endif\n" + impl
 impl = '#include "b200_implementation.h"\n' + impl
 open(os.path.join(out, "implementation_b200.cpp"), "w").write(impl)
 

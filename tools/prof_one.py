@@ -19,6 +19,9 @@ nbytes = int(sys.argv[2]) if len(sys.argv) > 2 else 256 << 20
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 lib = b.load()
 b.set_device(0)
+for kv in filter(None, os.environ.get("B200_BENCH_TUNE", "").split(",")):  # experiments: "conv_minb=4"
+    k, v = kv.split("=")
+    b.set_tuning(k, int(v))
 dev = torch.device("cuda", 0)
 sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 res = torch.zeros(4, dtype=torch.int64, device=dev)
