@@ -1249,8 +1249,8 @@ int b200_host_set_devices(int n) {
 }
 int b200_host_get_devices(void) { return tl_host_devices; }
 int b200_set_tuning(const char *name, int value) {
-  static const char *const names[] = {"conv_minb", "segment_mb", "no_nccl"};
-  for (int k = 0; k < 3; k++) {
+  static const char *const names[] = {"conv_minb", "segment_mb", "no_nccl", "conv_variant", "conv_stagger", "dbg_lo", "dbg_hi"};
+  for (int k = 0; k < 7; k++) {
     if (name && std::strcmp(name, names[k]) == 0) {
       g_tuning[k].store(value, std::memory_order_relaxed);
       return 0;

@@ -19,6 +19,10 @@ def text(kind):
         cps = rng.integers(0x20, 0x7F, N)
     elif kind == "ascii+5%latin":
         cps = np.where(rng.random(N) < 0.05, rng.integers(0xC0, 0x180, N), rng.integers(0x20, 0x7F, N))
+    elif kind == "ascii+0.5%latin":
+        cps = np.where(rng.random(N) < 0.005, rng.integers(0xC0, 0x180, N), rng.integers(0x20, 0x7F, N))
+    elif kind == "pure cyrillic":
+        cps = rng.integers(0x410, 0x450, N)
     elif kind == "cyrillic words":
         cps = np.where(rng.random(N) < 0.15, 0x20, rng.integers(0x410, 0x450, N))
     elif kind == "cjk":
@@ -38,7 +42,7 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-for kind in ("ascii", "ascii+5%latin", "cyrillic words", "cjk", "emoji"):
+for kind in ("ascii", "ascii+0.5%latin", "ascii+5%latin", "pure cyrillic", "cyrillic words", "cjk", "emoji"):
     d = text(kind); n = d.numel(); p = ctypes.c_void_p(d.data_ptr())
     units = b.utf16_length_from_utf8(d)
     o = torch.empty(units, dtype=torch.int16, device=dev); op = ctypes.c_void_p(o.data_ptr())
