@@ -137,7 +137,7 @@ def build_reference_integration(ref: str = "/root/reference", tests: bool = True
            "-I" + os.path.join(ROOT, "include")]
     if not _newer(lib, srcs + [LIB]):
         _run([sys.executable, gen, ref, WITH_B200])
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DSIMDUTF_INTERNAL_TESTS", "-o", lib] + inc +
+        _run(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-DSIMDUTF_INTERNAL_TESTS", "-o", lib] + inc +
              [os.path.join(WITH_B200, "simdutf_b200_unity.cpp"), os.path.join(CSRC, "b200_implementation.cpp"),
               "-L" + PKG, "-lsimdutf_b200", "-Wl,-rpath,$ORIGIN/../.."])
         # the two patched translation units are derived from reference sources: they exist only for this compile
@@ -155,7 +155,7 @@ def build_reference_integration(ref: str = "/root/reference", tests: bool = True
         def cc(job):
             src, obj = job
             if not _newer(obj, [src]):
-                _run(["g++", "-O2", "-std=c++17", "-c", src, "-o", obj] + tinc)
+                _run(["g++", "-O2", "-std=c++20", "-c", src, "-o", obj] + tinc)
 
         with ThreadPoolExecutor(max_workers=8) as ex:
             list(ex.map(cc, zip(helpers, hobjs)))
@@ -174,7 +174,7 @@ def build_reference_integration(ref: str = "/root/reference", tests: bool = True
             exe = os.path.join(WITH_B200, name)
             src = os.path.join(ref, "tests", name + ".cpp")
             if not _newer(exe, [src, lib]):
-                _run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, src] + arch + tinc +
+                _run(["g++", "-O2", "-std=c++20", "-pthread", "-o", exe, src] + arch + tinc +
                      ["-L" + WITH_B200, "-lsimdutf_with_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../.."])
 
         with ThreadPoolExecutor(max_workers=8) as ex:

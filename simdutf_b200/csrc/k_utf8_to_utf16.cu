@@ -3,25 +3,23 @@
 // src/scalar/utf8_to_utf32/utf8_to_utf32.h:106-212).
 //
 // ONE launch, the input crosses HBM once (round 1 shipped a counts kernel + a transcoding kernel: the text was read
-// twice, which capped the roofline fraction at 2/3).  A persistent grid hands out CTA-tiles (8 warps x 32 lanes x K
-// blocks x 32 contiguous bytes = 16 KiB for K = 2) in increasing order through an atomic ticket.  Per CTA-tile:
+// twice, which capped the roofline fraction at 2/3).  A persistent grid of CTAs of NW worker warps + one scan warp
+// takes CTA-tiles (NW warp-tiles of 32 lanes x K blocks x 32 contiguous bytes) in increasing order through an atomic
+// ticket.  Per warp-tile:
 //
-//   pass 1   every lane loads its 32K contiguous bytes, transposes each 32-byte block into 8 BIT PLANES (bitplane.h)
-//            and derives the block's emit mask; popcounts -> lane count -> warp inclusive scan -> warp total.
-//   scan     the eight warp totals meet in shared memory; warp 0 publishes the CTA aggregate and resolves the tile's
-//            global output offset with a decoupled look-back over epoch-tagged descriptors.  The look-back window is
-//            128 descriptors per round (4 per lane): with ~450 CTAs in flight a tile's inclusive prefix appears
-//            about one L2 round trip after its aggregate, i.e. 50-90 tiles behind the newest ticket, so a 32-wide
-//            window needs several dependent rounds and never catches up (round 1's experiment stalled 56-86 % of
-//            its samples there), while a 128-wide window finishes in one.
+//   pass 1   every lane loads its 32K contiguous bytes (one 256-bit load per block), transposes each 32-byte block into
+//            8 BIT PLANES (bitplane.h) and derives the block's emit mask; popcounts -> lane count -> warp inclusive scan
+//            -> warp total, handed to the scan warp.
 //   pass 2   bp::utf8_to_utf16_block (validation detector + the 16 planes of the candidate unit of all 32
 //            positions, ~75 bitwise instructions per block), transposition back to 16-bit units, compaction with
-//            predicated 16-bit shared stores into the WARP's contiguous staging buffer (lane l starts at the warp
-//            prefix of the lane counts, shifted so that staging vectors line up with 16-byte-aligned output
-//            addresses), then a warp-cooperative copy-out: LDS.128 -> STG.128, 512 contiguous bytes per
-//            instruction; only the first and last partial vector of a warp-tile are written element-wise.
+//            predicated 16-bit shared stores into the WARP's staging buffer at alignment zero (lane l starts at the
+//            warp prefix of the lane counts): no global offset is needed to get this far.
+//   copy-out two tiles later, when the look-back has long delivered the tile's global offset: 32-bit words, 128
+//            contiguous bytes per warp instruction, one byte permute per word when the destination starts on an odd
+//            unit.
 //
-// The planes stay in registers across the scan, so counting costs nothing beyond what the transcoder needs anyway.
+// The planes stay in registers from pass 1 to pass 2, so counting costs nothing beyond what the transcoder needs anyway.
+// The header of k_utf8_transcode_v3 explains how the chained scan is kept off the workers' path.
 //
 // Emission rule (bitplane.h): a unit is emitted at the LAST byte of its character (high surrogates at the third
 // byte of a 4-byte sequence), so everything except one "is the next byte a continuation" bit looks backwards.
@@ -41,26 +39,20 @@ using bpd::kWarpsPerCta;
 using bpd::sts_u16;
 using bpd::sts_u32;
 
-// W32 = false: UTF-16 output (16-bit units, 8 per 16-byte vector); W32 = true: UTF-32 (4 per vector).
-template <int K, bool W32>
-struct Geom {
-  static constexpr uint32_t kRegionBytes = 32u * K;              // contiguous input bytes per lane
-  static constexpr uint32_t kTileBytes = 32u * kRegionBytes;     // per warp
-  static constexpr uint32_t kCtaTileBytes = 7u * kTileBytes;           // kWorkers warp-tiles
-  static constexpr uint32_t kVec = W32 ? 4u : 8u;                // output elements per 16-byte vector
-  static constexpr uint32_t kUnitBytes = W32 ? 4u : 2u;
-  // a warp emits at most one element per input byte, in front of which sit up to kVec-1 elements of alignment pad
-  static constexpr uint32_t kStageBytes = ((kTileBytes + kVec) * kUnitBytes + 15u) & ~15u;
-  static constexpr uint32_t kSmemBytes = 7u * (kStageBytes + kTileBytes);  // per worker warp: staging + plane stash
-};
-
-__device__ __forceinline__ InView make_view16(const void *p, size_t len_bytes) {
+// The input as 32-byte granules: a 32-byte-aligned base and the half-open range [vbeg, vend) of byte offsets that belong
+// to the caller's buffer (the kernel loads 32 bytes per instruction).
+__device__ __forceinline__ InView make_view32(const void *p, size_t len_bytes) {
   InView v;
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
-  v.vbeg = a & 15u;
+  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(31));
+  v.vbeg = a & 31u;
   v.vend = v.vbeg + len_bytes;
   return v;
+}
+__device__ __forceinline__ void ldg_v8(const void *p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
 }
 
 __device__ __forceinline__ bool tail_truncated16(const InView &in) {
@@ -90,498 +82,48 @@ __device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long
   return mhi & ~mlo;
 }
 
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-  return r;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Decoupled look-back over CTA-tile descriptors, 128 descriptors per round (lane l reads the four descriptors
-// base - 4l .. base - 4l - 3).  Called by all 32 lanes of ONE warp; returns the exclusive prefix of `tile` (the number
-// of elements every earlier tile emits) and publishes the tile's inclusive prefix.  Tiles are handed out in
-// increasing order by an atomic ticket, so every predecessor is finished, running, or reserved by a CTA whose
-// current tile is smaller still: the waits are bounded.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long cta_lookback128(unsigned long long *desc, uint32_t epoch, uint32_t tile,
-                                                              uint32_t agg, Scratch *scr) {
-  const unsigned lane = threadIdx.x & 31u;
-  if (tile == 0) {
-    if (lane == 0) st_relaxed_u64(desc, desc_pack(epoch, kStatusPrefix, 0, agg));
-    return 0ull;
-  }
-  if (lane == 0) st_relaxed_u64(desc + tile, desc_pack(epoch, kStatusAggregate, 0, agg));
-  unsigned long long sum = 0;
-  long long base = (long long)tile - 1;
-  while (true) {
-    unsigned long long d[4];
-    const long long i0 = base - 4ll * (long long)lane;
-#pragma unroll
-    for (int j = 0; j < 4; j++) d[j] = (i0 - j >= 0) ? ld_relaxed_u64(desc + (i0 - j)) : desc_pack(epoch, kStatusPrefix, 0, 0);
-    for (uint32_t spins = 0;; spins++) {
-      bool ready = true;
-#pragma unroll
-      for (int j = 0; j < 4; j++) ready = ready && desc_epoch(d[j]) == epoch && desc_status(d[j]) != 0u;
-      if (ready) break;
-      if (spins > (1u << 22)) {  // cannot happen (see above); never hang the device on a logic error
-        report_error(scr, err_key(0, kOther));
-        break;
-      }
-      __nanosleep(20);
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (i0 - j >= 0) d[j] = ld_relaxed_u64(desc + (i0 - j));
-    }
-    // lane-local walk from the nearest descriptor backwards, up to and including the first inclusive prefix
-    uint32_t aggs = 0;
-    unsigned long long pref = 0;
-    bool found = false;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (!found) {
-        if (desc_status(d[j]) == kStatusPrefix) {
-          pref = desc_value(d[j]);
-          found = true;
-        } else {
-          aggs += (uint32_t)desc_value(d[j]);
-        }
-      }
-    }
-    const unsigned pm = __ballot_sync(kFull, found);
-    const unsigned first = pm ? (unsigned)(__ffs((int)pm) - 1) : 32u;
-    sum += (unsigned long long)__reduce_add_sync(kFull, lane <= first ? aggs : 0u);
-    if (pm) {
-      const uint32_t lo = __shfl_sync(kFull, (uint32_t)pref, first), hi = __shfl_sync(kFull, (uint32_t)(pref >> 32), first);
-      sum += ((unsigned long long)hi << 32) | lo;
-      break;
-    }
-    base -= 128;
-  }
-  if (lane == 0) st_relaxed_u64(desc + tile, desc_pack(epoch, kStatusPrefix, 0, sum + agg));
-  return sum;
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3: the single-pass bit-plane transcoder.
-// BE (UTF-16 only): big-endian units — the low and high byte planes of the unit trade places before the
-// transposition back (free), the ASCII paths put the byte into the upper half.
-//
-// Warp roles.  kWorkers = 7 worker warps transcode; warp 7 is the SCAN warp: it takes the tickets, publishes the CTA
-// aggregates, runs the look-backs and hands the tile offsets to the workers.  The workers are software-pipelined by one
-// tile: in iteration i they run pass 1 of tile i (planes, masks, counts), park the planes in a lane-private shared-
-// memory stash, and then run pass 2 of tile i-1, whose offset the scan warp resolved while they were busy.  Nobody
-// waits for a look-back: a chained scan makes tile t wait for the SLOWEST of its in-flight predecessors to publish,
-// and with ~590 CTAs in flight that straggler costs several microseconds per tile (measured: 1.2-1.5 ms per GiB with
-// the look-back on the workers' critical path, against ~0.9 for the transcoding itself); one tile of slack absorbs it.
-// Producer/consumer hand-offs use mbarriers in shared memory, never a CTA-wide barrier.
-// ---------------------------------------------------------------------------------------------
+// The workspace (one descriptor per CTA-tile) is sized for CTA-tiles of at least kWorkers warp-tiles.
 constexpr int kWorkers = 7;
-constexpr int kScanWarp = kWorkers;
+
 // Hand-offs go through mbarrier objects in shared memory (one arrival releases any number of waiters, and waiters do not
-// wait for EACH OTHER the way the threads of a bar.sync do): a worker that is ahead never waits for a slower worker,
-// only for the scan warp's data.
+// wait for EACH OTHER the way the threads of a bar.sync do): a worker that is ahead never waits for a slower worker.
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {  // release: this thread's earlier shared-memory writes are visible to waiters
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {  // acquire
-  uint32_t done;
-  do {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-template <int K, int MINB, bool W32, bool BE>
-__global__ void __launch_bounds__(kThreads, MINB)
-k_utf8_transcode_sp(const char *ptr, size_t len, typename std::conditional<W32, uint32_t, uint16_t>::type *out,
-                    unsigned long long *desc, uint32_t epoch, uint32_t num_tiles, uint32_t num_cta_tiles, Scratch *scr,
-                    ResultPOD *res) {
-  using Gm = Geom<K, W32>;
-  using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
-  constexpr uint32_t kUB = Gm::kUnitBytes;
-  extern __shared__ __align__(16) uint32_t smem[];  // [kWorkers staging buffers][kWorkers plane stashes]
-  __shared__ uint32_t s_tot[2][8];               // workers -> scan warp: the warp totals of tile i (slot i & 1)
-  __shared__ unsigned long long s_goff[2][8];    // scan warp -> workers: every worker's global output offset for tile i
-  __shared__ uint32_t s_ticket[2];               // scan warp -> workers: the CTA-tile of iteration i
-  __shared__ __align__(8) unsigned long long s_mbar[6];  // [0,1] ticket posted, [2,3] offsets posted, [4,5] totals in
-  const InView in = make_view16(ptr, len);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s_mbar);
-  if (threadIdx.x == 0) {
-    mbar_init(mb + 0, 1); mbar_init(mb + 8, 1);
-    mbar_init(mb + 16, 1); mbar_init(mb + 24, 1);
-    mbar_init(mb + 32, kWorkers); mbar_init(mb + 40, kWorkers);
-  }
-  __syncthreads();
-
-  if (warp == kScanWarp) {
-    // ================================ scan warp ================================
-    // Slot / phase discipline: the barrier of slot p = i & 1 completes its (i >> 1)-th phase for iteration i.  Nobody
-    // can be two phases behind: the scan warp posts ticket i+2 only after every worker has delivered the totals of
-    // tile i+1, i.e. has long consumed ticket i and offsets i-1.
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(&scr->ticket, 1u);
-    t = __shfl_sync(kFull, t, 0);
-    if (lane == 0) {
-      s_ticket[0] = t;
-      mbar_arrive(mb + 0);
-    }
-    for (uint32_t iter = 0; t < num_cta_tiles; iter++) {
-      const uint32_t par = iter & 1u, ph = (iter >> 1) & 1u;
-      mbar_wait(mb + 32 + 8 * par, ph);  // the workers' totals of tile t
-      // reserve the next tile NOW: the workers pick it up a whole pass 2 later, so the ticket's round trip and the L2
-      // prefetch of exactly that tile are off their critical path
-      uint32_t tn = 0;
-      if (lane == 0) tn = atomicAdd(&scr->ticket, 1u);
-      tn = __shfl_sync(kFull, tn, 0);
-      if (lane == 0) {
-        s_ticket[par ^ 1u] = tn;
-        mbar_arrive(mb + 8 * (par ^ 1u));
-      }
-      if (tn < num_cta_tiles) {
-        const char *nx = reinterpret_cast<const char *>(in.base) + (unsigned long long)tn * Gm::kCtaTileBytes;
-#pragma unroll
-        for (uint32_t k = 0; k < (Gm::kCtaTileBytes + 4095u) / 4096u; k++) {
-          const uint32_t off = k * 4096u + lane * 128u;
-          if (off < Gm::kCtaTileBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
-        }
-      }
-      const uint32_t mine = lane < (unsigned)kWorkers ? s_tot[par][lane] : 0u;
-      const uint32_t incl = bpd::warp_inclusive_u32(mine);
-      const uint32_t agg = __shfl_sync(kFull, incl, 31);
-      const unsigned long long excl = cta_lookback128(desc, epoch, t, agg, scr);
-      if (lane < (unsigned)kWorkers) s_goff[par][lane] = excl + (incl - mine);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(mb + 16 + 8 * par);
-      t = tn;
-    }
-  } else {
-    // ================================ workers ================================
-    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(smem) + warp * Gm::kStageBytes;
-    const OutT *stage = reinterpret_cast<const OutT *>(smem) + (size_t)warp * (Gm::kStageBytes / kUB);
-    const uint32_t stash_addr = (uint32_t)__cvta_generic_to_shared(smem) + kWorkers * Gm::kStageBytes + warp * Gm::kTileBytes + lane * 16u;
-    const bool poison = starts_with_continuation(in);
-    const unsigned long long out_units = (unsigned long long)(reinterpret_cast<uintptr_t>(out) / sizeof(OutT));
-    const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (see bpd::bump)
-
-    // the tile whose pass 2 is pending (per-lane: masks, lane offset, word before the region; warp-uniform: the rest)
-    bool have_prev = false;
-    uint32_t p_em[K], p_excl = 0, p_pw = 0, p_tile = 0, p_wtot = 0, p_par = 0, p_ph = 0;
-    bool p_ascii = false, p_interior = false, p_active = false;
-#pragma unroll
-    for (int j = 0; j < K; j++) p_em[j] = 0;
-
-    for (uint32_t iter = 0;; iter++) {
-      const uint32_t par = iter & 1u, ph = (iter >> 1) & 1u;
-      mbar_wait(mb + 8 * par, ph);
-      const uint32_t ct = s_ticket[par];
-      const bool more = ct < num_cta_tiles;  // CTA-uniform
-      uint32_t B[K][8];
-      uint32_t c_em[K], c_excl = 0, c_pw = 0, c_wtot = 0;
-      bool c_ascii = false, c_interior = false, c_active = false;
-      const uint32_t tile = ct * kWorkers + warp;
-      if (more) {
-        c_active = tile < num_tiles;                                               // warp-uniform
-        const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;   // virtual byte offsets from in.base
-        const unsigned long long r0 = t0 + (unsigned long long)lane * Gm::kRegionBytes;
-        c_interior = c_active && t0 >= in.vbeg + 16ull && t0 + Gm::kTileBytes + 16ull <= in.vend;
-        // ---- this lane's 32K contiguous bytes, the word before them and the byte after them ----
-        uint32_t nbyte = 0;
-        if (c_interior) {
-          const uint4 *gp = in.base + (r0 >> 4);
-#pragma unroll
-          for (int j = 0; j < K; j++) {
-            const uint4 v0 = __ldg(gp + 2 * j), v1 = __ldg(gp + 2 * j + 1);
-            B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
-            B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
-          }
-          c_pw = __ldg(reinterpret_cast<const uint32_t *>(in.base) + (r0 >> 2) - 1);
-          nbyte = __ldg(reinterpret_cast<const uint8_t *>(in.base) + r0 + Gm::kRegionBytes);
-        } else if (c_active) {
-#pragma unroll
-          for (int j = 0; j < K; j++) {
-            bool ins;
-            load_granule(in, (r0 >> 4) + 2ull * j, &B[j][0], ins);
-            load_granule(in, (r0 >> 4) + 2ull * j + 1ull, &B[j][4], ins);
-          }
-          c_pw = load_word_guarded(in, (long long)(r0 >> 2) - 1);
-          const unsigned long long np = r0 + Gm::kRegionBytes;
-          nbyte = (np >= in.vbeg && np < in.vend) ? (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(in.base) + np) : 0u;
-        } else {
-#pragma unroll
-          for (int j = 0; j < K; j++) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) B[j][i] = 0u;
-          }
-        }
-        // ---- pass 1: planes, emit masks, counts ----
-        uint32_t hi = c_pw;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) hi |= B[j][i];
-        }
-        c_ascii = !__any_sync(kFull, (hi & kH) != 0u);
-        uint32_t cnt = 0;
-        if (!c_ascii) {
-          uint32_t prev_l4;
-          {
-            uint32_t v[8];
-            bp::planes_of_tail_word(c_pw, v);
-            prev_l4 = v[7] & v[6] & v[5] & v[4];
-          }
-#pragma unroll
-          for (int j = 0; j < K; j++) {
-            const uint32_t nb = (j + 1 < K) ? B[(j + 1 < K) ? j + 1 : j][0] : nbyte;  // read BEFORE block j+1 is transposed
-            const uint32_t next_nc = ((nb & 0xC0u) != 0x80u) ? 1u : 0u;
-            bp::transpose_in(B[j]);
-            uint32_t m = W32 ? bp::emit32_mask(B[j], next_nc) : bp::emit16_mask(B[j], prev_l4, next_nc);
-            prev_l4 = B[j][7] & B[j][6] & B[j][5] & B[j][4];
-            if (!c_interior) m &= range_mask32(in, r0 + 32ull * j);
-            if (poison) m = 0;
-            c_em[j] = m;
-            cnt += (uint32_t)__popc(m);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < K; j++) {
-            uint32_t m = c_active ? 0xFFFFFFFFu : 0u;
-            if (!c_interior && c_active) m &= range_mask32(in, r0 + 32ull * j);
-            if (poison) m = 0;
-            c_em[j] = m;
-            cnt += (uint32_t)__popc(m);
-          }
-        }
-        const uint32_t incl = bpd::warp_inclusive_u32(cnt);
-        c_wtot = __shfl_sync(kFull, incl, 31);
-        c_excl = incl - cnt;
-        if (lane == 0) {
-          s_tot[par][warp] = c_wtot;
-          mbar_arrive(mb + 32 + 8 * par);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < K; j++) c_em[j] = 0;
-      }
-
-      // ---- the planes of tile i go to the stash, those of tile i-1 come back ----
-      if (more || have_prev) {
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-          uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-          if (have_prev) {
-            v0 = lds_v4(stash_addr + (2u * j) * 512u);
-            v1 = lds_v4(stash_addr + (2u * j + 1u) * 512u);
-          }
-          if (more) {
-            sts_v4(stash_addr + (2u * j) * 512u, B[j][0], B[j][1], B[j][2], B[j][3]);
-            sts_v4(stash_addr + (2u * j + 1u) * 512u, B[j][4], B[j][5], B[j][6], B[j][7]);
-          }
-          B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
-          B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
-        }
-      }
-
-      if (have_prev) {
-        // ---- pass 2 of the pending tile ----
-        mbar_wait(mb + 16 + 8 * p_par, p_ph);
-        const unsigned long long goff = s_goff[p_par][warp];
-        const unsigned long long r0 = (unsigned long long)p_tile * Gm::kTileBytes + (unsigned long long)lane * Gm::kRegionBytes;
-        const uint32_t a_w = (uint32_t)((out_units + goff) & (Gm::kVec - 1u));  // offset of the tile inside a 16-byte output vector
-        uint32_t badblocks = 0;
-        bool staged = false;
-        if (p_active) {
-          // The running store address lives in a 32-bit shared-space register; it advances through the multiplier
-          // (`one` * 2 + address) and the upper unit of a word is extracted with IMAD.HI, so that the compaction
-          // costs the ALU pipe nothing but the predicate extraction.
-          if (!p_ascii) {
-            staged = true;
-            bp::Carry carry = bp::carry_from_word(p_pw);
-            uint32_t spa = stage_addr + kUB * (a_w + p_excl);
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              // four independent store chains (positions 0-7, 8-15, 16-23, 24-31): a chain's address register can
-              // only advance once the store before it has read it, so one chain alone would serialise the block
-              const uint32_t m = p_em[j];
-              uint32_t s0 = spa;
-              uint32_t s1 = spa + kUB * (uint32_t)__popc(m & 0xFFu);
-              uint32_t s2 = spa + kUB * (uint32_t)__popc(m & 0xFFFFu);
-              uint32_t s3 = spa + kUB * (uint32_t)__popc(m & 0xFFFFFFu);
-              spa += kUB * (uint32_t)__popc(m);
-              if (W32) {
-                uint32_t C[32];
-                const uint32_t err = bp::utf8_to_utf32_block<true>(B[j], carry, C);
-                if (err) badblocks |= 1u << j;
-                bp::transpose_out21(C);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                  if (m & (1u << i)) {
-                    sts_u32(s0, C[i]);
-                    s0 = bpd::bump<4>(s0, one);
-                  }
-                  if (m & (1u << (8 + i))) {
-                    sts_u32(s1, C[8 + i]);
-                    s1 = bpd::bump<4>(s1, one);
-                  }
-                  if (m & (1u << (16 + i))) {
-                    sts_u32(s2, C[16 + i]);
-                    s2 = bpd::bump<4>(s2, one);
-                  }
-                  if (m & (1u << (24 + i))) {
-                    sts_u32(s3, C[24 + i]);
-                    s3 = bpd::bump<4>(s3, one);
-                  }
-                }
-              } else {
-                uint32_t U[16];
-                const uint32_t err = bp::utf8_to_utf16_block<true>(B[j], carry, U);
-                if (err) badblocks |= 1u << j;
-                if (BE) {
-#pragma unroll
-                  for (int k = 0; k < 8; k++) {
-                    const uint32_t t = U[k];
-                    U[k] = U[k + 8];
-                    U[k + 8] = t;
-                  }
-                }
-                bp::transpose_out16(U);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                  if (m & (1u << i)) {
-                    sts_u16(s0, U[i]);
-                    s0 = bpd::bump<2>(s0, one);
-                  }
-                  if (m & (1u << (8 + i))) {
-                    sts_u16(s1, U[8 + i]);
-                    s1 = bpd::bump<2>(s1, one);
-                  }
-                  if (m & (1u << (16 + i))) {
-                    sts_u16(s2, __umulhi(U[i], 65536u));
-                    s2 = bpd::bump<2>(s2, one);
-                  }
-                  if (m & (1u << (24 + i))) {
-                    sts_u16(s3, __umulhi(U[8 + i], 65536u));
-                    s3 = bpd::bump<2>(s3, one);
-                  }
-                }
-              }
-            }
-          } else if (p_interior && !poison && a_w == 0u) {
-            // every lane emits exactly 32K elements and the tile's output is vector-aligned: widen in registers and
-            // store straight to global memory (nothing staged, no errors possible in an all-ASCII interior tile)
-            uint4 *gv = reinterpret_cast<uint4 *>(out + goff + p_excl);
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-#pragma unroll
-              for (int k = 0; k < 8; k++) {
-                const uint32_t w = B[j][k];
-                if (W32) {
-                  stg_stream_v4(gv + 8 * j + k, make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24));
-                } else if ((k & 1) == 0) {
-                  const uint32_t w1 = B[j][k + 1];
-                  constexpr uint32_t s01 = BE ? 0x1404u : 0x4140u, s23 = BE ? 0x3424u : 0x4342u;
-                  stg_stream_v4(gv + 4 * j + (k >> 1), make_uint4(__byte_perm(w, 0u, s01), __byte_perm(w, 0u, s23),
-                                                                   __byte_perm(w1, 0u, s01), __byte_perm(w1, 0u, s23)));
-                }
-              }
-            }
-          } else {
-            staged = true;
-            uint32_t spa = stage_addr + kUB * (a_w + p_excl);
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              const uint32_t m = p_em[j];
-#pragma unroll
-              for (int p = 0; p < 32; p++) {
-                if (m & (1u << p)) {
-                  const uint32_t byte = (B[j][p >> 2] >> (8 * (p & 3))) & 0xFFu;
-                  if (W32) {
-                    sts_u32(spa, byte);
-                    spa = bpd::bump<4>(spa, one);
-                  } else {
-                    sts_u16(spa, BE ? byte << 8 : byte);
-                    spa = bpd::bump<2>(spa, one);
-                  }
-                }
-              }
-            }
-          }
-          // ---- exact error location (rare): the detector only says "in this block or the 3 bytes before it" ----
-          if (!p_interior) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              const unsigned long long b0 = r0 + 32ull * j;
-              if (b0 < in.vend && in.vend <= b0 + 32ull && tail_truncated16(in)) badblocks |= 1u << j;
-            }
-          }
-          if (badblocks) {
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-              const long long b0 = (long long)(r0 + 32ull * j);
-              if (badblocks & (1u << j)) u8_locate_error(in, scr, b0 - 3, b0 + 32);
-            }
-          }
-        }
-        __syncwarp();
-        // ---- staging -> global: the warp's elements [a_w, a_w + wtot) of the staging buffer go to out[goff ...] ----
-        if (staged && p_wtot) {
-          OutT *gbase = out + goff - a_w;  // 16-byte aligned
-          const uint32_t end = a_w + p_wtot;
-          const uint32_t v0 = a_w ? 1u : 0u, v1 = end / Gm::kVec;
-          const uint32_t head_end = a_w ? (end < Gm::kVec ? end : Gm::kVec) : 0u;
-          for (uint32_t v = v0 + lane; v < v1; v += 32u)
-            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, lds_v4(stage_addr + 16u * v));
-          if (lane >= a_w && lane < head_end) gbase[lane] = stage[lane];  // first partial vector (shared with the previous tile)
-          const uint32_t ti = v1 * Gm::kVec + lane;                        // last partial vector (shared with the next tile)
-          if (lane < Gm::kVec && ti >= head_end && ti < end) gbase[ti] = stage[ti];
-        }
-        __syncwarp();  // the staging buffer is rewritten by the next tile
-      }
-      if (!more) break;
-      have_prev = true;
-#pragma unroll
-      for (int j = 0; j < K; j++) p_em[j] = c_em[j];
-      p_excl = c_excl; p_pw = c_pw; p_tile = tile; p_wtot = c_wtot; p_par = par; p_ph = ph;
-      p_ascii = c_ascii; p_interior = c_interior; p_active = c_active;
-    }
-  }
-
-  if (grid_last_thread(scr)) {
-    const unsigned long long total = num_cta_tiles ? desc_value(ld_relaxed_u64(desc + (num_cta_tiles - 1u))) : 0ull;
-    bpd::write_result_from_key(res, ld_relaxed_u64(&scr->err_key), total);
-    scratch_reset(scr);
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------
-// K3 v3: the same single pass with the look-back OFF the workers' path.
+// The single-pass transcoder, with the look-back OFF the workers' path.
 //
-// In k_utf8_transcode_sp a worker needs the tile's global output offset BEFORE it compacts (the staging position carries
-// the alignment of the output address), so the planes are parked in shared memory for one tile and every hiccup of the
-// chained scan shows up as a wait in front of pass 2 (ncu: 24 % of all samples on that one mbarrier).  Here a worker
-// transcodes and compacts tile i into staging buffer i & 1 at alignment ZERO, knowing nothing but the warp's own lane
-// prefix; the global offset is needed only by the copy-out, and the copy-out of tile i runs TWO tiles later, between
-// pass 1 and pass 2 of tile i + 2 (just before that buffer is overwritten): the look-back of a tile has two whole tile
-// times to finish.  The copy-out realigns: the destination is only 2-byte aligned, so it goes out as 32-bit words (128
-// contiguous bytes per warp instruction), one byte permute per word when the destination starts on an odd unit.
+// In this round's first single-pass kernel (k_utf8_transcode_sp, git history) a worker needed the tile's global output
+// offset BEFORE it compacted (the staging position carried the alignment of the output address), so the planes were
+// parked in shared memory for one tile and every hiccup of the chained scan showed up as a wait in front of pass 2
+// (ncu: 24 % of all samples on that one mbarrier).  Here a worker transcodes and compacts tile i into staging buffer
+// i & 1 at alignment ZERO, knowing nothing but the warp's own lane prefix; the global offset is needed only by the
+// copy-out, and the copy-out of tile i runs TWO tiles later, between pass 1 and pass 2 of tile i + 2 (just before that
+// buffer is overwritten): the look-back of a tile has two whole tile times to finish.
 //
-// Who does what (measured on B200 with clock64 instrumentation, 1 GiB of mixed text, 444 CTAs):
+// Who does what, and why (each step measured on B200 with the clock64 / globaltimer instrumentation of the DBG
+// instantiation, tools/dbg_timing.py; 1 GiB of mixed text):
 //   * the worker that delivers the LAST warp total of a tile publishes the CTA aggregate itself.  With the scan warp
 //     publishing it, an aggregate waited for the scan warp's previous look-back, which waited for other CTAs'
 //     aggregates, ...: 13 us and 25 polls per look-back; published by the workers, 5 us and 5 polls;
-//   * the worker that reaches pass 2 FIRST reserves the CTA's next tile (global atomic ticket); the ticket's round trip
-//     hides behind its pass 2.  Tickets keep the scan deadlock-free when not all CTAs are resident;
-//   * the scan warp only looks back (coalesced: a warp load reads 32 consecutive descriptors) and posts the offsets.
+//   * the same worker reserves the CTA's next tile (global atomic ticket); the ticket's round trip hides behind its
+//     copy-out.  Reserved by the FIRST worker to finish, a CTA whose warps had drifted apart held a ticket for up to two
+//     tile times before its aggregate appeared: the 32 nearest predecessors of a tile published 7 us AFTER it on
+//     average, every look-back waited that long, and the workers stalled 1.2 us per tile on the offsets; reserved by
+//     the last one, 2 us and 0.06 us.  Tickets (not blockIdx) keep the scan deadlock-free when not all CTAs are resident;
+//   * the scan warp only looks back and posts the offsets.  Its loads are COALESCED (a warp load reads 32 consecutive
+//     descriptors = 8 sectors, and a lane re-reads only a descriptor that is not ready): a persistent grid of equal
+//     tiles drifts into lockstep, then no predecessor of the current wave has its prefix yet and every CTA reads the
+//     whole in-flight window, G descriptors G times per wave, on a few dozen L2 lines — with lane-strided loads
+//     widening the window from 128 to 512 descriptors took the kernel from 2.3 to 5.6 ms per GiB.
+// Not the bottleneck (measured, so that nobody tries again): the shared-store bank conflicts of the warp-contiguous
+// staging buffer (3.5 wavefronts per store on the mix; a conflict-free but wrong placement ran 0.853 instead of 0.867
+// ms), hiding the tile's global loads behind the copy-out (0.893), lane-private staging regions with per-lane vector
+// stores (1.59: the eight alignment-specialised copy loops overflowed the instruction cache).
 // ---------------------------------------------------------------------------------------------
 template <int K, bool W32, int NW>
 struct Geom3 {
@@ -700,7 +242,7 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
   __shared__ uint32_t s_elect[4];                // workers that have reached pass 2
   __shared__ __align__(8) unsigned long long s_mbar[12];  // [0,4) ticket posted, [4,8) offsets posted, [8,12) totals in
   static_assert(NW <= 15, "one scan warp lane per worker; 16-bit packing of the warp totals");
-  const InView in = make_view16(ptr, len);
+  const InView in = make_view32(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s_mbar);
   constexpr uint32_t kMbTicket = 0u, kMbGoff = 32u, kMbTotals = 64u;
@@ -864,11 +406,7 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
       if (interior) {
         const uint4 *gp = in.base + (r0 >> 4);
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-          const uint4 v0 = __ldg(gp + 2 * j), v1 = __ldg(gp + 2 * j + 1);
-          B[j][0] = v0.x; B[j][1] = v0.y; B[j][2] = v0.z; B[j][3] = v0.w;
-          B[j][4] = v1.x; B[j][5] = v1.y; B[j][6] = v1.z; B[j][7] = v1.w;
-        }
+        for (int j = 0; j < K; j++) ldg_v8(gp + 2 * j, B[j]);  // one 256-bit load per block: half the LSU wavefronts of two 128-bit ones
         // the word before / the byte after the region sit in the neighbour lanes' registers: a strided load of them would
         // touch 16 lines per warp instruction (ncu: the three loads of this kernel were 130 of its 400 LSU wavefronts
         // per tile); only lanes 0 and 31 go to memory
@@ -1029,23 +567,21 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
               }
             }
             bp::transpose_out16(U);
+            // One store chain per byte of the emit mask, its eight predicates extracted together: ptxas turns that into
+            // one R2P + one LOP3 where a test per position costs eight LOP3 on the ALU pipe (measured: 0.885 -> 0.868 ms
+            // per GiB).  Chain c covers positions 8c .. 8c + 7; its address advances on the FMA pipe.
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-              if (m & (1u << i)) {
-                sts_u16(s0, U[i]);
-                s0 = bpd::bump<2>(s0, one);
-              }
-              if (m & (1u << (8 + i))) {
-                sts_u16(s1, U[8 + i]);
-                s1 = bpd::bump<2>(s1, one);
-              }
-              if (m & (1u << (16 + i))) {
-                sts_u16(s2, __umulhi(U[i], 65536u));
-                s2 = bpd::bump<2>(s2, one);
-              }
-              if (m & (1u << (24 + i))) {
-                sts_u16(s3, __umulhi(U[8 + i], 65536u));
-                s3 = bpd::bump<2>(s3, one);
+            for (int c = 0; c < 4; c++) {
+              bool pr[8];
+#pragma unroll
+              for (int i = 0; i < 8; i++) pr[i] = ((m >> (8 * c + i)) & 1u) != 0u;
+              uint32_t sc = c == 0 ? s0 : (c == 1 ? s1 : (c == 2 ? s2 : s3));
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                if (pr[i]) {
+                  sts_u16(sc, c < 2 ? U[8 * c + i] : __umulhi(U[8 * (c - 2) + i], 65536u));
+                  sc = bpd::bump<2>(sc, one);
+                }
               }
             }
           }
@@ -1087,38 +623,19 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
   }
 }
 
-inline size_t tiles_for(const void *in, size_t len_bytes, int k) {
-  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
+inline size_t tiles_for(const void *in, size_t len_bytes, int k, unsigned align_mask = 15u) {
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & align_mask) + len_bytes;
   const size_t per_tile = (size_t)1024 * k;
   return (span + per_tile - 1) / per_tile;
 }
 inline size_t cta_tiles_for(size_t tiles) { return (tiles + kWorkers - 1) / kWorkers; }
-
-template <int K, int MINB, bool W32, bool BE>
-cudaError_t launch_sp(const LaunchCtx &c, const char *in, size_t len, void *out, void *res) {
-  using Gm = Geom<K, W32>;
-  using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
-  const size_t tiles = tiles_for(in, len, K), cta_tiles = cta_tiles_for(tiles);
-  if (cta_tiles + 1 > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  static KernelCache kc;
-  int per_sm = 1;
-  cudaError_t e = kernel_per_sm(kc, c.device, k_utf8_transcode_sp<K, MINB, W32, BE>, kThreads, Gm::kSmemBytes, &per_sm);
-  if (e != cudaSuccess) return e;
-  const size_t cap = (size_t)c.sm_count * per_sm;
-  const unsigned grid = (unsigned)(cta_tiles < cap ? (cta_tiles ? cta_tiles : 1) : cap);
-  k_utf8_transcode_sp<K, MINB, W32, BE><<<grid, kThreads, Gm::kSmemBytes, c.stream>>>(
-      in, len, static_cast<OutT *>(out), c.desc, c.epoch, (uint32_t)tiles, (uint32_t)cta_tiles, c.scratch,
-      static_cast<ResultPOD *>(res));
-  count_launch(1);
-  return cudaGetLastError();
-}
 
 template <int K, int MINB, bool W32, bool BE, int NW, bool DBG = false>
 cudaError_t launch_v3(const LaunchCtx &c, const char *in, size_t len, void *out, void *res) {
   using Gm = Geom3<K, W32, NW>;
   using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
   static_assert(NW >= kWorkers, "the workspace is sized for CTA-tiles of at least kWorkers warp-tiles");
-  const size_t tiles = tiles_for(in, len, K), cta_tiles = (tiles + NW - 1) / NW;
+  const size_t tiles = tiles_for(in, len, K, 31u), cta_tiles = (tiles + NW - 1) / NW;
   if (cta_tiles + 1 > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
   static KernelCache kc;
   int per_sm = 1;
@@ -1137,24 +654,22 @@ cudaError_t launch_v3(const LaunchCtx &c, const char *in, size_t len, void *out,
 }  // namespace
 
 // Workspace, in 8-byte descriptor slots, the kernel needs for an input of `len` bytes: one descriptor per CTA-tile.
-size_t utf8_to_utf16_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 2)) + 2; }
-size_t utf8_to_utf32_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 2)) + 2; }
+size_t utf8_to_utf16_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 2, 31u)) + 2; }
+size_t utf8_to_utf32_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 1, 31u)) + 2; }
 
 cudaError_t launch_convert_utf8_to_utf16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res,
                                          bool big_endian) {
-  if (big_endian) return launch_v3<2, 3, false, true, 7>(c, in, len, out, res);
-  switch (tuning(kTuneConvVariant)) {
-    case 1: return launch_sp<2, 3, false, false>(c, in, len, out, res);
-    case 4: return launch_v3<2, 2, false, false, 11>(c, in, len, out, res);
-    case 8: return launch_v3<2, 3, false, false, 7, true>(c, in, len, out, res);
-    case 9: return launch_v3<2, 2, false, false, 11, true>(c, in, len, out, res);
-    default: return launch_v3<2, 3, false, false, 7>(c, in, len, out, res);
-  }
+  // 11 workers + the scan warp per CTA, two CTAs per SM.  Measured on B200, 1 GiB of the mixed distribution
+  // (tools/variant_check.py): 7 workers x 3 CTAs 0.934 ms, 11 x 2 0.885, 12 x 2 0.893, 13 x 2 0.954; 11 x 2 with the
+  // compaction predicates through R2P 0.868.
+  if (big_endian) return launch_v3<2, 2, false, true, 11>(c, in, len, out, res);
+  if (tuning(kTuneConvVariant) == 8) return launch_v3<2, 2, false, false, 11, true>(c, in, len, out, res);  // clock64 instrumentation (tools/dbg_timing.py)
+  return launch_v3<2, 2, false, false, 11>(c, in, len, out, res);
 }
 
 cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res) {
-  if (tuning(kTuneConvVariant) == 1) return launch_sp<2, 2, true, false>(c, in, len, out, res);
-  return launch_v3<2, 2, true, false, 7>(c, in, len, out, res);
+  // 32-bit elements double the staging buffers: one block per lane (1 KiB warp-tiles) keeps two CTAs of 11 workers on an SM
+  return launch_v3<1, 2, true, false, 11>(c, in, len, out, res);
 }
 
 }  // namespace b200

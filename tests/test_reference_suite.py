@@ -53,7 +53,7 @@ HOT = [
     "atomic_base64_tests", "internal_tests",
 ]
 # what a passing run must print besides exiting 0 (default: the harness's "OK")
-MARKER = {"select_implementation": None, "random_fuzzer": "testing: b200", "internal_tests": "b200_host_path_over_all_devices"}
+MARKER = {"select_implementation": None, "random_fuzzer": "testing: b200", "internal_tests": "b200 host path over all devices"}
 
 # Green as well, but made of 10^6..10^8 calls on <= 256-byte inputs (a CPU does those in nanoseconds, a host-path call
 # costs ~30-60 us): minutes to half an hour each on the GPU box.  Run with B200_SLOW_TESTS=1.  Measured on a B200:

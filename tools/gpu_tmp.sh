@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 150 python tools/variant_check.py 0,4 1073741824 0 > gpurun_out/r2_variant_check7.log 2>&1; echo "variant rc=$?"; tail -n 6 gpurun_out/r2_variant_check7.log
-timeout 100 python tools/dbg_timing.py 8,9 > gpurun_out/r2_dbg_timing5.log 2>&1; echo "rc=$?"; cat gpurun_out/r2_dbg_timing5.log
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or utf8_small or utf8_error or utf8_medium or bitplane or utf16be or utf32_family or repeated or beyond_4gib or host_streaming or config2" > gpurun_out/r2_k3_final_parity.log 2>&1; echo "parity rc=$?"; tail -n 3 gpurun_out/r2_k3_final_parity.log
+timeout 100 python tools/prof_one.py convert16 1073741824 10 2>&1 | tail -1
+timeout 100 python tools/prof_one.py convert32 1073741824 10 2>&1 | tail -1
+timeout 100 python tools/dbg_timing.py 8 2>&1 | tail -4
