@@ -426,8 +426,46 @@ SIMDUTF_B200_API int b200_mgpu_last_gather(void);
 /* results are folded exactly like shards.  Default 1.  Small inputs always use one device.                          */
 SIMDUTF_B200_API int b200_host_set_devices(int n);
 SIMDUTF_B200_API int b200_host_get_devices(void);
-/* Experiment knobs for tools/ and profiles/ ("conv_minb", "segment_mb", "no_nccl"; 0 = default).  The library never */
-/* reads the environment.                                                                                            */
+/* ------------------------------------------------------------------------- */
+/* Many small strings per launch ("callers at the right   */
+/* granularity"; the reference's callers of this shape: tools/sutf.cpp:131-336,  */
+/* the per-string loops of tests/validate_utf8_with_errors_tests.cpp:54-69).     */
+/* A single-string call costs a launch and a synchronisation however short the  */
+/* string; a batch pays them once.  String i is d_data[d_offsets[i] ..           */
+/* d_offsets[i + 1]) — one packed buffer and n + 1 offsets, the layout of an      */
+/* Arrow string column — and gets the result the single-string entry point of    */
+/* the same name gives (implementation::validate_utf8_with_errors :3396,         */
+/* count_utf8 :4802, utf16_length_from_utf8 :3863, convert_utf8_to_utf16le/be    */
+/* _with_errors :3727-3760).  convert: string i's units start at                 */
+/* d_out[d_out_offsets[i]], or, with d_out_offsets == NULL, at d_out[d_offsets[i]]*/
+/* (a string never yields more units than it has bytes, so a d_out of            */
+/* d_offsets[n] units needs no length pass); d_results[i].count is the number    */
+/* of units.  The host flavour packs the strings into a pinned window itself.    */
+/* ------------------------------------------------------------------------- */
+SIMDUTF_B200_API int b200_validate_utf8_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n,
+                                                    b200_result *d_results, void *stream);
+SIMDUTF_B200_API int b200_count_utf8_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n,
+                                                 uint64_t *d_counts, void *stream);
+SIMDUTF_B200_API int b200_utf16_length_from_utf8_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n,
+                                                             uint64_t *d_counts, void *stream);
+SIMDUTF_B200_API int b200_convert_utf8_to_utf16le_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n,
+                                                              uint16_t *d_out, const uint64_t *d_out_offsets,
+                                                              b200_result *d_results, void *stream);
+SIMDUTF_B200_API int b200_convert_utf8_to_utf16be_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n,
+                                                              uint16_t *d_out, const uint64_t *d_out_offsets,
+                                                              b200_result *d_results, void *stream);
+SIMDUTF_B200_API int b200_host_validate_utf8_batch(const char *const *h_strings, const size_t *h_lens, size_t n,
+                                                   b200_result *h_results);
+SIMDUTF_B200_API int b200_host_count_utf8_batch(const char *const *h_strings, const size_t *h_lens, size_t n,
+                                                uint64_t *h_counts);
+SIMDUTF_B200_API int b200_host_utf16_length_from_utf8_batch(const char *const *h_strings, const size_t *h_lens, size_t n,
+                                                            uint64_t *h_counts);
+/* h_outs[i] must hold utf16_length_from_utf8(string i) units; it is written only when string i converts without error */
+SIMDUTF_B200_API int b200_host_convert_utf8_to_utf16le_batch(const char *const *h_strings, const size_t *h_lens, size_t n,
+                                                             uint16_t *const *h_outs, b200_result *h_results);
+
+/* Experiment knobs for tools/ and profiles/ ("segment_mb", "no_nccl", "conv_variant", "dbg_lo", "dbg_hi"; 0 = default). */
+/* The library never reads the environment.                                                                          */
 SIMDUTF_B200_API int b200_set_tuning(const char *name, int value);
 
 #ifdef __cplusplus

@@ -131,6 +131,12 @@ for _name in ["validate_utf8_with_errors", "utf16_length_from_utf8", "convert_ut
               "convert_utf16le_to_utf8"]:
     SYMBOLS[f"b200_mgpu_{_name}"] = (_I, [_vp, _I, _vp])
 SYMBOLS["b200_mgpu_last_gather"] = (_I, [])
+for _name in ["validate_utf8", "count_utf8", "utf16_length_from_utf8"]:
+    SYMBOLS[f"b200_{_name}_batch_async"] = (_I, [_vp, _vp, _sz, _vp, _vp])
+    SYMBOLS[f"b200_host_{_name}_batch"] = (_I, [_vp, _vp, _sz, _vp])
+for _name in ["convert_utf8_to_utf16le", "convert_utf8_to_utf16be"]:
+    SYMBOLS[f"b200_{_name}_batch_async"] = (_I, [_vp, _vp, _sz, _vp, _vp, _vp, _vp])
+SYMBOLS["b200_host_convert_utf8_to_utf16le_batch"] = (_I, [_vp, _vp, _sz, _vp, _vp])
 SYMBOLS["b200_host_set_devices"] = (_I, [_I])
 SYMBOLS["b200_host_get_devices"] = (_I, [])
 SYMBOLS["b200_set_tuning"] = (_I, [ctypes.c_char_p, _I])
@@ -512,3 +518,60 @@ def maximal_binary_length_from_base64(data: bytes) -> int:
 def trim_partial_utf8(data: bytes) -> int:
     ptr, n, _keep = _host_view(data, 1)
     return int(load().b200_host_trim_partial_utf8(ptr, n))
+
+
+# ---------------------------------------------------------------------------------------------
+# Many small strings per launch (include/simdutf_b200.h, "Many small strings per launch"; kernels in csrc/k_batch.cu)
+# ---------------------------------------------------------------------------------------------
+def _batch_views(strings):
+    n = len(strings)
+    bufs = [bytes(x) for x in strings]
+    ptrs = (ctypes.c_char_p * max(n, 1))(*bufs)
+    lens = (ctypes.c_size_t * max(n, 1))(*[len(x) for x in bufs])
+    return n, bufs, ptrs, lens
+
+
+def validate_utf8_batch(strings):
+    """[(error, count)] of simdutf::validate_utf8_with_errors for every string of a list of host byte strings: one
+    upload, one launch, one download."""
+    n, _keep, ptrs, lens = _batch_views(strings)
+    res = (Result * max(n, 1))()
+    _check(load().b200_host_validate_utf8_batch(ptrs, lens, n, res), "validate_utf8_batch")
+    return [res[i].astuple() for i in range(n)]
+
+
+def utf16_length_from_utf8_batch(strings):
+    n, _keep, ptrs, lens = _batch_views(strings)
+    out = (ctypes.c_uint64 * max(n, 1))()
+    _check(load().b200_host_utf16_length_from_utf8_batch(ptrs, lens, n, out), "utf16_length_from_utf8_batch")
+    return [int(out[i]) for i in range(n)]
+
+
+def count_utf8_batch(strings):
+    n, _keep, ptrs, lens = _batch_views(strings)
+    out = (ctypes.c_uint64 * max(n, 1))()
+    _check(load().b200_host_count_utf8_batch(ptrs, lens, n, out), "count_utf8_batch")
+    return [int(out[i]) for i in range(n)]
+
+
+def convert_utf8_to_utf16le_batch(strings):
+    """[((error, count), units-as-bytes or None)] for every string; a string's output buffer is sized by its byte
+    length (never fewer units than that)."""
+    n, bufs, ptrs, lens = _batch_views(strings)
+    outs = [ctypes.create_string_buffer(2 * len(x) + 2) for x in bufs]
+    optrs = (ctypes.c_void_p * max(n, 1))(*[ctypes.addressof(o) for o in outs])
+    res = (Result * max(n, 1))()
+    _check(load().b200_host_convert_utf8_to_utf16le_batch(ptrs, lens, n, optrs, res), "convert_utf8_to_utf16le_batch")
+    return [(res[i].astuple(), outs[i].raw[: 2 * res[i].count] if res[i].error == 0 else None) for i in range(n)]
+
+
+def validate_utf8_batch_device(data, offsets, results=None):
+    """Device flavour: `data` uint8 CUDA tensor, `offsets` int64/uint64 CUDA tensor of n + 1 entries; returns an int64 CUDA
+    tensor [n, 2] viewed from b200_result (error in the low 32 bits of column 0)."""
+    import torch
+    n = offsets.numel() - 1
+    if results is None:
+        results = torch.empty((max(n, 1), 2), dtype=torch.int64, device=data.device)
+    _check(load().b200_validate_utf8_batch_async(int(data.data_ptr()), int(offsets.data_ptr()), n, int(results.data_ptr()),
+                                                  _stream_of(data)), "validate_utf8_batch_async")
+    return results[:n]

@@ -252,6 +252,8 @@ struct HostPath {
   void *m_out = nullptr;
   unsigned long long *d_trip = nullptr;  // sharded entry points: [3] triplet, [3 * kMaxShards] gathered, [4] combined (device)
   void *h_comb = nullptr;                // pinned copy of the combined result
+  void *h_pack = nullptr;                // batch entry points: pinned [offsets | packed strings] / results window (grow-only)
+  size_t h_pack_cap = 0;
   struct Slot {
     void *d_in = nullptr;
     size_t d_in_cap = 0;
@@ -301,6 +303,7 @@ struct HostPath {
     cudaFree(d_trip);
     if (h_slot) cudaFreeHost(h_slot);
     if (h_comb) cudaFreeHost(h_comb);
+    if (h_pack) cudaFreeHost(h_pack);
     if (m_in) cudaFreeHost(m_in);
     if (m_out) cudaFreeHost(m_out);
     if (s_main) cudaStreamDestroy(s_main);
@@ -1257,6 +1260,131 @@ int b200_set_tuning(const char *name, int value) {
     }
   }
   return fail(B200_E_BAD_ARGUMENT, "unknown tuning knob");
+}
+
+// ---- many small strings per launch (kernels in k_batch.cu) ----
+namespace {
+int batch_async(int mode, bool be, const char *d_data, const uint64_t *d_offsets, size_t n, uint16_t *d_out,
+                const uint64_t *d_out_offsets, void *d_res, void *stream) {
+  if (n == 0) return 0;
+  if (!d_data || !d_offsets || !d_res || (mode == 3 && !d_out)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
+  int err;
+  DeviceGuard guard;
+  DeviceCtx *c = enter_device(call_device(d_data, d_offsets, d_res), guard, &err);
+  if (!c) return err;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned long long *offs = reinterpret_cast<const unsigned long long *>(d_offsets);
+  if (mode == 3) {
+    B200_CUDA(launch_utf8_to_utf16_batch(c->sm_count, s, be, d_data, offs, n, d_out,
+                                         reinterpret_cast<const unsigned long long *>(d_out_offsets), d_res));
+  } else {
+    B200_CUDA(launch_utf8_batch(c->sm_count, s, mode, d_data, offs, n, d_res));
+  }
+  return 0;
+}
+
+// host strings: packed into one pinned window [n + 1 offsets | bytes], one upload, one launch, one download
+int batch_host(int mode, const char *const *h_strings, const size_t *h_lens, size_t n, uint16_t *const *h_outs, void *h_res) {
+  if (n == 0) return 0;
+  if (!h_strings || !h_lens || !h_res || (mode == 3 && !h_outs)) return fail(B200_E_BAD_ARGUMENT, "null pointer");
+  if (device_count() <= 0) return fail(B200_E_NO_DEVICE, "no usable sm_100 device");
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (h_lens[i] && !h_strings[i]) return fail(B200_E_BAD_ARGUMENT, "null string");
+    total += h_lens[i];
+  }
+  int err;
+  DeviceGuard guard;
+  DeviceCtx *c = enter_device(tl_device, guard, &err);
+  if (!c) return err;
+  HostPath *h = nullptr;
+  if ((err = host_path(tl_device, &h))) return err;
+  const size_t off_bytes = (n + 1) * sizeof(unsigned long long);
+  const size_t data_off = (off_bytes + 15) & ~size_t(15);
+  const size_t in_bytes = data_off + total + 16;
+  const size_t res_elem = mode == 0 || mode == 3 ? sizeof(b200_result) : sizeof(uint64_t);
+  const size_t res_bytes = (n * res_elem + 15) & ~size_t(15);
+  const size_t out_bytes = res_bytes + (mode == 3 ? 2 * total + 16 : 0);
+  const size_t pack_need = in_bytes > out_bytes ? in_bytes : out_bytes;
+  if (pack_need > h->h_pack_cap) {
+    if (h->h_pack) {
+      B200_CUDA(cudaStreamSynchronize(h->s_main));
+      B200_CUDA(cudaFreeHost(h->h_pack));
+      h->h_pack = nullptr;
+      h->h_pack_cap = 0;
+    }
+    const size_t want = pack_need + pack_need / 4 + 4096;
+    cudaError_t e = cudaHostAlloc(&h->h_pack, want, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail((int)e, "cudaHostAlloc(batch window)");
+    h->h_pack_cap = want;
+  }
+  if ((err = ensure(&h->d_in, &h->d_in_cap, in_bytes, h->s_main))) return err;
+  if ((err = ensure(&h->d_out, &h->d_out_cap, out_bytes + 16, h->s_main))) return err;
+  unsigned long long *offs = static_cast<unsigned long long *>(h->h_pack);
+  char *bytes = static_cast<char *>(h->h_pack) + data_off;
+  size_t at = 0;
+  for (size_t i = 0; i < n; i++) {
+    offs[i] = at;
+    if (h_lens[i]) std::memcpy(bytes + at, h_strings[i], h_lens[i]);
+    at += h_lens[i];
+  }
+  offs[n] = at;
+  B200_CUDA(cudaMemcpyAsync(h->d_in, h->h_pack, data_off + total, cudaMemcpyHostToDevice, h->s_main));
+  const char *d_data = static_cast<const char *>(h->d_in) + data_off;
+  const unsigned long long *d_offs = static_cast<const unsigned long long *>(h->d_in);
+  char *d_res = static_cast<char *>(h->d_out);
+  uint16_t *d_units = reinterpret_cast<uint16_t *>(d_res + res_bytes);
+  if (mode == 3) {
+    B200_CUDA(launch_utf8_to_utf16_batch(c->sm_count, h->s_main, false, d_data, d_offs, n, d_units, nullptr, d_res));
+  } else {
+    B200_CUDA(launch_utf8_batch(c->sm_count, h->s_main, mode, d_data, d_offs, n, d_res));
+  }
+  // the packed strings are on the device: the window is free to receive the results (and the units)
+  B200_CUDA(cudaMemcpyAsync(h->h_pack, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->s_main));
+  B200_CUDA(cudaStreamSynchronize(h->s_main));
+  std::memcpy(h_res, h->h_pack, n * res_elem);
+  if (mode == 3) {
+    const b200_result *r = static_cast<const b200_result *>(h_res);
+    const uint16_t *units = reinterpret_cast<const uint16_t *>(static_cast<const char *>(h->h_pack) + res_bytes);
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (r[i].error == 0 && r[i].count && h_outs[i]) std::memcpy(h_outs[i], units + o, r[i].count * sizeof(uint16_t));
+      o += h_lens[i];
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+int b200_validate_utf8_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n, b200_result *d_results, void *stream) {
+  return batch_async(0, false, d_data, d_offsets, n, nullptr, nullptr, d_results, stream);
+}
+int b200_count_utf8_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n, uint64_t *d_counts, void *stream) {
+  return batch_async(1, false, d_data, d_offsets, n, nullptr, nullptr, d_counts, stream);
+}
+int b200_utf16_length_from_utf8_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n, uint64_t *d_counts, void *stream) {
+  return batch_async(2, false, d_data, d_offsets, n, nullptr, nullptr, d_counts, stream);
+}
+int b200_convert_utf8_to_utf16le_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n, uint16_t *d_out,
+                                             const uint64_t *d_out_offsets, b200_result *d_results, void *stream) {
+  return batch_async(3, false, d_data, d_offsets, n, d_out, d_out_offsets, d_results, stream);
+}
+int b200_convert_utf8_to_utf16be_batch_async(const char *d_data, const uint64_t *d_offsets, size_t n, uint16_t *d_out,
+                                             const uint64_t *d_out_offsets, b200_result *d_results, void *stream) {
+  return batch_async(3, true, d_data, d_offsets, n, d_out, d_out_offsets, d_results, stream);
+}
+int b200_host_validate_utf8_batch(const char *const *h_strings, const size_t *h_lens, size_t n, b200_result *h_results) {
+  return batch_host(0, h_strings, h_lens, n, nullptr, h_results);
+}
+int b200_host_count_utf8_batch(const char *const *h_strings, const size_t *h_lens, size_t n, uint64_t *h_counts) {
+  return batch_host(1, h_strings, h_lens, n, nullptr, h_counts);
+}
+int b200_host_utf16_length_from_utf8_batch(const char *const *h_strings, const size_t *h_lens, size_t n, uint64_t *h_counts) {
+  return batch_host(2, h_strings, h_lens, n, nullptr, h_counts);
+}
+int b200_host_convert_utf8_to_utf16le_batch(const char *const *h_strings, const size_t *h_lens, size_t n, uint16_t *const *h_outs,
+                                            b200_result *h_results) {
+  return batch_host(3, h_strings, h_lens, n, h_outs, h_results);
 }
 
 // ---- sharded multi-device entry points ----

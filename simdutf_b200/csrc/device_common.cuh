@@ -38,6 +38,13 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *p) {
                : "l"(p));
   return r;
 }
+// Coherent streaming load: for kernels whose output may alias their input (in-place to_well_formed_utf16 /
+// change_endianness_utf16): PTX defines ld.global.nc only for memory that stays read-only for the kernel's lifetime.
+__device__ __forceinline__ uint4 ld_cs_v4(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ void stg_stream_v4(uint4 *p, const uint4 &v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

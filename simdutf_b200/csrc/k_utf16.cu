@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kBlock) k_swap_utf16(const uint16_t *in, size_
     const uint4 *vi = reinterpret_cast<const uint4 *>(in + head);
     uint4 *vo = reinterpret_cast<uint4 *>(out + head);
     for (size_t v = tid; v < nvec; v += nthreads) {
-      uint4 x = ldg_stream_v4(vi + v);
+      uint4 x = ld_cs_v4(vi + v);
       x.x = swap16x2(x.x); x.y = swap16x2(x.y); x.z = swap16x2(x.z); x.w = swap16x2(x.w);
       stg_stream_v4(vo + v, x);
     }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kBlock) k_well_formed_utf16(const uint16_t *in
     uint4 *vo = reinterpret_cast<uint4 *>(out + head);
     for (size_t v = tid; v < nvec; v += nthreads) {
       const size_t i0 = head + 8 * v;
-      const uint4 x = ldg_stream_v4(vi + v);
+      const uint4 x = ld_cs_v4(vi + v);
       const uint32_t w[4] = {x.x, x.y, x.z, x.w};
       uint32_t u[10];
       u[0] = i0 ? in[i0 - 1] : 0u;

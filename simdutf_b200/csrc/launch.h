@@ -115,6 +115,14 @@ cudaError_t launch_binary_to_base64(const LaunchCtx &c, const char *in, size_t l
 cudaError_t launch_sharded_combine(const unsigned long long *gathered, int world, int rank, int count_is_length,
                                    unsigned long long *out, cudaStream_t stream);
 
+// many small strings per launch (k_batch.cu): string i = data[offs[i] .. offs[i + 1]); mode 0 validate (res = b200_result[n]),
+// 1 count_utf8, 2 utf16_length_from_utf8 (res = uint64[n])
+cudaError_t launch_utf8_batch(int sm_count, cudaStream_t stream, int mode, const char *data, const unsigned long long *offs,
+                              unsigned long long n, void *res);
+cudaError_t launch_utf8_to_utf16_batch(int sm_count, cudaStream_t stream, bool big_endian, const char *data,
+                                       const unsigned long long *offs, unsigned long long n, uint16_t *out,
+                                       const unsigned long long *out_offs, void *res);
+
 void count_launch(int n);  // bumps the library-wide launch counter (b200_launch_count)
 
 // Experiment knobs (b200_set_tuning in the C ABI; tools/ and profiles/ use them to compare kernel variants inside

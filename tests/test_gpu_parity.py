@@ -1106,3 +1106,51 @@ def test_host_streaming_segments(b, oracle):
     u[p] = 0xDC00
     assert b.validate_utf16le_with_errors(u) == (6, p)
     assert b.convert_utf16le_to_utf8_with_errors(u, back) == (6, p)
+
+
+def test_batch_of_small_strings(b, oracle):
+    """many small strings per launch.  Every string of a batch gets the result the
+    single-string entry point gives (the oracle's), for valid, truncated, overlong, surrogate and too-large
+    strings, empty strings included, in one launch per operation (reference
+    tests/validate_utf8_with_errors_tests.cpp:54-69 walks such strings one call at a time)."""
+    import random
+    rng = random.Random(20261018)
+    pool = ["a", "é", "€", "😀", "\x00", "z" * 40, "日本語" * 11, "😀" * 9]
+    strings = [b"", b"A", b"\xff", b"\x80", b"\xc0\x80", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe2\x82", b"ab\xf0\x9f\x98"]
+    for _ in range(3000):
+        k = rng.randrange(0, 60)
+        s = "".join(rng.choice(pool) for _ in range(k)).encode()
+        roll = rng.random()
+        if roll < 0.15 and s:      # cut a character short / corrupt a byte
+            s = s[: rng.randrange(1, len(s) + 1)]
+        elif roll < 0.25 and s:
+            i = rng.randrange(len(s))
+            s = s[:i] + bytes([rng.choice([0x80, 0xC0, 0xF5, 0xFF, 0xED, 0xA0])]) + s[i + 1:]
+        strings.append(s)
+    strings += [("x" * n).encode() for n in (31, 32, 33, 1023, 1024, 1025)] + [("é" * 700).encode(), ("€" * 341 + "a").encode()]
+    launches0 = b.launch_count()
+    got_v = b.validate_utf8_batch(strings)
+    got_l = b.utf16_length_from_utf8_batch(strings)
+    got_c = b.count_utf8_batch(strings)
+    got_t = b.convert_utf8_to_utf16le_batch(strings)
+    assert b.launch_count() - launches0 == 4, "a batch is ONE launch per operation"
+    for i, s in enumerate(strings):
+        assert got_v[i] == oracle.validate_utf8_with_errors(s), (i, s)
+        assert got_l[i] == oracle.utf16_length_from_utf8(s), (i, s)
+        assert got_c[i] == oracle.count_utf8(s), (i, s)
+        (werr, wcnt), wout = oracle.convert_utf8_to_utf16le_with_errors(s)
+        assert got_t[i][0] == (werr, wcnt), (i, s)
+        if werr == 0:
+            assert got_t[i][1] == wout.tobytes(), (i, s)
+    # device flavour on a packed buffer at odd offsets
+    import torch
+    packed = b"".join(strings)
+    offs = [0]
+    for s in strings:
+        offs.append(offs[-1] + len(s))
+    d = torch.frombuffer(bytearray(b"#" + packed), dtype=torch.uint8).cuda()[1:]
+    o = torch.tensor(offs, dtype=torch.int64).cuda()
+    r = b.validate_utf8_batch_device(d, o).cpu()
+    for i, s in enumerate(strings):
+        assert (int(r[i, 0]) & 0xFFFFFFFF, int(r[i, 1])) == oracle.validate_utf8_with_errors(s), (i, s)
+    assert b.validate_utf8_batch([]) == []

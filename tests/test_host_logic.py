@@ -117,6 +117,8 @@ def test_no_device_means_loud_failure(lib):
         lambda: b.convert_utf16le_to_latin1_with_errors(u16, out), lambda: b.convert_utf32_to_latin1_with_errors(u32, out),
         lambda: b.to_well_formed_utf16le(u16, out.view(np.uint16)[:3]), lambda: b.detect_encodings(data),
         lambda: b.base64_to_binary_details(b"QUJD", out, 0, 0), lambda: b.binary_to_base64(data, out, 0),
+        lambda: b.validate_utf8_batch([data, b"x"]), lambda: b.utf16_length_from_utf8_batch([data]),
+        lambda: b.count_utf8_batch([data]), lambda: b.convert_utf8_to_utf16le_batch([data, b""]),
     ]
     for i, call in enumerate(calls):
         with pytest.raises(b.B200Error):

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or utf8_small or utf8_error or utf8_medium or bitplane or utf16be or utf32_family or repeated or beyond_4gib or host_streaming or config2" > gpurun_out/r2_k3_final_parity.log 2>&1; echo "parity rc=$?"; tail -n 3 gpurun_out/r2_k3_final_parity.log
-timeout 100 python tools/prof_one.py convert16 1073741824 10 2>&1 | tail -1
-timeout 100 python tools/prof_one.py convert32 1073741824 10 2>&1 | tail -1
-timeout 100 python tools/dbg_timing.py 8 2>&1 | tail -4
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "batch" > gpurun_out/r2_batch.log 2>&1; echo "batch rc=$?"; tail -n 15 gpurun_out/r2_batch.log
+timeout 100 python tools/prof_one.py validate_mixed 1073741824 10 > gpurun_out/r2_k1_mixed.log 2>&1; tail -n 1 gpurun_out/r2_k1_mixed.log
+timeout 100 python tools/prof_one.py validate_ascii 1073741824 10 > gpurun_out/r2_k1_ascii.log 2>&1; tail -n 1 gpurun_out/r2_k1_ascii.log
+timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "well_formed or utf16be or utf16_random" > gpurun_out/r2_wf.log 2>&1; echo "wf rc=$?"; tail -n 3 gpurun_out/r2_wf.log
