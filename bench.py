@@ -738,6 +738,31 @@ def side_measurements(b, lib, synth, torch, device, stream, sp, peak, K):
     rec("next_convert_latin1_to_utf32", timeit(lambda: lib.b200_convert_latin1_to_utf32_async(p_(lat), nl, p_(o32), res_p, sp), K), nl, 4 * nl)
     rec("next_convert_utf32_to_latin1", timeit(lambda: lib.b200_convert_utf32_to_latin1_async(p_(o32), nl, p_(ol), res_p, sp), K), 4 * nl, nl)
     assert int(d_res[0].item()) & 0xFFFFFFFF == 0 and int(d_res[1].item()) == nl
+    # §8f rank 4: the batched front end — one million strings of 64 bytes of the mixed distribution in ONE launch per
+    # operation (device flavour), next to the same strings validated one host call at a time (a sample of them)
+    nstr, slen = 1 << 20, 64
+    one = torch.tensor([0xE4, 0xB8, 0x80] * 10 + [0xC3, 0xA9] * 8 + [0xF0, 0x9F, 0x98, 0x80] * 4 + [0x61, 0x62], dtype=torch.uint8, device=device)
+    assert one.numel() == slen  # a valid 64-byte string with 1-, 2-, 3- and 4-byte characters
+    packed = one.repeat(nstr).contiguous()
+    offs = (torch.arange(nstr + 1, dtype=torch.int64, device=device) * slen).contiguous()
+    bres = torch.zeros((nstr, 2), dtype=torch.int64, device=device)
+    ms = timeit(lambda: lib.b200_validate_utf8_batch_async(p_(packed), p_(offs), nstr, p_(bres), sp), K)
+    out["next_validate_utf8_batch_1Mi_strings_x_64B"] = {"input_gbs": nstr * slen / ms / 1e6, "ms": ms, "strings_per_s": nstr / ms * 1e3,
+                                                          "frac_of_peak": nstr * slen / ms / 1e6 / peak}
+    bunits = torch.empty(nstr * slen, dtype=torch.int16, device=device)
+    ms = timeit(lambda: lib.b200_convert_utf8_to_utf16le_batch_async(p_(packed), p_(offs), nstr, p_(bunits), None, p_(bres), sp), half)
+    out["next_convert_utf8_to_utf16le_batch_1Mi_strings_x_64B"] = {"input_gbs": nstr * slen / ms / 1e6, "ms": ms, "strings_per_s": nstr / ms * 1e3}
+    hs = packed[: 2000 * slen].cpu().numpy().tobytes()
+    hstr = [hs[k * slen:(k + 1) * slen] for k in range(2000)]
+    t0 = time.perf_counter()
+    for x in hstr:
+        b.validate_utf8_with_errors(x)
+    one_by_one = (time.perf_counter() - t0) / len(hstr)
+    t0 = time.perf_counter()
+    b.validate_utf8_batch(hstr)
+    out["next_host_validate_utf8_2000_strings_x_64B"] = {"us_per_string_single_calls": one_by_one * 1e6,
+                                                          "us_per_string_one_batch_call": (time.perf_counter() - t0) / len(hstr) * 1e6}
+    del packed, offs, bres, bunits
     return out
 
 
