@@ -399,6 +399,37 @@ def test_bitplane_edge_paths(b, oracle):
             run_b64(b, oracle, dense, opt, lc, misalign=rng.randrange(16), host_too=False)
 
 
+def test_single_pass_transcoder_structure(b, oracle):
+    """K3 (k_utf8_transcode_v3): sizes around its CTA-tile (11 warp-tiles = 22 KiB; UTF-32: 11 KiB), around one wave of
+    the persistent grid (296 CTAs) and a few waves beyond it — ticket hand-out past the first wave, the four-slot
+    hand-off rings wrapping, look-backs longer than one 128-descriptor window — with whole-tile ASCII runs (copied out
+    without staging) between mixed text, every output alignment class (the deferred copy-out realigns by words), an
+    error in the last wave, and a buffer that is nothing but sentinel tickets for most CTAs."""
+    rng = random.Random(4711)
+    tile = 11 * 2048
+    base = rand_text(rng, 1024 * 1024)
+    for n in (1, 2047, 2048, 2049, tile - 1, tile, tile + 1, 2 * tile + 17, 296 * tile - 5, 296 * tile + 2048, 3 * 296 * tile + 12345):
+        data = bytearray((base * (n // len(base) + 1))[:n])
+        while data and (data[-1] & 0xC0) == 0x80:   # do not end inside a character ...
+            data.pop()
+        if data and data[-1] >= 0xC0:               # ... nor on a lead
+            data.pop()
+        # whole-tile ASCII runs at tile-aligned and unaligned places
+        for k in range(3 * tile + 5, len(data) - 4 * tile, 37 * tile + 1000):
+            data[k:k + 3 * tile] = bytes(0x41 + (i % 26) for i in range(3 * tile))
+        data = bytes(data)
+        for mis in (0, 1, 5, 15):
+            run_utf8(b, oracle, _repair(data), misalign=mis, host_too=False)
+    big = bytearray(_repair(bytes((base * 9)[: 3 * 296 * tile + 999])))
+    big[len(big) - 3 * tile - 7] = 0xFF            # an error in the last wave
+    run_utf8(b, oracle, bytes(big), misalign=3, host_too=False)
+
+
+def _repair(data: bytes) -> bytes:
+    """Make a spliced byte string valid UTF-8 again: decode leniently and re-encode."""
+    return data.decode("utf-8", errors="ignore").encode("utf-8")
+
+
 def test_utf16be_twins(b, oracle):
     """the UTF-16BE twins and change_endianness_utf16 against the oracle — random text, every
     misalignment class, surrogate errors at tile edges, the host path."""
