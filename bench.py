@@ -550,8 +550,8 @@ def one_process_e2e(b, lib, synth, torch, device, world, total_bytes, total_unit
             "ms_per_step": sec * 1e3}
 
 
-CONVERT_KERNEL_NAME = ("k_utf8_transcode_v3 (convert_utf8_to_utf16le_with_errors = ONE launch: bit-plane transcoder, 11 worker warps + "
-                       "a scan warp per CTA; output offsets from a decoupled look-back that runs two tiles ahead of the copy-out; "
+CONVERT_KERNEL_NAME = ("k_utf8_transcode_v3 (convert_utf8_to_utf16le_with_errors = ONE launch: bit-plane transcoder, one CTA of 16 worker warps + "
+                       "a scan warp per SM; output offsets from a decoupled look-back that runs two tiles ahead of the copy-out; "
                        "the input crosses HBM once)")
 
 

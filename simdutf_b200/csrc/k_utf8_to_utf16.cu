@@ -235,13 +235,13 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
   constexpr uint32_t kUB = Gm::kUnitBytes;
   extern __shared__ __align__(16) uint32_t smem[];  // [NW][2] staging buffers
   // hand-off rings, slot i & 3 for the CTA's i-th tile
-  __shared__ uint32_t s_tot[4][16];               // workers -> scan warp: the warp totals
-  __shared__ unsigned long long s_goff[4][16];    // scan warp -> workers: every worker's global output offset
+  __shared__ uint32_t s_tot[4][32];               // workers -> scan warp: the warp totals
+  __shared__ unsigned long long s_goff[4][32];    // scan warp -> workers: every worker's global output offset
   __shared__ uint32_t s_ticket[4];               // the CTA-tile index
   __shared__ uint32_t s_acc[4];                  // arrivals << 16 | sum of the warp totals
   __shared__ uint32_t s_elect[4];                // workers that have reached pass 2
   __shared__ __align__(8) unsigned long long s_mbar[12];  // [0,4) ticket posted, [4,8) offsets posted, [8,12) totals in
-  static_assert(NW <= 15, "one scan warp lane per worker; 16-bit packing of the warp totals");
+  static_assert(NW <= 31 && (uint32_t)NW * Gm::kTileBytes < 65536u, "one scan warp lane per worker; 16-bit packing of the warp totals");
   const InView in = make_view32(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s_mbar);
@@ -653,22 +653,29 @@ cudaError_t launch_v3(const LaunchCtx &c, const char *in, size_t len, void *out,
 }  // namespace
 
 // Workspace, in 8-byte descriptor slots, the kernel needs for an input of `len` bytes: one descriptor per CTA-tile.
-size_t utf8_to_utf16_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 2, 31u)) + 2; }
+size_t utf8_to_utf16_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 1, 31u)) + 2; }
 size_t utf8_to_utf32_tiles(const void *in, size_t len) { return cta_tiles_for(tiles_for(in, len, 1, 31u)) + 2; }
 
 cudaError_t launch_convert_utf8_to_utf16(const LaunchCtx &c, const char *in, size_t len, uint16_t *out, void *res,
                                          bool big_endian) {
-  // 11 workers + the scan warp per CTA, two CTAs per SM.  Measured on B200, 1 GiB of the mixed distribution
-  // (tools/variant_check.py): 7 workers x 3 CTAs 0.934 ms, 11 x 2 0.885, 12 x 2 0.893, 13 x 2 0.954; 11 x 2 with the
-  // compaction predicates through R2P 0.868.
-  if (big_endian) return launch_v3<2, 2, false, true, 11>(c, in, len, out, res);
-  if (tuning(kTuneConvVariant) == 8) return launch_v3<2, 2, false, false, 11, true>(c, in, len, out, res);  // clock64 instrumentation (tools/dbg_timing.py)
-  return launch_v3<2, 2, false, false, 11>(c, in, len, out, res);
+  // ONE CTA per SM: 16 worker warps (four per warp scheduler) + the scan warp, 96 bytes per lane (3 KiB warp-tiles, 48 KiB
+  // CTA-tiles), 96 registers.  Measured on B200, 1 GiB of the mixed distribution, ms per launch (K = blocks per lane,
+  // workers x CTAs per SM):
+  //   K = 2:  7 x 3  0.934   11 x 2  0.868   12 x 2  0.893   13 x 2  0.954   16 x 1  0.917   20 x 1  0.856   24 x 1  0.844
+  //   K = 3: 11 x 1  0.963   12 x 1  0.890   15 x 1  0.826   16 x 1  0.786   17 x 1  0.924   18 x 1  0.847
+  //   K = 1: 15 x 2  1.021;  K = 4: 12 x 1  0.967
+  // The workers of a CTA are coupled through the tile hand-offs, so the scheduler with the most workers sets the pace:
+  // 16 (4-4-4-4) beats 15 and 17; larger tiles amortise the per-tile hand-offs, and the fatter warps (96-126 registers)
+  // make up for the lower occupancy.
+  if (big_endian) return launch_v3<3, 1, false, true, 16>(c, in, len, out, res);
+  if (tuning(kTuneConvVariant) == 8) return launch_v3<3, 1, false, false, 16, true>(c, in, len, out, res);  // clock64 instrumentation (tools/dbg_timing.py)
+  return launch_v3<3, 1, false, false, 16>(c, in, len, out, res);
 }
 
 cudaError_t launch_convert_utf8_to_utf32(const LaunchCtx &c, const char *in, size_t len, uint32_t *out, void *res) {
-  // 32-bit elements double the staging buffers: one block per lane (1 KiB warp-tiles) keeps two CTAs of 11 workers on an SM
-  return launch_v3<1, 2, true, false, 11>(c, in, len, out, res);
+  // 32-bit elements double the staging buffers: 64 bytes per lane, 12 workers (three per scheduler), one CTA per SM
+  // (1.052 ms per GiB; one block per lane, 11 x 2: 1.169; 16 x 1: 1.255; 24 x 1: 1.100)
+  return launch_v3<2, 1, true, false, 12>(c, in, len, out, res);
 }
 
 }  // namespace b200

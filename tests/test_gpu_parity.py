@@ -400,15 +400,15 @@ def test_bitplane_edge_paths(b, oracle):
 
 
 def test_single_pass_transcoder_structure(b, oracle):
-    """K3 (k_utf8_transcode_v3): sizes around its CTA-tile (11 warp-tiles = 22 KiB; UTF-32: 11 KiB), around one wave of
-    the persistent grid (296 CTAs) and a few waves beyond it — ticket hand-out past the first wave, the four-slot
+    """K3 (k_utf8_transcode_v3): sizes around its CTA-tile (16 warp-tiles of 3 KiB = 48 KiB; UTF-32: 12 x 2 KiB), around
+    one wave of the persistent grid (one CTA per SM: 148) and a few waves beyond it — ticket hand-out past the first wave, the four-slot
     hand-off rings wrapping, look-backs longer than one 128-descriptor window — with whole-tile ASCII runs (copied out
     without staging) between mixed text, every output alignment class (the deferred copy-out realigns by words), an
     error in the last wave, and a buffer that is nothing but sentinel tickets for most CTAs."""
     rng = random.Random(4711)
-    tile = 11 * 2048
+    tile, grid = 16 * 3072, 148
     base = rand_text(rng, 1024 * 1024)
-    for n in (1, 2047, 2048, 2049, tile - 1, tile, tile + 1, 2 * tile + 17, 296 * tile - 5, 296 * tile + 2048, 3 * 296 * tile + 12345):
+    for n in (1, 2047, 2048, 2049, tile - 1, tile, tile + 1, 2 * tile + 17, 12 * 2048 + 3, grid * tile - 5, grid * tile + 3072, 3 * grid * tile + 12345):
         data = bytearray((base * (n // len(base) + 1))[:n])
         while data and (data[-1] & 0xC0) == 0x80:   # do not end inside a character ...
             data.pop()
@@ -420,7 +420,7 @@ def test_single_pass_transcoder_structure(b, oracle):
         data = bytes(data)
         for mis in (0, 1, 5, 15):
             run_utf8(b, oracle, _repair(data), misalign=mis, host_too=False)
-    big = bytearray(_repair(bytes((base * 9)[: 3 * 296 * tile + 999])))
+    big = bytearray(_repair(bytes((base * 9)[: 3 * grid * tile + 999])))
     big[len(big) - 3 * tile - 7] = 0xFF            # an error in the last wave
     run_utf8(b, oracle, bytes(big), misalign=3, host_too=False)
 
