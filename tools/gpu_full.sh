@@ -1,8 +1,9 @@
 #!/bin/bash
-# Full GPU check: parity tests, smoke, bench (own arm + reference arm), reference test binaries.
+# Full GPU check: every -m gpu test (parity, full-size configs against the reference, the reference's own binaries,
+# the sharded path), smoke, then bench (own arm + reference arm).
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -n 5 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/smoke.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"; cat gpurun_out/bench_ref.json
+timeout 1700 python -m pytest tests -m gpu -q --durations=25 > gpurun_out/r02_pytest_gpu_full.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r02_pytest_gpu_full.log
+tail -n 8 gpurun_out/r02_pytest_gpu_full.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/r02_smoke.log
+timeout 600 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02_bench.json; tail -n 3 gpurun_out/r02_bench.err
+timeout 300 python bench.py --impl reference > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; echo "bench ref rc=$?"; cut -c1-300 gpurun_out/r02_bench_ref.json
