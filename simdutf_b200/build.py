@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libsimdutf_b200.so")
 SOURCES = ["k_utf8.cu", "k_utf8_to_utf16.cu", "k_utf16.cu", "k_utf16_to_utf8.cu", "k_utf32.cu", "k_latin1.cu", "k_base64.cu", "k_sharded.cu", "k_batch.cu", "capi.cu"]
-HEADERS = ["swar.h", "bitplane.h", "bp_device.cuh", "elem_device.cuh", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
+HEADERS = ["swar.h", "bitplane.h", "bp_device.cuh", "sp_device.cuh", "elem_device.cuh", "device_common.cuh", "launch.h", os.path.join("..", "..", "include", "simdutf_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -483,6 +483,13 @@ B200_HD Carry16 carry16_from_unit(uint32_t pu) {
   c.w1 = (pu & 2u) << 30;
   return c;
 }
+// e1 / e2 alone (units that emit a second / a third byte): what the counting pass of the single-pass transcoder needs.
+B200_HD void utf16_emit_masks(const uint32_t (&W)[16], uint32_t &e1, uint32_t &e2) {
+  const uint32_t ge800 = W[11] | W[12] | W[13] | W[14] | W[15];
+  const uint32_t sur = W[15] & W[14] & ~W[13] & W[12] & W[11];
+  e1 = ge800 | W[7] | W[8] | W[9] | W[10];
+  e2 = ge800 & ~sur;
+}
 B200_HD uint32_t utf16_to_utf8_block(const uint32_t (&W)[16], Carry16 &c, uint32_t (&X)[32], uint32_t &e1, uint32_t &e2) {
   const uint32_t ge800 = W[11] | W[12] | W[13] | W[14] | W[15];
   const uint32_t na = ge800 | W[7] | W[8] | W[9] | W[10];                // not ASCII

@@ -2,15 +2,11 @@
 // (reference include/simdutf/implementation.h:4038-4080; semantics src/scalar/utf16_to_utf8/utf16_to_utf8.h:82-153,
 // surrogate rule src/scalar/utf16.h:39-67).
 //
-// Same shape as the UTF-8 -> UTF-16 transcoder (k_utf8_to_utf16.cu):
-//   K6a  k_utf8len_tile_counts   per warp-tile (32 lanes x 32 units = 2 KiB of input) the number of UTF-8 bytes it
-//        emits — utf8_length_from_utf16le restricted to the tile (reference src/scalar/utf16.h:80-94; every unit
-//        contributes on its own, a surrogate counts 2) — then chunk totals -> exclusive chunk offsets.  16-bit-lane
-//        SWAR + popcount, HBM-bound.
-//   K6b  k_utf16_to_utf8_bp      bit-plane transcoder (bitplane.h: utf16_to_utf8_block): every lane transposes its 32
-//        contiguous units into 16 planes, builds the 24 planes of (byte0, byte1, byte2) of every unit, transposes them
-//        back to one 24-bit word per unit and compacts the 1..3 bytes per unit with predicated byte stores into its
-//        private staging region, which it then streams out as 16-byte vectors.
+// ONE launch, the single-pass skeleton of the UTF-8 -> UTF-16 transcoder (k_utf8_to_utf16.cu, sp_device.cuh): every lane
+// transposes its 32 contiguous units into 16 planes (bitplane.h: utf16_to_utf8_block), builds the 24 planes of (byte0,
+// byte1, byte2) of every unit, transposes them back to one 24-bit word per unit and compacts the 1..3 bytes per unit with
+// predicated byte stores into the warp's staging buffer; the output offsets come from a decoupled look-back that runs two
+// tiles ahead of the copy-out.  (Round 1: a counts kernel + a transcoder, the input read twice.)
 // First error = minimum over flagged blocks of the exact surrogate verdict.
 #include <cstdlib>
 
@@ -18,30 +14,12 @@
 #include "bp_device.cuh"
 #include "device_common.cuh"
 #include "launch.h"
+#include "sp_device.cuh"
 
 namespace b200 {
 
 namespace {
 
-using bpd::kChunkTiles;
-using bpd::kThreads;
-using bpd::kWarpsPerCta;
-
-constexpr uint32_t kRegionBytes = 64u;                 // 32 units per lane
-constexpr uint32_t kTileBytes = 32u * kRegionBytes;    // 2 KiB per warp
-constexpr uint32_t kTileGranules = kTileBytes / 16u;   // 128
-constexpr uint32_t kStrideWords = ((96u + 16u) / 4u) | 1u;  // <= 96 bytes + 15 bytes of alignment pad, odd stride
-constexpr uint32_t kSmemBytes = kWarpsPerCta * 32u * kStrideWords * 4u;
-constexpr uint32_t kMaxVec = (96u + 15u) / 16u;
-
-__device__ __forceinline__ InView make_view_u16(const uint16_t *p, size_t len_units) {
-  InView v;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
-  v.vbeg = a & 15u;
-  v.vend = v.vbeg + 2ull * len_units;
-  return v;
-}
 
 __device__ __forceinline__ uint32_t swap16x2(uint32_t w) { return __byte_perm(w, 0u, 0x2301); }
 
@@ -73,69 +51,6 @@ static __device__ __noinline__ void u16_locate_error(const uint4 *base, unsigned
       return;
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K6a: per-tile byte counts (granule layout: lane l, item j owns granule g0 + 32 j + l)
-// ---------------------------------------------------------------------------------------------
-template <bool BE>
-__device__ __forceinline__ uint32_t count_tile_utf8len(const InView &in, unsigned long long g0) {
-  const unsigned lane = threadIdx.x & 31u;
-  const bool interior = g0 * 16ull >= in.vbeg && (g0 + kTileGranules) * 16ull <= in.vend;
-  uint32_t cnt = 0;
-  if (interior) {
-    uint4 v[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) v[j] = ldg_stream_v4(in.base + g0 + (unsigned long long)j * 32u + lane);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-      if (BE) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = swap16x2(w[k]);
-      }
-      uint32_t m = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        // per 16-bit lane: bit 15 of ge80 / ge800 / notsur <=> unit >= 0x80 / >= 0x800 / not in D800..DFFF
-        const uint32_t h = w[k] >> 1;
-        const uint32_t ge80 = (h & 0x7FC07FC0u) + 0x7FC07FC0u;
-        const uint32_t ge800 = (h & 0x7C007C00u) + 0x7C007C00u;
-        const uint32_t z = (w[k] ^ 0xD800D800u) & 0xF800F800u;
-        const uint32_t notsur = (z >> 1) + 0x7C007C00u;
-        const uint32_t mk = (ge80 & 0x80008000u) | ((ge800 & notsur & 0x80008000u) >> 1);
-        m |= mk >> (2 * k);
-      }
-      cnt += 8u + (uint32_t)__popc(m);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-      uint32_t w[4];
-      bool inside;
-      load_granule(in, g, w, inside);
-      if (BE) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = swap16x2(w[k]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const unsigned long long pos = g * 16ull + 2u * i;
-        if (pos >= in.vbeg && pos < in.vend) cnt += u16_utf8_bytes(u16_unit(w, i));
-      }
-    }
-  }
-  return bpd::warp_sum_u32(cnt);
-}
-
-template <bool BE>
-__global__ void __launch_bounds__(kThreads) k_utf8len_tile_counts(const uint16_t *ptr, size_t len, uint16_t *tile_cnt,
-                                                                   unsigned long long *chunk_off, uint32_t num_tiles,
-                                                                   uint32_t num_chunks, Scratch *scr) {
-  const InView in = make_view_u16(ptr, len);
-  bpd::counts_pass([&](uint32_t t) -> uint32_t { return count_tile_utf8len<BE>(in, (unsigned long long)t * kTileGranules); },
-                   tile_cnt, chunk_off, num_tiles, num_chunks, scr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -187,221 +102,271 @@ __device__ __forceinline__ void compact_block(const uint32_t (&X)[32], uint32_t 
   }
 }
 
-template <int MINB, bool BE>
-__global__ void __launch_bounds__(kThreads, MINB)
-k_utf16_to_utf8_bp(const uint16_t *ptr, size_t len, uint8_t *out, const uint16_t *tile_cnt,
-                   const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
-                   ResultPOD *res) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  const InView in = make_view_u16(ptr, len);
+// ---------------------------------------------------------------------------------------------
+// K6 single pass (round 2): the skeleton of k_utf8_transcode_v3 (k_utf8_to_utf16.cu, sp_device.cuh) with UTF-16 in and
+// bytes out.  ONE launch, the input crosses HBM once: a persistent grid of CTAs of NW worker warps + one scan warp takes
+// CTA-tiles through an atomic ticket; a worker loads its 32K contiguous units (256-bit loads), transposes them, counts
+// the bytes they emit (pass 1: utf16_emit_masks), hands the warp total to the scan warp — the worker that delivers the
+// CTA's last total publishes the aggregate and reserves the next tile — builds the 24 byte planes, transposes back and
+// compacts into the warp's staging buffer i & 1 at alignment ZERO (pass 2), and copies tile i out two tiles later, when
+// the look-back has long delivered its global offset: 32-bit words, 128 contiguous bytes per warp instruction,
+// realigned to the destination's word grid by one byte permute.
+// ---------------------------------------------------------------------------------------------
+template <int K, int NW>
+struct GeomV3 {
+  static constexpr uint32_t kRegionBytes = 64u * K;                      // 32K units per lane
+  static constexpr uint32_t kTileBytes = 32u * kRegionBytes;
+  static constexpr uint32_t kCtaTileBytes = (uint32_t)NW * kTileBytes;
+  static constexpr uint32_t kTileUnits = kTileBytes / 2u;
+  static constexpr uint32_t kStageBytes = 3u * kTileUnits + 16u;         // <= 3 bytes per unit, + the word behind the last byte
+  static constexpr uint32_t kSmemBytes = (uint32_t)NW * 2u * kStageBytes;
+  static constexpr int kThreads = (NW + 1) * 32;
+};
+
+__device__ __forceinline__ InView make_view_u16_32(const uint16_t *p, size_t len_units) {  // 32-byte-aligned base
+  InView v;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(31));
+  v.vbeg = a & 31u;
+  v.vend = v.vbeg + 2ull * len_units;
+  return v;
+}
+
+// staging (bytes [0, n) at alignment zero) -> dst[0 .. n)
+__device__ __forceinline__ void copy_out_bytes(uint32_t stage_addr, uint32_t n, uint8_t *dst, unsigned lane) {
+  uint32_t h = (uint32_t)(0u - (uint32_t)reinterpret_cast<uintptr_t>(dst)) & 3u;  // bytes in front of the first aligned word
+  if (h > n) h = n;
+  if (lane < h) dst[lane] = (uint8_t)sp::lds_u8(stage_addr + lane);
+  const uint32_t nw = (n - h) >> 2;
+  uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + h);
+  const uint32_t sel = 0x3210u + 0x1111u * h;  // word w of the destination = staging bytes [h + 4w, h + 4w + 4)
+#pragma unroll 4
+  for (uint32_t w = lane; w < nw; w += 32u) {
+    const uint32_t a = sp::lds_u32(stage_addr + 4u * w), b = sp::lds_u32(stage_addr + 4u * w + 4u);
+    sp::stg_cs_u32(d32 + w, __byte_perm(a, b, sel));
+  }
+  const uint32_t done = h + 4u * nw;
+  if (lane < n - done) dst[done + lane] = (uint8_t)sp::lds_u8(stage_addr + done + lane);
+}
+
+struct PendingU16 {
+  uint32_t wtot = 0, iter = 0;
+  bool valid = false;
+};
+
+template <int K, int NW, bool BE, int MINB = 1>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB)
+k_utf16_to_utf8_v3(const uint16_t *ptr, size_t len, uint8_t *out, unsigned long long *desc, uint32_t epoch, uint32_t num_tiles,
+                   uint32_t num_cta_tiles, Scratch *scr, ResultPOD *res) {
+  using Gm = GeomV3<K, NW>;
+  extern __shared__ __align__(16) uint32_t smem[];  // [NW][2] staging buffers
+  __shared__ sp::Rings rg;
+  static_assert(NW <= 31, "one scan warp lane per worker");
+  const InView in = make_view_u16_32(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
-  uint32_t *region_w = smem + (warp * 32u + lane) * kStrideWords;  // this lane's private staging region
-  uint8_t *region = reinterpret_cast<uint8_t *>(region_w);
-  const unsigned long long out_addr = (unsigned long long)reinterpret_cast<uintptr_t>(out);
-  const uint32_t one = blockDim.x >> 8;  // 1, but not a constant the assembler can fold (bpd::bump)
-  const long long last_unit = (long long)(in.vend >> 1) - 1;  // virtual index of the buffer's last unit
+  if (threadIdx.x == 0) sp::init_rings(rg, NW);
+  __syncthreads();
 
-  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
-    const unsigned long long t0 = (unsigned long long)tile * kTileBytes;
-    const unsigned long long r0 = t0 + (unsigned long long)lane * kRegionBytes;
-    const bool interior = t0 >= in.vbeg + 16ull && t0 + kTileBytes + 2ull <= in.vend;  // never the tile of the last unit
-    if (tile + nwarps < num_tiles) {
-      const char *nx = reinterpret_cast<const char *>(in.base) + r0 + (unsigned long long)nwarps * kTileBytes;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-    }
-    uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
-    const unsigned long long coff = chunk_off[tile / kChunkTiles];
+  if (warp == (unsigned)NW) {
+    sp::scan_warp<NW, 1>(rg, desc, epoch, num_cta_tiles, scr, nullptr, nullptr);
+  } else {
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(smem) + warp * 2u * Gm::kStageBytes;
+    const uint32_t one = (blockDim.x >> 5) - (uint32_t)NW;  // 1, but not a constant the assembler can fold (bpd::bump)
+    const long long last_unit = (long long)(in.vend >> 1) - 1;  // virtual index of the buffer's last unit
+    PendingU16 q1, q2;  // tiles i - 1 and i - 2
+    auto copy_out = [&](const PendingU16 &q) {
+      const unsigned long long goff = sp::wait_goff(rg, q.iter, warp);
+      if (q.wtot) copy_out_bytes(stage0 + (q.iter & 1u) * Gm::kStageBytes, q.wtot, out + goff, lane);
+      __syncwarp();  // the staging buffer is about to be rewritten
+    };
 
-    // ---- this lane's 32 contiguous units and the unit before them ----
-    uint32_t W[16];
-    uint32_t pu;
-    if (interior) {
-      const uint4 *gp = in.base + (r0 >> 4);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint4 v = __ldg(gp + j);
-        W[4 * j] = v.x; W[4 * j + 1] = v.y; W[4 * j + 2] = v.z; W[4 * j + 3] = v.w;
+    for (uint32_t iter = 0;; iter++) {
+      const uint32_t slot = iter & 3u;
+      const uint32_t ct = sp::wait_ticket(rg, iter);
+      if (ct >= num_cta_tiles) {  // CTA-uniform: drain
+        if (q2.valid) copy_out(q2);
+        if (q1.valid) copy_out(q1);
+        break;
       }
-      pu = unit_guarded(in, (long long)(r0 >> 1) - 1, BE);
-    } else {
+      const uint32_t tile = ct * (uint32_t)NW + warp;
+      const uint32_t stage_cur = stage0 + (iter & 1u) * Gm::kStageBytes;
+      const bool active = tile < num_tiles;
+      const unsigned long long t0 = (unsigned long long)tile * Gm::kTileBytes;
+      const unsigned long long r0 = t0 + (unsigned long long)lane * Gm::kRegionBytes;
+      const bool interior = active && t0 >= in.vbeg + 32ull && t0 + Gm::kTileBytes + 2ull <= in.vend;  // never the tile of the last unit
+      // ---- this lane's 32K contiguous units and the unit before them ----
+      uint32_t W[K][16];
+      uint32_t pu = 0;
+      if (interior) {
+        const uint4 *gp = in.base + (r0 >> 4);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        bool ins;
-        load_granule(in, (r0 >> 4) + (unsigned long long)j, &W[4 * j], ins);
-      }
-      pu = unit_guarded(in, (long long)(r0 >> 1) - 1, BE);
-    }
-    if (BE) {  // host order from here on
+        for (int j = 0; j < K; j++) {
+          sp::ldg_v8(gp + 4 * j, &W[j][0]);
+          sp::ldg_v8(gp + 4 * j + 2, &W[j][8]);
+        }
+        if (lane == 0) pu = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(in.base) + (r0 >> 1) - 1);
+        const uint32_t up = __shfl_up_sync(kFull, W[K - 1][15], 1);
+        if (lane != 0) pu = up >> 16;
+        if (BE) pu = ((pu >> 8) | (pu << 8)) & 0xFFFFu;
+      } else if (active) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) W[i] = swap16x2(W[i]);
-    }
-    before = bpd::warp_sum_u32(before);
-    const unsigned long long goff = coff + before;
-
-    uint32_t hi = 0;
+        for (int j = 0; j < K; j++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) hi |= W[i];
-    hi = (hi & 0xFF80FF80u) | (pu & 0xFF80u);
-    const bool ascii_tile = !__any_sync(kFull, hi != 0u);
-
-    uint32_t e0 = 0xFFFFFFFFu, e1 = 0, e2 = 0, err = 0;
-    uint32_t X[32];
-    if (!interior) e0 = range_mask_split(in, r0);
-    if (!ascii_tile) {
-      bp::transpose_in16(W);
-      bp::Carry16 carry = bp::carry16_from_unit(pu);
-      err = bp::utf16_to_utf8_block(W, carry, X, e1, e2);
-      e1 &= e0;
-      e2 &= e0;
-    }
-    const uint32_t cnt = (uint32_t)__popc(e0) + (uint32_t)__popc(e1) + (uint32_t)__popc(e2);
-    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
-    const unsigned long long G = goff + (incl - cnt);        // global index of this lane's first byte
-    const uint32_t a = (uint32_t)((out_addr + G) & 15ull);   // its offset inside a 16-byte output vector
-
-    // ---- bytes, compaction into the private region ----
-    {
-      const uint32_t spa = (uint32_t)__cvta_generic_to_shared(region + a);
-      if (!ascii_tile) {
-        bp::transpose_out_n<24>(X);
-        if (interior) compact_block<true>(X, e0, e1, e2, spa, one);
-        else compact_block<false>(X, e0, e1, e2, spa, one);
+          for (int g = 0; g < 4; g++) {
+            bool ins;
+            load_granule(in, (r0 >> 4) + 4ull * j + (unsigned long long)g, &W[j][4 * g], ins);
+          }
+        }
+        pu = unit_guarded(in, (long long)(r0 >> 1) - 1, BE);
       } else {
-        uint32_t sp = spa;
 #pragma unroll
-        for (int s = 0; s < 32; s++) {
-          if (e0 & (1u << bp::split_pos(s))) {
-            bpd::sts_u8(sp, W[s >> 1] >> (16 * (s & 1)));
-            sp = bpd::bump<1>(sp, one);
-          }
+        for (int j = 0; j < K; j++) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) W[j][i] = 0u;
         }
       }
-    }
-    // ---- exact error location (rare) ----
-    {
-      const long long u0 = (long long)(r0 >> 1);
-      bool bad = err != 0u;
-      if (!interior && last_unit >= u0 && last_unit < u0 + 32 && in.vend > in.vbeg) {
-        const uint32_t lu = unit_guarded(in, last_unit, BE);
-        bad = bad || (lu & 0xFC00u) == 0xD800u;  // a high surrogate cut off by the end of the buffer
+      if (BE) {  // host order from here on
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) W[j][i] = swap16x2(W[j][i]);
+        }
       }
-      if (bad) u16_locate_error(in.base, in.vbeg, in.vend, scr, u0 - 1, u0 + 32, BE);
-    }
-    __syncwarp();
-
-    // ---- staging -> global ----
-    {
-      uint8_t *gbase = out + G - a;  // 16-byte aligned
-      const uint32_t end = a + cnt;
-      if (__all_sync(kFull, cnt >= 16u)) {
-        // every lane owns the 16-byte vectors that hold its bytes, except its last partial one (owned by the lane to
-        // its right, which copies the bytes in front of its own first one from this lane's tail; that source starts
-        // on a vector boundary of the region: prev_end = a mod 16)
-        const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
-        if (lane > 0) {
-          const uint32_t *src = region_w - kStrideWords + ((prev_end - a) >> 2);
+      // ---- pass 1: planes, emit masks, counts ----
+      uint32_t hi = 0;
 #pragma unroll
-          for (uint32_t u = 0; u < 3; u++)
-            if (4u * u + 4u <= a) region_w[u] = src[u];
-          uint32_t i = a & ~3u;
-          if (a & 2u) {
-            *reinterpret_cast<uint16_t *>(region + i) = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(src) + i);
-            i += 2u;
-          }
-          if (a & 1u) region[i] = reinterpret_cast<const uint8_t *>(src)[i];
-        }
-        const uint32_t vfull = end >> 4;
-        uint32_t v0 = 0;
-        if (lane == 0 && a > 0) {  // the tile's first partial vector is shared with the previous tile: 1 + 2 + 4 + 8 bytes
-          uint32_t i = a;
-          if (i & 1u) { gbase[i] = region[i]; i++; }
-          if (i & 2u) { *reinterpret_cast<uint16_t *>(gbase + i) = *reinterpret_cast<const uint16_t *>(region + i); i += 2u; }
-          if (i & 4u) { *reinterpret_cast<uint32_t *>(gbase + i) = region_w[i >> 2]; i += 4u; }
-          if (i == 8u) *reinterpret_cast<uint2 *>(gbase + 8) = make_uint2(region_w[2], region_w[3]);
-          v0 = 1;
-        }
-        if (lane == 31) {  // the tile's last partial vector is shared with the next tile: 8 + 4 + 2 + 1 bytes
-          const uint32_t r = end & 15u;
-          uint32_t i = vfull * 16u;
-          if (r & 8u) { *reinterpret_cast<uint2 *>(gbase + i) = make_uint2(region_w[i >> 2], region_w[(i >> 2) + 1u]); i += 8u; }
-          if (r & 4u) { *reinterpret_cast<uint32_t *>(gbase + i) = region_w[i >> 2]; i += 4u; }
-          if (r & 2u) { *reinterpret_cast<uint16_t *>(gbase + i) = *reinterpret_cast<const uint16_t *>(region + i); i += 2u; }
-          if (r & 1u) gbase[i] = region[i];
-        }
+      for (int j = 0; j < K; j++) {
 #pragma unroll
-        for (uint32_t v = 0; v < kMaxVec; v++) {
-          if (v >= v0 && v < vfull) {
-            uint4 x;
-            x.x = region_w[4u * v];
-            x.y = region_w[4u * v + 1u];
-            x.z = region_w[4u * v + 2u];
-            x.w = region_w[4u * v + 3u];
-            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, x);
-          }
+        for (int i = 0; i < 16; i++) hi |= W[j][i];
+      }
+      hi = (hi & 0xFF80FF80u) | (pu & 0xFF80u);
+      const bool ascii = interior && !__any_sync(kFull, hi != 0u);  // every lane emits exactly 32K bytes
+      uint32_t e0[K];
+      uint32_t cnt = 0;
+      if (!ascii) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          bp::transpose_in16(W[j]);
+          e0[j] = interior ? 0xFFFFFFFFu : (active ? range_mask_split(in, r0 + 64ull * j) : 0u);
+          uint32_t e1, e2;
+          bp::utf16_emit_masks(W[j], e1, e2);
+          cnt += (uint32_t)__popc(e0[j]) + (uint32_t)__popc(e1 & e0[j]) + (uint32_t)__popc(e2 & e0[j]);
         }
       } else {
-        // edge tiles: byte by byte
-        for (uint32_t i = a; i < end; i++) gbase[i] = region[i];
+        cnt = 32u * K;
       }
+      const uint32_t incl = bpd::warp_inclusive_u32(cnt);
+      const uint32_t wtot = __shfl_sync(kFull, incl, 31);
+      const uint32_t excl = incl - cnt;
+      uint32_t tn = 0;
+      bool took = sp::post_totals<NW>(rg, slot, warp, lane, wtot, ct, desc, epoch, scr, tn);
+      // ---- the tile before the previous one leaves its staging buffer, which is this tile's ----
+      if (q2.valid) copy_out(q2);
+      auto post = [&]() {
+        tn = sp::post_ticket(rg, iter + 1u, tn, lane);
+        if (tn < num_cta_tiles) {  // pull the next CTA-tile into L2
+          const char *nx = reinterpret_cast<const char *>(in.base) + (unsigned long long)tn * Gm::kCtaTileBytes;
+#pragma unroll
+          for (uint32_t k = 0; k < (Gm::kCtaTileBytes + 4095u) / 4096u; k++) {
+            const uint32_t off = k * 4096u + lane * 128u;
+            if (off < Gm::kCtaTileBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
+          }
+        }
+        took = false;
+      };
+      // ---- pass 2: byte planes, transposition back, compaction into the staging buffer at alignment zero ----
+      if (active && !ascii) {
+        bp::Carry16 carry = bp::carry16_from_unit(pu);
+        uint32_t spa = stage_cur + excl;
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          uint32_t X[32];
+          uint32_t e1, e2;
+          const uint32_t err = bp::utf16_to_utf8_block(W[j], carry, X, e1, e2);
+          e1 &= e0[j];
+          e2 &= e0[j];
+          bp::transpose_out_n<24>(X);
+          if (interior) compact_block<true>(X, e0[j], e1, e2, spa, one);
+          else compact_block<false>(X, e0[j], e1, e2, spa, one);
+          spa += (uint32_t)__popc(e0[j]) + (uint32_t)__popc(e1) + (uint32_t)__popc(e2);
+          if (err) {
+            const long long u0 = (long long)((r0 + 64ull * j) >> 1);
+            u16_locate_error(in.base, in.vbeg, in.vend, scr, u0 - 1, u0 + 32, BE);
+          }
+          if (j == 0 && took) post();  // the ticket has had a block's worth of time to come back
+          (void)bad;
+        }
+        if (!interior) {  // a high surrogate cut off by the end of the buffer
+          const long long u0 = (long long)(r0 >> 1);
+          if (last_unit >= u0 && last_unit < u0 + 32 * K && in.vend > in.vbeg) {
+            const uint32_t lu = unit_guarded(in, last_unit, BE);
+            if ((lu & 0xFC00u) == 0xD800u) u16_locate_error(in.base, in.vbeg, in.vend, scr, last_unit - 1, last_unit + 1, BE);
+          }
+        }
+      } else if (ascii) {
+        // 32K units -> 32K bytes per lane, at byte excl = 32K * lane of the staging buffer
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          uint32_t b[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) b[i] = __byte_perm(W[j][2 * i], W[j][2 * i + 1], 0x6420);
+          sp::sts_v4(stage_cur + excl + 32u * j, b[0], b[1], b[2], b[3]);
+          sp::sts_v4(stage_cur + excl + 32u * j + 16u, b[4], b[5], b[6], b[7]);
+        }
+      }
+      if (took) post();
+      __syncwarp();  // the staged bytes are visible to the whole warp
+      q2 = q1;
+      q1.valid = true; q1.wtot = wtot; q1.iter = iter;
     }
-    __syncwarp();  // the regions are rewritten by the next tile
   }
 
   if (grid_last_thread(scr)) {
-    bpd::write_result_from_key(res, ld_relaxed_u64(&scr->err_key), chunk_off[num_chunks]);
+    const unsigned long long total = num_cta_tiles ? desc_value(ld_relaxed_u64(desc + (num_cta_tiles - 1u))) : 0ull;
+    bpd::write_result_from_key(res, ld_relaxed_u64(&scr->err_key), total);
     scratch_reset(scr);
   }
 }
 
-inline size_t tiles_for(const void *in, size_t len_bytes) {
-  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
-  return (span + kTileBytes - 1) / kTileBytes;
-}
-inline size_t workspace_slots(size_t tiles) {
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
-}
-
-template <int MINB, bool BE>
-cudaError_t launch_u16to8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res, size_t tiles) {
+template <int K, int NW, bool BE, int MINB = 1>
+cudaError_t launch_u16to8_v3(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res) {
+  using Gm = GeomV3<K, NW>;
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & 31u) + 2 * len;
+  const size_t tiles = (span + Gm::kTileBytes - 1) / Gm::kTileBytes, cta_tiles = (tiles + NW - 1) / NW;
+  if (cta_tiles + 1 > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
   static KernelCache kc;
   int per_sm = 1;
-  {
-    cudaError_t e = kernel_per_sm(kc, c.device, k_utf16_to_utf8_bp<MINB, BE>, kThreads, kSmemBytes, &per_sm);
-    if (e != cudaSuccess) return e;
-  }
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  unsigned long long *chunk_off = c.desc;
-  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
-  {
-    const size_t cap = (size_t)c.sm_count * 8;
-    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_utf8len_tile_counts<BE><<<grid, kThreads, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks,
-                                                          c.scratch);
-  }
-  {
-    const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t cap = (size_t)c.sm_count * per_sm;
-    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_utf16_to_utf8_bp<MINB, BE><<<grid, kThreads, kSmemBytes, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), tile_cnt,
-                                                                      chunk_off, (uint32_t)tiles, (uint32_t)chunks,
-                                                                      c.scratch, static_cast<ResultPOD *>(res));
-  }
-  count_launch(2);
+  cudaError_t e = kernel_per_sm(kc, c.device, k_utf16_to_utf8_v3<K, NW, BE, MINB>, Gm::kThreads, Gm::kSmemBytes, &per_sm);
+  if (e != cudaSuccess) return e;
+  const size_t cap = (size_t)c.sm_count * per_sm;
+  const unsigned grid = (unsigned)(cta_tiles < cap ? (cta_tiles ? cta_tiles : 1) : cap);
+  k_utf16_to_utf8_v3<K, NW, BE, MINB><<<grid, Gm::kThreads, Gm::kSmemBytes, c.stream>>>(
+      in, len, reinterpret_cast<uint8_t *>(out), c.desc, c.epoch, (uint32_t)tiles, (uint32_t)cta_tiles, c.scratch,
+      static_cast<ResultPOD *>(res));
+  count_launch(1);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-size_t utf16_convert_tiles(const void *in, size_t len) { return workspace_slots(tiles_for(in, 2 * len)); }
+// Workspace, in 8-byte descriptor slots: one look-back descriptor per CTA-tile.
+constexpr int kU16Workers = 7;
+size_t utf16_convert_tiles(const void *in, size_t len) {
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & 31u) + 2 * len;
+  const size_t tiles = (span + GeomV3<1, kU16Workers>::kTileBytes - 1) / GeomV3<1, kU16Workers>::kTileBytes;
+  return (tiles + kU16Workers - 1) / kU16Workers + 2;
+}
 
 cudaError_t launch_convert_utf16_to_utf8(const LaunchCtx &c, const uint16_t *in, size_t len, char *out, void *res,
                                          bool big_endian) {
-  const size_t tiles = tiles_for(in, 2 * len);
-  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  if (big_endian) return launch_u16to8<3, true>(c, in, len, out, res, tiles);
-  return launch_u16to8<3, false>(c, in, len, out, res, tiles);  // three CTAs per SM measured best (2: -6 %, 4: spills)
+  // four CTAs of 7 workers + the scan warp per SM, 64 bytes (32 units) per lane.  Measured on B200, 2 GiB of mixed
+  // UTF-16, ms per launch (K = blocks per lane, workers x CTAs): K=2 16x1 2.58; K=1 16x1 2.49, 20x1 2.36, 9x3 2.06,
+  // 8x3 2.05, 5x5 2.04, 7x4 1.99, 6x4 1.99; round 1's two launches (counts + transcoder with lane-private staging): 2.24.
+  // Unlike UTF-8 -> UTF-16 (one fat CTA per SM), this transcoder is bound by its byte stores (three predicated shared
+  // stores per unit), and many small CTAs hide their latency best.
+  if (big_endian) return launch_u16to8_v3<1, kU16Workers, true, 4>(c, in, len, out, res);
+  return launch_u16to8_v3<1, kU16Workers, false, 4>(c, in, len, out, res);
 }
 
 }  // namespace b200

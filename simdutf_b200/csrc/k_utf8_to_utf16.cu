@@ -29,6 +29,7 @@
 #include "bp_device.cuh"
 #include "device_common.cuh"
 #include "launch.h"
+#include "sp_device.cuh"
 
 namespace b200 {
 
@@ -38,6 +39,12 @@ using bpd::kThreads;
 using bpd::kWarpsPerCta;
 using bpd::sts_u16;
 using bpd::sts_u32;
+using sp::atom_add_u32;
+using sp::lds_u16;
+using sp::lds_u32;
+using sp::mbar_arrive;
+using sp::mbar_wait_hint;
+using sp::stg_cs_u32;
 
 // The input as 32-byte granules: a 32-byte-aligned base and the half-open range [vbeg, vend) of byte offsets that belong
 // to the caller's buffer (the kernel loads 32 bytes per instruction).
@@ -87,12 +94,6 @@ constexpr int kWorkers = 7;
 
 // Hand-offs go through mbarrier objects in shared memory (one arrival releases any number of waiters, and waiters do not
 // wait for EACH OTHER the way the threads of a bar.sync do): a worker that is ahead never waits for a slower worker.
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t addr) {  // release: this thread's earlier shared-memory writes are visible to waiters
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // The single-pass transcoder, with the look-back OFF the workers' path.
@@ -136,34 +137,6 @@ struct Geom3 {
   static constexpr int kThreads = (NW + 1) * 32;
 };
 
-__device__ __forceinline__ void mbar_wait_hint(uint32_t addr, uint32_t parity) {  // acquire; the hardware parks the thread
-  uint32_t done;
-  do {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(1000000u)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-  uint32_t r;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
-  return r;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-  uint32_t r;
-  asm volatile("{ .reg .b16 t; ld.shared.b16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(r) : "r"(addr));
-  return r;
-}
-__device__ __forceinline__ void stg_cs_u32(void *p, uint32_t v) {
-  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t atom_add_u32(unsigned int *p, uint32_t v) {
-  uint32_t r;
-  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
-  return r;
-}
 
 // staging (elements [0, n) at alignment zero) -> dst[0 .. n)
 template <bool W32, class OutT>
@@ -234,132 +207,18 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
   using OutT = typename std::conditional<W32, uint32_t, uint16_t>::type;
   constexpr uint32_t kUB = Gm::kUnitBytes;
   extern __shared__ __align__(16) uint32_t smem[];  // [NW][2] staging buffers
-  // hand-off rings, slot i & 3 for the CTA's i-th tile
-  __shared__ uint32_t s_tot[4][32];               // workers -> scan warp: the warp totals
-  __shared__ unsigned long long s_goff[4][32];    // scan warp -> workers: every worker's global output offset
-  __shared__ uint32_t s_ticket[4];               // the CTA-tile index
-  __shared__ uint32_t s_acc[4];                  // arrivals << 16 | sum of the warp totals
-  __shared__ uint32_t s_elect[4];                // workers that have reached pass 2
-  __shared__ __align__(8) unsigned long long s_mbar[12];  // [0,4) ticket posted, [4,8) offsets posted, [8,12) totals in
-  static_assert(NW <= 31 && (uint32_t)NW * Gm::kTileBytes < 65536u, "one scan warp lane per worker; 16-bit packing of the warp totals");
+  __shared__ sp::Rings rg;  // hand-off rings, slot i & 3 for the CTA's i-th tile
+  static_assert(NW <= 31, "one scan warp lane per worker");
   const InView in = make_view32(ptr, len);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s_mbar);
-  constexpr uint32_t kMbTicket = 0u, kMbGoff = 32u, kMbTotals = 64u;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (uint32_t k = 0; k < 4; k++) {
-      mbar_init(mb + kMbTicket + 8u * k, 1);
-      mbar_init(mb + kMbGoff + 8u * k, 1);
-      mbar_init(mb + kMbTotals + 8u * k, NW);
-      s_acc[k] = 0;
-      s_elect[k] = 0;
-    }
-  }
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(rg.mbar);
+  constexpr uint32_t kMbTicket = sp::kMbTicket, kMbGoff = sp::kMbGoff, kMbTotals = sp::kMbTotals;
+  if (threadIdx.x == 0) sp::init_rings(rg, NW);
   __syncthreads();
 
   if (warp == (unsigned)NW) {
     // ================================ scan warp ================================
-    // the CTA's first kAhead tiles; every later one is reserved by a worker, kAhead tiles before it is due (kAhead = 2
-    // removes the workers' 0.4 us wait for the ticket and costs as much again on the offsets: 0.884 vs 0.867 ms per GiB)
-    uint32_t t = 0;
-    if (lane < (unsigned)kAhead) {
-      t = atomicAdd(&scr->ticket, 1u);
-      s_ticket[lane] = t;
-      mbar_arrive(mb + kMbTicket + 8u * lane);
-    }
-    long long dbg_wait = 0, dbg_lb = 0, dbg_lbmax = 0, dbg_polls = 0, dbg_n = 0, dbg_late = 0, dbg_seen = 0, dbg_start = 0;
-    for (uint32_t iter = 0;; iter++) {
-      const uint32_t slot = iter & 3u, ph = (iter >> 2) & 1u;
-      mbar_wait_hint(mb + kMbTicket + 8u * slot, ph);
-      t = s_ticket[slot];
-      if (t >= num_cta_tiles) break;
-      const long long c0 = dbg ? clock64() : 0;
-      mbar_wait_hint(mb + kMbTotals + 8u * slot, ph);
-      const long long c1 = dbg ? clock64() : 0;
-      unsigned long long now0 = 0;
-      if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now0));
-      const uint32_t mine = lane < (unsigned)NW ? s_tot[slot][lane] : 0u;
-      const uint32_t incl = bpd::warp_inclusive_u32(mine);
-      const uint32_t agg = __shfl_sync(kFull, incl, 31);
-      unsigned long long sum = 0;
-      if (t == 0) {
-        if (lane == 0) st_relaxed_u64(desc, desc_pack(epoch, kStatusPrefix, 0, agg));
-      } else {
-        // Look-back, COALESCED: descriptor base - 32 j - lane goes to lane `lane` of load j, so a warp load touches 256
-        // contiguous bytes (8 sectors), and a lane polls only a descriptor that is not ready yet.  (A persistent grid
-        // of equal tiles drifts into lockstep: then no predecessor of the current wave has its prefix yet and every
-        // CTA reads the whole in-flight window, G descriptors G times per wave, on a few dozen L2 lines.)
-        constexpr int kR = 4;
-        long long base = (long long)t - 1;
-        unsigned long long d[kR];
-#pragma unroll
-        for (int j = 0; j < kR; j++) {
-          const long long idx = base - 32ll * j - (long long)lane;
-          d[j] = idx >= 0 ? ld_relaxed_u64(desc + idx) : desc_pack(epoch, kStatusPrefix, 0, 0);
-        }
-        bool done = false;
-        while (!done) {
-#pragma unroll
-          for (int j = 0; j < kR; j++) {
-            if (!done) {  // warp-uniform
-              const long long idx = base - 32ll * j - (long long)lane;
-              uint32_t spins = 0;
-              while (__any_sync(kFull, desc_epoch(d[j]) != epoch || desc_status(d[j]) == 0u)) {
-                if (desc_epoch(d[j]) != epoch || desc_status(d[j]) == 0u) d[j] = ld_relaxed_u64(desc + idx);  // idx >= 0 here
-                dbg_polls++;
-                if (++spins > (1u << 24)) {  // cannot happen (tickets are handed out in order); never hang the device on a logic error
-                  report_error(scr, err_key(0, kOther));
-                  break;
-                }
-              }
-              if (dbg && j == 0 && base == (long long)t - 1 && t >= 64) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                const long long mine_ts = (long long)ld_relaxed_u64(ts + t), pred_ts = (long long)ld_relaxed_u64(ts + idx);
-                long long late = pred_ts - mine_ts;  // > 0: this predecessor published after me
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  const long long x = __shfl_xor_sync(kFull, late, o);
-                  late = x > late ? x : late;
-                }
-                dbg_late += late; dbg_seen += (long long)now - (mine_ts + (late > 0 ? late : 0));
-                dbg_start += (long long)now0 - mine_ts;
-              }
-              const unsigned pm = __ballot_sync(kFull, desc_status(d[j]) == kStatusPrefix);
-              const unsigned first = pm ? (unsigned)(__ffs((int)pm) - 1) : 32u;
-              sum += (unsigned long long)__reduce_add_sync(kFull, lane < first ? (uint32_t)desc_value(d[j]) : 0u);
-              if (pm) {
-                const uint32_t lo = __shfl_sync(kFull, (uint32_t)desc_value(d[j]), first);
-                const uint32_t hi = __shfl_sync(kFull, (uint32_t)(desc_value(d[j]) >> 32), first);
-                sum += ((unsigned long long)hi << 32) | lo;
-                done = true;
-              }
-            }
-          }
-          if (!done) {
-            base -= 32 * kR;
-#pragma unroll
-            for (int j = 0; j < kR; j++) {
-              const long long idx = base - 32ll * j - (long long)lane;
-              d[j] = idx >= 0 ? ld_relaxed_u64(desc + idx) : desc_pack(epoch, kStatusPrefix, 0, 0);
-            }
-          }
-        }
-        if (lane == 0) st_relaxed_u64(desc + t, desc_pack(epoch, kStatusPrefix, 0, sum + agg));
-      }
-      if (lane < (unsigned)NW) s_goff[slot][lane] = sum + (incl - mine);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(mb + kMbGoff + 8u * slot);
-      if (dbg) {
-        const long long c2 = clock64();
-        dbg_wait += c1 - c0; dbg_lb += c2 - c1; dbg_lbmax = (c2 - c1) > dbg_lbmax ? (c2 - c1) : dbg_lbmax; dbg_n++;
-      }
-    }
-    if (dbg && lane == 0) {
-      unsigned long long *o = dbg + 16ull * blockIdx.x;
-      o[0] = dbg_n; o[1] = dbg_wait; o[2] = dbg_lb; o[3] = dbg_lbmax; o[4] = dbg_polls; o[5] = dbg_late; o[6] = dbg_seen; o[7] = dbg_start;
-    }
+    sp::scan_warp<NW, kAhead>(rg, desc, epoch, num_cta_tiles, scr, dbg, ts);
   } else {
     // ================================ workers ================================
     long long dbg_wt = 0, dbg_p1 = 0, dbg_wg = 0, dbg_copy = 0, dbg_p2 = 0, dbg_n = 0;
@@ -373,7 +232,7 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
       const uint32_t qs = q.iter & 3u;
       mbar_wait_hint(mb + kMbGoff + 8u * qs, (q.iter >> 2) & 1u);  // always: a worker never runs ahead of the offsets ring
       if (q.wtot) {
-        OutT *dst = out + s_goff[qs][warp];
+        OutT *dst = out + rg.goff[qs][warp];
         if (q.ascii)
           copy_out_ascii<W32, BE, Gm::kTileBytes>(reinterpret_cast<const uint8_t *>(in.base) + (unsigned long long)q.tile * Gm::kTileBytes, dst, lane);
         else
@@ -387,7 +246,7 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
       const long long w0 = dbg ? clock64() : 0;
       mbar_wait_hint(mb + kMbTicket + 8u * slot, ph);
       const long long w1 = dbg ? clock64() : 0;
-      const uint32_t ct = s_ticket[slot];
+      const uint32_t ct = rg.ticket[slot];
       if (ct >= num_cta_tiles) {  // CTA-uniform: drain
         if (q2.valid) copy_out(q2);
         if (q1.valid) copy_out(q1);
@@ -469,20 +328,20 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
       uint32_t tn = 0;
       bool took = false;
       if (lane == 0) {
-        s_tot[slot][warp] = wtot;
+        rg.tot[slot][warp] = wtot;
         // the worker that arrives last publishes the CTA aggregate (it never waits for the scan warp, header comment)
         // and reserves the CTA's next tile; the ticket's round trip hides behind its copy-out
-        const uint32_t old = atomicAdd(&s_acc[slot], (1u << 16) | wtot);
-        if ((old >> 16) == (uint32_t)NW - 1u) {
+        const uint32_t old = atomicAdd(&rg.acc[slot], (1u << 24) | wtot);
+        if ((old >> 24) == (uint32_t)NW - 1u) {
           tn = atom_add_u32(&scr->ticket, 1u);
           took = true;
-          s_acc[slot] = 0;
+          rg.acc[slot] = 0;
           if (dbg) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             ts[ct] = now;
           }
-          st_relaxed_u64(desc + ct, desc_pack(epoch, kStatusAggregate, 0, (old & 0xFFFFu) + wtot));
+          st_relaxed_u64(desc + ct, desc_pack(epoch, kStatusAggregate, 0, (old & 0xFFFFFFu) + wtot));
         }
         mbar_arrive(mb + kMbTotals + 8u * slot);
       }
@@ -490,7 +349,7 @@ k_utf8_transcode_v3(const char *ptr, size_t len, typename std::conditional<W32, 
       auto post_ticket = [&]() {
         tn = __shfl_sync(kFull, tn, 0);
         if (lane == 0) {
-          s_ticket[(iter + (uint32_t)kAhead) & 3u] = tn;
+          rg.ticket[(iter + (uint32_t)kAhead) & 3u] = tn;
           mbar_arrive(mb + kMbTicket + 8u * ((iter + (uint32_t)kAhead) & 3u));
         }
         if (tn < num_cta_tiles) {  // pull the next CTA-tile into L2
