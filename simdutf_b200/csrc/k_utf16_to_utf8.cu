@@ -132,23 +132,6 @@ __device__ __forceinline__ InView make_view_u16_32(const uint16_t *p, size_t len
   return v;
 }
 
-// staging (bytes [0, n) at alignment zero) -> dst[0 .. n)
-__device__ __forceinline__ void copy_out_bytes(uint32_t stage_addr, uint32_t n, uint8_t *dst, unsigned lane) {
-  uint32_t h = (uint32_t)(0u - (uint32_t)reinterpret_cast<uintptr_t>(dst)) & 3u;  // bytes in front of the first aligned word
-  if (h > n) h = n;
-  if (lane < h) dst[lane] = (uint8_t)sp::lds_u8(stage_addr + lane);
-  const uint32_t nw = (n - h) >> 2;
-  uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + h);
-  const uint32_t sel = 0x3210u + 0x1111u * h;  // word w of the destination = staging bytes [h + 4w, h + 4w + 4)
-#pragma unroll 4
-  for (uint32_t w = lane; w < nw; w += 32u) {
-    const uint32_t a = sp::lds_u32(stage_addr + 4u * w), b = sp::lds_u32(stage_addr + 4u * w + 4u);
-    sp::stg_cs_u32(d32 + w, __byte_perm(a, b, sel));
-  }
-  const uint32_t done = h + 4u * nw;
-  if (lane < n - done) dst[done + lane] = (uint8_t)sp::lds_u8(stage_addr + done + lane);
-}
-
 struct PendingU16 {
   uint32_t wtot = 0, iter = 0;
   bool valid = false;
@@ -176,7 +159,7 @@ k_utf16_to_utf8_v3(const uint16_t *ptr, size_t len, uint8_t *out, unsigned long 
     PendingU16 q1, q2;  // tiles i - 1 and i - 2
     auto copy_out = [&](const PendingU16 &q) {
       const unsigned long long goff = sp::wait_goff(rg, q.iter, warp);
-      if (q.wtot) copy_out_bytes(stage0 + (q.iter & 1u) * Gm::kStageBytes, q.wtot, out + goff, lane);
+      if (q.wtot) sp::copy_out_bytes(stage0 + (q.iter & 1u) * Gm::kStageBytes, q.wtot, out + goff, lane);
       __syncwarp();  // the staging buffer is about to be rewritten
     };
 

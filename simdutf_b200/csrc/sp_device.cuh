@@ -233,5 +233,23 @@ __device__ __forceinline__ void ldg_v8(const void *p, uint32_t *r) {
                : "l"(p));
 }
 
+// staging (bytes [0, n) at alignment zero) -> dst[0 .. n)
+__device__ __forceinline__ void copy_out_bytes(uint32_t stage_addr, uint32_t n, uint8_t *dst, unsigned lane) {
+  uint32_t h = (uint32_t)(0u - (uint32_t)reinterpret_cast<uintptr_t>(dst)) & 3u;  // bytes in front of the first aligned word
+  if (h > n) h = n;
+  if (lane < h) dst[lane] = (uint8_t)lds_u8(stage_addr + lane);
+  const uint32_t nw = (n - h) >> 2;
+  uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + h);
+  const uint32_t sel = 0x3210u + 0x1111u * h;  // word w of the destination = staging bytes [h + 4w, h + 4w + 4)
+#pragma unroll 4
+  for (uint32_t w = lane; w < nw; w += 32u) {
+    const uint32_t a = lds_u32(stage_addr + 4u * w), b = lds_u32(stage_addr + 4u * w + 4u);
+    stg_cs_u32(d32 + w, __byte_perm(a, b, sel));
+  }
+  const uint32_t done = h + 4u * nw;
+  if (lane < n - done) dst[done + lane] = (uint8_t)lds_u8(stage_addr + done + lane);
+}
+
+
 }  // namespace sp
 }  // namespace b200
