@@ -1,7 +1,7 @@
 // elem_device.cuh — the per-element transcoder shared by the UTF-32 family (k_utf32.cu) and the Latin-1 family
-// (k_latin1.cu): a counts pass (per-tile output counts -> chunk offsets, bp_device.cuh) and a warp-independent
-// emit pass in which every lane owns 64 contiguous input bytes, compacts its output into a lane-private staging
-// region (odd word stride, aligned to the destination's 16-byte vectors) and streams its own vectors out.
+// (k_latin1.cu): ONE launch on the single-pass skeleton (sp_device.cuh) in which every lane owns 64 contiguous input
+// bytes, counts its output, hands the warp total to the scan warp, compacts its output into the warp's staging buffer
+// and copies the tile out two tiles later, when the look-back has delivered its global offset.
 // A conversion is a traits class:
 //   In / Out            element types (1, 2 or 4 bytes)
 //   kMax                most output elements one input element produces
@@ -27,9 +27,6 @@
 namespace b200 {
 namespace elem {
 
-using bpd::kChunkTiles;
-using bpd::kThreads;
-using bpd::kWarpsPerCta;
 
 constexpr uint32_t kTileBytes = 2048u;  // 64 input bytes per lane
 
@@ -50,9 +47,6 @@ struct Shape {
   static constexpr uint32_t kInPerLane = 64u / sizeof(In);            // 16 code points or 32 units
   static constexpr uint32_t kVec = 16u / sizeof(Out);                 // output elements per 16-byte vector
   static constexpr uint32_t kMaxOut = kInPerLane * T::kMax;           // per lane
-  static constexpr uint32_t kStrideWords = (((kMaxOut + kVec) * sizeof(Out) + 3u) / 4u) | 1u;
-  static constexpr uint32_t kSmemBytes = kWarpsPerCta * 32u * kStrideWords * 4u;
-  static constexpr uint32_t kMaxVec = (kMaxOut + kVec - 1u) / kVec;
 };
 
 // Element i (virtual index from the aligned base) of the input; zero outside the buffer.
@@ -88,39 +82,6 @@ __device__ __forceinline__ uint32_t lane_elem(const uint32_t (&w)[16], int i) {
   return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
 }
 
-// ---- counts pass -----------------------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(kThreads) k_elem_tile_counts(const void *ptr, size_t bytes, uint16_t *tile_cnt,
-                                                                unsigned long long *chunk_off, uint32_t num_tiles,
-                                                                uint32_t num_chunks, Scratch *scr) {
-  using S = Shape<T>;
-  using In = typename T::In;
-  const InView in = make_view_elems(ptr, bytes);
-  const unsigned lane = threadIdx.x & 31u;
-  bpd::counts_pass(
-      [&](uint32_t t) -> uint32_t {
-        const unsigned long long t0 = (unsigned long long)t * kTileBytes, r0 = t0 + lane * 64ull;
-        const bool interior = t0 >= in.vbeg && t0 + kTileBytes <= in.vend;
-        uint32_t w[16];
-        load_lane<In>(in, r0, interior, w);
-        uint32_t cnt = 0;
-        if constexpr (T::kFast) {
-          if (interior) {
-            bool bad;
-            return bpd::warp_sum_u32(T::fast_pass1(w, 0u, 0u, bad));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < (int)S::kInPerLane; i++) {
-          const unsigned long long pos = r0 + (unsigned long long)i * sizeof(In);
-          const uint32_t c = T::count(lane_elem<In>(w, i), 0u, 0u);
-          cnt += (interior || (pos >= in.vbeg && pos < in.vend)) ? c : 0u;
-        }
-        return bpd::warp_sum_u32(cnt);
-      },
-      tile_cnt, chunk_off, num_tiles, num_chunks, scr);
-}
-
 // ---- emit pass -------------------------------------------------------------------------------------------
 template <class Out>
 __device__ __forceinline__ void sts_elem(uint32_t addr, uint32_t v) {
@@ -129,174 +90,8 @@ __device__ __forceinline__ void sts_elem(uint32_t addr, uint32_t v) {
   else bpd::sts_u32(addr, v);
 }
 
-template <class T, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-k_elem_transcode(const void *ptr, size_t bytes, typename T::Out *out, const uint16_t *tile_cnt,
-                 const unsigned long long *chunk_off, uint32_t num_tiles, uint32_t num_chunks, Scratch *scr,
-                 ResultPOD *res) {
-  using S = Shape<T>;
-  using In = typename T::In;
-  using Out = typename T::Out;
-  extern __shared__ __align__(16) uint32_t smem[];
-  const InView in = make_view_elems(ptr, bytes);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
-  uint32_t *region_w = smem + (warp * 32u + lane) * S::kStrideWords;
-  Out *region = reinterpret_cast<Out *>(region_w);
-  const unsigned long long out_elems = (unsigned long long)(reinterpret_cast<uintptr_t>(out) / sizeof(Out));
-  const long long first_elem = (long long)(in.vbeg / sizeof(In)), end_elem = (long long)(in.vend / sizeof(In));
-
-  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
-    const unsigned long long t0 = (unsigned long long)tile * kTileBytes, r0 = t0 + lane * 64ull;
-    const bool interior = t0 >= in.vbeg + 16ull && t0 + kTileBytes + 16ull <= in.vend;
-    const uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
-    const unsigned long long coff = chunk_off[tile / kChunkTiles];
-    uint32_t w[16];
-    load_lane<In>(in, r0, interior, w);
-    const long long e0 = (long long)(r0 / sizeof(In));  // virtual index of this lane's first element
-    uint32_t pv = 0, nv = 0;
-    if (T::kNeedsNeighbours) {
-      pv = elem_guarded<In>(in, e0 - 1);
-      nv = elem_guarded<In>(in, e0 + (long long)S::kInPerLane);
-    }
-    const unsigned long long goff = coff + bpd::warp_sum_u32(before);
-
-    // One element: its output count, packed output and error (filler outside the buffer produces nothing).
-    auto eval = [&](int i, uint32_t &Pi, int &err) -> uint32_t {
-      const long long idx = e0 + i;
-      const bool inside = interior || (idx >= first_elem && idx < end_elem);
-      const uint32_t v = lane_elem<In>(w, i);
-      const uint32_t p = i ? lane_elem<In>(w, i ? i - 1 : 0) : pv;
-      const uint32_t nx = i + 1 < (int)S::kInPerLane ? lane_elem<In>(w, i + 1 < (int)S::kInPerLane ? i + 1 : i) : nv;
-      uint32_t c = T::emit(v, p, nx, idx > first_elem, idx + 1 < end_elem, Pi, err);
-      if (!inside) { c = 0; err = 0; }
-      return c;
-    };
-    auto store = [&](uint32_t &sp, uint32_t Pi, uint32_t ni) {
-#pragma unroll
-      for (uint32_t k = 0; k < T::kMax; k++) {
-        if (k < ni) sts_elem<Out>(sp + k * (uint32_t)sizeof(Out), sizeof(Out) == 4 ? Pi : Pi >> (8u * (uint32_t)sizeof(Out) * k));
-      }
-      sp += ni * (uint32_t)sizeof(Out);
-    };
-    // Count first (the lane's offset decides where its region starts), then compact into the private region.
-    // 16 / 32 elements per lane keep their packed outputs in registers between the two steps; 64 (byte input)
-    // would not fit, so the second step evaluates the elements again.
-    constexpr bool kKeep = S::kInPerLane <= 32u;
-    uint32_t P[kKeep ? S::kInPerLane : 1u];
-    uint32_t n[kKeep ? S::kInPerLane : 1u];
-    uint32_t cnt = 0;
-    long long bad_at = -1;
-    int bad_code = 0;
-    bool fast = false, suspect = true;
-    if constexpr (T::kFast) {
-      fast = interior;
-      if (fast) cnt = T::fast_pass1(w, pv, nv, suspect);
-    }
-    if (!fast || suspect) {  // element by element: the count (the same number) and the first error
-      cnt = 0;
-#pragma unroll
-      for (int i = 0; i < (int)S::kInPerLane; i++) {
-        int err;
-        uint32_t Pi;
-        const uint32_t c = eval(i, Pi, err);
-        if (err && bad_at < 0) { bad_at = e0 + i; bad_code = err; }
-        if (kKeep) { P[i] = Pi; n[i] = c; }
-        cnt += c;
-      }
-    }
-    if (bad_at >= 0) {
-      const unsigned long long key = err_key((unsigned long long)(bad_at - first_elem), bad_code);
-      if (key < ld_relaxed_u64(&scr->err_key)) report_error(scr, key);
-    }
-    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
-    const unsigned long long G = goff + (incl - cnt);
-    const uint32_t a = (uint32_t)((out_elems + G) & (S::kVec - 1u));
-    bool word_emit = false;
-    if constexpr (T::kFast) {
-      word_emit = fast && !suspect;  // a screened lane of a tile inside the buffer: four input bytes per step
-      if (word_emit) {
-        uint32_t sp = (uint32_t)__cvta_generic_to_shared(region + a);
-#pragma unroll
-        for (int j = 0; j < 16; j++) T::emit_word(w[j], j < 15 ? w[j < 15 ? j + 1 : j] : nv, sp);
-      }
-    }
-    if (!word_emit) {
-      uint32_t sp = (uint32_t)__cvta_generic_to_shared(region + a);
-#pragma unroll
-      for (int i = 0; i < (int)S::kInPerLane; i++) {
-        if (kKeep) {
-          store(sp, P[i], n[i]);
-        } else if (fast) {  // inside the buffer: no bounds, no error bookkeeping
-          int err;
-          uint32_t Pi;
-          const uint32_t nx = i + 1 < (int)S::kInPerLane ? lane_elem<In>(w, i + 1 < (int)S::kInPerLane ? i + 1 : i) : nv;
-          const uint32_t c = T::emit(lane_elem<In>(w, i), 0u, nx, true, true, Pi, err);
-          store(sp, Pi, c);
-        } else {
-          int err;
-          uint32_t Pi;
-          const uint32_t c = eval(i, Pi, err);
-          store(sp, Pi, c);
-        }
-      }
-    }
-    __syncwarp();
-
-    // staging -> global: a lane owns the 16-byte vectors that hold its elements except its last partial one, which
-    // the lane to its right completes (it copies the elements in front of its own first one from this lane's tail)
-    {
-      Out *gbase = out + G - a;
-      const uint32_t end = a + cnt;
-      if (__all_sync(kFull, cnt >= S::kVec)) {
-        const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
-        if (lane > 0) {
-          const Out *src = region - S::kStrideWords * (4u / (uint32_t)sizeof(Out)) + (prev_end - a);
-#pragma unroll
-          for (uint32_t u = 0; u + 1 < S::kVec; u++)
-            if (u < a) region[u] = src[u];
-        }
-        const uint32_t vfull = end / S::kVec;
-        uint32_t v0 = 0;
-        if (lane == 0 && a > 0) {
-#pragma unroll
-          for (uint32_t u = 1; u < S::kVec; u++)
-            if (u >= a) gbase[u] = region[u];
-          v0 = 1;
-        }
-        if (lane == 31) {
-#pragma unroll
-          for (uint32_t u = 0; u + 1 < S::kVec; u++) {
-            const uint32_t i = vfull * S::kVec + u;
-            if (i < end) gbase[i] = region[i];
-          }
-        }
-#pragma unroll
-        for (uint32_t v = 0; v < S::kMaxVec; v++) {
-          if (v >= v0 && v < vfull) {
-            uint4 x;
-            x.x = region_w[4u * v];
-            x.y = region_w[4u * v + 1u];
-            x.z = region_w[4u * v + 2u];
-            x.w = region_w[4u * v + 3u];
-            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, x);
-          }
-        }
-      } else {
-        for (uint32_t i = a; i < end; i++) gbase[i] = region[i];
-      }
-    }
-    __syncwarp();
-  }
-
-  if (grid_last_thread(scr)) {
-    bpd::write_result_from_key(res, ld_relaxed_u64(&scr->err_key), chunk_off[num_chunks]);
-    scratch_reset(scr);
-  }
-}
-
-// ---- single pass (round 2): the emit pass above on the skeleton of sp_device.cuh ------------------------------
-// ONE launch: the lane counts of the emit pass ARE the counts, so the counts kernel (a second read of the input) goes.
+// ---- the transcoder: ONE launch on the single-pass skeleton of sp_device.cuh (round 2) ------------------------
+// Round 1 ran a counts kernel first (a second read of the input); the lane counts of the emit pass ARE the counts.
 // A worker hands its warp total to the scan warp, compacts into the warp's staging buffer at alignment zero (byte
 // offset = the lane's exclusive prefix) and copies the tile out two tiles later, when the look-back has delivered its
 // global offset (sp::copy_out_bytes: 32-bit words realigned to the destination by one byte permute).
@@ -494,49 +289,18 @@ inline size_t tiles_for(const void *in, size_t bytes) {
   const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + bytes;
   return (span + kTileBytes - 1) / kTileBytes;
 }
-inline size_t workspace_slots(size_t tiles) {
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
-}
+// look-back descriptors (8-byte slots) for CTA-tiles of >= 7 warp-tiles
+inline size_t workspace_slots(size_t tiles) { return (tiles + 6) / 7 + 2; }
 
+// Geometry, measured on B200 (1 GiB inputs, ms per launch; workers x CTAs per SM; round 1's two launches first):
+//   UTF-32 -> UTF-8   2.016 | 7x4 1.549   8x3 1.543   7x2 2.123   16x1 2.043
+//   UTF-32 -> UTF-16  1.363 | 7x4 1.230   8x3 1.184   7x2 1.220
+//   UTF-16 -> UTF-32  1.495 | 7x3 1.641   8x3 1.527   7x2 1.573   16x1 1.620   (32 elements per lane keep 64 registers busy)
+//   Latin-1 -> UTF-8  1.349 | 7x3 0.946   8x3 0.937   7x2 0.937
+//   UTF-8 -> Latin-1  1.644 | 7x4 1.087   8x3 1.103   7x2 1.084
 template <class T>
 cudaError_t launch_elem(const LaunchCtx &c, const void *in, size_t len, void *out, void *res) {
-  using S = Shape<T>;
-  {
-    const int v = tuning(kTuneConvVariant);
-    constexpr int kM = ShapeV3<T, 7>::kStageBytes > 3000u ? 3 : 4;
-    if (v == 71) return launch_elem_v3<T, 7, kM>(c, in, len, out, res);
-    if (v == 72) return launch_elem_v3<T, 8, 3>(c, in, len, out, res);
-    if (v == 73) return launch_elem_v3<T, 11, 2>(c, in, len, out, res);
-  }
-  constexpr int MINB = sizeof(typename T::In) == 4 ? 3 : 2;  // 16 elements per lane leave room for a third CTA per SM
-  const size_t bytes = len * sizeof(typename T::In);
-  const size_t tiles = tiles_for(in, bytes);
-  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  static KernelCache kc;
-  int per_sm = 1;
-  {
-    cudaError_t e = kernel_per_sm(kc, c.device, k_elem_transcode<T, MINB>, kThreads, S::kSmemBytes, &per_sm);
-    if (e != cudaSuccess) return e;
-  }
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  unsigned long long *chunk_off = c.desc;
-  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
-  {
-    const size_t cap = (size_t)c.sm_count * 8;
-    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_elem_tile_counts<T><<<grid, kThreads, 0, c.stream>>>(in, bytes, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch);
-  }
-  {
-    const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t cap = (size_t)c.sm_count * per_sm;
-    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_elem_transcode<T, MINB><<<grid, kThreads, S::kSmemBytes, c.stream>>>(
-        in, bytes, static_cast<typename T::Out *>(out), tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, c.scratch,
-        static_cast<ResultPOD *>(res));
-  }
-  count_launch(2);
-  return cudaGetLastError();
+  return launch_elem_v3<T, 8, 3>(c, in, len, out, res);
 }
 
 }  // namespace elem
