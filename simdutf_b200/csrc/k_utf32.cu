@@ -113,7 +113,51 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf32(const uint32_t *in, size_
       total += 1u + (w > 0xFFFFu);
     }
   };
-  for (size_t v = tid; v < nvec; v += nthreads) {
+  // four vectors per thread and round, all four loads in flight before the first is used (one load per round left the
+  // kernel latency-bound: 0.68 of the copy bandwidth).  Validation folds the 16 words of a round into two extremes —
+  // the largest word and the smallest (word ^ 0xD800), which is < 0x800 exactly for a surrogate (the reference keeps a
+  // running maximum the same way, src/icelake/icelake_utf32_validation.inl.cpp) — and looks at single words only in a
+  // round that tripped one of them.
+  size_t v = tid;
+  bool stop = false;  // warp-uniform
+  for (; (v - lane) + 31u + 3 * nthreads < nvec && !stop; v += 4 * nthreads) {  // whole warps only: the round votes
+    uint4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[k] = ldg_stream_v4(vi + v + (size_t)k * nthreads);
+    if (MODE == 0) {
+      uint32_t mx = 0u, mn = 0xFFFFFFFFu;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        mx = max(max(mx, x[k].x), max(x[k].y, max(x[k].z, x[k].w)));
+        mn = min(min(mn, x[k].x ^ 0xD800u), min(x[k].y ^ 0xD800u, min(x[k].z ^ 0xD800u, x[k].w ^ 0xD800u)));
+      }
+      if (__any_sync(kFull, mx > 0x10FFFFu || mn < 0x800u)) {
+        // An error in front of this round that is already on record ends the warp's work: the first error wins and the
+        // warp's indices only grow.  Otherwise the round's first error goes on record NOW (one atomic per warp), so that
+        // text in another encoding (detect_encodings) is given up after one round instead of being searched word by word.
+        unsigned long long cur = ld_relaxed_u64(&scr->err_key);
+        cur = __shfl_sync(kFull, cur, 0);
+        if (cur != kNoError && (cur >> 8) < head + 4 * (v - lane)) {
+          stop = true;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const size_t i = head + 4 * (v + (size_t)k * nthreads);
+            one(x[k].x, i); one(x[k].y, i + 1); one(x[k].z, i + 2); one(x[k].w, i + 3);
+          }
+          const unsigned long long wbest = warp_min_u64(best);
+          if (lane == 0 && wbest != kNoError) report_error(scr, wbest);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const size_t i = head + 4 * (v + (size_t)k * nthreads);
+        one(x[k].x, i); one(x[k].y, i + 1); one(x[k].z, i + 2); one(x[k].w, i + 3);
+      }
+    }
+  }
+  for (; v < nvec && !stop; v += nthreads) {
     const uint4 x = ldg_stream_v4(vi + v);
     const size_t i = head + 4 * v;
     one(x.x, i); one(x.y, i + 1); one(x.z, i + 2); one(x.w, i + 3);

@@ -349,6 +349,33 @@ def test_base64_large_with_whitespace(b, oracle):
         run_b64(b, oracle, cand, options=1 if url else 0, host_too=False)
 
 
+def test_base64_single_pass_structure(b, oracle):
+    """The single-pass decoder's own cases: warp-tiles without any whitespace (the 128-bit staging path), next to tiles
+    with whitespace, tiles of nothing but whitespace (their successors fetch the carried sextets from far back), every
+    phase of the tile's first quantum, every length of the trailing partial quantum, sizes around the CTA-tile."""
+    import base64 as pyb64
+    rng = random.Random(909)
+    raw = bytes(rng.getrandbits(8) for _ in range(300_000))
+    dense = pyb64.b64encode(raw)  # 400 000 characters, no whitespace, no padding
+    cta_tile = 7 * 2048
+    for n in (64, 2047, 2048, 2049, 4096, cta_tile - 1, cta_tile, cta_tile + 1, 3 * cta_tile + 5, 148 * 4 * cta_tile // 8 + 3, 399_999, 400_000):
+        for mis in (0, 1, 31):
+            run_b64(b, oracle, dense[:n], 0, 0, misalign=mis, host_too=False)
+    for lc in (0, 1, 2):  # trailing partial quanta of 1, 2, 3 sextets behind dense tiles, with and without padding
+        for tail in (b"", b"Q", b"QQ", b"QQ=", b"QQ==", b"QQQ", b"QQQ=", b"QUE", b"QUE=", b"QR", b"QR=="):
+            run_b64(b, oracle, dense[:40_000] + tail, 0, lc, misalign=3, host_too=False)
+    # dense and sparse tiles interleaved; a run of whitespace longer than several tiles; whitespace that shifts the phase
+    for k in range(1, 6):
+        mixed = dense[:10_000 + k] + b" " * k + dense[10_000 + k:60_000] + b"\r\n" * 5000 + dense[60_000:200_000 - k] + b"\t" + dense[200_000 - k:300_000]
+        run_b64(b, oracle, mixed, 0, 0, misalign=k, host_too=(k == 1))
+        run_b64(b, oracle, mixed, 4, 0, misalign=k, host_too=False)
+    # an invalid character in a dense tile, in a sparse tile, in the first and in the last tile
+    for q in (0, 5000, 10_002, 75_000, 299_999):
+        bad = bytearray(dense[:10_000] + b" " + dense[10_000:300_000]); bad[q] = ord("*")
+        run_b64(b, oracle, bytes(bad), 0, 0, host_too=False)
+        run_b64(b, oracle, bytes(bad), 4, 0, host_too=False)  # tolerant: the character is skipped, phases shift
+
+
 def test_bitplane_edge_paths(b, oracle):
     """Paths the bit-plane kernels take only on unusual inputs: all-ASCII tiles next to non-ASCII ones, lanes that
     emit fewer than one vector (unit-by-unit copy-out), a buffer that starts with a continuation byte, UTF-16

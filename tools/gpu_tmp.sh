@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_reference_suite.py -m gpu -x -q -k "utf32_family or latin1_family or golden or convert_utf32_to_utf8 or convert_utf32_to_utf16 or convert_utf16le_to_utf32 or convert_utf16be_to_utf32 or convert_latin1_to_utf8 or convert_utf8_to_latin1 or basic_fuzzer or special_tests" --durations=5 > gpurun_out/r2_k8v3_full.log 2>&1; echo "rc=$?"; tail -n 12 gpurun_out/r2_k8v3_full.log
-for op in utf32to8 utf32to16 utf16to32 l1to8 u8tol1; do
-timeout 100 python tools/prof_one.py $op 1073741824 5 2>&1 | tail -1
-done
+timeout 700 python -m pytest tests/test_gpu_parity.py tests/test_reference_suite.py -m gpu -x -q -k "base64 or utf32_family or well_formed_and_detect or golden or detect_encodings or validate_utf32_with_errors" --durations=8 > gpurun_out/r2_b64v3_tests.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/r2_b64v3_tests.log
+timeout 500 python tools/prof_b64.py 1073741824 5 > gpurun_out/r2_b64v3_prof.log 2>&1; echo "prof rc=$?"; cat gpurun_out/r2_b64v3_prof.log | tail -n 60
