@@ -226,8 +226,9 @@ __device__ __forceinline__ void report_error(Scratch *scr, unsigned long long ke
 
 // Exact UTF-8 first-error search over byte positions [lo, hi) (virtual positions, clipped to the buffer),
 // reading the bytes straight from global memory.  Called only by threads whose granule tripped
-// bit-plane detector / the truncated-tail check.  Skips the work if an earlier error is already recorded.
-static __device__ __noinline__ void u8_locate_error_impl(const uint4 *base, unsigned long long vbeg,
+// bit-plane detector / the truncated-tail check.  Skips the work if an earlier error is already recorded.  Returns true
+// when nothing behind `lo` can be the first error any more (an error was found here, or an earlier one is on record).
+static __device__ __noinline__ bool u8_locate_error_impl(const uint4 *base, unsigned long long vbeg,
                                                          unsigned long long vend, Scratch *scr, long long lo,
                                                          long long hi) {
   InView in;
@@ -236,9 +237,9 @@ static __device__ __noinline__ void u8_locate_error_impl(const uint4 *base, unsi
   in.vend = vend;
   if (lo < (long long)in.vbeg) lo = (long long)in.vbeg;
   if (hi > (long long)in.vend) hi = (long long)in.vend;
-  if (lo >= hi) return;
+  if (lo >= hi) return false;
   const unsigned long long cur = ld_relaxed_u64(&scr->err_key);
-  if (cur != kNoError && (cur >> 8) < (unsigned long long)lo - in.vbeg) return;
+  if (cur != kNoError && (cur >> 8) < (unsigned long long)lo - in.vbeg) return true;
   const uint8_t *p = reinterpret_cast<const uint8_t *>(in.base) + in.vbeg;
   const unsigned long long len = in.vend - in.vbeg;
   auto at = [p](unsigned long long j) -> uint32_t { return (uint32_t)p[j]; };
@@ -247,13 +248,14 @@ static __device__ __noinline__ void u8_locate_error_impl(const uint4 *base, unsi
     const int code = u8_verdict(at, i, len);
     if (code != kSuccess) {
       report_error(scr, err_key(i, code));
-      return;
+      return true;
     }
   }
+  return false;
 }
 
-__device__ __forceinline__ void u8_locate_error(const InView &in, Scratch *scr, long long lo, long long hi) {
-  u8_locate_error_impl(in.base, in.vbeg, in.vend, scr, lo, hi);
+__device__ __forceinline__ bool u8_locate_error(const InView &in, Scratch *scr, long long lo, long long hi) {
+  return u8_locate_error_impl(in.base, in.vbeg, in.vend, scr, lo, hi);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,22 +1,14 @@
-// k_base64.cu — K7: WHATWG forgiving-base64 decode on sm_100a
+// k_base64.cu — K7: WHATWG forgiving-base64 decode on sm_100a, and binary_to_base64
 //   implementation::base64_to_binary[_details] for `char` input, every base64_options /
 //   last_chunk_handling_options value (reference src/generic/base64.h:40-246, src/scalar/base64.h:33-216,
 //   src/tables/base64_tables.h:791-849).
 //
-// Two streaming kernels of independent warps, same shape as the UTF transcoders:
-//   K7a  k_b64_tile_counts   per warp-tile (32 lanes x 64 characters) the number of sextet characters, in bit-plane
-//        form (bitplane.h: base64_classify, ~45 bitwise instructions per 32 characters instead of a table lookup
-//        per character); chunk totals -> exclusive chunk offsets by the CTA that finishes last.
-//   K7b  k_b64_decode_bp     classifies again, builds the six planes of the sextet value, transposes them back to
-//        one byte per character and compacts the sextets (this is where whitespace disappears) into the warp's
-//        staging region at their rank modulo the tile; the <= 3 sextets in front of the tile that complete its
-//        first 4-sextet quantum are fetched by scanning the input backwards.  A quantum belongs to the tile that
-//        holds its last sextet; lanes pack one quantum (4 sextets -> 3 bytes) each into the warp's output staging
-//        region, laid out so that its 16-byte vectors coincide with 16-byte-aligned output addresses, and the warp
-//        streams the vectors out.
-//   The first invalid character is an atomicMin on its index; the CTA that finishes last strips the trailing
-//   whitespace / '=' (block-cooperative backward scan), fetches the last <= 3 sextet characters and applies the
-//   last-chunk and padding rules (swar.h:b64_finish).
+// ONE launch on the single-pass skeleton of the transcoders (sp_device.cuh); the header of k_b64_decode_v3 has the
+// details.  Characters are classified in bit-plane form (bitplane.h: base64_classify, ~45 bitwise instructions per 32
+// characters for the classes + ~45 for the six sextet planes, instead of a table lookup per character).  The first
+// invalid character is an atomicMin on its index; the CTA that finishes last strips the trailing whitespace / '='
+// (block-cooperative backward scan), fetches the last <= 3 sextet characters and applies the last-chunk and padding
+// rules (swar.h:b64_finish).
 #include "bitplane.h"
 #include "bp_device.cuh"
 #include "device_common.cuh"
@@ -27,67 +19,7 @@ namespace b200 {
 
 namespace {
 
-using bpd::kChunkTiles;
-using bpd::kWarpsPerCta;
-
-constexpr uint32_t kTileChars = 32u * 64u;                 // 2 KiB of text per warp-tile, 64 characters per lane
-constexpr uint32_t kSxBytes = kTileChars + 16u;           // sextet staging: <= 3 carried + 2048 + slack
-constexpr uint32_t kOutBytes = kTileChars / 4u * 3u + 48u;  // output staging: <= 15 of alignment + 1536 + 2 + slack
-
-struct B64Smem {
-  alignas(16) uint8_t sx[kWarpsPerCta][kSxBytes];
-  alignas(16) uint8_t out[kWarpsPerCta][kOutBytes];
-  uint8_t lut[256];
-  unsigned long long found;  // 1 + index, 0 = none
-  int is_last;
-};
-
-__device__ __forceinline__ InView make_view(const void *p, size_t len_bytes) {
-  InView v;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  v.base = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
-  v.vbeg = a & 15u;
-  v.vend = v.vbeg + len_bytes;
-  return v;
-}
-
-// Largest j in [0, end) with (lut[p[j]] == 64) != want_ws ... generalised: largest j whose class satisfies
-// `sextet_only ? class <= 63 : class != 64`; -1 if none.  Whole CTA participates.
-__device__ long long block_find_last(const uint8_t *p, long long end, bool sextet_only, B64Smem &sm) {
-  constexpr long long kPer = 16;
-  for (long long hi = end; hi > 0; hi -= (long long)blockDim.x * kPer) {
-    __syncthreads();
-    if (threadIdx.x == 0) sm.found = 0ull;
-    __syncthreads();
-    long long best = -1;
-    const long long lo = hi - (long long)(threadIdx.x + 1) * kPer;  // thread 0 looks at the highest 16 bytes
-    for (long long j = lo + kPer - 1; j >= lo && j >= 0; j--) {
-      const uint32_t c = sm.lut[p[j]];
-      if (sextet_only ? (c <= 63u) : (c != 64u)) { best = j; break; }
-    }
-    if (best >= 0) atomicMax(&sm.found, (unsigned long long)best + 1ull);
-    __syncthreads();
-    const long long f = (long long)sm.found - 1;
-    if (f >= 0) return f;
-  }
-  __syncthreads();
-  return -1;
-}
-
-// Planes of the 32 characters at virtual byte offset b0 (zero filler outside the buffer).
-template <bool INTERIOR>
-__device__ __forceinline__ void load_block32(const InView &in, unsigned long long b0, uint32_t (&B)[8]) {
-  if (INTERIOR) {
-    const uint4 *gp = in.base + (b0 >> 4);
-    const uint4 v0 = __ldg(gp), v1 = __ldg(gp + 1);
-    B[0] = v0.x; B[1] = v0.y; B[2] = v0.z; B[3] = v0.w;
-    B[4] = v1.x; B[5] = v1.y; B[6] = v1.z; B[7] = v1.w;
-  } else {
-    bool ins;
-    load_granule(in, b0 >> 4, &B[0], ins);
-    load_granule(in, (b0 >> 4) + 1ull, &B[4], ins);
-  }
-}
+// Bit p set iff byte b0 + p lies inside the buffer.
 __device__ __forceinline__ uint32_t range_mask32(const InView &in, unsigned long long b0) {
   long long lo = (long long)in.vbeg - (long long)b0, hi = (long long)in.vend - (long long)b0;
   lo = lo < 0 ? 0 : (lo > 32 ? 32 : lo);
@@ -102,288 +34,16 @@ struct B64Opts {
 };
 
 // ---------------------------------------------------------------------------------------------
-// K7a: sextet characters per tile
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_b64_tile_counts(const char *ptr, size_t len, uint16_t *tile_cnt,
-                                                             unsigned long long *chunk_off, uint32_t num_tiles,
-                                                             uint32_t num_chunks, B64Opts o, Scratch *scr) {
-  const InView in = make_view(ptr, len);
-  const unsigned lane = threadIdx.x & 31u;
-  bpd::counts_pass(
-      [&](uint32_t t) -> uint32_t {
-        const unsigned long long t0 = (unsigned long long)t * kTileChars, r0 = t0 + lane * 64ull;
-        const bool interior = t0 >= in.vbeg && t0 + kTileChars <= in.vend;
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          uint32_t B[8], S[6];
-          if (interior) load_block32<true>(in, r0 + 32ull * j, B);
-          else load_block32<false>(in, r0 + 32ull * j, B);
-          bp::transpose_in(B);
-          uint32_t v = bp::base64_classify<false>(B, o.plus_ok, o.slash_ok, o.minus_ok, o.under_ok, S).valid;
-          if (!interior) v &= range_mask32(in, r0 + 32ull * j);
-          cnt += (uint32_t)__popc(v);
-        }
-        return bpd::warp_sum_u32(cnt);
-      },
-      tile_cnt, chunk_off, num_tiles, num_chunks, scr);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K7b: decode
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 3) k_b64_decode_bp(const char *ptr, size_t len, uint8_t *out, Scratch *scr,
-                                                             const uint16_t *tile_cnt,
-                                                             const unsigned long long *chunk_off, uint32_t num_tiles,
-                                                             uint32_t num_chunks, B64Opts o, uint32_t opt_url,
-                                                             uint32_t opt_both, uint32_t opt_garbage,
-                                                             unsigned long long last_chunk, FullResultPOD *res) {
-  __shared__ B64Smem sm;
-  const InView in = make_view(ptr, len);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  sm.lut[threadIdx.x] = (uint8_t)b64_class(threadIdx.x, opt_url != 0, opt_both != 0);
-  __syncthreads();
-  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
-  const uint32_t one = blockDim.x >> 8;  // 1, opaque to the assembler (bpd::bump)
-  uint8_t *sx = sm.sx[warp];
-  uint8_t *so = sm.out[warp];
-  const unsigned long long V_total = chunk_off[num_chunks];  // written by the counts pass
-
-  for (uint32_t tile = blockIdx.x * kWarpsPerCta + warp; tile < num_tiles; tile += nwarps) {
-    const unsigned long long t0 = (unsigned long long)tile * kTileChars, r0 = t0 + lane * 64ull;
-    const bool interior = t0 >= in.vbeg && t0 + kTileChars <= in.vend;
-    if (tile + nwarps < num_tiles) {
-      const char *nx = reinterpret_cast<const char *>(in.base) + r0 + (unsigned long long)nwarps * kTileChars;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-    }
-    const uint32_t before = bpd::tile_before_partial(tile_cnt, tile);
-    const unsigned long long coff = chunk_off[tile / kChunkTiles];
-
-    // ---- classify, sextet planes, counts ----
-    uint32_t S[2][8], V[2];
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      uint32_t B[8], Sv[6];
-      if (interior) load_block32<true>(in, r0 + 32ull * j, B);
-      else load_block32<false>(in, r0 + 32ull * j, B);
-      bp::transpose_in(B);
-      const bp::B64Class c = bp::base64_classify<true>(B, o.plus_ok, o.slash_ok, o.minus_ok, o.under_ok, Sv);
-      uint32_t v = c.valid, bad = ~(c.valid | c.ws);
-      if (!interior) {
-        const uint32_t r = range_mask32(in, r0 + 32ull * j);
-        v &= r;
-        bad &= r;
-      }
-      if (bad && !opt_garbage) {
-        const unsigned long long pos = r0 + 32ull * j + (unsigned)(__ffs((int)bad) - 1) - in.vbeg;
-        const unsigned long long key = err_key(pos, kInvalidBase64Character);
-        if (key < ld_relaxed_u64(&scr->err_key)) report_error(scr, key);
-      }
-#pragma unroll
-      for (int k = 0; k < 6; k++) S[j][k] = Sv[k];
-      S[j][6] = 0u;
-      S[j][7] = 0u;
-      V[j] = v;
-      cnt += (uint32_t)__popc(v);
-    }
-    const unsigned long long goff = coff + bpd::warp_sum_u32(before);  // rank of the tile's first sextet
-    const uint32_t incl = bpd::warp_inclusive_u32(cnt);
-    const uint32_t total = __shfl_sync(kFull, incl, 31);
-    const uint32_t pad = (uint32_t)(goff & 3ull);  // sextets of the tile's first quantum that precede the tile
-
-    // ---- compact the sextets: sx[i] = sextet of rank 4 * (goff / 4) + i ----
-    {
-      uint32_t spa = (uint32_t)__cvta_generic_to_shared(sx) + pad + (incl - cnt);
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        bp::transpose_out8(S[j]);  // S[j][w] = sextets of characters 4w..4w+3, one per byte
-        const uint32_t m = V[j];
-        uint32_t s[4];
-        s[0] = spa;
-        s[1] = spa + (uint32_t)__popc(m & 0xFFu);
-        s[2] = spa + (uint32_t)__popc(m & 0xFFFFu);
-        s[3] = spa + (uint32_t)__popc(m & 0xFFFFFFu);
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const int p = 8 * c + i;
-            if (m & (1u << p)) {
-              const uint32_t w = S[j][p >> 2];
-              const uint32_t b = (p & 3) == 0 ? w : __umulhi(w, 1u << (32 - 8 * (p & 3)));
-              bpd::sts_u8(s[c], b);
-              s[c] = bpd::bump<1>(s[c], one);
-            }
-          }
-        }
-        spa += (uint32_t)__popc(m);
-      }
-    }
-    if (lane == 0 && pad) {  // the sextets just before the tile: scan the input backwards (whitespace is skipped)
-      uint32_t need = pad;
-      const uint8_t *p8 = reinterpret_cast<const uint8_t *>(in.base);
-      for (long long pos = (long long)t0 - 1; need && pos >= (long long)in.vbeg; pos--) {
-        const uint32_t cls = sm.lut[p8[pos]];
-        if (cls <= 63u) sx[--need] = (uint8_t)cls;
-      }
-    }
-    __syncwarp();
-
-    // ---- pack: one quantum (4 sextets -> 3 bytes) per lane and round ----
-    const unsigned long long q0 = goff >> 2;
-    const uint32_t have = pad + total;
-    const uint32_t nq = have >> 2;
-    // the tile that holds the stream's last sextet also emits the 1 or 2 bytes of a trailing partial quantum
-    const bool is_last = total > 0u && goff + total == V_total;
-    const uint32_t xb = (is_last && (have & 3u) >= 2u) ? (have & 3u) - 1u : 0u;
-    const uint32_t nb = 3u * nq + xb;                       // output bytes of this tile
-    uint8_t *gdst = out + 3ull * q0;                        // where they go
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
-    {
-      // four quanta per lane and round: 16 sextets (one 128-bit load) -> 12 bytes (three 32-bit stores); staging byte
-      // 3 j + k is byte k of quantum j; whatever is packed beyond `nb` bytes is never copied out
-      const uint4 *sx128 = reinterpret_cast<const uint4 *>(sx);
-      uint32_t *so32 = reinterpret_cast<uint32_t *>(so);
-      const uint32_t ngroups = (nq + (xb ? 1u : 0u) + 3u) >> 2;
-      for (uint32_t g = lane; g < ngroups; g += 32u) {
-        const uint4 q = sx128[g];
-        // (& 0x3F: the sextets past the end of a trailing partial quantum are stale staging bytes)
-        const uint32_t w[4] = {q.x & 0x3F3F3F3Fu, q.y & 0x3F3F3F3Fu, q.z & 0x3F3F3F3Fu, q.w & 0x3F3F3F3Fu};
-        uint32_t y[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t t1 = (w[k] & 0x00FF00FFu) * 64u + ((w[k] >> 8) & 0x00FF00FFu);  // s0:s1 | s2:s3, 12 bits each
-          const uint32_t x = (t1 & 0xFFFFu) * 4096u + (t1 >> 16);                       // 24 bits, first byte on top
-          y[k] = __byte_perm(x, 0u, 0x4012);                                             // first byte lowest
-        }
-        so32[3u * g] = __byte_perm(y[0], y[1], 0x4210);
-        so32[3u * g + 1u] = __byte_perm(y[1], y[2], 0x5421);
-        so32[3u * g + 2u] = __byte_perm(y[2], y[3], 0x6542);
-      }
-    }
-    __syncwarp();
-
-    // ---- staging -> global.  Destination coordinates e are relative to gbase = gdst - mis (16-byte aligned): the
-    // data occupies [mis, end); full vectors are funnel-shifted out of the staging words, the partial first and
-    // last vectors are written bytewise by lanes 0-15 and 16-31.
-    {
-      uint8_t *gbase = gdst - mis;
-      const uint32_t end = mis + nb;
-      const uint32_t v_lo = (mis + 15u) >> 4, v_hi = end >> 4;
-      const uint32_t sh = (16u - mis) & 15u;            // staging byte offset of destination vector v is 16 v - mis
-      const uint32_t wsel = sh >> 2;                    // = 16 (v - 1) + sh for v >= 1
-      const uint32_t psel = 0x3210u + 0x1111u * (sh & 3u);
-      const uint4 *sv = reinterpret_cast<const uint4 *>(so);
-      for (uint32_t v = v_lo + lane; v < v_hi; v += 32u) {
-        uint4 o;
-        if (mis == 0u) {
-          o = sv[v];
-        } else {
-          const uint4 lo = sv[v - 1u], hi = sv[v];
-          uint32_t t0, t1, t2, t3, t4;
-          switch (wsel) {  // warp-uniform
-            case 0: t0 = lo.x; t1 = lo.y; t2 = lo.z; t3 = lo.w; t4 = hi.x; break;
-            case 1: t0 = lo.y; t1 = lo.z; t2 = lo.w; t3 = hi.x; t4 = hi.y; break;
-            case 2: t0 = lo.z; t1 = lo.w; t2 = hi.x; t3 = hi.y; t4 = hi.z; break;
-            default: t0 = lo.w; t1 = hi.x; t2 = hi.y; t3 = hi.z; t4 = hi.w; break;
-          }
-          o.x = __byte_perm(t0, t1, psel);
-          o.y = __byte_perm(t1, t2, psel);
-          o.z = __byte_perm(t2, t3, psel);
-          o.w = __byte_perm(t3, t4, psel);
-        }
-        stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, o);
-      }
-      const uint32_t head_end = 16u * v_lo < end ? 16u * v_lo : end;
-      if (lane < 16u) {
-        const uint32_t e = mis + lane;
-        if (e < head_end) gbase[e] = so[lane];
-      } else if (v_hi >= v_lo) {
-        const uint32_t e = 16u * v_hi + (lane - 16u);
-        if (e >= mis && e < end) gbase[e] = so[e - mis];
-      }
-    }
-    __syncwarp();  // the staging regions are rewritten by the next tile
-  }
-
-  // ---- epilogue by the CTA that finishes last -----------------------------------------------------
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    sm.is_last = (atomicAdd(&scr->done, 1u) == gridDim.x - 1) ? 1 : 0;
-    __threadfence();
-  }
-  __syncthreads();
-  if (!sm.is_last) return;
-
-  const uint8_t *p = reinterpret_cast<const uint8_t *>(ptr);
-  unsigned long long srclen = len, equallocation = len;
-  uint32_t equalsigns = 0;
-  if (!opt_garbage) {  // reference src/generic/base64.h:50-73
-    srclen = (unsigned long long)(block_find_last(p, (long long)srclen, false, sm) + 1);
-    equallocation = srclen;
-    if (srclen > 0 && p[srclen - 1] == '=') {
-      equallocation = srclen - 1;
-      srclen--;
-      equalsigns = 1;
-      srclen = (unsigned long long)(block_find_last(p, (long long)srclen, false, sm) + 1);
-      if (srclen > 0 && p[srclen - 1] == '=') {
-        equallocation = srclen - 1;
-        srclen--;
-        equalsigns = 2;
-      }
-    }
-  }
-  const unsigned long long key = ld_relaxed_u64(&scr->err_key);
-  const unsigned long long V = V_total;
-  const bool invalid = key != kNoError && (key >> 8) < srclen;
-  uint32_t tail_val[3] = {0, 0, 0};
-  uint64_t tail_pos[3] = {0, 0, 0};
-  if (!invalid && srclen > 0) {
-    long long end = (long long)srclen;
-    const uint32_t idx = (uint32_t)(V & 3ull);
-    for (uint32_t k = 0; k < idx; k++) {
-      const long long f = block_find_last(p, end, true, sm);
-      if (f < 0) break;
-      tail_pos[k] = (uint64_t)f;
-      tail_val[k] = sm.lut[p[f]];
-      end = f;
-    }
-  }
-  if (threadIdx.x == 0) {
-    if (invalid) {
-      res->error = kInvalidBase64Character;
-      res->reserved_ = 0;
-      res->input_count = key >> 8;
-      res->output_count = 0;  // not pinned by the reference: its own kernels disagree here
-    } else {
-      int error;
-      uint64_t in_count, out_count;
-      b64_finish(srclen, equalsigns, equallocation, V, opt_garbage != 0, last_chunk, tail_val, tail_pos, &error,
-                 &in_count, &out_count);
-      res->error = error;
-      res->reserved_ = 0;
-      res->input_count = in_count;
-      res->output_count = out_count;
-    }
-    scratch_reset(scr);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // K7 single pass (round 2): the skeleton of k_utf8_transcode_v3 / k_utf16_to_utf8_v3 (sp_device.cuh) with base64
-// characters in and bytes out.  ONE launch, the text crosses HBM once (the two kernels above read it twice and classify
-// it twice).  A worker loads its 32K contiguous characters (256-bit loads), transposes them, classifies them ONCE
+// characters in and bytes out.  ONE launch, the text crosses HBM once (round 1 shipped a counting kernel and a decoding
+// kernel that read the text twice and classified it twice).  A worker loads its 32K contiguous characters (256-bit loads), transposes them, classifies them ONCE
 // (valid mask, whitespace mask, the six sextet planes), hands the warp's sextet count to the scan warp — the worker that
 // delivers the CTA's last total publishes the aggregate and reserves the next tile — transposes the sextet planes back
 // and compacts the sextets into the warp's staging buffer i & 1 at alignment ZERO.  Tile i leaves two tiles later, when
 // the look-back has long delivered its global sextet rank `goff`: only then is the tile's phase in the 4-sextet quanta
 // known (pad = goff & 3 sextets of its first quantum precede the tile; lane 0 fetches them by scanning the input
 // backwards, whitespace skipped), the quanta are packed 4 sextets -> 3 bytes into the warp's output staging region and
-// streamed out as 16-byte vectors funnel-shifted to the destination's alignment — the copy-out of the two-launch
-// kernel, reading the sextets at a byte offset of 16 - pad.  A quantum belongs to the tile that holds its last sextet;
+// streamed out as 16-byte vectors funnel-shifted to the destination's alignment.  A quantum belongs to the tile that holds its last sextet;
 // the 1 or 2 bytes of a trailing partial quantum are written by the epilogue, which fetches the stream's last <= 3
 // sextets for the last-chunk rules anyway.  A tile without whitespace (interior, every character a sextet) stores its
 // sextets with two 128-bit shared stores per block instead of 32 predicated byte stores.
@@ -420,7 +80,8 @@ struct PendingB64 {
   bool valid = false;
 };
 
-// block_find_last over the single-pass kernel's shared state
+// Largest j in [0, end) whose class satisfies `sextet_only ? class <= 63 : class != 64` (64 = whitespace); -1 if none.
+// The whole CTA takes part.
 template <class SM>
 __device__ long long block_find_last_t(const uint8_t *p, long long end, bool sextet_only, SM &sm) {
   constexpr long long kPer = 16;
@@ -746,15 +407,6 @@ k_b64_decode_v3(const char *ptr, size_t len, uint8_t *out, unsigned long long *d
   }
 }
 
-inline size_t tiles_for(const void *in, size_t len_bytes) {
-  const size_t span = (reinterpret_cast<uintptr_t>(in) & 15u) + len_bytes;
-  return (span + kTileChars - 1) / kTileChars;
-}
-inline size_t workspace_slots(size_t tiles) {
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  return chunks + 1 + (tiles * sizeof(uint16_t) + 7) / 8 + 1;
-}
-
 // ---------------------------------------------------------------------------------------------
 // binary_to_base64 (reference include/simdutf/implementation.h:4941-4960, semantics
 // src/scalar/base64.h:435-491): a fixed 3 -> 4 map, no scan.  A thread takes 48 input bytes (three 128-bit loads) to
@@ -854,13 +506,19 @@ cudaError_t launch_b64_v3(const LaunchCtx &c, const char *in, size_t len, char *
 
 }  // namespace
 
-// Workspace in 8-byte slots: enough for either flavour (the single-pass kernel needs one look-back descriptor per CTA-tile
-// of at least 7 KiB; the two-launch kernels chunk offsets + 16-bit tile counts).
+// Geometry of the shipped kernel: 64 characters per lane (2 KiB warp-tiles), 7 workers + the scan warp per CTA, four
+// CTAs per SM.  Measured on B200, ms per GiB of CRLF-wrapped text / of text without whitespace (K = 32-character blocks
+// per lane, workers x CTAs per SM):  K=2 7x4 0.893 / 0.734   8x3 0.887 / 0.760   11x2 0.936 / 0.795   16x1 1.055 / 0.939;
+// K=3 16x1 0.927 / 0.822;  K=1 7x4 1.113 / 0.958;  round 1's two launches 1.067 / 2.39.  Like UTF-16 -> UTF-8 this
+// decoder is bound by its byte stores, which many small CTAs hide best.
+constexpr int kB64K = 2, kB64Workers = 7, kB64Ctas = 4;
+
+// Workspace in 8-byte slots: one look-back descriptor per CTA-tile.
 size_t base64_tiles(const void *in, size_t len) {
-  const size_t tiles = tiles_for(in, len);
-  const size_t single_pass = tiles / 3 + 4;
-  const size_t two_launch = workspace_slots(tiles);
-  return single_pass > two_launch ? single_pass : two_launch;
+  using Gm = GeomB64<kB64K, kB64Workers>;
+  const size_t span = (reinterpret_cast<uintptr_t>(in) & 31u) + len;
+  const size_t tiles = (span + Gm::kTileChars - 1) / Gm::kTileChars;
+  return (tiles + kB64Workers - 1) / kB64Workers + 2;
 }
 
 cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t len, char *out, uint64_t options,
@@ -872,44 +530,7 @@ cudaError_t launch_base64_to_binary(const LaunchCtx &c, const char *in, size_t l
   B64Opts o;
   o.plus_ok = o.slash_ok = (both || !url) ? 0xFFFFFFFFu : 0u;
   o.minus_ok = o.under_ok = (both || url) ? 0xFFFFFFFFu : 0u;
-  const int variant = tuning(kTuneConvVariant);
-  if (variant != 20) {  // ONE launch (variant 20: the two-launch kernels, kept for the A/B of this round's profiles)
-    switch (variant) {
-      case 21: return launch_b64_v3<2, 16, 1>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
-      case 22: return launch_b64_v3<2, 8, 3>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
-      case 23: return launch_b64_v3<2, 11, 2>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
-      case 24: return launch_b64_v3<3, 16, 1>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
-      case 25: return launch_b64_v3<1, 7, 4>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
-      default: return launch_b64_v3<2, 7, 4>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
-    }
-  }
-  const size_t tiles = tiles_for(in, len);
-  if (workspace_slots(tiles) > c.desc_capacity || tiles > 0xFFFFFF00ull) return cudaErrorInvalidValue;
-  static KernelCache kc;
-  int per_sm = 1;
-  {
-    cudaError_t e = kernel_per_sm(kc, c.device, k_b64_decode_bp, kBlock, 0, &per_sm);
-    if (e != cudaSuccess) return e;
-  }
-  const size_t chunks = (tiles + kChunkTiles - 1) / kChunkTiles;
-  unsigned long long *chunk_off = c.desc;
-  uint16_t *tile_cnt = reinterpret_cast<uint16_t *>(c.cnt);
-  {
-    const size_t cap = (size_t)c.sm_count * 8;
-    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    k_b64_tile_counts<<<grid, kBlock, 0, c.stream>>>(in, len, tile_cnt, chunk_off, (uint32_t)tiles, (uint32_t)chunks, o,
-                                                    c.scratch);
-  }
-  {
-    const size_t ctas = (tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t cap = (size_t)c.sm_count * per_sm;
-    const unsigned grid = (unsigned)(ctas < cap ? ctas : cap);
-    k_b64_decode_bp<<<grid, kBlock, 0, c.stream>>>(in, len, reinterpret_cast<uint8_t *>(out), c.scratch, tile_cnt, chunk_off,
-                                                  (uint32_t)tiles, (uint32_t)chunks, o, url, both, garbage, last_chunk,
-                                                  static_cast<FullResultPOD *>(full_res));
-  }
-  count_launch(2);
-  return cudaGetLastError();
+  return launch_b64_v3<kB64K, kB64Workers, kB64Ctas>(c, in, len, out, o, url, both, garbage, last_chunk, full_res);
 }
 
 // base64_to_binary for char16_t input (reference include/simdutf/implementation.h:4922-4939; the scalar decoder reads

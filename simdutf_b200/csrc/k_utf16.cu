@@ -40,10 +40,7 @@ __device__ __forceinline__ void check_surrogates(const InView &in, Scratch *scr,
   // any unit in D800..DFFF?  (u & 0xF800) == 0xD800, on both halves of each word at once
   uint32_t any = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint32_t x = (w[k] & 0xF800F800u) ^ 0xD800D800u;           // halves equal to zero are surrogates
-    any |= ~((x | ((x & 0x7FFF7FFFu) + 0x7FFF7FFFu)) | 0x7FFF7FFFu);  // 0x8000 per zero half
-  }
+  for (int k = 0; k < 4; k++) any |= u16_sur_flags(w[k]);  // swar.h; the screen below reuses these flags
   if (!any) return;
   // Surrogates present (common in real text: every supplementary character is a pair).  Exact screen on both halves
   // of each word at once: the low surrogates must be exactly the units behind the high surrogates — the unit before

@@ -136,10 +136,23 @@ __global__ void __launch_bounds__(kBlock) k_validate_utf8(const char *ptr, size_
       cur = __shfl_sync(kFull, cur, 0);
       const long long first = (long long)(g0 * 16ull) - 3 - (long long)in.vbeg;
       if (cur != kNoError && (long long)(cur >> 8) < first) break;
+      // The flagged lanes take turns, lowest first, and the warp stops at the first one that pins an error down: every
+      // error lies in the window of a flagged block, windows grow with the lane, so the first hit is the chunk's first
+      // error.  (All flagged lanes searching at once cost text in the wrong encoding one atomic per LANE before the
+      // first error was on record: validate_utf8 on 1 GiB of UTF-16 text took 0.14 ms to give up.)
+      unsigned bm = __ballot_sync(kFull, badblocks != 0u);
+      while (bm) {
+        const unsigned l = (unsigned)__ffs((int)bm) - 1u;
+        int found = 0;
+        if (lane == l) {
 #pragma unroll
-      for (int j = 0; j < ITEMS / 2; j++) {
-        const long long b0 = (long long)(r0 + 32ull * j);
-        if (badblocks & (1u << j)) u8_locate_error(in, scr, b0 - 3, b0 + 32);
+          for (int j = 0; j < ITEMS / 2; j++) {
+            const long long b0 = (long long)(r0 + 32ull * j);
+            if (!found && (badblocks & (1u << j))) found = u8_locate_error(in, scr, b0 - 3, b0 + 32) ? 1 : 0;
+          }
+        }
+        if (__shfl_sync(kFull, found, l)) break;
+        bm &= bm - 1u;
       }
     }
   }

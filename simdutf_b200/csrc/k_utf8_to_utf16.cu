@@ -35,8 +35,6 @@ namespace b200 {
 
 namespace {
 
-using bpd::kThreads;
-using bpd::kWarpsPerCta;
 using bpd::sts_u16;
 using bpd::sts_u32;
 using sp::atom_add_u32;

@@ -151,18 +151,20 @@ B200_HD bool u16_bad(uint32_t u, uint32_t pu, bool has_prev, uint32_t nu, bool h
 // one of them is bad OR the unit before is a lone high / the unit after a lone low surrogate (reported by their
 // own groups): callers treat non-zero as "search this group unit by unit".
 // ---------------------------------------------------------------------------------------------
-B200_HD uint32_t u16_is_tag(uint32_t x, uint32_t tag) {  // 0x8000 per 16-bit half with (half & 0xFC00) == tag's half
-  const uint32_t z = (x & 0xFC00FC00u) ^ tag;
+B200_HD uint32_t u16_sur_flags(uint32_t x) {  // 0x8000 per 16-bit half in D800..DFFF
+  const uint32_t z = (x & 0xF800F800u) ^ 0xD800D800u;
   return ~(((z & 0x7FFF7FFFu) + 0x7FFF7FFFu) | z) & 0x80008000u;
 }
+// One surrogate test per word; bit 10 of a surrogate tells low from high (x << 5 moves it onto the flag's bit).
 B200_HD uint32_t u16_pairing_screen(const uint32_t w[4], uint32_t pw, uint32_t nw) {
-  uint32_t wrong = 0, hprev = u16_is_tag(pw, 0xD800D800u);
+  uint32_t wrong = 0, hprev = u16_sur_flags(pw) & ~(pw << 5);
   for (int k = 0; k < 4; k++) {
-    const uint32_t H = u16_is_tag(w[k], 0xD800D800u), L = u16_is_tag(w[k], 0xDC00DC00u);
+    const uint32_t S = u16_sur_flags(w[k]), T = w[k] << 5;
+    const uint32_t H = S & ~T, L = S & T;
     wrong |= ((H << 16) | (hprev >> 16)) ^ L;  // the high-surrogate flags moved to the unit behind them
     hprev = H;
   }
-  return wrong | ((hprev >> 16) ^ (u16_is_tag(nw, 0xDC00DC00u) & 0x8000u));
+  return wrong | ((hprev >> 16) ^ (u16_sur_flags(nw) & (nw << 5) & 0x8000u));
 }
 
 // ---------------------------------------------------------------------------------------------
