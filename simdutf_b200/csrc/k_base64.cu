@@ -135,12 +135,29 @@ k_b64_decode_v3(const char *ptr, size_t len, uint8_t *out, unsigned long long *d
       if (q.wtot) {
         const uint32_t sx = wbase + (q.iter & 1u) * Gm::kSxBytes + 16u;  // sextet of rank goff + i at sx + i
         const uint32_t pad = (uint32_t)(goff & 3ull);                   // sextets of the first quantum that precede the tile
-        if (lane == 0 && pad) {  // fetch them: scan the input backwards (whitespace and, in the tolerant modes, garbage skipped)
-          uint32_t need = pad;
+        if (pad) {
+          // fetch them from the input in front of the tile (whitespace and, in the tolerant modes, garbage skipped): the
+          // 16 characters before the tile go to 16 lanes at once — one round trip, where a backward walk by one lane was
+          // a chain of dependent loads (ncu: 7 % of the kernel's stall samples) — and the nearest `pad` sextets among
+          // them are kept; only a longer run of whitespace is walked
           const uint8_t *p8 = reinterpret_cast<const uint8_t *>(in.base);
-          for (long long pos = (long long)q.tile * Gm::kTileChars - 1; need && pos >= (long long)in.vbeg; pos--) {
-            const uint32_t cls = sm.lut[p8[pos]];
-            if (cls <= 63u) bpd::sts_u8(sx - pad + (--need), cls);
+          const long long t0q = (long long)q.tile * Gm::kTileChars;
+          const long long pos = t0q - 1 - (long long)lane;
+          uint32_t cls = 255u;
+          if (lane < 16u && pos >= (long long)in.vbeg) cls = sm.lut[p8[pos]];
+          const unsigned bm = __ballot_sync(kFull, cls <= 63u);
+          const uint32_t rank = (uint32_t)__popc(bm & ((1u << lane) - 1u));
+          if (cls <= 63u && rank < pad) bpd::sts_u8(sx - 1u - rank, cls);
+          const uint32_t got = (uint32_t)__popc(bm);
+          if (got < pad && lane == 0) {
+            uint32_t need = pad - got;
+            for (long long pos2 = t0q - 17; need && pos2 >= (long long)in.vbeg; pos2--) {
+              const uint32_t c2 = sm.lut[p8[pos2]];
+              if (c2 <= 63u) {
+                bpd::sts_u8(sx - 1u - (pad - need), c2);
+                need--;
+              }
+            }
           }
         }
         __syncwarp();
