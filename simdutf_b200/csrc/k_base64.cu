@@ -125,7 +125,6 @@ k_b64_decode_v3(const char *ptr, size_t len, uint8_t *out, unsigned long long *d
   } else {
     const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(smem) + warp * Gm::kWarpBytes;
     const uint32_t so_addr = wbase + 2u * Gm::kSxBytes;
-    uint8_t *so = reinterpret_cast<uint8_t *>(smem) + warp * Gm::kWarpBytes + 2u * Gm::kSxBytes;
     const uint32_t one = (blockDim.x >> 5) - (uint32_t)NW;  // 1, opaque to the assembler (bpd::bump)
     PendingB64 q1, q2;  // tiles i - 1 and i - 2
 
@@ -165,7 +164,6 @@ k_b64_decode_v3(const char *ptr, size_t len, uint8_t *out, unsigned long long *d
         const uint32_t nq = have >> 2;
         const uint32_t nb = 3u * nq;                           // output bytes of this tile
         uint8_t *gdst = out + 3ull * (goff >> 2);              // where they go
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
         {
           // four quanta per lane and round: 16 sextets (five words, realigned by one byte permute each) -> 12 bytes
           // (three 32-bit stores); staging byte 3 j + k is byte k of quantum j; the stale bytes behind the last whole
@@ -192,46 +190,7 @@ k_b64_decode_v3(const char *ptr, size_t len, uint8_t *out, unsigned long long *d
           }
         }
         __syncwarp();
-        // staging -> global.  Destination coordinates e are relative to gbase = gdst - mis (16-byte aligned): the data
-        // occupies [mis, end); full vectors are funnel-shifted out of the staging words, the partial first and last
-        // vectors are written bytewise by lanes 0-15 and 16-31.
-        {
-          uint8_t *gbase = gdst - mis;
-          const uint32_t end = mis + nb;
-          const uint32_t v_lo = (mis + 15u) >> 4, v_hi = end >> 4;
-          const uint32_t sh = (16u - mis) & 15u;            // staging byte offset of destination vector v is 16 v - mis
-          const uint32_t wsel = sh >> 2;
-          const uint32_t psel = 0x3210u + 0x1111u * (sh & 3u);
-          const uint4 *sv = reinterpret_cast<const uint4 *>(so);
-          for (uint32_t v = v_lo + lane; v < v_hi; v += 32u) {
-            uint4 ov;
-            if (mis == 0u) {
-              ov = sv[v];
-            } else {
-              const uint4 lo = sv[v - 1u], hi = sv[v];
-              uint32_t t0, t1, t2, t3, t4;
-              switch (wsel) {  // warp-uniform
-                case 0: t0 = lo.x; t1 = lo.y; t2 = lo.z; t3 = lo.w; t4 = hi.x; break;
-                case 1: t0 = lo.y; t1 = lo.z; t2 = lo.w; t3 = hi.x; t4 = hi.y; break;
-                case 2: t0 = lo.z; t1 = lo.w; t2 = hi.x; t3 = hi.y; t4 = hi.z; break;
-                default: t0 = lo.w; t1 = hi.x; t2 = hi.y; t3 = hi.z; t4 = hi.w; break;
-              }
-              ov.x = __byte_perm(t0, t1, psel);
-              ov.y = __byte_perm(t1, t2, psel);
-              ov.z = __byte_perm(t2, t3, psel);
-              ov.w = __byte_perm(t3, t4, psel);
-            }
-            stg_stream_v4(reinterpret_cast<uint4 *>(gbase) + v, ov);
-          }
-          const uint32_t head_end = 16u * v_lo < end ? 16u * v_lo : end;
-          if (lane < 16u) {
-            const uint32_t e = mis + lane;
-            if (e < head_end) gbase[e] = so[lane];
-          } else if (v_hi >= v_lo) {
-            const uint32_t e = 16u * v_hi + (lane - 16u);
-            if (e >= mis && e < end) gbase[e] = so[e - mis];
-          }
-        }
+        sp::copy_out_bytes_v16(so_addr, nb, gdst, lane);  // the destination's own 16-byte vectors, funnel-shifted out of the staging words
       }
       __syncwarp();  // the staging buffers are about to be rewritten
     };

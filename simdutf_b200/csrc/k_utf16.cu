@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kBlock) k_well_formed_utf16(const uint16_t *in
       uint32_t ws[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) ws[k] = BE ? swap16x2(w[k]) : w[k];
-      const uint32_t wrong = u16_pairing_screen(ws, BE ? swap16x2(u[0] << 16) : u[0] << 16, BE ? swap16x2(u[9]) : u[9]);
+      const uint32_t wrong = u16_pairing_screen_tags(ws, BE ? swap16x2(u[0] << 16) : u[0] << 16, BE ? swap16x2(u[9]) : u[9]);
       if (!wrong) {
         o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
       } else {

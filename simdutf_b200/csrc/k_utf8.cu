@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(kBlock) k_validate_utf8(const char *ptr, size_
        chunk += nwarps) {
     const unsigned long long g0 = chunk * chunk_gran;
     uint32_t w[ITEMS][4];
+    // (Measured and dropped: pulling the warp's next chunk into L2 with prefetch.global.L2 — ncu puts 27 % of the stall
+    // samples of the non-ASCII path on the wait for the chunk's own loads — made mixed text 5 % and ASCII 5-15 % SLOWER;
+    // 3, 5 or 6 resident CTAs per SM (70 / 48 / 40 registers) are within 2 % of each other.)
     // interior chunks (every granule inside the buffer; all but the first and the last chunk) skip the per-granule
     // range tests: the mixed-text path is ALU-bound (ncu: ALU pipe 79 %), and the guards were a tenth of its instructions
     if (g0 * 16ull >= in.vbeg && (g0 + chunk_gran) * 16ull <= in.vend) {

@@ -415,7 +415,8 @@ static void test_u16_screen() {
   const uint32_t wrong = b200::u16_pairing_screen(w, pw, nw);
   CHECK(!(any_bad && wrong == 0), "u16 screen missed a bad surrogate");
   CHECK(!(wrong != 0 && !any_bad && !next_lone_low), "u16 screen raised without cause %08x: %04x | %04x %04x %04x %04x %04x %04x %04x %04x | %04x", wrong,
-        u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7], u[8], u[9]);
+        u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7], u[8], u[9]);  // the two-tag form (to_well_formed_utf16) gives the same answer
+  CHECK((b200::u16_pairing_screen_tags(w, pw, nw) != 0) == (wrong != 0), "the two forms of the u16 screen disagree");
 }
 // u8l1_screen64: the continuation count is exact; suspect == false implies the oracle's walk over the 64 bytes
 // (with the byte before and after) reports nothing inside them.

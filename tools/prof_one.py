@@ -2,7 +2,7 @@
 usage: python tools/prof_one.py <op> [bytes] [reps]
    op: convert16 | convert32 | validate_ascii | validate_mixed | length | utf16to8 | base64 |
        utf32to8 | utf32to16 | utf32to16be | utf16to32 | validate32 | len8from32 | b64encode |
-       l1to8 | l1to16 | l1to32 | u8tol1 | u16tol1 | u32tol1 | validate_ascii_op | len8froml1
+       l1to8 | l1to16 | l1to32 | u8tol1 | u16tol1 | u32tol1 | validate_ascii_op | len8froml1 | wellformed | validate16
 """
 import ctypes
 import os
@@ -62,6 +62,15 @@ elif op == "validate_ascii":
     d = synth.ascii_text(nbytes, seed=1, device=dev)
     n = d.numel()
     run(lambda: lib.b200_validate_utf8_with_errors_async(ctypes.c_void_p(d.data_ptr()), n, rp, sp), n, 0)
+elif op in ("wellformed", "validate16"):
+    u = synth.mixed_utf16le(nbytes // 2, seed=3, device=dev)
+    n = u.numel()
+    if op == "wellformed":
+        o = torch.empty_like(u)
+        run(lambda: lib.b200_to_well_formed_utf16le_async(ctypes.c_void_p(u.data_ptr()), n, ctypes.c_void_p(o.data_ptr()), rp, sp), 2 * n, 2 * n)
+        assert torch.equal(o, u)
+    else:
+        run(lambda: lib.b200_validate_utf16le_with_errors_async(ctypes.c_void_p(u.data_ptr()), n, rp, sp), 2 * n, 0)
 elif op == "utf16to8":
     u = synth.mixed_utf16le(nbytes // 2, seed=3, device=dev)
     n = u.numel()
