@@ -1,9 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 4 5 3 0 6 1 2; do
-echo "variant $v"
-B200_BENCH_TUNE="conv_minb=$v" timeout 100 python tools/prof_one.py validate_mixed 1073741824 10 2>&1 | tail -1
-B200_BENCH_TUNE="conv_minb=$v" timeout 100 python tools/prof_one.py validate_ascii 1073741824 10 2>&1 | tail -1
-done
-timeout 100 python tools/prof_one.py wellformed 1073741824 5 2>&1 | tail -1
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "well_formed or utf8_small_random or utf8_error_classes or utf8_medium or golden" 2>&1 | tail -2
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29527 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/r02_bench_4gpu.json 2> gpurun_out/r02_bench_4gpu.err; echo "bench4 rc=$?"; cut -c1-300 gpurun_out/r02_bench_4gpu.json; tail -n 3 gpurun_out/r02_bench_4gpu.err
