@@ -558,7 +558,8 @@ size_t out_elem_bytes(Op op) {
 bool bad_args(const void *in, size_t len, const void *res) { return res == nullptr || (in == nullptr && len != 0); }
 
 // Workspace lookup + launches of one operation, atomically with respect to other threads using the same device
-// (a two-launch operation must not interleave with another call on the same stream's workspace).
+// (a multi-launch operation — detect_encodings, base64 from char16_t — must not interleave with another call on the same
+// stream's workspace).
 int locked_enqueue(DeviceCtx *c, cudaStream_t stream, Op op, const void *in, size_t len, void *out, void *res, uint64_t opt,
                    uint64_t lastc) {
   std::lock_guard<std::mutex> lock(c->mu);

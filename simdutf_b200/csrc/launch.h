@@ -128,6 +128,6 @@ void count_launch(int n);  // bumps the library-wide launch counter (b200_launch
 // Experiment knobs (b200_set_tuning in the C ABI; tools/ and profiles/ use them to compare kernel variants inside
 // one build).  The library never reads the environment.
 enum TuneKey { kTuneConvMinB = 0, kTuneSegMB = 1, kTuneNoNccl = 2, kTuneConvVariant = 3, kTuneConvStagger = 4, kTuneDbgLo = 5, kTuneDbgHi = 6, kTuneKeyCount = 8 };
-int tuning(int key);  // 0 = default  // bumps the library-wide launch counter (b200_launch_count)
+int tuning(int key);  // 0 = default (conv_minb and conv_stagger are not read by any kernel at present)
 
 }  // namespace b200
