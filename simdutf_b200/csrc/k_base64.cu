@@ -177,16 +177,11 @@ k_b64_decode_v3(const char *ptr, size_t len, uint8_t *out, unsigned long long *d
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4) : "r"(a));
             const uint32_t w[4] = {__byte_perm(x0, x1, sel) & 0x3F3F3F3Fu, __byte_perm(x1, x2, sel) & 0x3F3F3F3Fu,
                                    __byte_perm(x2, x3, sel) & 0x3F3F3F3Fu, __byte_perm(x3, x4, sel) & 0x3F3F3F3Fu};
-            uint32_t y[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const uint32_t t1 = (w[k] & 0x00FF00FFu) * 64u + ((w[k] >> 8) & 0x00FF00FFu);  // s0:s1 | s2:s3, 12 bits each
-              const uint32_t x = (t1 & 0xFFFFu) * 4096u + (t1 >> 16);                       // 24 bits, first byte on top
-              y[k] = __byte_perm(x, 0u, 0x4012);                                             // first byte lowest
-            }
-            bpd::sts_u32(so_addr + 12u * g, __byte_perm(y[0], y[1], 0x4210));
-            bpd::sts_u32(so_addr + 12u * g + 4u, __byte_perm(y[1], y[2], 0x5421));
-            bpd::sts_u32(so_addr + 12u * g + 8u, __byte_perm(y[2], y[3], 0x6542));
+            uint32_t o3[3];
+            b64_pack_quanta4(w, o3);  // swar.h (host-tested)
+            bpd::sts_u32(so_addr + 12u * g, o3[0]);
+            bpd::sts_u32(so_addr + 12u * g + 4u, o3[1]);
+            bpd::sts_u32(so_addr + 12u * g + 8u, o3[2]);
           }
         }
         __syncwarp();

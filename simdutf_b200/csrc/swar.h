@@ -251,6 +251,21 @@ B200_HD uint32_t b64_class(uint32_t c, bool url, bool both) {
   return 255u;
 }
 
+// Four sextets (one per byte of w, the first in the lowest byte) -> the three bytes of their quantum in the low 24 bits,
+// first byte lowest (reference src/scalar/base64.h:100-131: triple = s0 << 18 | s1 << 12 | s2 << 6 | s3, big-endian).
+B200_HD uint32_t b64_pack_quantum(uint32_t w) {
+  const uint32_t t1 = (w & 0x00FF00FFu) * 64u + ((w >> 8) & 0x00FF00FFu);  // s0:s1 | s2:s3, 12 bits each
+  const uint32_t x = (t1 & 0xFFFFu) * 4096u + (t1 >> 16);                 // 24 bits, first byte on top
+  return prmt(x, 0u, 0x4012);                                              // first byte lowest
+}
+// Sixteen sextets (four words) -> twelve bytes (three words), stream order.
+B200_HD void b64_pack_quanta4(const uint32_t w[4], uint32_t out[3]) {
+  const uint32_t y0 = b64_pack_quantum(w[0]), y1 = b64_pack_quantum(w[1]), y2 = b64_pack_quantum(w[2]), y3 = b64_pack_quantum(w[3]);
+  out[0] = prmt(y0, y1, 0x4210);
+  out[1] = prmt(y1, y2, 0x5421);
+  out[2] = prmt(y2, y3, 0x6542);
+}
+
 // Output bytes fully determined by the first R sextets of the stream: floor(6R/8) — i.e. 3 per complete
 // quantum, +1 for 2 leftover sextets, +2 for 3 (reference src/scalar/base64.h:160-200, loose mode).
 B200_HD uint64_t b64_bytes_from_sextets(uint64_t r) { return (r * 6) >> 3; }

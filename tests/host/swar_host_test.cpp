@@ -335,6 +335,70 @@ static void test_b64_bitplane(const std::vector<uint8_t> &d, uint64_t options) {
   }
 }
 
+// ---- the single-pass decoder's tile pipeline (k_base64.cu: k_b64_decode_v3) with a sequential stand-in for the CUDA
+// plumbing: per tile of `tile` characters the sextets are compacted into a staging buffer at alignment zero (16 bytes of
+// headroom), the tile's rank goff tells how many sextets of its first quantum precede it (pad = goff & 3, fetched by
+// walking the input backwards), groups of 16 sextets are read at byte offset 16 - pad with the kernel's byte-permute
+// selectors and packed by swar.h:b64_pack_quanta4, a quantum belongs to the tile that holds its last sextet, and the
+// epilogue writes the 1-2 bytes of a trailing partial quantum.  The bytes must equal the oracle's decode.
+static void test_b64_single_pass(const std::vector<uint8_t> &d, uint64_t options, size_t tile) {
+  const bool url = options & 1, both = options & 8, garbage = (options == 4 || options == 5 || options == 12);
+  std::vector<uint8_t> want(d.size() + 8);
+  const oracle_full_result r = oracle_base64_to_binary_details(d.data(), d.size(), want.data(), options, 0);
+  if (r.error != kSuccess) return;  // output is pinned for successful decodes only
+  std::vector<uint8_t> out(d.size() + 64, 0xEE);
+  uint64_t goff = 0;
+  for (size_t t0 = 0; t0 < d.size(); t0 += tile) {
+    std::vector<uint8_t> stage(16 + tile + 32, 0xAA);  // stale bytes behind the sextets, as in shared memory
+    uint32_t wtot = 0;
+    for (size_t i = t0; i < std::min(d.size(), t0 + tile); i++) {
+      const uint32_t c = b64_class(d[i], url, both);
+      if (c <= 63) stage[16 + wtot++] = (uint8_t)c;
+    }
+    const uint32_t pad = (uint32_t)(goff & 3);
+    if (wtot) {
+      uint32_t need = pad;
+      for (long long pos = (long long)t0 - 1; need && pos >= 0; pos--) {
+        const uint32_t c = b64_class(d[pos], url, both);
+        if (c <= 63) stage[16 - pad + (--need)] = (uint8_t)c;
+      }
+      CHECK(need == 0, "b64 single pass: carried sextets missing");
+      const uint32_t have = pad + wtot, nq = have >> 2, nb = 3 * nq;
+      const uint32_t ngroups = (nq + 3) >> 2;
+      const uint32_t sel = 0x3210u + 0x1111u * (4u - pad);
+      std::vector<uint8_t> so(12 * ngroups + 16);
+      for (uint32_t g = 0; g < ngroups; g++) {
+        uint32_t x[5];
+        memcpy(x, &stage[16 + 16 * g - 4], 20);
+        uint32_t w[4], o3[3];
+        for (int k = 0; k < 4; k++) w[k] = prmt(x[k], x[k + 1], sel) & 0x3F3F3F3Fu;
+        b64_pack_quanta4(w, o3);
+        memcpy(&so[12 * g], o3, 12);
+      }
+      memcpy(&out[3 * (goff >> 2)], so.data(), nb);
+    }
+    goff += wtot;
+  }
+  const uint64_t V = goff;
+  if ((V & 3) >= 2) {  // the epilogue's tail bytes: tail_val[0] is the stream's last sextet
+    uint32_t tv[3] = {0, 0, 0};
+    long long end = (long long)d.size();
+    if (!garbage) { while (end > 0 && (b64_class(d[end - 1], url, both) == 64 || d[end - 1] == '=')) end--; }
+    for (uint32_t k = 0; k < (V & 3); k++) {
+      long long f = end - 1;
+      while (f >= 0 && b64_class(d[f], url, both) > 63) f--;
+      if (f < 0) break;
+      tv[k] = b64_class(d[f], url, both);
+      end = f;
+    }
+    uint8_t *tail = &out[3 * (V >> 2)];
+    if ((V & 3) == 2) tail[0] = (uint8_t)((tv[1] << 2) | (tv[0] >> 4));
+    else { tail[0] = (uint8_t)((tv[2] << 2) | (tv[1] >> 4)); tail[1] = (uint8_t)((tv[1] << 4) | (tv[0] >> 2)); }
+  }
+  CHECK(memcmp(out.data(), want.data(), r.output_count) == 0, "b64 single pass: output differs, tile %zu opt %llu in=%s", tile,
+        (unsigned long long)options, hex(d).c_str());
+}
+
 // ---- generators ----------------------------------------------------------------------------------------
 static const uint8_t kSpecial[] = {0x20, 0x41, 0x7F, 0x80, 0x8F, 0x90, 0x9F, 0xA0, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1, 0xF3, 0xF4, 0xF5, 0xF7, 0xF8, 0xFF};
 static void push_cp(std::vector<uint8_t> &o, uint32_t cp) {
@@ -502,6 +566,7 @@ int main(int argc, char **argv) {
     static const uint64_t opts[] = {0, 1, 2, 3, 4, 5, 8, 12};
     test_b64(b, opts[rnd(8)], rnd(3));
     test_b64_bitplane(b, opts[rnd(8)]);
+    { static const size_t tiles[] = {1, 3, 4, 5, 16, 17, 32, 64}; test_b64_single_pass(b, opts[rnd(8)], tiles[rnd(8)]); }
     if (it < 256) { std::vector<uint8_t> all(256); for (int i = 0; i < 256; i++) all[i] = (uint8_t)(i + it); test_b64_bitplane(all, opts[it & 7]); }
     for (int k = 0; k < 8; k++) { test_u16_screen(); test_u8l1_screen(); }
     if (failures > 50) break;
