@@ -486,6 +486,14 @@ def main():
                 "length_kernel_gbs": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9,
                 "length_kernel_frac": n / (sum(len_ms) / len(len_ms) * 1e-3) / 1e9 / peak}
         roof.update(val)
+        # BASELINE.json's configs 3 and 4, so that a record that keeps only the roofline dict carries them too
+        for src, dst in (("config3_convert_utf16le_to_utf8_2GiB", "convert_utf16le_to_utf8"),
+                         ("config4_base64_to_binary_2GiB", "base64_to_binary")):
+            row = extras.get(src)
+            if isinstance(row, dict):
+                for k_src, k_dst in (("ms", "_ms"), ("input_gbs", "_input_gbs"), ("frac_of_peak", "_frac")):
+                    if k_src in row:
+                        roof[dst + k_dst] = row[k_src]
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
