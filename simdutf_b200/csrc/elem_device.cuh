@@ -6,9 +6,9 @@
 //   In / Out            element types (1, 2 or 4 bytes)
 //   kMax                most output elements one input element produces
 //   kNeedsNeighbours    whether emit() looks at the element before / after
-//   count(v)            output elements of input element v (what the length query of the conversion returns)
-//   emit(v, prev, next, has_prev, has_next, P, err)  the same count, the elements packed little-endian into P
-//                       (first element lowest, Out-sized fields) and the element's own error code
+//   emit(v, prev, next, has_prev, has_next, P, err)  the number of output elements of input element v (what the length
+//                       query of the conversion counts), the elements packed little-endian into P (first element
+//                       lowest, Out-sized fields) and the element's own error code
 //   kFast               byte input only: the trait also has fast_pass1(w, prev, next, bad) — the lane's output count
 //                       from SWAR arithmetic on its 16 input words, plus "some element of this lane may be in error"
 //                       (conservative) — and emit_word(w, next_word, sp), which stages the output of four input

@@ -27,7 +27,6 @@ struct L1ToU8 {
   static constexpr uint32_t kMax = 2;
   static constexpr bool kNeedsNeighbours = false;
   static constexpr bool kFast = true;
-  __device__ static uint32_t count(uint32_t b, uint32_t, uint32_t) { return 1u + (b >> 7); }
   // 64 + the number of bytes >= 0x80: the high bits summed as packed byte counters (<= 16 each)
   __device__ static uint32_t fast_pass1(const uint32_t (&w)[16], uint32_t, uint32_t, bool &bad) {
     bad = false;
@@ -65,7 +64,6 @@ struct U8ToL1 {
   static constexpr uint32_t kMax = 1;
   static constexpr bool kNeedsNeighbours = true;
   static constexpr bool kFast = true;
-  __device__ static uint32_t count(uint32_t b, uint32_t, uint32_t) { return (b & 0xC0u) != 0x80u; }
   // 64 - the number of continuation bytes; `bad` (conservative) unless every byte >= 0xC0 is C2 / C3 and the
   // continuation bytes are exactly the bytes behind those leads (the lane's neighbours pb / nb included)
   __device__ static uint32_t fast_pass1(const uint32_t (&w)[16], uint32_t pb, uint32_t nb, bool &bad) {
@@ -136,9 +134,9 @@ __global__ void __launch_bounds__(kBlock) k_latin1_map(const In *in, size_t len,
     const In *p = gin + g * kG;
     if (in_vec) {
       uint32_t w[kInBytes / 4u];
-      if (kInBytes == 4u) {
+      if constexpr (kInBytes == 4u) {
         w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
-      } else if (kInBytes == 8u) {
+      } else if constexpr (kInBytes == 8u) {
         const uint2 x = __ldg(reinterpret_cast<const uint2 *>(p));
         w[0] = x.x; w[1] = x.y;
       } else {

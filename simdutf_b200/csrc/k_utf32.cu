@@ -21,15 +21,14 @@ namespace {
 using namespace elem;
 
 // ---- per-element rules -----------------------------------------------------------------------------------
-// count(v, nv): output elements of input element v; emit(): the same count, the elements packed little-endian
-// into P (first element lowest; OutT-sized fields), and the element's own error code.
+// emit(): the number of output elements of input element v (what the conversion's length query counts), the elements
+// packed little-endian into P (first element lowest; OutT-sized fields), and the element's own error code.
 struct U32ToU8 {
   using In = uint32_t;
   using Out = uint8_t;
   static constexpr uint32_t kMax = 4;
   static constexpr bool kNeedsNeighbours = false;
   static constexpr bool kFast = false;
-  __device__ static uint32_t count(uint32_t w, uint32_t, uint32_t) { return 1u + (w > 0x7Fu) + (w > 0x7FFu) + (w > 0xFFFFu); }
   // (a select-only form of this was measured: 13 % slower — the four candidate encodings cost more than the divergence)
   __device__ static uint32_t emit(uint32_t w, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = w > 0x10FFFFu ? kTooLarge : ((w & 0xFFFFF800u) == 0xD800u ? kSurrogate : kSuccess);
@@ -48,7 +47,6 @@ struct U32ToU16 {
   static constexpr uint32_t kMax = 2;
   static constexpr bool kNeedsNeighbours = false;
   static constexpr bool kFast = false;
-  __device__ static uint32_t count(uint32_t w, uint32_t, uint32_t) { return 1u + (w > 0xFFFFu); }
   __device__ static uint32_t emit(uint32_t w, uint32_t, uint32_t, bool, bool, uint32_t &P, int &err) {
     err = w > 0x10FFFFu ? kTooLarge : ((w & 0xFFFFF800u) == 0xD800u ? kSurrogate : kSuccess);
     if (w <= 0xFFFFu) {
@@ -70,10 +68,6 @@ struct U16ToU32 {
   static constexpr bool kFast = false;
   // one code point per unit that is not a low surrogate (== count_utf16 / utf32_length_from_utf16, so a buffer
   // sized by that query is never overrun); a high surrogate emits the pair's code point, looking one unit ahead
-  __device__ static uint32_t count(uint32_t u, uint32_t, uint32_t) {
-    if (BE) u = bswap16(u);
-    return (u & 0xFC00u) != 0xDC00u;
-  }
   __device__ static uint32_t emit(uint32_t u, uint32_t pu, uint32_t nu, bool has_prev, bool has_next, uint32_t &P, int &err) {
     if (BE) { u = bswap16(u); pu = bswap16(pu); nu = bswap16(nu); }
     const bool low = (u & 0xFC00u) == 0xDC00u, high = (u & 0xFC00u) == 0xD800u;
