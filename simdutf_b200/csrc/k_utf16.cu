@@ -6,6 +6,8 @@
 // Same data path as k_utf8.cu: 16-byte granules (8 units) loaded with coalesced 128-bit streaming loads,
 // neighbour unit by warp shuffle.  Surrogate verdicts are exact per unit, so the first error is
 // a plain atomicMin of (unit index << 8 | SURROGATE).
+#include <type_traits>
+
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -95,10 +97,21 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size
   unsigned long long total = 0;
   for (unsigned long long chunk = (unsigned long long)blockIdx.x * kWarps + warp; chunk < nchunks; chunk += nwarps) {
     const unsigned long long g0 = chunk * chunk_gran;
+    // chunks wholly inside the buffer (all but the first and the last): unguarded loads, no per-granule range tests
+    const bool interior = g0 * 16ull >= in.vbeg && (g0 + chunk_gran) * 16ull <= in.vend;  // warp-uniform
     uint32_t w[ITEMS][4];
     bool inside[ITEMS];
+    if (interior) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+      for (int j = 0; j < ITEMS; j++) {
+        const uint4 v = ldg_stream_v4(in.base + g0 + (unsigned long long)j * 32u + lane);
+        w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
+        inside[j] = true;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
+    }
     if (BE && MODE != 2) {
 #pragma unroll
       for (int j = 0; j < ITEMS; j++) {
@@ -125,42 +138,46 @@ __global__ void __launch_bounds__(kBlock) k_scan_utf16(const uint16_t *ptr, size
         check_surrogates(in, scr, g, w[j], pw[j], nw[j], valid);
       }
     } else {
-      uint32_t cnt = 0;
+      auto count_chunk = [&](auto interior_tag) -> uint32_t {
+        constexpr bool kInterior = decltype(interior_tag)::value;
+        uint32_t cnt = 0;
 #pragma unroll
-      for (int j = 0; j < ITEMS; j++) {
-        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-        if (inside[j]) {
-          // 16-bit-lane SWAR: bit 15 of a lane <=> the predicate holds for that unit; the four words of the granule
-          // share one popcount (POPC issues at a quarter of the logic rate: one per word made the kernel POPC-bound)
-          uint32_t m = 0;
+        for (int j = 0; j < ITEMS; j++) {
+          const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+          if (kInterior || inside[j]) {
+            // 16-bit-lane SWAR: bit 15 of a lane <=> the predicate holds for that unit; the four words of the granule
+            // share one popcount (POPC issues at a quarter of the logic rate: one per word made the kernel POPC-bound)
+            uint32_t m = 0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint32_t x = w[j][k];
-            if (MODE == 0) {
-              const uint32_t z = (x ^ 0xDC00DC00u) & 0xFC00FC00u;         // zero lane <=> low surrogate
-              const uint32_t notlow = (z >> 1) + 0x7E007E00u;
-              m |= (notlow & 0x80008000u) >> k;
-            } else {
-              const uint32_t h = x >> 1;
-              const uint32_t ge80 = (h & 0x7FC07FC0u) + 0x7FC07FC0u;
-              const uint32_t ge800 = (h & 0x7C007C00u) + 0x7C007C00u;
-              const uint32_t z = (x ^ 0xD800D800u) & 0xF800F800u;         // zero lane <=> surrogate
-              const uint32_t notsur = (z >> 1) + 0x7C007C00u;
-              m |= ((ge80 & 0x80008000u) | ((ge800 & notsur & 0x80008000u) >> 1)) >> (2 * k);
+            for (int k = 0; k < 4; k++) {
+              const uint32_t x = w[j][k];
+              if (MODE == 0) {
+                const uint32_t z = (x ^ 0xDC00DC00u) & 0xFC00FC00u;         // zero lane <=> low surrogate
+                const uint32_t notlow = (z >> 1) + 0x7E007E00u;
+                m |= (notlow & 0x80008000u) >> k;
+              } else {
+                const uint32_t h = x >> 1;
+                const uint32_t ge80 = (h & 0x7FC07FC0u) + 0x7FC07FC0u;
+                const uint32_t ge800 = (h & 0x7C007C00u) + 0x7C007C00u;
+                const uint32_t z = (x ^ 0xD800D800u) & 0xF800F800u;         // zero lane <=> surrogate
+                const uint32_t notsur = (z >> 1) + 0x7C007C00u;
+                m |= ((ge80 & 0x80008000u) | ((ge800 & notsur & 0x80008000u) >> 1)) >> (2 * k);
+              }
+            }
+            cnt += (MODE == 0 ? 0u : 8u) + (uint32_t)__popc(m);
+          } else {
+            const uint32_t valid = inrange_units(in, g);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const uint32_t u = u16_unit(w[j], i);
+              const uint32_t c = MODE == 0 ? (uint32_t)((u & 0xFC00u) != 0xDC00u) : u16_utf8_bytes(u);
+              cnt += ((valid >> i) & 1u) ? c : 0u;
             }
           }
-          cnt += (MODE == 0 ? 0u : 8u) + (uint32_t)__popc(m);
-        } else {
-          const uint32_t valid = inrange_units(in, g);
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const uint32_t u = u16_unit(w[j], i);
-            const uint32_t c = MODE == 0 ? (uint32_t)((u & 0xFC00u) != 0xDC00u) : u16_utf8_bytes(u);
-            cnt += ((valid >> i) & 1u) ? c : 0u;
-          }
         }
-      }
-      total += cnt;
+        return cnt;
+      };
+      total += interior ? count_chunk(std::true_type{}) : count_chunk(std::false_type{});
     }
   }
   if (MODE != 2) {

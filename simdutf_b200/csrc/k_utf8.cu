@@ -9,6 +9,7 @@
 // OR-reduction and a vote; any other chunk is re-laid-out through shared memory so that every lane holds 64
 // contiguous bytes and checked in bit-plane form (bitplane.h); first error = atomicMin of position<<8|code.
 #include <cstdlib>
+#include <type_traits>
 
 #include "bitplane.h"
 #include "device_common.cuh"
@@ -181,50 +182,68 @@ __global__ void __launch_bounds__(kBlock) k_count_utf8(const char *ptr, size_t l
   unsigned long long total = 0;
   for (unsigned long long chunk = (unsigned long long)blockIdx.x * kWarps + warp; chunk < nchunks; chunk += nwarps) {
     const unsigned long long g0 = chunk * chunk_gran;
-    uint32_t w[ITEMS][4];
-    bool inside[ITEMS];
+    // Chunks wholly inside the buffer (all but the first and the last) take unguarded loads and none of the per-granule
+    // range tests: the same split as in k_validate_utf8, where the guards were a tenth of the instructions.
+    auto chunk_count = [&](auto interior_tag) -> uint32_t {
+      constexpr bool kInterior = decltype(interior_tag)::value;
+      uint32_t w[ITEMS][4];
+      bool inside[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-      const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
-      if (inside[j] && MODE == 1) {
-        // utf16_length: only the HIGH NIBBLE of a byte matters (a byte starts a character unless it is 10xx, and brings
-        // a second unit when it is 1111), so two words are packed into one word of eight high nibbles and classified
-        // together: per nibble n3 n2 n1 n0, "starts a character" = ~n3 | n2 lands on bit 3, ">= 0xF0" = n3 n2 n1 n0 on
-        // bit 2, and the second pair of words goes to bits 1 and 0: ONE popcount per granule, half the logic
-        // instructions of the per-word form (ncu: this kernel was ALU-bound at 72 % of the pipe and 0.88 of the copy
-        // bandwidth).
-        uint32_t m = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k += 2) {
-          const uint32_t x = bp::bitsel(w[j][k], w[j][k + 1] >> 4, 0xF0F0F0F0u);
-          const uint32_t s1 = x << 1;
-          const uint32_t nc = (~x | s1) & 0x88888888u;
-          const uint32_t a = x & s1;                       // bit 3: n3 n2, bit 1: n1 n0
-          const uint32_t f0 = a & (a << 2) & 0x88888888u;  // bit 3: n3 n2 n1 n0
-          const uint32_t mk = nc | (f0 >> 1);
-          m |= k == 0 ? mk : (mk >> 2);
-        }
-        cnt += (uint32_t)__popc(m);
-      } else if (inside[j]) {
-        // the masks of the four words share one popcount: word k's bit 7s move down by (3 - k)
-        uint32_t m = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) m |= u8_noncont(w[j][k]) >> (3 - k);
-        cnt += (uint32_t)__popc(m);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          uint32_t m = u8_noncont(w[j][k]);
-          if (MODE == 1) m |= u8_ge_f0(w[j][k]) >> 1;  // bit 6 of the same byte: one popc counts both
-          const uint32_t r = inrange_mask_word(in, g, k);
-          m &= r | (r >> 1);
-          cnt += (uint32_t)__popc(m);
+      for (int j = 0; j < ITEMS; j++) {
+        if constexpr (kInterior) {
+          const uint4 v = ldg_stream_v4(in.base + g0 + (unsigned long long)j * 32u + lane);
+          w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
+          inside[j] = true;
+        } else {
+          load_granule(in, g0 + (unsigned long long)j * 32u + lane, w[j], inside[j]);
         }
       }
-    }
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++) {
+        const unsigned long long g = g0 + (unsigned long long)j * 32u + lane;
+        if ((kInterior || inside[j]) && MODE == 1) {
+          // utf16_length: only the HIGH NIBBLE of a byte matters (a byte starts a character unless it is 10xx, and brings
+          // a second unit when it is 1111), so two words are packed into one word of eight high nibbles and classified
+          // together: per nibble n3 n2 n1 n0, "starts a character" = ~n3 | n2 lands on bit 3, ">= 0xF0" = n3 n2 n1 n0 on
+          // bit 2, and the second pair of words goes to bits 1 and 0: ONE popcount per granule, half the logic
+          // instructions of the per-word form (ncu: this kernel was ALU-bound at 72 % of the pipe and 0.88 of the copy
+          // bandwidth).
+          uint32_t m = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k += 2) {
+            const uint32_t x = bp::bitsel(w[j][k], w[j][k + 1] >> 4, 0xF0F0F0F0u);
+            const uint32_t s1 = x << 1;
+            const uint32_t nc = (~x | s1) & 0x88888888u;
+            const uint32_t a = x & s1;                       // bit 3: n3 n2, bit 1: n1 n0
+            const uint32_t f0 = a & (a << 2) & 0x88888888u;  // bit 3: n3 n2 n1 n0
+            const uint32_t mk = nc | (f0 >> 1);
+            m |= k == 0 ? mk : (mk >> 2);
+          }
+          cnt += (uint32_t)__popc(m);
+        } else if (kInterior || inside[j]) {
+          // the masks of the four words share one popcount: word k's bit 7s move down by (3 - k)
+          uint32_t m = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) m |= u8_noncont(w[j][k]) >> (3 - k);
+          cnt += (uint32_t)__popc(m);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            uint32_t m = u8_noncont(w[j][k]);
+            if (MODE == 1) m |= u8_ge_f0(w[j][k]) >> 1;  // bit 6 of the same byte: one popc counts both
+            const uint32_t r = inrange_mask_word(in, g, k);
+            m &= r | (r >> 1);
+            cnt += (uint32_t)__popc(m);
+          }
+        }
+      }
+      return cnt;
+    };
+    // (utf16_length only: 0.895 -> 0.955 of the copy bandwidth inside the bench step; count_utf8 — one popcount per
+    // granule, at 1.0 with the guarded loads — lost 5 % with the split and keeps the one path)
+    const bool interior = MODE == 1 && g0 * 16ull >= in.vbeg && (g0 + chunk_gran) * 16ull <= in.vend;  // warp-uniform
+    const uint32_t cnt = interior ? chunk_count(std::true_type{}) : chunk_count(std::false_type{});
     total += cnt;
   }
   total = warp_sum_u64(total);
